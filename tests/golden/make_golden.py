@@ -1,0 +1,401 @@
+"""Generate the golden fixtures in this directory by running the REAL reference
+(/root/reference, read-only) on CPU fp32 with the runtime shim of SURVEY.md §8(c).
+
+Run in the build container only (`python tests/golden/make_golden.py`); the GPU box has no
+/root/reference — tests read the committed .npz/.json files, never this script's imports.
+
+What is dumped (all fp32, sub-sampled where large so the directory stays < 10 MB):
+  state_dict_<cfg>.json      names + shapes of the reference state_dict (checkpoint layout)
+  image_hiera_t_1024.npz     config 1: set_image + predict(point) on a 1024² random image
+  image_hiera_s_1024.npz     config 2 (B=2): set_image_batch + predict_batch on fundus images
+  video_hiera_s_512.npz      config 3 shape, shrunk: 7 slices @512², bbox on 0,2,4, 1 object
+  video_hiera_t_512_2obj.npz 2 objects, object 2 absent on slice 2 (mask prompt of zeros)
+  modules_hiera_t.npz        per-module known answers (memory attention / encoder, decoder)
+  cc_*.npz                   connected-component labels from a transliteration of the .cu kernels
+"""
+
+import importlib
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from synth_data import seeded_weights, random_image, fundus_images, btcv_volume  # noqa: E402
+
+
+# ----------------------------------------------------------------------------- reference loader
+def _stub_hydra():
+    for name in ("hydra", "hydra.utils", "omegaconf"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["hydra"].initialize_config_module = lambda *a, **k: None
+    sys.modules["hydra"].compose = None
+    sys.modules["hydra.utils"].instantiate = None
+    sys.modules["omegaconf"].OmegaConf = None
+
+
+_FLOAT_RE = re.compile(r"^[-+]?\d+(\.\d*)?[eE][-+]?\d+$")
+
+
+def _instantiate(node):
+    if isinstance(node, dict):
+        if "_target_" in node:
+            mod, cls = node["_target_"].rsplit(".", 1)
+            kwargs = {k: _instantiate(v) for k, v in node.items() if k != "_target_"}
+            return getattr(importlib.import_module(mod), cls)(**kwargs)
+        return {k: _instantiate(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_instantiate(v) for v in node]
+    if isinstance(node, str) and _FLOAT_RE.match(node):
+        return float(node)
+    return node
+
+
+def load_reference(cfg_name, video, image_size=1024, fill_hole_area=8):
+    """Reference model + shim (i)-(iii); CPU: Tensor.cuda -> identity; _C pre-bound to the scipy CC."""
+    _stub_hydra()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    tree = yaml.safe_load(open(f"{REF}/sam2_train/{cfg_name}.yaml"))["model"]
+    extra = dict(dynamic_multimask_via_stability=True, dynamic_multimask_stability_delta=0.05,
+                 dynamic_multimask_stability_thresh=0.98)
+    tree["sam_mask_decoder_extra_args"] = extra
+    if video:
+        tree["_target_"] = "sam2_train.sam2_video_predictor.SAM2VideoPredictor"
+        tree["binarize_mask_from_pts_for_mem_enc"] = True
+        tree["fill_hole_area"] = fill_hole_area
+    import sam2_train  # noqa
+    from oracle.sam2_oracle import connected_components_np
+    cc_mod = types.ModuleType("sam2_train._C")
+
+    def _cc(x):
+        l, c = connected_components_np(x.cpu().numpy())
+        return [torch.from_numpy(l), torch.from_numpy(c)]
+    cc_mod.get_connected_componnets = _cc
+    sam2_train._C = cc_mod
+    sys.modules["sam2_train._C"] = cc_mod
+    m = _instantiate(tree)
+    # shim (i): undo the hard-coded image_size=256 (sam2_base.py:160)
+    m.image_size = image_size
+    m.sam_image_embedding_size = image_size // 16
+    pe = m.sam_prompt_encoder
+    pe.image_embedding_size = (image_size // 16, image_size // 16)
+    pe.input_image_size = (image_size, image_size)
+    pe.mask_input_size = (image_size // 4, image_size // 4)
+    # shim (ii): cell_nums defaults to None (mask_decoder.py:118)
+    dec = m.sam_mask_decoder
+    orig_fwd = dec.forward
+
+    def fwd(*a, cell_nums=None, **k):
+        return orig_fwd(*a, cell_nums=cell_nums, **k)
+    dec.forward = fwd
+    # shim (iii): prompt_encoder.py:190 interpolates to (16,16); make it identity on the dense size
+    import sam2_train.modeling.sam.prompt_encoder as pem
+    real_interp = torch.nn.functional.interpolate
+
+    class _F:
+        def __getattr__(self, k):
+            return getattr(torch.nn.functional, k)
+
+        @staticmethod
+        def interpolate(x, size=None, **kw):
+            return x
+    pem.F = _F()
+    m.eval()
+    return m
+
+
+def ref_state_dict_layout(m):
+    return {k: list(v.shape) for k, v in m.state_dict().items()}
+
+
+def sub(t, step):
+    """Sub-sample the last two dims."""
+    return t[..., ::step, ::step].contiguous()
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- fixtures
+def golden_layout():
+    for cfg in ("sam2_hiera_s", "sam2_hiera_t"):
+        m = load_reference(cfg, video=True)
+        json.dump(ref_state_dict_layout(m), open(f"{OUT}/state_dict_{cfg}.json", "w"), indent=0)
+        print(cfg, len(m.state_dict()))
+
+
+def load_seeded(m, seed=0, obj_score_bias=4.0):
+    spec = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    # draw in the ORACLE's canonical order (oracle.weights.param_spec) so the oracle, the
+    # product and the reference get identical tensors regardless of module registration order
+    from oracle.weights import param_spec
+    from oracle.config import get_config
+    name = "sam2_hiera_s" if len(spec) == 516 else "sam2_hiera_t"
+    ospec = param_spec(get_config(name))
+    assert set(ospec) == set(spec), set(ospec) ^ set(spec)
+    for k in ospec:
+        assert tuple(ospec[k]) == spec[k], (k, ospec[k], spec[k])
+    sd = seeded_weights(ospec, seed=seed, obj_score_bias=obj_score_bias)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return sd
+
+
+@torch.no_grad()
+def golden_image_t():
+    m = load_reference("sam2_hiera_t", video=False)
+    from sam2_train.sam2_image_predictor import SAM2ImagePredictor
+    load_seeded(m)
+    pred = SAM2ImagePredictor(m)
+    img = random_image(1024, 0)
+    pred.set_image(img)
+    out = {}
+    out["image_embed_sub"] = npy(sub(pred._features["image_embed"], 4))
+    out["high_res0_sub"] = npy(sub(pred._features["high_res_feats"][0], 16))
+    out["high_res1_sub"] = npy(sub(pred._features["high_res_feats"][1], 8))
+    masks, ious, low = pred.predict(point_coords=np.array([[512, 512]]), point_labels=np.array([1]),
+                                    multimask_output=True, return_logits=True)
+    out["low_res"] = low
+    out["ious"] = ious
+    out["masks_sub"] = masks[:, ::4, ::4]
+    masks1, ious1, low1 = pred.predict(box=np.array([300, 350, 700, 800]), multimask_output=False, return_logits=True)
+    out["box_low_res"] = low1
+    out["box_ious"] = ious1
+    np.savez_compressed(f"{OUT}/image_hiera_t_1024.npz", **out)
+    print("image_t", {k: v.shape for k, v in out.items()}, float(np.abs(low).mean()))
+
+
+@torch.no_grad()
+def golden_image_s():
+    m = load_reference("sam2_hiera_s", video=False)
+    from sam2_train.sam2_image_predictor import SAM2ImagePredictor
+    load_seeded(m)
+    pred = SAM2ImagePredictor(m)
+    imgs, pts = fundus_images(2, 1024, 0)
+    pred.set_image_batch(imgs)
+    masks, ious, low = pred.predict_batch(point_coords_batch=pts, point_labels_batch=[np.array([1])] * 2,
+                                          multimask_output=True, return_logits=True)
+    out = {"image_embed_sub": npy(sub(pred._features["image_embed"], 4)),
+           "low_res": np.stack(low), "ious": np.stack(ious)}
+    np.savez_compressed(f"{OUT}/image_hiera_s_1024.npz", **out)
+    print("image_s", {k: v.shape for k, v in out.items()})
+
+
+def _run_video(m, vol, boxes, prompt_frames, absent=(), size=512):
+    """Replays func_3d/function.py:226-274: per prompted frame, per object bbox (or zeros mask
+    when the object is absent), then propagate_in_video."""
+    st = m.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
+    st["device"] = st["storage_device"] = torch.device("cpu")
+    n_obj = len(boxes[0])
+    with torch.no_grad():
+        for f in prompt_frames:
+            for o in range(n_obj):
+                if (f, o) in absent:
+                    m.train_add_new_mask(inference_state=st, frame_idx=f, obj_id=o + 1,
+                                         mask=torch.zeros(size, size))
+                else:
+                    m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=o + 1,
+                                         bbox=torch.tensor(boxes[f][o]), clear_old_points=False)
+    outs = {}
+    for f, obj_ids, masks in m.propagate_in_video(st, start_frame_idx=0):
+        outs[f] = masks.clone()
+    return st, outs
+
+
+def golden_video(cfg, size, n_slices, n_obj, prompt_frames, absent, fname, seed):
+    m = load_reference(cfg, video=True, image_size=size)
+    load_seeded(m)
+    vol, boxes = btcv_volume(n_slices, size, seed, n_obj)
+    st, outs = _run_video(m, vol, boxes, prompt_frames, absent, size)
+    out = {"video_res_masks_sub": np.stack([npy(sub(outs[f], 4)) for f in range(n_slices)])}
+    od = st["output_dict"]
+    for f in range(n_slices):
+        o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+        out[f"obj_ptr_{f}"] = npy(o["obj_ptr"])
+        out[f"maskmem_sub_{f}"] = npy(sub(o["maskmem_features"], 4))
+        out[f"pred_masks_{f}"] = npy(o["pred_masks"])
+    np.savez_compressed(f"{OUT}/{fname}", **out)
+    print(fname, out["video_res_masks_sub"].shape,
+          [float((out["video_res_masks_sub"][f] > 0).mean()) for f in range(n_slices)])
+
+
+@torch.no_grad()
+def golden_modules():
+    """Teacher-forced per-module answers on small random inputs (hiera_t weights)."""
+    m = load_reference("sam2_hiera_t", video=True, image_size=512)
+    load_seeded(m)
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    B, HW = 2, 32 * 32
+    curr = torch.randn(HW, B, 256, generator=g)
+    curr_pos = torch.randn(HW, B, 256, generator=g)
+    Lk = 2 * HW + 8
+    memory = torch.randn(Lk, B, 64, generator=g)
+    memory_pos = torch.randn(Lk, B, 64, generator=g)
+    y = m.memory_attention(curr=[curr], curr_pos=[curr_pos], memory=memory, memory_pos=memory_pos,
+                           num_obj_ptr_tokens=8)
+    out["memattn_out_sub"] = npy(y[::4])
+    pix = torch.randn(HW, B, 256, generator=g)
+    hi = torch.randn(B, 1, 512, 512, generator=g) * 3
+    for flag in (False, True):
+        f, pe = m._encode_new_memory([pix], [(32, 32)], hi, is_mask_from_pts=flag)
+        out[f"memenc_feat_{int(flag)}"] = npy(f)
+    out["memenc_pos"] = npy(pe[0][0])
+    emb = torch.randn(B, 256, 32, 32, generator=g)
+    hr0 = torch.randn(B, 32, 128, 128, generator=g)
+    hr1 = torch.randn(B, 64, 64, 64, generator=g)
+    pts = {"point_coords": torch.tensor([[[100.0, 200.0], [300.0, 50.0]], [[10.0, 20.0], [400.0, 500.0]]]),
+           "point_labels": torch.tensor([[1, 0], [2, 3]], dtype=torch.int32)}
+    for mm in (False, True):
+        r = m._forward_sam_heads(emb, point_inputs=pts, high_res_features=[hr0, hr1], multimask_output=mm)
+        out[f"heads_low_{int(mm)}"] = npy(r[0])
+        out[f"heads_ious_{int(mm)}"] = npy(r[2])
+        out[f"heads_ptr_{int(mm)}"] = npy(r[5])
+        out[f"heads_obj_{int(mm)}"] = npy(r[6])
+    mask_in = (torch.rand(B, 1, 512, 512, generator=g) > 0.5).float()
+    r = m._use_mask_as_output(emb, [hr0, hr1], mask_in)
+    out["maskout_low"] = npy(r[0])
+    out["maskout_ptr"] = npy(r[5])
+    out["dense_pe"] = npy(m.sam_prompt_encoder.get_dense_pe())
+    np.savez_compressed(f"{OUT}/modules_hiera_t.npz", **out)
+    print("modules", {k: v.shape for k, v in out.items()})
+
+
+# ----------------------------------------------------------------------------- CC transliteration
+def cc_transliterated(img):
+    """Sequential transliteration of csrc/connected_components.cu:30-209 for ONE image [H,W]
+    (pure-Python loops; small cases only). Thread order does not change the result because
+    union_ is a min-union and the final label is the root after full compression."""
+    H, W = img.shape
+    label = np.zeros(H * W, np.int64)
+    f = img.reshape(-1).astype(bool)
+
+    def find(n):
+        while label[n] != n:
+            n = label[n]
+        return n
+
+    def union(a, b):
+        while True:
+            a, b = find(a), find(b)
+            if a < b:
+                old = label[b]
+                label[b] = min(old, a)
+                if old == b:
+                    return
+                b = old
+            elif b < a:
+                old = label[a]
+                label[a] = min(old, b)
+                if old == a:
+                    return
+                a = old
+            else:
+                return
+    for r in range(0, H, 2):
+        for c in range(0, W, 2):
+            label[r * W + c] = r * W + c
+    for r in range(0, H, 2):
+        for c in range(0, W, 2):
+            idx = r * W + c
+            P = 0
+            if f[idx]:
+                P |= 0x777
+            if r + 1 < H and f[idx + W]:
+                P |= 0x777 << 4
+            if c + 1 < W and f[idx + 1]:
+                P |= 0x777 << 1
+            if c == 0:
+                P &= 0xEEEE
+            if c + 1 >= W:
+                P &= 0x3333
+            elif c + 2 >= W:
+                P &= 0x7777
+            if r == 0:
+                P &= 0xFFF0
+            if r + 1 >= H:
+                P &= 0xFF
+            if P > 0:
+                if (P >> 0) & 1 and f[idx - W - 1]:
+                    union(idx, idx - 2 * W - 2)
+                if ((P >> 1) & 1 and f[idx - W]) or ((P >> 2) & 1 and f[idx - W + 1]):
+                    union(idx, idx - 2 * W)
+                if (P >> 3) & 1 and f[idx + 2 - W]:
+                    union(idx, idx - 2 * W + 2)
+                if ((P >> 4) & 1 and f[idx - 1]) or ((P >> 8) & 1 and f[idx + W - 1]):
+                    union(idx, idx - 2)
+    out = np.zeros(H * W, np.int32)
+    for r in range(0, H, 2):
+        for c in range(0, W, 2):
+            idx = r * W + c
+            y = find(idx) + 1
+            for dr, dc in ((0, 0), (0, 1), (1, 0), (1, 1)):
+                if r + dr < H and c + dc < W:
+                    j = idx + dr * W + dc
+                    out[j] = y if f[j] else 0
+    cnt_init = np.zeros(H * W, np.int32)
+    for j in range(H * W):
+        if out[j] > 0:
+            cnt_init[out[j] - 1] += 1
+    cnt = np.where(out > 0, cnt_init[np.maximum(out - 1, 0)], 0).astype(np.int32)
+    return out.reshape(H, W), cnt.reshape(H, W)
+
+
+def golden_cc():
+    rng = np.random.default_rng(5)
+    masks, labels, counts = [], [], []
+    cases = [(8, 8, 0.5), (16, 12, 0.3), (32, 32, 0.6), (64, 64, 0.45), (64, 64, 0.8), (2, 2, 1.0),
+             (10, 64, 0.55), (64, 64, 0.0), (64, 64, 1.0)]
+    out = {}
+    for i, (h, w, d) in enumerate(cases):
+        mk = (rng.random((h, w)) < d).astype(np.uint8)
+        l, c = cc_transliterated(mk)
+        out[f"mask_{i}"], out[f"labels_{i}"], out[f"counts_{i}"] = mk, l, c
+    # structured: rings (holes), diagonal chains (8-connectivity), a spiral
+    mk = np.zeros((64, 64), np.uint8)
+    mk[4:20, 4:20] = 1
+    mk[8:16, 8:16] = 0
+    for k in range(30):
+        mk[30 + k, 10 + k] = 1
+    mk[40:60, 40] = 1
+    mk[40, 40:60] = 1
+    mk[59, 41:60] = 1
+    i = len(cases)
+    l, c = cc_transliterated(mk)
+    out[f"mask_{i}"], out[f"labels_{i}"], out[f"counts_{i}"] = mk, l, c
+    out["n"] = np.array(i + 1)
+    np.savez_compressed(f"{OUT}/cc_cases.npz", **out)
+    print("cc cases", i + 1)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ["layout", "cc", "modules", "image_t", "image_s", "video_s", "video_t2"]
+    if "layout" in which:
+        golden_layout()
+    if "cc" in which:
+        golden_cc()
+    if "modules" in which:
+        golden_modules()
+    if "image_t" in which:
+        golden_image_t()
+    if "image_s" in which:
+        golden_image_s()
+    if "video_s" in which:
+        golden_video("sam2_hiera_s", 512, 7, 1, (0, 2, 4), (), "video_hiera_s_512.npz", 1234)
+    if "video_t2" in which:
+        golden_video("sam2_hiera_t", 512, 6, 2, (0, 3), ((3, 1),), "video_hiera_t_512_2obj.npz", 77)
