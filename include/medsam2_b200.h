@@ -1,0 +1,165 @@
+/*
+ * medsam2_b200 — C-ABI of the B200-native (sm_100a) kernels behind Medical-SAM2's per-slice
+ * inference hot path.  This library replaces the reference's only native boundary
+ * (sam2_train/_C.so built from sam2_train/csrc/connected_components.cu:213-289) and, in
+ * addition, every tensor op the reference delegates to torch (cuBLAS/cuDNN/SDPA) on that path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers are DEVICE pointers unless named h_*; sizes are element counts;
+ *   - `dt` arguments: MS2_F32 (0) or MS2_BF16 (1);
+ *   - stream-ordered on `stream` (a cudaStream_t), no implicit synchronisation, no allocation
+ *     (workspaces are passed in), no global state besides cached TMA descriptors;
+ *   - return 0 on success, <0 on error; ms2_last_error() gives the message (thread-local);
+ *   - inputs are borrowed and never modified unless documented "in place".
+ * Layouts are token-major (NHWC / [tokens, C]) unless stated.
+ */
+#ifndef MEDSAM2_B200_H
+#define MEDSAM2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS2_F32 0
+#define MS2_BF16 1
+
+#define MS2_ACT_NONE 0
+#define MS2_ACT_GELU 1 /* exact erf GELU (nn.GELU default) */
+#define MS2_ACT_RELU 2
+#define MS2_ACT_SIGMOID 3
+
+typedef void* ms2_stream_t; /* cudaStream_t */
+
+int ms2_version(void);
+const char* ms2_last_error(void);
+/* 1 if the running device is compute capability 10.x (tcgen05 path usable) */
+int ms2_device_is_sm100(void);
+
+/* ---- connected components: replaces _C.get_connected_componnets
+ *      (reference sam2_train/csrc/connected_components.cu:213-282; caller utils/misc.py:47-63).
+ *      mask uint8 [N,1,H,W] (H,W even) -> labels,counts int32 [N,1,H,W].
+ *      label(p) = 1 + min over p's 8-connected component of ((row&~1)*W + (col&~1)); 0 for bg.
+ *      workspace: int32 [N*H*W], only read/written when H*W/4 exceeds the shared-memory path
+ *      (may be NULL otherwise). */
+int ms2_cc_label(const uint8_t* mask, int32_t* labels, int32_t* counts, int32_t* workspace,
+                 int N, int H, int W, ms2_stream_t stream);
+/* fused hole filling (reference utils/misc.py:247-258): out = (bg component of (in<=thresh) with
+ * area<=max_area) ? fill_value : in.  in/out fp32 [N,1,H,W]; requires the shared-memory path
+ * (H*W/4 <= 28672 blocks, e.g. 256x256). */
+int ms2_fill_holes(const float* in, float* out, int N, int H, int W, float thresh, int max_area,
+                   float fill_value, ms2_stream_t stream);
+
+/* ---- LayerNorm over the last dim (nn.LayerNorm / LayerNorm2d in NHWC):
+ *      y = act(LN(x [+ add]) * gamma + beta); x,add fp32 [M,C]; y dtype y_dt. */
+int ms2_layernorm(const float* x, const float* add, const float* gamma, const float* beta, void* y,
+                  int y_dt, int M, int C, float eps, int act, ms2_stream_t stream);
+
+/* ---- GEMM with fused epilogue (every nn.Linear / 1x1 conv / ConvTranspose k2s2 / im2col conv):
+ *      out[M,N] = residual + colscale * act(A[M,K] @ W[N,K]^T + bias)
+ *      A dtype a_dt (row stride lda), W dtype w_dt (row stride K), bias/colscale fp32 [N] or NULL,
+ *      residual fp32 (row stride ldr) or NULL, out dtype o_dt (row stride ldo).
+ *      impl: 0 = auto, 1 = SIMT fp32-accumulate reference kernel, 2 = tcgen05/TMA (bf16 only). */
+int ms2_gemm(const void* A, int a_dt, long lda, const void* W, int w_dt, const float* bias,
+             const float* colscale, const float* residual, long ldr, void* out, int o_dt, long ldo,
+             int M, int N, int K, int act, int impl, ms2_stream_t stream);
+
+/* ---- scaled-dot-product attention, no mask (F.scaled_dot_product_attention call sites:
+ *      hieradet.py:72-76, transformer.py:252-258, :318).  Dense mode:
+ *      q [B,Hh,Lq,D] / k,v [B,Hh,Lk,D] / o [B,Hh,Lq,D] addressed through element strides
+ *      (batch, head, token); D in {16,32,64,96,128,256}; dtype dt for q,k,v,o. */
+int ms2_attention(const void* q, const void* k, const void* v, void* o, int dt,
+                  long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts,
+                  long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts,
+                  int B, int Hh, int Lq, int Lk, int D, float scale, int impl, ms2_stream_t stream);
+
+/* ---- Hiera windowed attention with window partition / zero-pad-as-bias-key / q max-pool /
+ *      unpartition+crop folded into the loads and stores (hieradet.py:58-83,136-159,
+ *      backbones/utils.py:16-62).  qkv [B,H,W,3,heads,D] dtype dt (the qkv Linear output on the
+ *      UNPADDED tokens), qkv_bias fp32 [3*heads*D] (value of q/k/v at zero-padded positions),
+ *      out [B,Ho,Wo,heads*D] dtype dt with Ho=H/(qpool?2:1).  ws = window size (on the input grid). */
+int ms2_window_attention(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
+                         int heads, int D, int ws, int qpool, float scale, ms2_stream_t stream);
+
+/* ---- 2x2 max pool, stride 2, NHWC fp32 (hieradet.py:23-34 on the shortcut). */
+int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int C, ms2_stream_t stream);
+
+/* ---- PatchEmbed: conv 7x7 stride 4 pad 3, 3->Cout, NCHW fp32 image -> NHWC fp32 tokens,
+ *      + precomputed pos-embed table [Ho,Wo,Cout] (backbones/utils.py:87-95, hieradet.py:269-284).
+ *      w fp32 [Cout,3,7,7]. */
+int ms2_patch_embed(const float* img, const float* w, const float* bias, const float* pos, float* out,
+                    int B, int Hin, int Win, int Cout, ms2_stream_t stream);
+
+/* ---- elementwise family (fp32 unless noted) */
+/* y = a*x + b*z + c; x fp32 [n]; z fp32 [zn] or NULL, broadcast as z[i mod zn] (zn divides n);
+ * y dtype y_dt.  Covers residual adds, `curr + 0.1*curr_pos` (memory_attention.py:137-138),
+ * `mask*20-10` (sam2_base.py:418-420) and add-then-cast to the GEMM operand type. */
+int ms2_axpby(const float* x, float a, const float* z, float b, float c, void* y, int y_dt, long n, long zn,
+              ms2_stream_t stream);
+/* y[b,:] = gate[b] > 0 ? x[b,:] : fill   (NO_OBJ_SCORE gating, sam2_base.py:354-363); P elements per row */
+int ms2_gate_rows(const float* x, const float* gate, float fill, float* y, int B, long P, ms2_stream_t stream);
+/* y[b,:] = x[b, idx[b], :]  (best-IoU / stability mask selection, sam2_base.py:376-383,
+ * mask_decoder.py:289-316); x fp32 [B,M,P], idx int32 [B] (clamped to [0,M-1]) */
+int ms2_select_plane(const float* x, const int32_t* idx, float* y, int B, int M, long P, ms2_stream_t stream);
+/* y[m,c] = x[m,c] + s*v[c]  (row-vector broadcast) */
+int ms2_add_rowvec(const float* x, const float* v, float s, float* y, long M, int C, ms2_stream_t stream);
+/* dtype cast between fp32 and dt (n elements) */
+int ms2_cast(const void* x, int x_dt, void* y, int y_dt, long n, ms2_stream_t stream);
+/* y = act(x) */
+int ms2_activation(const float* x, float* y, long n, int act, ms2_stream_t stream);
+/* FPN top-down: fine[b,y,x,c] += coarse[b,y/2,x/2,c]  (image_encoder.py:113-124, nearest x2) */
+int ms2_upsample2x_add(float* fine, const float* coarse, int B, int H, int W, int C, ms2_stream_t stream);
+/* NHWC <-> NCHW fp32 transposes for the reference-facing API tensors */
+int ms2_nhwc_to_nchw(const float* x, float* y, int B, int H, int W, int C, ms2_stream_t stream);
+int ms2_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, ms2_stream_t stream);
+
+/* ---- axial RoPE, in place on a strided [rows, D] matrix of dtype dt (position_encoding.py:167-216).
+ *      row r uses table position (r mod table_len); cos/sin fp32 [table_len, D/2]; rows >= n_rope_rows
+ *      of each batch are left untouched (object-pointer tokens, transformer.py:309-315). */
+int ms2_rope(void* x, int dt, long batch_stride, long row_stride, int B, int rows, int n_rope_rows, int D,
+             const float* cos_t, const float* sin_t, int table_len, ms2_stream_t stream);
+
+/* ---- im2col for the small strided convs (memory_encoder.py:38-58, prompt_encoder.py:54-62,
+ *      sam2_base.py:108): x fp32 NHWC [B,H,W,Cin] -> cols dtype dt [B*Ho*Wo, k*k*Cin]
+ *      (tap order ky,kx,ci), zero padding.  pre: 0 none, 1 sigmoid, 2 (x>0); then x*pre_scale+pre_bias
+ *      is applied to in-range inputs before padding (sam2_base.py:686-696). */
+int ms2_im2col(const float* x, void* cols, int dt, int B, int H, int W, int Cin, int k, int stride, int pad,
+               int pre, float pre_scale, float pre_bias, ms2_stream_t stream);
+
+/* ---- depthwise conv 7x7 pad 3, NHWC fp32, w fp32 [C,7,7] (memory_encoder.py:84-90). */
+int ms2_dwconv7x7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C,
+                  ms2_stream_t stream);
+
+/* ---- ConvTranspose2d k2 s2 epilogue (mask_decoder.py:66-73,233-236): g fp32 [B,H,W,4*C]
+ *      ((dy,dx,c) column order, bias NOT yet added) -> out fp32 [B,2H,2W,C] = act(g + bias + skip). */
+int ms2_pixel_shuffle_add(const float* g, const float* bias, const float* skip, float* out, int B, int H,
+                          int W, int C, int act, ms2_stream_t stream);
+
+/* ---- hypernetwork mask product (mask_decoder.py:247-248): masks[b,m,p] = sum_c hyper[b,m,c]*up[b,p,c]
+ *      up dtype fp32 [B,P,C], hyper fp32 [B,Mk,C], masks fp32 [B,Mk,P]; C<=64, Mk<=8. */
+int ms2_hyper_mask(const float* up, const float* hyper, float* masks, int B, int P, int C, int Mk,
+                   ms2_stream_t stream);
+
+/* ---- bilinear resize, align_corners=False, fp32 planes [N,H,W]->[N,Ho,Wo]
+ *      (F.interpolate call sites sam2_base.py:368, video_predictor:736,831,844, transforms.py:98);
+ *      antialias!=0 selects the triangle-filter variant (sam2_base.py:321-327,421-427). */
+int ms2_resize_bilinear(const float* x, float* y, int N, int H, int W, int Ho, int Wo, int antialias,
+                        ms2_stream_t stream);
+
+/* ---- prompt encoder random-Fourier features (position_encoding.py:130-136,151-158):
+ *      coords fp32 [n,2] already normalised to [0,1]; gauss fp32 [2,F]; out fp32 [n,2F] = [sin|cos]. */
+int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, int F, ms2_stream_t stream);
+
+/* ---- frame ingest (utils/misc.py:215-244, transforms.py:28-42): out fp32 NCHW = (x/255 - mean)/std.
+ *      x is fp32 NCHW (video tensor, in_layout 0) or uint8 NHWC (image predictor, in_layout 1). */
+int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, ms2_stream_t stream);
+
+/* ---- mask statistics for the stability fallback (mask_decoder.py:269-317): per (b) plane of fp32
+ *      logits [N,P]: counts[n,0] = #(x>delta), counts[n,1] = #(x>-delta). */
+int ms2_mask_stability_counts(const float* x, int32_t* counts, int N, long P, float delta, ms2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,74 @@
+// Shared helpers for the medsam2_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define MS2_OK 0
+#define MS2_ERR_ARG (-1)
+#define MS2_ERR_CUDA (-2)
+#define MS2_ERR_UNSUPPORTED (-3)
+
+#define MS2_F32 0
+#define MS2_BF16 1
+
+extern "C" void ms2_set_error(const char* fmt, ...);
+
+#define MS2_CHECK_ARG(cond, ...)                       \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ms2_set_error(__VA_ARGS__);                      \
+      return MS2_ERR_ARG;                              \
+    }                                                  \
+  } while (0)
+
+#define MS2_CHECK_LAUNCH(name)                                             \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      ms2_set_error("%s: %s", name, cudaGetErrorString(e__));              \
+      return MS2_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+#define MS2_CUDA(call, name)                                               \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) {                                              \
+      ms2_set_error("%s: %s", name, cudaGetErrorString(e__));              \
+      return MS2_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+// dtype dispatch helper: calls F<T>() with T = float or bf16
+#define MS2_DISPATCH_DTYPE(dt, T, ...)                                     \
+  do {                                                                     \
+    if ((dt) == MS2_F32) { typedef float T; __VA_ARGS__; }                 \
+    else if ((dt) == MS2_BF16) { typedef bf16 T; __VA_ARGS__; }            \
+    else { ms2_set_error("bad dtype %d", (int)(dt)); return MS2_ERR_ARG; } \
+  } while (0)

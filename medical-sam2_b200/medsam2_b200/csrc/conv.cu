@@ -1,0 +1,189 @@
+// Convolution-shaped kernels of the hot path that are NOT plain GEMMs:
+//   patch_embed  — Hiera PatchEmbed 7x7/s4/p3, 3->96, NCHW image -> NHWC tokens (+pos-embed table)
+//                  (backbones/utils.py:87-95, hieradet.py:279-284)
+//   im2col       — tap gather for the small strided convs (mask down-sampler 3x3/s2, prompt-encoder
+//                  2x2/s2, mask_downsample 4x4/s4) whose contraction then runs through ms2_gemm
+//   dwconv7x7    — CXBlock depth-wise 7x7 (memory_encoder.py:84-90), NHWC, HBM/L2-bound
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ patch embed
+constexpr int PE_T = 8;                      // 8x8 output pixels per CTA
+constexpr int PE_IN = PE_T * 4 + 3;          // 35 input rows/cols
+template <int COUT>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ pos, float* __restrict__ out, int Hin, int Win, int Ho, int Wo) {
+  extern __shared__ float sm[];
+  float* ws = sm;                                  // [147][COUT]
+  float* patch = sm + 147 * COUT;                  // [3][35][36]
+  constexpr int PS = PE_IN + 1;
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * PE_T, ox0 = blockIdx.x * PE_T;
+  for (int i = threadIdx.x; i < 147 * COUT; i += blockDim.x) {
+    int co = i / 147, tap = i - co * 147;          // w is [COUT][3][7][7] = [COUT][147]
+    ws[tap * COUT + co] = w[i];
+  }
+  const int iy0 = oy0 * 4 - 3, ix0 = ox0 * 4 - 3;
+  for (int i = threadIdx.x; i < 3 * PE_IN * PE_IN; i += blockDim.x) {
+    int ci = i / (PE_IN * PE_IN);
+    int r = i - ci * PE_IN * PE_IN;
+    int yy = r / PE_IN, xx = r - yy * PE_IN;
+    int gy = iy0 + yy, gx = ix0 + xx;
+    float v = 0.f;
+    if (gy >= 0 && gy < Hin && gx >= 0 && gx < Win) v = img[(((long)b * 3 + ci) * Hin + gy) * Win + gx];
+    patch[(ci * PE_IN + yy) * PS + xx] = v;
+  }
+  __syncthreads();
+  constexpr int NCG = COUT / 4;                    // channel groups of 4
+  const int t = threadIdx.x;
+  if (t >= NCG * PE_T) return;
+  const int cg = t % NCG, pg = t / NCG;            // pg = output row inside the tile
+  float acc[4][PE_T];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < PE_T; ++j) acc[i][j] = 0.f;
+  for (int ci = 0; ci < 3; ++ci)
+    for (int ky = 0; ky < 7; ++ky) {
+      const float* prow = patch + (ci * PE_IN + pg * 4 + ky) * PS;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float4 wv = *reinterpret_cast<const float4*>(ws + ((ci * 7 + ky) * 7 + kx) * COUT + cg * 4);
+#pragma unroll
+        for (int j = 0; j < PE_T; ++j) {
+          const float x = prow[j * 4 + kx];
+          acc[0][j] = fmaf(x, wv.x, acc[0][j]);
+          acc[1][j] = fmaf(x, wv.y, acc[1][j]);
+          acc[2][j] = fmaf(x, wv.z, acc[2][j]);
+          acc[3][j] = fmaf(x, wv.w, acc[3][j]);
+        }
+      }
+    }
+  const int oy = oy0 + pg;
+  if (oy >= Ho) return;
+#pragma unroll
+  for (int j = 0; j < PE_T; ++j) {
+    const int ox = ox0 + j;
+    if (ox >= Wo) continue;
+    const long tok = ((long)oy * Wo + ox) * COUT + cg * 4;
+    float4 o;
+    o.x = acc[0][j] + bias[cg * 4 + 0];
+    o.y = acc[1][j] + bias[cg * 4 + 1];
+    o.z = acc[2][j] + bias[cg * 4 + 2];
+    o.w = acc[3][j] + bias[cg * 4 + 3];
+    if (pos) {
+      const float4 pv = *reinterpret_cast<const float4*>(pos + tok);
+      o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+    }
+    *reinterpret_cast<float4*>(out + (long)b * Ho * Wo * COUT + tok) = o;
+  }
+}
+
+// ------------------------------------------------------------------ im2col
+template <typename T>
+__global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ cols, int B, int H, int W, int Cin, int k,
+                              int stride, int pad, int Ho, int Wo, int pre, float pre_scale, float pre_bias) {
+  const int KK = k * k * Cin;
+  const long n = (long)B * Ho * Wo * KK;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int col = i % KK;
+    long t = i / KK;
+    int xo = t % Wo; t /= Wo;
+    int yo = t % Ho;
+    int b = t / Ho;
+    int ci = col % Cin;
+    int tap = col / Cin;
+    int ky = tap / k, kx = tap - ky * k;
+    int y = yo * stride - pad + ky, xx = xo * stride - pad + kx;
+    float v = 0.f;
+    if (y >= 0 && y < H && xx >= 0 && xx < W) {
+      v = x[(((long)b * H + y) * W + xx) * Cin + ci];
+      if (pre == 1) v = 1.f / (1.f + expf(-v));
+      else if (pre == 2) v = v > 0.f ? 1.f : 0.f;
+      v = v * pre_scale + pre_bias;
+    }
+    cols[i] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------ depth-wise 7x7
+__global__ void __launch_bounds__(256)
+dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ y, int B, int H, int W, int C) {
+  __shared__ float ws[49][64];
+  const int c0 = blockIdx.y * 64;
+  const int cl = threadIdx.x & 63, pl = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) {
+    int c = i / 49, tap = i - c * 49;
+    ws[tap][c] = (c0 + c < C) ? w[(long)(c0 + c) * 49 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int c = c0 + cl;
+  if (c >= C) return;
+  const long npix = (long)B * H * W;
+  for (long p = (long)blockIdx.x * 4 + pl; p < npix; p += (long)gridDim.x * 4) {
+    int xx = p % W;
+    long t = p / W;
+    int yy = t % H;
+    int b = t / H;
+    float acc = bias ? bias[c] : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      int sy = yy + ky - 3;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        int sx = xx + kx - 3;
+        if (sx < 0 || sx >= W) continue;
+        acc = fmaf(x[(((long)b * H + sy) * W + sx) * C + c], ws[ky * 7 + kx][cl], acc);
+      }
+    }
+    y[p * C + c] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int ms2_patch_embed(const float* img, const float* w, const float* bias, const float* pos, float* out,
+                               int B, int Hin, int Win, int Cout, void* stream) {
+  MS2_CHECK_ARG(img && w && bias && out, "patch_embed: null pointer");
+  MS2_CHECK_ARG(Cout == 96, "patch_embed: only embed_dim 96 is instantiated (got %d)", Cout);
+  const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
+  if (!B) return MS2_OK;
+  size_t smem = sizeof(float) * (147 * 96 + 3 * PE_IN * (PE_IN + 1));
+  MS2_CUDA(cudaFuncSetAttribute(patch_embed_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+           "patch_embed attr");
+  dim3 grid(ceil_div(Wo, PE_T), ceil_div(Ho, PE_T), B);
+  patch_embed_kernel<96><<<grid, 256, smem, (cudaStream_t)stream>>>(img, w, bias, pos, out, Hin, Win, Ho, Wo);
+  MS2_CHECK_LAUNCH("patch_embed");
+  return MS2_OK;
+}
+
+extern "C" int ms2_im2col(const float* x, void* cols, int dt, int B, int H, int W, int Cin, int k, int stride, int pad,
+                          int pre, float pre_scale, float pre_bias, void* stream) {
+  MS2_CHECK_ARG(x && cols && k > 0 && stride > 0, "im2col: bad args");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  long n = (long)B * Ho * Wo * k * k * Cin;
+  if (!n) return MS2_OK;
+  long blocks = (n + 255) / 256;
+  int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
+  MS2_DISPATCH_DTYPE(dt, T, (im2col_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(
+                                x, (T*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, pre, pre_scale, pre_bias)));
+  MS2_CHECK_LAUNCH("im2col");
+  return MS2_OK;
+}
+
+extern "C" int ms2_dwconv7x7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C,
+                             void* stream) {
+  MS2_CHECK_ARG(x && w && y, "dwconv7x7: null pointer");
+  long npix = (long)B * H * W;
+  if (!npix) return MS2_OK;
+  long gx = (npix + 3) / 4;
+  if (gx > 148L * 8) gx = 148L * 8;
+  dim3 grid((int)gx, ceil_div(C, 64));
+  dwconv7x7_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C);
+  MS2_CHECK_LAUNCH("dwconv7x7");
+  return MS2_OK;
+}

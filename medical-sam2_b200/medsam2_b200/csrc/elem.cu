@@ -1,0 +1,328 @@
+// Memory-bound element-wise / layout kernels of the hot path (HBM roofline; all are single-pass,
+// coalesced along the channel (innermost) dimension, grid-stride with a grid sized to the SM count).
+#include "common.cuh"
+
+namespace {
+
+inline int grid_for(long n, int threads = 256) {
+  long b = (n + threads - 1) / threads;
+  const long cap = 148L * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename TO>
+__global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ z, float b, float c,
+                             TO* __restrict__ y, long n, long zn) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = from_f<TO>(a * x[i] + (z ? b * z[i % zn] : 0.f) + c);
+}
+
+__global__ void gate_rows_kernel(const float* __restrict__ x, const float* __restrict__ gate, float fill,
+                                 float* __restrict__ y, long n, long P) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = gate[i / P] > 0.f ? x[i] : fill;
+}
+
+__global__ void select_plane_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                    float* __restrict__ y, int B, int M, long P) {
+  const long n = (long)B * P;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long b = i / P, p = i - b * P;
+    int m = idx[b];
+    m = m < 0 ? 0 : (m >= M ? M - 1 : m);
+    y[i] = x[(b * M + m) * P + p];
+  }
+}
+
+__global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ v, float s,
+                                  float* __restrict__ y, long n, int C) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = x[i] + s * v[i % C];
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = from_f<TO>(to_f(x[i]));
+}
+
+__global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, long n, int act) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (act == 1) v = gelu_erf(v);
+    else if (act == 2) v = fmaxf(v, 0.f);
+    else if (act == 3) v = 1.f / (1.f + expf(-v));
+    y[i] = v;
+  }
+}
+
+__global__ void upsample2x_add_kernel(float* __restrict__ fine, const float* __restrict__ coarse, int B, int H,
+                                      int W, int C) {
+  const long n = (long)B * H * W * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = i % C;
+    long t = i / C;
+    int x = t % W; t /= W;
+    int y = t % H;
+    int b = t / H;
+    fine[i] += coarse[(((long)b * (H / 2) + y / 2) * (W / 2) + x / 2) * C + c];
+  }
+}
+
+// tiled transpose of [R, Cc] -> [Cc, R] per batch (NHWC<->NCHW with R=H*W)
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, long R, int Cc) {
+  __shared__ float tile[32][33];
+  const long b = blockIdx.z;
+  const float* xb = x + b * R * Cc;
+  float* yb = y + b * R * Cc;
+  long r0 = (long)blockIdx.y * 32;
+  int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long r = r0 + i;
+    int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? xb[r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long r = r0 + threadIdx.x;
+    if (r < R && c < Cc) yb[(long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long n = (long)B * Ho * Wo * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = i % C;
+    long t = i / C;
+    int xo = t % Wo; t /= Wo;
+    int yo = t % Ho;
+    int b = t / Ho;
+    const float* p = x + (((long)b * H + 2 * yo) * W + 2 * xo) * C + c;
+    y[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(long)W * C], p[(long)W * C + C]));
+  }
+}
+
+__global__ void pixel_shuffle_add_kernel(const float* __restrict__ g, const float* __restrict__ bias,
+                                         const float* __restrict__ skip, float* __restrict__ out, int B, int H,
+                                         int W, int C, int act) {
+  const long n = (long)B * 2 * H * 2 * W * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = i % C;
+    long t = i / C;
+    int xo = t % (2 * W); t /= (2 * W);
+    int yo = t % (2 * H);
+    int b = t / (2 * H);
+    int dy = yo & 1, dx = xo & 1;
+    float v = g[((((long)b * H + (yo >> 1)) * W + (xo >> 1)) * 4 + dy * 2 + dx) * C + c];
+    if (bias) v += bias[c];
+    if (skip) v += skip[i];
+    if (act == 1) v = gelu_erf(v);
+    out[i] = v;
+  }
+}
+
+// one warp per pixel: lanes own channels, Mk dot products reduced by shuffles
+__global__ void hyper_mask_kernel(const float* __restrict__ up, const float* __restrict__ hyper,
+                                  float* __restrict__ masks, int B, int P, int C, int Mk) {
+  __shared__ float hs[8 * 64];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < Mk * C; i += blockDim.x) hs[i] = hyper[(long)b * Mk * C + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int p = blockIdx.x * wpb + warp; p < P; p += gridDim.x * wpb) {
+    const float* u = up + ((long)b * P + p) * C;
+    float u0 = lane < C ? u[lane] : 0.f;
+    float u1 = lane + 32 < C ? u[lane + 32] : 0.f;
+    for (int m = 0; m < Mk; ++m) {
+      float s = u0 * (lane < C ? hs[m * C + lane] : 0.f) + u1 * (lane + 32 < C ? hs[m * C + lane + 32] : 0.f);
+      s = warp_sum(s);
+      if (lane == 0) masks[((long)b * Mk + m) * P + p] = s;
+    }
+  }
+}
+
+__global__ void fourier_pe_kernel(const float* __restrict__ coords, const float* __restrict__ gauss,
+                                  float* __restrict__ out, int n, int F) {
+  const long total = (long)n * F;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int f = i % F;
+    long r = i / F;
+    float cx = 2.f * coords[r * 2] - 1.f, cy = 2.f * coords[r * 2 + 1] - 1.f;
+    float v = cx * gauss[f] + cy * gauss[F + f];
+    v = 6.283185307179586f * v;
+    out[r * 2 * F + f] = sinf(v);
+    out[r * 2 * F + F + f] = cosf(v);
+  }
+}
+
+__global__ void normalize_image_kernel(const void* __restrict__ x, int in_layout, float* __restrict__ out, int B,
+                                       int H, int W) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const long n = (long)B * 3 * H * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    int xw = t % W; t /= W;
+    int yh = t % H; t /= H;
+    int c = t % 3;
+    int b = t / 3;
+    float v;
+    if (in_layout == 0) v = ((const float*)x)[i];
+    else v = (float)((const uint8_t*)x)[(((long)b * H + yh) * W + xw) * 3 + c];
+    out[i] = (v / 255.0f - mean[c]) / stdv[c];
+  }
+}
+
+__global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
+  const int nidx = blockIdx.y;
+  const float* xp = x + (long)nidx * P;
+  int hi = 0, lo = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long)gridDim.x * blockDim.x) {
+    float v = xp[i];
+    hi += v > delta;
+    lo += v > -delta;
+  }
+  hi = __reduce_add_sync(0xffffffffu, hi);
+  lo = __reduce_add_sync(0xffffffffu, lo);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(counts + nidx * 2, hi);
+    atomicAdd(counts + nidx * 2 + 1, lo);
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int ms2_axpby(const float* x, float a, const float* z, float b, float c, void* y, int y_dt, long n,
+                         long zn, void* stream) {
+  MS2_CHECK_ARG(x && y && n >= 0, "axpby: bad args");
+  MS2_CHECK_ARG(!z || (zn > 0 && n % zn == 0), "axpby: z length must divide n");
+  if (!n) return MS2_OK;
+  MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_kernel<TO><<<grid_for(n), 256, 0, ST>>>(x, a, z, b, c, (TO*)y, n, z ? zn : 1)));
+  MS2_CHECK_LAUNCH("axpby");
+  return MS2_OK;
+}
+extern "C" int ms2_gate_rows(const float* x, const float* gate, float fill, float* y, int B, long P, void* stream) {
+  MS2_CHECK_ARG(x && gate && y, "gate_rows: null");
+  long n = (long)B * P;
+  if (!n) return MS2_OK;
+  gate_rows_kernel<<<grid_for(n), 256, 0, ST>>>(x, gate, fill, y, n, P);
+  MS2_CHECK_LAUNCH("gate_rows");
+  return MS2_OK;
+}
+extern "C" int ms2_select_plane(const float* x, const int32_t* idx, float* y, int B, int M, long P, void* stream) {
+  MS2_CHECK_ARG(x && idx && y && M > 0, "select_plane: bad args");
+  long n = (long)B * P;
+  if (!n) return MS2_OK;
+  select_plane_kernel<<<grid_for(n), 256, 0, ST>>>(x, idx, y, B, M, P);
+  MS2_CHECK_LAUNCH("select_plane");
+  return MS2_OK;
+}
+extern "C" int ms2_add_rowvec(const float* x, const float* v, float s, float* y, long M, int C, void* stream) {
+  MS2_CHECK_ARG(x && v && y && M >= 0 && C > 0, "add_rowvec: bad args");
+  if (!M) return MS2_OK;
+  add_rowvec_kernel<<<grid_for(M * C), 256, 0, ST>>>(x, v, s, y, M * C, C);
+  MS2_CHECK_LAUNCH("add_rowvec");
+  return MS2_OK;
+}
+extern "C" int ms2_cast(const void* x, int x_dt, void* y, int y_dt, long n, void* stream) {
+  MS2_CHECK_ARG(x && y && n >= 0, "cast: bad args");
+  if (!n) return MS2_OK;
+  int g = grid_for(n);
+  if (x_dt == MS2_F32 && y_dt == MS2_BF16) cast_kernel<float, bf16><<<g, 256, 0, ST>>>((const float*)x, (bf16*)y, n);
+  else if (x_dt == MS2_BF16 && y_dt == MS2_F32) cast_kernel<bf16, float><<<g, 256, 0, ST>>>((const bf16*)x, (float*)y, n);
+  else if (x_dt == MS2_F32 && y_dt == MS2_F32) cast_kernel<float, float><<<g, 256, 0, ST>>>((const float*)x, (float*)y, n);
+  else if (x_dt == MS2_BF16 && y_dt == MS2_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, ST>>>((const bf16*)x, (bf16*)y, n);
+  else { ms2_set_error("cast: bad dtype"); return MS2_ERR_ARG; }
+  MS2_CHECK_LAUNCH("cast");
+  return MS2_OK;
+}
+extern "C" int ms2_activation(const float* x, float* y, long n, int act, void* stream) {
+  MS2_CHECK_ARG(x && y && n >= 0, "activation: bad args");
+  if (!n) return MS2_OK;
+  act_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n, act);
+  MS2_CHECK_LAUNCH("activation");
+  return MS2_OK;
+}
+extern "C" int ms2_upsample2x_add(float* fine, const float* coarse, int B, int H, int W, int C, void* stream) {
+  MS2_CHECK_ARG(fine && coarse && (H % 2 == 0) && (W % 2 == 0), "upsample2x_add: bad args");
+  long n = (long)B * H * W * C;
+  if (!n) return MS2_OK;
+  upsample2x_add_kernel<<<grid_for(n), 256, 0, ST>>>(fine, coarse, B, H, W, C);
+  MS2_CHECK_LAUNCH("upsample2x_add");
+  return MS2_OK;
+}
+static int transpose_launch(const float* x, float* y, int B, long R, int Cc, cudaStream_t st) {
+  if (!B || !R || !Cc) return MS2_OK;
+  dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(x, y, R, Cc);
+  MS2_CHECK_LAUNCH("transpose");
+  return MS2_OK;
+}
+extern "C" int ms2_nhwc_to_nchw(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  MS2_CHECK_ARG(x && y, "nhwc_to_nchw: null");
+  return transpose_launch(x, y, B, (long)H * W, C, ST);
+}
+extern "C" int ms2_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  MS2_CHECK_ARG(x && y, "nchw_to_nhwc: null");
+  // input viewed as [C, HW] -> output [HW, C]
+  if (!B) return MS2_OK;
+  dim3 grid(ceil_div((long)H * W, 32), ceil_div(C, 32), B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ST>>>(x, y, (long)C, H * W);
+  MS2_CHECK_LAUNCH("transpose");
+  return MS2_OK;
+}
+extern "C" int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  MS2_CHECK_ARG(x && y && (H % 2 == 0) && (W % 2 == 0), "maxpool2x2: bad args");
+  long n = (long)B * (H / 2) * (W / 2) * C;
+  if (!n) return MS2_OK;
+  maxpool2x2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, B, H, W, C);
+  MS2_CHECK_LAUNCH("maxpool2x2");
+  return MS2_OK;
+}
+extern "C" int ms2_pixel_shuffle_add(const float* g, const float* bias, const float* skip, float* out, int B, int H,
+                                     int W, int C, int act, void* stream) {
+  MS2_CHECK_ARG(g && out, "pixel_shuffle_add: null");
+  long n = (long)B * 4 * H * W * C;
+  if (!n) return MS2_OK;
+  pixel_shuffle_add_kernel<<<grid_for(n), 256, 0, ST>>>(g, bias, skip, out, B, H, W, C, act);
+  MS2_CHECK_LAUNCH("pixel_shuffle_add");
+  return MS2_OK;
+}
+extern "C" int ms2_hyper_mask(const float* up, const float* hyper, float* masks, int B, int P, int C, int Mk,
+                              void* stream) {
+  MS2_CHECK_ARG(up && hyper && masks && C <= 64 && Mk <= 8, "hyper_mask: bad args (C<=64, Mk<=8)");
+  if (!B || !P) return MS2_OK;
+  dim3 grid(148 * 4, B);
+  hyper_mask_kernel<<<grid, 256, 0, ST>>>(up, hyper, masks, B, P, C, Mk);
+  MS2_CHECK_LAUNCH("hyper_mask");
+  return MS2_OK;
+}
+extern "C" int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, int F, void* stream) {
+  MS2_CHECK_ARG(coords && gauss && out, "fourier_pe: null");
+  if (!n) return MS2_OK;
+  fourier_pe_kernel<<<grid_for((long)n * F), 256, 0, ST>>>(coords, gauss, out, n, F);
+  MS2_CHECK_LAUNCH("fourier_pe");
+  return MS2_OK;
+}
+extern "C" int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, void* stream) {
+  MS2_CHECK_ARG(x && out && (in_layout == 0 || in_layout == 1), "normalize_image: bad args");
+  long n = (long)B * 3 * H * W;
+  if (!n) return MS2_OK;
+  normalize_image_kernel<<<grid_for(n), 256, 0, ST>>>(x, in_layout, out, B, H, W);
+  MS2_CHECK_LAUNCH("normalize_image");
+  return MS2_OK;
+}
+extern "C" int ms2_mask_stability_counts(const float* x, int32_t* counts, int N, long P, float delta, void* stream) {
+  MS2_CHECK_ARG(x && counts, "mask_stability_counts: null");
+  if (!N) return MS2_OK;
+  MS2_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 2 * N, ST), "stability memset");
+  dim3 grid(64, N);
+  stability_counts_kernel<<<grid, 256, 0, ST>>>(x, counts, P, delta);
+  MS2_CHECK_LAUNCH("stability_counts");
+  return MS2_OK;
+}

@@ -1,0 +1,84 @@
+// Bilinear resampling of fp32 planes, align_corners=False (torch F.interpolate semantics):
+//   plain     — mask logits x4 up-sampling (sam2_base.py:368), video-resolution output
+//               (sam2_video_predictor.py:736,831,844), image-predictor post-processing (transforms.py:98)
+//   antialias — triangle-filter down-sampling of mask prompts (sam2_base.py:321-327,421-427)
+// HBM-bound: reads H*W*4, writes Ho*Wo*4 bytes per plane; one thread per output pixel, x fastest.
+#include "common.cuh"
+
+namespace {
+
+__global__ void bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int Ho,
+                                int Wo, float sh, float sw) {
+  const long n = (long)N * Ho * Wo;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int xo = i % Wo;
+    long t = i / Wo;
+    int yo = t % Ho;
+    long pl = t / Ho;
+    float sy = fmaxf(sh * (yo + 0.5f) - 0.5f, 0.f);
+    float sx = fmaxf(sw * (xo + 0.5f) - 0.5f, 0.f);
+    int y0 = (int)sy, x0 = (int)sx;
+    int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    float ly = sy - y0, lx = sx - x0;
+    const float* p = x + pl * (long)H * W;
+    float v00 = p[(long)y0 * W + x0], v01 = p[(long)y0 * W + x1];
+    float v10 = p[(long)y1 * W + x0], v11 = p[(long)y1 * W + x1];
+    y[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
+__device__ __forceinline__ void aa_bounds(int o, float scale, int in, float& center, float& support, float& inv,
+                                          int& lo, int& size) {
+  support = (scale >= 1.f) ? scale : 1.f;
+  inv = (scale >= 1.f) ? 1.f / scale : 1.f;
+  center = scale * (o + 0.5f);
+  lo = max((int)(center - support + 0.5f), 0);
+  size = min((int)(center + support + 0.5f), in) - lo;
+}
+
+__global__ void bilinear_aa_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int Ho,
+                                   int Wo, float sh, float sw) {
+  const long n = (long)N * Ho * Wo;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int xo = i % Wo;
+    long t = i / Wo;
+    int yo = t % Ho;
+    long pl = t / Ho;
+    float cy, supy, invy, cx, supx, invx;
+    int ylo, ysz, xlo, xsz;
+    aa_bounds(yo, sh, H, cy, supy, invy, ylo, ysz);
+    aa_bounds(xo, sw, W, cx, supx, invx, xlo, xsz);
+    float wxs = 0.f;
+    for (int j = 0; j < xsz; ++j) wxs += fmaxf(0.f, 1.f - fabsf((j + xlo - cx + 0.5f) * invx));
+    float wys = 0.f;
+    for (int j = 0; j < ysz; ++j) wys += fmaxf(0.f, 1.f - fabsf((j + ylo - cy + 0.5f) * invy));
+    const float* p = x + pl * (long)H * W;
+    float acc = 0.f;
+    for (int jy = 0; jy < ysz; ++jy) {
+      float wy = fmaxf(0.f, 1.f - fabsf((jy + ylo - cy + 0.5f) * invy)) / wys;
+      float row = 0.f;
+      for (int jx = 0; jx < xsz; ++jx) {
+        float wx = fmaxf(0.f, 1.f - fabsf((jx + xlo - cx + 0.5f) * invx)) / wxs;
+        row = fmaf(wx, p[(long)(ylo + jy) * W + xlo + jx], row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
+    y[i] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int ms2_resize_bilinear(const float* x, float* y, int N, int H, int W, int Ho, int Wo, int antialias,
+                                   void* stream) {
+  MS2_CHECK_ARG(x && y && H > 0 && W > 0 && Ho > 0 && Wo > 0, "resize_bilinear: bad args");
+  long n = (long)N * Ho * Wo;
+  if (!n) return MS2_OK;
+  long blocks = (n + 255) / 256;
+  int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
+  float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  if (antialias) bilinear_aa_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, Ho, Wo, sh, sw);
+  else bilinear_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, Ho, Wo, sh, sw);
+  MS2_CHECK_LAUNCH("resize_bilinear");
+  return MS2_OK;
+}

@@ -1,0 +1,40 @@
+// Axial rotary position encoding applied in place (position_encoding.py:167-216; call site
+// transformer.py:301-315).  Adjacent channel pairs (2i,2i+1) rotate by the table angle of the token's
+// position inside its 64x64 frame; memory keys restart at 0 every table_len rows (rope_k_repeat) and
+// the trailing object-pointer rows are not rotated.  fp32 math, like the reference's complex fp32.
+#include "common.cuh"
+
+namespace {
+template <typename T>
+__global__ void rope_kernel(T* __restrict__ x, long batch_stride, long row_stride, int B, int rows, int n_rope_rows,
+                            int D, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int table_len) {
+  const int half = D / 2;
+  const long n = (long)B * n_rope_rows * half;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int pr = i % half;
+    long t = i / half;
+    int r = t % n_rope_rows;
+    int b = t / n_rope_rows;
+    int pos = r % table_len;
+    float c = cos_t[(long)pos * half + pr], s = sin_t[(long)pos * half + pr];
+    T* p = x + b * batch_stride + r * row_stride + 2 * pr;
+    float a = to_f(p[0]), bb = to_f(p[1]);
+    p[0] = from_f<T>(a * c - bb * s);
+    p[1] = from_f<T>(a * s + bb * c);
+  }
+}
+}  // namespace
+
+extern "C" int ms2_rope(void* x, int dt, long batch_stride, long row_stride, int B, int rows, int n_rope_rows, int D,
+                        const float* cos_t, const float* sin_t, int table_len, void* stream) {
+  MS2_CHECK_ARG(x && cos_t && sin_t && D % 2 == 0 && table_len > 0, "rope: bad args");
+  MS2_CHECK_ARG(n_rope_rows <= rows, "rope: n_rope_rows > rows");
+  long n = (long)B * n_rope_rows * (D / 2);
+  if (n <= 0) return MS2_OK;
+  long blocks = (n + 255) / 256;
+  int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
+  MS2_DISPATCH_DTYPE(dt, T, (rope_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(
+                                (T*)x, batch_stride, row_stride, B, rows, n_rope_rows, D, cos_t, sin_t, table_len)));
+  MS2_CHECK_LAUNCH("rope");
+  return MS2_OK;
+}

@@ -1,0 +1,416 @@
+"""SAM2Base: per-frame glue of the hot path (reference modeling/sam2_base.py:22-830).
+
+Same constructor arguments, sub-module attribute names, learned tokens and method signatures as the
+reference, so `state_dict`s load strictly and `func_2d` / `func_3d` style callers work unchanged;
+`image_size` follows the config (the fork hard-codes 256, SURVEY.md §0 finding 1).  Internally every
+tensor is token-major and all arithmetic runs in the kernels of `medsam2_b200.ops`.
+"""
+import torch
+from torch import nn
+from torch.nn.init import trunc_normal_
+
+from .. import ops
+from ..runtime import CACHE, compute_dtype, conv_w_c, p32, w_c
+from .sam.mask_decoder import MaskDecoder
+from .sam.prompt_encoder import PromptEncoder
+from .sam.transformer import TwoWayTransformer
+from .sam2_utils import (MLP, Linear, as_nchw_view, as_nhwc, select_closest_cond_frames, seq_to_tokens,
+                         to_compute)
+
+NO_OBJ_SCORE = -1024.0
+
+
+class SAM2Base(nn.Module):
+    def __init__(self, image_encoder, memory_attention, memory_encoder, num_maskmem=7, image_size=512,
+                 backbone_stride=16, sigmoid_scale_for_mem_enc=1.0, sigmoid_bias_for_mem_enc=0.0,
+                 binarize_mask_from_pts_for_mem_enc=False, use_mask_input_as_output_without_sam=False,
+                 max_cond_frames_in_attn=-1, directly_add_no_mem_embed=False, use_high_res_features_in_sam=False,
+                 multimask_output_in_sam=False, multimask_min_pt_num=1, multimask_max_pt_num=1,
+                 multimask_output_for_tracking=False, use_multimask_token_for_obj_ptr=False,
+                 iou_prediction_use_sigmoid=False, memory_temporal_stride_for_eval=1,
+                 add_all_frames_to_correct_as_cond=False, non_overlap_masks_for_mem_enc=False,
+                 use_obj_ptrs_in_encoder=False, max_obj_ptrs_in_encoder=16, add_tpos_enc_to_obj_ptrs=True,
+                 proj_tpos_enc_in_obj_ptrs=False, only_obj_ptrs_in_the_past_for_eval=False,
+                 pred_obj_scores=False, pred_obj_scores_mlp=False, fixed_no_obj_ptr=False, soft_no_obj_ptr=False,
+                 use_mlp_for_obj_ptr_proj=False, sam_mask_decoder_extra_args=None, compile_image_encoder=False):
+        super().__init__()
+        self.image_encoder = image_encoder
+        self.use_high_res_features_in_sam = use_high_res_features_in_sam
+        self.num_feature_levels = 3 if use_high_res_features_in_sam else 1
+        self.use_obj_ptrs_in_encoder = use_obj_ptrs_in_encoder
+        self.max_obj_ptrs_in_encoder = max_obj_ptrs_in_encoder
+        if use_obj_ptrs_in_encoder:
+            self.mask_downsample = nn.Conv2d(1, 1, kernel_size=4, stride=4)
+        self.add_tpos_enc_to_obj_ptrs = add_tpos_enc_to_obj_ptrs
+        if proj_tpos_enc_in_obj_ptrs:
+            assert add_tpos_enc_to_obj_ptrs
+        self.proj_tpos_enc_in_obj_ptrs = proj_tpos_enc_in_obj_ptrs
+        self.only_obj_ptrs_in_the_past_for_eval = only_obj_ptrs_in_the_past_for_eval
+        self.memory_attention = memory_attention
+        self.hidden_dim = memory_attention.d_model
+        self.memory_encoder = memory_encoder
+        self.mem_dim = self.hidden_dim
+        if hasattr(self.memory_encoder, "out_proj") and hasattr(self.memory_encoder.out_proj, "weight"):
+            self.mem_dim = self.memory_encoder.out_proj.weight.shape[0]
+        self.num_maskmem = num_maskmem
+        self.maskmem_tpos_enc = nn.Parameter(torch.zeros(num_maskmem, 1, 1, self.mem_dim))
+        trunc_normal_(self.maskmem_tpos_enc, std=0.02)
+        self.no_mem_embed = nn.Parameter(torch.zeros(1, 1, self.hidden_dim))
+        self.no_mem_pos_enc = nn.Parameter(torch.zeros(1, 1, self.hidden_dim))
+        trunc_normal_(self.no_mem_embed, std=0.02)
+        trunc_normal_(self.no_mem_pos_enc, std=0.02)
+        self.directly_add_no_mem_embed = directly_add_no_mem_embed
+        self.sigmoid_scale_for_mem_enc = sigmoid_scale_for_mem_enc
+        self.sigmoid_bias_for_mem_enc = sigmoid_bias_for_mem_enc
+        self.binarize_mask_from_pts_for_mem_enc = binarize_mask_from_pts_for_mem_enc
+        self.non_overlap_masks_for_mem_enc = non_overlap_masks_for_mem_enc
+        self.memory_temporal_stride_for_eval = memory_temporal_stride_for_eval
+        self.use_mask_input_as_output_without_sam = use_mask_input_as_output_without_sam
+        self.multimask_output_in_sam = multimask_output_in_sam
+        self.multimask_min_pt_num = multimask_min_pt_num
+        self.multimask_max_pt_num = multimask_max_pt_num
+        self.multimask_output_for_tracking = multimask_output_for_tracking
+        self.use_multimask_token_for_obj_ptr = use_multimask_token_for_obj_ptr
+        self.iou_prediction_use_sigmoid = iou_prediction_use_sigmoid
+        self.image_size = image_size
+        self.backbone_stride = backbone_stride
+        self.sam_mask_decoder_extra_args = sam_mask_decoder_extra_args
+        self.pred_obj_scores = pred_obj_scores
+        self.pred_obj_scores_mlp = pred_obj_scores_mlp
+        self.fixed_no_obj_ptr = fixed_no_obj_ptr
+        self.soft_no_obj_ptr = soft_no_obj_ptr
+        if self.fixed_no_obj_ptr:
+            assert self.pred_obj_scores and self.use_obj_ptrs_in_encoder
+        if self.pred_obj_scores and self.use_obj_ptrs_in_encoder:
+            self.no_obj_ptr = nn.Parameter(torch.zeros(1, self.hidden_dim))
+            trunc_normal_(self.no_obj_ptr, std=0.02)
+        self.use_mlp_for_obj_ptr_proj = use_mlp_for_obj_ptr_proj
+        self._build_sam_heads()
+        self.add_all_frames_to_correct_as_cond = add_all_frames_to_correct_as_cond
+        self.max_cond_frames_in_attn = max_cond_frames_in_attn
+        assert not compile_image_encoder, "there is no tracing compiler on this path"
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("Please use the corresponding methods in SAM2VideoPredictor for inference.")
+
+    def _build_sam_heads(self):
+        self.sam_prompt_embed_dim = self.hidden_dim
+        self.sam_image_embedding_size = self.image_size // self.backbone_stride
+        e = self.sam_image_embedding_size
+        self.sam_prompt_encoder = PromptEncoder(embed_dim=self.sam_prompt_embed_dim, image_embedding_size=(e, e),
+                                                input_image_size=(self.image_size, self.image_size), mask_in_chans=16)
+        self.sam_mask_decoder = MaskDecoder(
+            num_multimask_outputs=3,
+            transformer=TwoWayTransformer(depth=2, embedding_dim=self.sam_prompt_embed_dim, mlp_dim=2048, num_heads=8),
+            transformer_dim=self.sam_prompt_embed_dim, iou_head_depth=3, iou_head_hidden_dim=256,
+            use_high_res_features=self.use_high_res_features_in_sam,
+            iou_prediction_use_sigmoid=self.iou_prediction_use_sigmoid, pred_obj_scores=self.pred_obj_scores,
+            pred_obj_scores_mlp=self.pred_obj_scores_mlp,
+            use_multimask_token_for_obj_ptr=self.use_multimask_token_for_obj_ptr,
+            **(self.sam_mask_decoder_extra_args or {}))
+        if self.use_obj_ptrs_in_encoder:
+            self.obj_ptr_proj = Linear(self.hidden_dim, self.hidden_dim)
+            if self.use_mlp_for_obj_ptr_proj:
+                self.obj_ptr_proj = MLP(self.hidden_dim, self.hidden_dim, self.hidden_dim, 3)
+        else:
+            self.obj_ptr_proj = nn.Identity()
+        if self.proj_tpos_enc_in_obj_ptrs:
+            self.obj_ptr_tpos_proj = Linear(self.hidden_dim, self.mem_dim)
+        else:
+            self.obj_ptr_tpos_proj = nn.Identity()
+
+    # ------------------------------------------------------------------ image features
+    def forward_image(self, img_batch):
+        """sam2_base.py:464-476: encoder + conv_s0/conv_s1 on the two high-resolution levels."""
+        feats = self.image_encoder.forward_tokens(img_batch.float().contiguous())
+        if self.use_high_res_features_in_sam:
+            d = self.sam_mask_decoder
+            feats[0] = ops.gemm(to_compute(feats[0]), w_c(d.conv_s0.weight), p32(d.conv_s0.bias))
+            feats[1] = ops.gemm(to_compute(feats[1]), w_c(d.conv_s1.weight), p32(d.conv_s1.bias))
+        pe = self.image_encoder.neck.position_encoding
+        B = img_batch.shape[0]
+        fpn = [as_nchw_view(f) for f in feats]
+        pos = [pe.table(f.shape[1], f.shape[2], f.device).permute(2, 0, 1)[None].expand(B, -1, -1, -1) for f in feats]
+        return {"vision_features": fpn[-1], "vision_pos_enc": pos, "backbone_fpn": fpn}
+
+    def _prepare_backbone_features(self, backbone_out):
+        """sam2_base.py:478-492 (views only)."""
+        backbone_out = backbone_out.copy()
+        assert len(backbone_out["backbone_fpn"]) == len(backbone_out["vision_pos_enc"])
+        assert len(backbone_out["backbone_fpn"]) >= self.num_feature_levels
+        feature_maps = backbone_out["backbone_fpn"][-self.num_feature_levels:]
+        vision_pos_embeds = backbone_out["vision_pos_enc"][-self.num_feature_levels:]
+        feat_sizes = [(x.shape[-2], x.shape[-1]) for x in vision_pos_embeds]
+        vision_feats = [x.flatten(2).permute(2, 0, 1) for x in feature_maps]
+        vision_pos_embeds = [x.flatten(2).permute(2, 0, 1) for x in vision_pos_embeds]
+        return backbone_out, vision_feats, vision_pos_embeds, feat_sizes
+
+    # ------------------------------------------------------------------ SAM heads
+    def _forward_sam_heads(self, backbone_features, point_inputs=None, mask_inputs=None, high_res_features=None,
+                           multimask_output=False):
+        """sam2_base.py:252-410.  backbone_features NCHW-shaped [B,C,h,w]."""
+        B = backbone_features.size(0)
+        device = backbone_features.device
+        assert backbone_features.size(1) == self.sam_prompt_embed_dim
+        assert backbone_features.size(2) == self.sam_image_embedding_size
+        assert backbone_features.size(3) == self.sam_image_embedding_size
+        if point_inputs is not None:
+            sam_point_coords = point_inputs["point_coords"]
+            sam_point_labels = point_inputs["point_labels"]
+            assert sam_point_coords.size(0) == B and sam_point_labels.size(0) == B
+        else:
+            sam_point_coords = torch.zeros(B, 1, 2, device=device)
+            sam_point_labels = -torch.ones(B, 1, dtype=torch.int32, device=device)
+        if mask_inputs is not None:
+            assert len(mask_inputs.shape) == 4 and mask_inputs.shape[:2] == (B, 1)
+            if tuple(mask_inputs.shape[-2:]) != tuple(self.sam_prompt_encoder.mask_input_size):
+                sam_mask_prompt = ops.resize_bilinear(mask_inputs.float().contiguous(),
+                                                      self.sam_prompt_encoder.mask_input_size, antialias=True)
+            else:
+                sam_mask_prompt = mask_inputs
+        else:
+            sam_mask_prompt = None
+        sparse, dense = self.sam_prompt_encoder(points=(sam_point_coords, sam_point_labels), boxes=None,
+                                                masks=sam_mask_prompt)
+        low_res_multimasks, ious, sam_output_tokens, object_score_logits = self.sam_mask_decoder(
+            image_embeddings=backbone_features, image_pe=self.sam_prompt_encoder.get_dense_pe(),
+            sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=multimask_output,
+            repeat_image=False, high_res_features=high_res_features)
+        low_res_multimasks = low_res_multimasks.float().contiguous()
+        if self.pred_obj_scores:
+            is_obj_appearing = object_score_logits > 0
+            low_res_multimasks = ops.gate_rows(low_res_multimasks, object_score_logits.float().contiguous().view(-1),
+                                               NO_OBJ_SCORE)
+        high_res_multimasks = ops.resize_bilinear(low_res_multimasks, (self.image_size, self.image_size))
+        sam_output_token = sam_output_tokens[:, 0]
+        if multimask_output:
+            best = torch.argmax(ious, dim=-1)
+            idx = best.to(torch.int32)
+            low_res_masks = ops.select_plane(low_res_multimasks, idx)
+            high_res_masks = ops.select_plane(high_res_multimasks, idx)
+            if sam_output_tokens.size(1) > 1:
+                sam_output_token = sam_output_tokens[torch.arange(B, device=device), best]
+        else:
+            low_res_masks, high_res_masks = low_res_multimasks, high_res_multimasks
+        obj_ptr = self.obj_ptr_proj(sam_output_token.contiguous())
+        if self.pred_obj_scores:
+            if self.soft_no_obj_ptr:
+                lam = object_score_logits.sigmoid()
+            else:
+                lam = is_obj_appearing.float()
+            if self.fixed_no_obj_ptr:
+                obj_ptr = lam * obj_ptr
+            obj_ptr = obj_ptr + (1 - lam) * p32(self.no_obj_ptr)
+        return (low_res_multimasks, high_res_multimasks, ious, low_res_masks, high_res_masks, obj_ptr,
+                object_score_logits)
+
+    def _use_mask_as_output(self, backbone_features, high_res_features, mask_inputs):
+        """sam2_base.py:412-462."""
+        out_scale, out_bias = 20.0, -10.0
+        mask_f = mask_inputs.float().contiguous()
+        B, _, H, W = mask_f.shape
+        high_res_masks = ops.axpby(mask_f, out_scale, None, 0.0, out_bias)
+        low_res_masks = ops.resize_bilinear(high_res_masks, (H // 4, W // 4), antialias=True)
+        ious = mask_inputs.new_ones(B, 1).float()
+        if not self.use_obj_ptrs_in_encoder:
+            obj_ptr = torch.zeros(B, self.hidden_dim, device=mask_inputs.device)
+        else:
+            md = self.mask_downsample
+            cols = ops.im2col(mask_f.view(B, H, W, 1), 4, 4, 0, compute_dtype())
+            down = ops.gemm(cols, conv_w_c(md.weight), p32(md.bias), out_dtype=torch.float32)   # [B,H/4,W/4,1]
+            _, _, _, _, _, obj_ptr, _ = self._forward_sam_heads(
+                backbone_features=backbone_features, mask_inputs=down.view(B, 1, H // 4, W // 4),
+                high_res_features=high_res_features)
+        counts = ops.mask_stability_counts(mask_f, 0.0)
+        lam = (counts[:, 0:1] > 0).float()
+        object_score_logits = out_scale * lam + out_bias
+        if self.pred_obj_scores:
+            if self.fixed_no_obj_ptr:
+                obj_ptr = lam * obj_ptr
+            obj_ptr = obj_ptr + (1 - lam) * p32(self.no_obj_ptr)
+        return low_res_masks, high_res_masks, ious, low_res_masks, high_res_masks, obj_ptr, object_score_logits
+
+    # ------------------------------------------------------------------ memory conditioning
+    def _mem_pos_table(self, h, w, slot, device):
+        """spatial sine-64 table + maskmem_tpos_enc[slot], token-major fp32 [h*w, mem_dim]
+        (sam2_base.py:573-580); constant per parameter version."""
+        pe = self.memory_encoder.position_encoding
+
+        def make(tp):
+            t = pe.table(h, w, device).reshape(h * w, -1)
+            return (t + tp[slot].float().reshape(1, -1)).contiguous()
+        return CACHE.get(self.maskmem_tpos_enc, ("mem_pos", h, w, slot, str(device)), make)
+
+    def _gather_memory(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device):
+        """sam2_base.py:518-637 -> (memory [B,Lk,mem_dim] fp32, memory_pos, num_obj_ptr_tokens)."""
+        C = self.hidden_dim
+        mems, poss = [], []
+        cond_outputs = output_dict["cond_frame_outputs"]
+        assert len(cond_outputs) > 0
+        selected, unselected = select_closest_cond_frames(frame_idx, cond_outputs, self.max_cond_frames_in_attn)
+        t_pos_and_prevs = [(0, out) for out in selected.values()]
+        r = self.memory_temporal_stride_for_eval
+        for t_pos in range(1, self.num_maskmem):
+            t_rel = self.num_maskmem - t_pos
+            if t_rel == 1:
+                prev_idx = frame_idx + t_rel if track_in_reverse else frame_idx - t_rel
+            elif not track_in_reverse:
+                prev_idx = ((frame_idx - 2) // r) * r - (t_rel - 2) * r
+            else:
+                prev_idx = -(-(frame_idx + 2) // r) * r + (t_rel - 2) * r
+            out = output_dict["non_cond_frame_outputs"].get(prev_idx, None)
+            if out is None:
+                out = unselected.get(prev_idx, None)
+            t_pos_and_prevs.append((t_pos, out))
+        for t_pos, prev in t_pos_and_prevs:
+            if prev is None:
+                continue
+            feats = prev["maskmem_features"].to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
+            h, w = feats.shape[-2:]
+            mems.append(as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim))
+            poss.append(self._mem_pos_table(h, w, self.num_maskmem - t_pos - 1, device)[None].expand(B, -1, -1))
+        n_ptr_tok = 0
+        if self.use_obj_ptrs_in_encoder:
+            max_ptrs = min(num_frames, self.max_obj_ptrs_in_encoder)
+            if not self.training and self.only_obj_ptrs_in_the_past_for_eval:
+                ptr_cond = {t: o for t, o in selected.items() if (t >= frame_idx if track_in_reverse else t <= frame_idx)}
+            else:
+                ptr_cond = selected
+            pos_and_ptrs = [(abs(frame_idx - t), o["obj_ptr"]) for t, o in ptr_cond.items()]
+            for t_diff in range(1, max_ptrs):
+                t = frame_idx + t_diff if track_in_reverse else frame_idx - t_diff
+                if t < 0 or (num_frames is not None and t >= num_frames):
+                    break
+                o = output_dict["non_cond_frame_outputs"].get(t, unselected.get(t, None))
+                if o is not None:
+                    pos_and_ptrs.append((t_diff, o["obj_ptr"]))
+            if pos_and_ptrs:
+                pos_list, ptrs_list = zip(*pos_and_ptrs)
+                ptrs = torch.stack([p.float() for p in ptrs_list], dim=1)                # [B,P,C]
+                P = ptrs.shape[1]
+                if self.add_tpos_enc_to_obj_ptrs:
+                    from .sam2_utils import get_1d_sine_pe
+                    t_diff_max = max_ptrs - 1
+                    tpos_dim = C if self.proj_tpos_enc_in_obj_ptrs else self.mem_dim
+                    obj_pos = get_1d_sine_pe(torch.tensor(pos_list, device=device) / t_diff_max, dim=tpos_dim)
+                    if self.proj_tpos_enc_in_obj_ptrs:
+                        obj_pos = self.obj_ptr_tpos_proj(obj_pos.contiguous())
+                    obj_pos = obj_pos[None].expand(B, -1, -1)
+                else:
+                    obj_pos = ptrs.new_zeros(B, P, self.mem_dim)
+                if self.mem_dim < C:
+                    rr = C // self.mem_dim
+                    ptrs = ptrs.reshape(B, P * rr, self.mem_dim)
+                    obj_pos = obj_pos.repeat_interleave(rr, dim=1)
+                mems.append(ptrs)
+                poss.append(obj_pos)
+                n_ptr_tok = ptrs.shape[1]
+        memory = torch.cat(mems, dim=1).contiguous()
+        memory_pos = torch.cat(poss, dim=1).contiguous()
+        return memory, memory_pos, n_ptr_tok
+
+    def _prepare_memory_conditioned_features(self, frame_idx, is_init_cond_frame, current_vision_feats,
+                                             current_vision_pos_embeds, feat_sizes, output_dict, num_frames,
+                                             track_in_reverse=False):
+        """sam2_base.py:494-663 -> NCHW-shaped [B,C,H,W]."""
+        B = current_vision_feats[-1].size(1)
+        C = self.hidden_dim
+        H, W = feat_sizes[-1]
+        device = current_vision_feats[-1].device
+        curr = seq_to_tokens(current_vision_feats[-1].float())                     # [B,HW,C]
+        if self.num_maskmem == 0:
+            return as_nchw_view(curr.view(B, H, W, C))
+        if is_init_cond_frame:
+            if self.directly_add_no_mem_embed:
+                out = ops.add_rowvec(curr, p32(self.no_mem_embed).view(-1))
+                return as_nchw_view(out.view(B, H, W, C))
+            memory = p32(self.no_mem_embed).expand(B, 1, self.mem_dim).contiguous()
+            memory_pos = p32(self.no_mem_pos_enc).expand(B, 1, self.mem_dim).contiguous()
+            n_ptr_tok = 0
+        else:
+            memory, memory_pos, n_ptr_tok = self._gather_memory(frame_idx, output_dict, num_frames, track_in_reverse,
+                                                                B, device)
+        curr_pos = seq_to_tokens(current_vision_pos_embeds[-1].float())
+        out = self.memory_attention.forward_tokens(curr, curr_pos, memory, memory_pos, n_ptr_tok)
+        return as_nchw_view(out.view(B, H, W, C))
+
+    def _encode_new_memory(self, current_vision_feats, feat_sizes, pred_masks_high_res, is_mask_from_pts):
+        """sam2_base.py:665-703 -> (maskmem_features NCHW-shaped, [pos NCHW-shaped])."""
+        B = current_vision_feats[-1].size(1)
+        C = self.hidden_dim
+        H, W = feat_sizes[-1]
+        pix = seq_to_tokens(current_vision_feats[-1].float()).view(B, H, W, C)
+        if self.non_overlap_masks_for_mem_enc and not self.training:
+            pred_masks_high_res = self._apply_non_overlapping_constraints(pred_masks_high_res)
+        binarize = self.binarize_mask_from_pts_for_mem_enc and is_mask_from_pts and not self.training
+        m = pred_masks_high_res.float().contiguous()
+        Hm, Wm = m.shape[-2:]
+        feats = self.memory_encoder.forward_tokens(pix, m.view(B, Hm, Wm, 1), pre=2 if binarize else 1,
+                                                   pre_scale=self.sigmoid_scale_for_mem_enc,
+                                                   pre_bias=self.sigmoid_bias_for_mem_enc)
+        feats_nchw = as_nchw_view(feats)
+        pos = self.memory_encoder.position_encoding(feats_nchw)
+        return feats_nchw, [pos]
+
+    # ------------------------------------------------------------------ one tracking step
+    def track_step(self, frame_idx, is_init_cond_frame, current_vision_feats, current_vision_pos_embeds, feat_sizes,
+                   point_inputs, mask_inputs, output_dict, num_frames, track_in_reverse=False, run_mem_encoder=True,
+                   prev_sam_mask_logits=None):
+        """sam2_base.py:705-800."""
+        current_out = {"point_inputs": point_inputs, "mask_inputs": mask_inputs}
+        if len(current_vision_feats) > 1:
+            high_res_features = [x.permute(1, 2, 0).view(x.size(1), x.size(2), *s)
+                                 for x, s in zip(current_vision_feats[:-1], feat_sizes[:-1])]
+        else:
+            high_res_features = None
+        if mask_inputs is not None and self.use_mask_input_as_output_without_sam:
+            pix_feat = current_vision_feats[-1].permute(1, 2, 0)
+            pix_feat = pix_feat.view(-1, self.hidden_dim, *feat_sizes[-1])
+            sam_outputs = self._use_mask_as_output(pix_feat, high_res_features, mask_inputs)
+        else:
+            pix_feat_with_mem = self._prepare_memory_conditioned_features(
+                frame_idx=frame_idx, is_init_cond_frame=is_init_cond_frame,
+                current_vision_feats=current_vision_feats[-1:],
+                current_vision_pos_embeds=current_vision_pos_embeds[-1:], feat_sizes=feat_sizes[-1:],
+                output_dict=output_dict, num_frames=num_frames, track_in_reverse=track_in_reverse)
+            if prev_sam_mask_logits is not None:
+                assert point_inputs is not None and mask_inputs is None
+                mask_inputs = prev_sam_mask_logits
+            multimask_output = self._use_multimask(is_init_cond_frame, point_inputs)
+            sam_outputs = self._forward_sam_heads(backbone_features=pix_feat_with_mem, point_inputs=point_inputs,
+                                                  mask_inputs=mask_inputs, high_res_features=high_res_features,
+                                                  multimask_output=multimask_output)
+        _, _, _, low_res_masks, high_res_masks, obj_ptr, _ = sam_outputs
+        current_out["pred_masks"] = low_res_masks
+        current_out["pred_masks_high_res"] = high_res_masks
+        current_out["obj_ptr"] = obj_ptr
+        if run_mem_encoder and self.num_maskmem > 0:
+            maskmem_features, maskmem_pos_enc = self._encode_new_memory(
+                current_vision_feats=current_vision_feats, feat_sizes=feat_sizes,
+                pred_masks_high_res=high_res_masks, is_mask_from_pts=(point_inputs is not None))
+            current_out["maskmem_features"] = maskmem_features
+            current_out["maskmem_pos_enc"] = maskmem_pos_enc
+        else:
+            current_out["maskmem_features"] = None
+            current_out["maskmem_pos_enc"] = None
+        return current_out
+
+    def _use_multimask(self, is_init_cond_frame, point_inputs):
+        """sam2_base.py:802-810."""
+        num_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
+        return (self.multimask_output_in_sam and (is_init_cond_frame or self.multimask_output_for_tracking)
+                and (self.multimask_min_pt_num <= num_pts <= self.multimask_max_pt_num))
+
+    def _apply_non_overlapping_constraints(self, pred_masks):
+        """sam2_base.py:812-830 (off in the shipped configs; plain tensor glue when enabled)."""
+        batch_size = pred_masks.size(0)
+        if batch_size == 1:
+            return pred_masks
+        max_obj_inds = torch.argmax(pred_masks, dim=0, keepdim=True)
+        batch_obj_inds = torch.arange(batch_size, device=pred_masks.device)[:, None, None, None]
+        keep = max_obj_inds == batch_obj_inds
+        return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))

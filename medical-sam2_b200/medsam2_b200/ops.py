@@ -1,0 +1,295 @@
+"""Tensor-level wrappers over the C-ABI kernels (include/medsam2_b200.h).
+
+PyTorch is used here for device memory (torch.empty), streams and nothing else: every function
+below validates its tensors, hands raw device pointers + the current CUDA stream to the native
+library and raises if the call fails.  There is no eager/PyTorch fallback.
+"""
+import math
+
+import torch
+
+from . import native
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise native.NativeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise native.NativeError(f"{name}: tensor must be contiguous, got strides {t.stride()}")
+    if dtype is not None and t.dtype != dtype:
+        raise native.NativeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _opt(t, name, dtype=torch.float32):
+    return None if t is None else _chk(t, name, dtype)
+
+
+def dt_of(t):
+    return _DT[t.dtype]
+
+
+# ------------------------------------------------------------------ connected components
+def cc_label(mask_u8):
+    """[N,1,H,W] uint8 -> (labels, counts) int32 (reference `_C.get_connected_componnets`)."""
+    if mask_u8.dim() != 4 or mask_u8.shape[1] != 1:
+        raise native.NativeError("inputs must be [N, 1, H, W] shape")
+    N, _, H, W = mask_u8.shape
+    p = _chk(mask_u8, "inputs", torch.uint8)
+    labels = torch.empty((N, 1, H, W), dtype=torch.int32, device=mask_u8.device)
+    counts = torch.empty_like(labels)
+    ws = None
+    if (H // 2) * (W // 2) > 28672:
+        ws = torch.empty((N, H, W), dtype=torch.int32, device=mask_u8.device)
+    native.call("ms2_cc_label", p, labels.data_ptr(), counts.data_ptr(), None if ws is None else ws.data_ptr(),
+                N, H, W, _st())
+    return labels, counts
+
+
+def fill_holes(scores, max_area, thresh=0.0, fill_value=0.1):
+    N, _, H, W = scores.shape
+    out = torch.empty_like(scores)
+    native.call("ms2_fill_holes", _chk(scores, "scores", torch.float32), out.data_ptr(), N, H, W, float(thresh),
+                int(max_area), float(fill_value), _st())
+    return out
+
+
+# ------------------------------------------------------------------ norm / gemm
+def layernorm(x, gamma, beta, eps, out_dtype=torch.float32, add=None, act=ACT_NONE):
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    native.call("ms2_layernorm", _chk(x, "x", torch.float32), _opt(add, "add"), _chk(gamma, "gamma", torch.float32),
+                _chk(beta, "beta", torch.float32), y.data_ptr(), _DT[out_dtype], M, C, float(eps), act, _st())
+    return y
+
+
+def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, colscale=None, impl=0, out=None):
+    """out[..., N] = residual + colscale * act(a[..., K] @ w[N, K]^T + bias)."""
+    K = a.shape[-1]
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise native.NativeError(f"gemm: K mismatch {a.shape} x {w.shape}")
+    M = a.numel() // K
+    lda = K
+    if a.dim() == 2 and a.stride(1) == 1 and a.stride(0) != K and a.is_cuda:
+        lda = a.stride(0)              # row-strided A (e.g. one token column of [B, Nt, C])
+        a_ptr = a.data_ptr()
+    else:
+        a_ptr = _chk(a, "a")
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (N,), dtype=out_dtype, device=a.device)
+    native.call("ms2_gemm", a_ptr, _DT[a.dtype], lda, _chk(w, "w"), _DT[w.dtype], _opt(bias, "bias"),
+                _opt(colscale, "colscale"), _opt(residual, "residual"), N, _chk(out, "out"), _DT[out.dtype], N,
+                M, N, K, act, impl, _st())
+    return out
+
+
+# ------------------------------------------------------------------ attention
+def attention(q, k, v, heads, scale=None, impl=0):
+    """q [B,Lq,heads*D], k/v [B,Lk,heads*D] (token-major, possibly column slices of a wider
+    matrix via as_strided views with last-dim stride 1) -> o [B,Lq,heads*D] contiguous."""
+    B, Lq, HD = q.shape
+    Lk = k.shape[1]
+    D = HD // heads
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.stride(-1) != 1:
+            raise native.NativeError(f"attention: {n} must be a CUDA tensor with unit inner stride")
+    o = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    native.call("ms2_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
+                q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), D, v.stride(1),
+                o.stride(0), D, o.stride(1), B, heads, Lq, Lk, D, float(scale), impl, _st())
+    return o
+
+
+def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool):
+    """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
+    Ho, Wo = (H // 2, W // 2) if qpool else (H, W)
+    out = torch.empty((B, Ho, Wo, heads * D), dtype=qkv.dtype, device=qkv.device)
+    native.call("ms2_window_attention", _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias", torch.float32),
+                out.data_ptr(), _DT[qkv.dtype], B, H, W, heads, D, ws, int(bool(qpool)), 1.0 / math.sqrt(D), _st())
+    return out
+
+
+# ------------------------------------------------------------------ element-wise / layout
+def maxpool2x2(x):
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+    native.call("ms2_maxpool2x2", _chk(x, "x", torch.float32), y.data_ptr(), B, H, W, C, _st())
+    return y
+
+
+def patch_embed(img, w, bias, pos):
+    B, _, Hin, Win = img.shape
+    Cout = w.shape[0]
+    Ho, Wo = (Hin + 6 - 7) // 4 + 1, (Win + 6 - 7) // 4 + 1
+    out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=img.device)
+    native.call("ms2_patch_embed", _chk(img, "img", torch.float32), _chk(w, "w", torch.float32),
+                _chk(bias, "bias", torch.float32), _opt(pos, "pos"), out.data_ptr(), B, Hin, Win, Cout, _st())
+    return out
+
+
+def axpby(x, a=1.0, z=None, b=1.0, c=0.0, out_dtype=torch.float32, out=None):
+    """y = a*x + b*z + c ; z broadcasts as z.flatten()[i mod z.numel()] (trailing-dims broadcast)."""
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device) if out is None else out
+    native.call("ms2_axpby", _chk(x, "x", torch.float32), float(a), _opt(z, "z"), float(b), float(c), y.data_ptr(),
+                _DT[y.dtype], x.numel(), 0 if z is None else z.numel(), _st())
+    return y
+
+
+def gate_rows(x, gate, fill):
+    """x fp32 [B, ...]; gate fp32 [B] (or [B,1]) -> where(gate>0, x, fill)."""
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    native.call("ms2_gate_rows", _chk(x, "x", torch.float32), _chk(gate, "gate", torch.float32), float(fill),
+                y.data_ptr(), B, x.numel() // max(B, 1), _st())
+    return y
+
+
+def select_plane(x, idx):
+    """x fp32 [B, M, ...], idx int32 [B] -> [B, 1, ...] = x[b, idx[b]]."""
+    B, M = x.shape[:2]
+    P = x.numel() // max(B * M, 1)
+    y = torch.empty((B, 1) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    native.call("ms2_select_plane", _chk(x, "x", torch.float32), _chk(idx, "idx", torch.int32), y.data_ptr(),
+                B, M, P, _st())
+    return y
+
+
+def add_rowvec(x, v, s=1.0):
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    native.call("ms2_add_rowvec", _chk(x, "x", torch.float32), _chk(v, "v", torch.float32), float(s), y.data_ptr(),
+                x.numel() // C, C, _st())
+    return y
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    native.call("ms2_cast", _chk(x, "x"), _DT[x.dtype], y.data_ptr(), _DT[dtype], x.numel(), _st())
+    return y
+
+
+def activation(x, act):
+    y = torch.empty_like(x)
+    native.call("ms2_activation", _chk(x, "x", torch.float32), y.data_ptr(), x.numel(), act, _st())
+    return y
+
+
+def upsample2x_add_(fine, coarse):
+    B, H, W, C = fine.shape
+    native.call("ms2_upsample2x_add", _chk(fine, "fine", torch.float32), _chk(coarse, "coarse", torch.float32),
+                B, H, W, C, _st())
+    return fine
+
+
+def nhwc_to_nchw(x):
+    B, H, W, C = x.shape
+    y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    native.call("ms2_nhwc_to_nchw", _chk(x, "x", torch.float32), y.data_ptr(), B, H, W, C, _st())
+    return y
+
+
+def nchw_to_nhwc(x):
+    B, C, H, W = x.shape
+    y = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    native.call("ms2_nchw_to_nhwc", _chk(x, "x", torch.float32), y.data_ptr(), B, C, H, W, _st())
+    return y
+
+
+def rope_(x, B, rows, n_rope_rows, D, cos_t, sin_t, batch_stride=None, row_stride=None):
+    """in place on x viewed as [B, rows, D] with the given element strides."""
+    if not x.is_cuda:
+        raise native.NativeError("rope: expected a CUDA tensor")
+    native.call("ms2_rope", x.data_ptr(), _DT[x.dtype], batch_stride if batch_stride is not None else rows * D,
+                row_stride if row_stride is not None else D, B, rows, n_rope_rows, D,
+                _chk(cos_t, "cos", torch.float32), _chk(sin_t, "sin", torch.float32), cos_t.shape[0], _st())
+    return x
+
+
+def im2col(x, k, stride, pad, out_dtype, pre=0, pre_scale=1.0, pre_bias=0.0):
+    B, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    cols = torch.empty((B, Ho, Wo, k * k * Cin), dtype=out_dtype, device=x.device)
+    native.call("ms2_im2col", _chk(x, "x", torch.float32), cols.data_ptr(), _DT[out_dtype], B, H, W, Cin, k, stride,
+                pad, pre, float(pre_scale), float(pre_bias), _st())
+    return cols
+
+
+def dwconv7x7(x, w, bias):
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    native.call("ms2_dwconv7x7", _chk(x, "x", torch.float32), _chk(w, "w", torch.float32), _opt(bias, "bias"),
+                y.data_ptr(), B, H, W, C, _st())
+    return y
+
+
+def pixel_shuffle_add(g, bias, skip, B, H, W, C, act=ACT_NONE):
+    out = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=g.device)
+    native.call("ms2_pixel_shuffle_add", _chk(g, "g", torch.float32), _opt(bias, "bias"), _opt(skip, "skip"),
+                out.data_ptr(), B, H, W, C, act, _st())
+    return out
+
+
+def hyper_mask(up, hyper):
+    B, P, C = up.shape
+    Mk = hyper.shape[1]
+    masks = torch.empty((B, Mk, P), dtype=torch.float32, device=up.device)
+    native.call("ms2_hyper_mask", _chk(up, "up", torch.float32), _chk(hyper, "hyper", torch.float32),
+                masks.data_ptr(), B, P, C, Mk, _st())
+    return masks
+
+
+def resize_bilinear(x, size, antialias=False):
+    """x fp32 [..., H, W] -> [..., Ho, Wo], align_corners=False."""
+    H, W = x.shape[-2:]
+    Ho, Wo = size
+    N = x.numel() // (H * W)
+    y = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.float32, device=x.device)
+    native.call("ms2_resize_bilinear", _chk(x, "x", torch.float32), y.data_ptr(), N, H, W, Ho, Wo,
+                int(bool(antialias)), _st())
+    return y
+
+
+def fourier_pe(coords01, gauss):
+    n = coords01.numel() // 2
+    Fh = gauss.shape[1]
+    out = torch.empty(coords01.shape[:-1] + (2 * Fh,), dtype=torch.float32, device=coords01.device)
+    native.call("ms2_fourier_pe", _chk(coords01, "coords", torch.float32), _chk(gauss, "gauss", torch.float32),
+                out.data_ptr(), n, Fh, _st())
+    return out
+
+
+def normalize_image(x):
+    """fp32 [B,3,H,W] in 0..255 or uint8 [B,H,W,3] -> fp32 NCHW (x/255-mean)/std."""
+    if x.dtype == torch.uint8:
+        B, H, W, _ = x.shape
+        layout = 1
+    else:
+        B, _, H, W = x.shape
+        layout = 0
+        _chk(x, "x", torch.float32)
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    native.call("ms2_normalize_image", _chk(x, "x"), layout, out.data_ptr(), B, H, W, _st())
+    return out
+
+
+def mask_stability_counts(x, delta):
+    """x fp32 [N, ...] -> int32 [N,2] = (#>delta, #>-delta)."""
+    N = x.shape[0]
+    P = x.numel() // max(N, 1)
+    counts = torch.empty((N, 2), dtype=torch.int32, device=x.device)
+    native.call("ms2_mask_stability_counts", _chk(x, "x", torch.float32), counts.data_ptr(), N, P, float(delta), _st())
+    return counts

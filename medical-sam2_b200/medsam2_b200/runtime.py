@@ -1,0 +1,88 @@
+"""Run-time settings shared by the host-side modules: the compute dtype of the GEMM/attention
+operands (bf16 by default, fp32 = exact mode) and a cache of kernel-ready parameter copies
+(compute-dtype weights, fp32 biases, re-laid-out conv weights) keyed on the parameter version so
+that `load_state_dict` / in-place updates invalidate them."""
+import contextlib
+import os
+
+import torch
+
+_COMPUTE = {"bf16": torch.bfloat16, "fp32": torch.float32}[os.environ.get("MS2_COMPUTE", "bf16")]
+
+
+def compute_dtype():
+    return _COMPUTE
+
+
+def set_compute_dtype(dtype):
+    global _COMPUTE
+    assert dtype in (torch.float32, torch.bfloat16)
+    _COMPUTE = dtype
+
+
+@contextlib.contextmanager
+def compute(dtype):
+    global _COMPUTE
+    old = _COMPUTE
+    set_compute_dtype(dtype)
+    try:
+        yield
+    finally:
+        _COMPUTE = old
+
+
+class ParamCache:
+    """derived tensors of parameters: get(param, key, fn) -> fn(param) cached per (version, ptr)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, params, key, fn):
+        if isinstance(params, torch.Tensor):
+            params = (params,)
+        sig = tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
+        k = (tuple(id(p) for p in params), key)
+        hit = self._d.get(k)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = fn(*params)
+        self._d[k] = (sig, val)
+        return val
+
+
+CACHE = ParamCache()
+
+
+def w_c(p):
+    """weight as a contiguous 2-D [N, K] matrix in the compute dtype."""
+    dt = compute_dtype()
+    return CACHE.get(p, ("wc", dt), lambda t: t.detach().reshape(t.shape[0], -1).to(dt).contiguous())
+
+
+def p32(p):
+    """parameter as contiguous fp32 (biases, LayerNorm affine, tables)."""
+    return CACHE.get(p, "p32", lambda t: t.detach().float().contiguous())
+
+
+def conv_w_c(p):
+    """conv weight [Cout,Cin,k,k] -> [Cout, k*k*Cin] (tap order ky,kx,ci) in the compute dtype."""
+    dt = compute_dtype()
+    return CACHE.get(p, ("convw", dt),
+                     lambda t: t.detach().permute(0, 2, 3, 1).reshape(t.shape[0], -1).to(dt).contiguous())
+
+
+def convT_w_c(p):
+    """ConvTranspose2d k2s2 weight [Cin,Cout,2,2] -> GEMM weight [(dy,dx,co), Cin] in the compute dtype."""
+    dt = compute_dtype()
+    return CACHE.get(p, ("convTw", dt),
+                     lambda t: t.detach().permute(2, 3, 1, 0).reshape(-1, t.shape[0]).to(dt).contiguous())
+
+
+def cat_w_c(*ps):
+    dt = compute_dtype()
+    return CACHE.get(ps, ("catw", dt), lambda *ts: torch.cat([t.detach().reshape(t.shape[0], -1) for t in ts], 0).to(dt).contiguous())
+
+
+def cat_p32(*ps):
+    return CACHE.get(ps, "cat32", lambda *ts: torch.cat([t.detach().float().reshape(-1) for t in ts], 0).contiguous())

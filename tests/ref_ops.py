@@ -1,0 +1,235 @@
+"""Plain-torch statements of every op in `medsam2_b200.ops` (same signatures).
+
+TEST INFRASTRUCTURE ONLY.  Two uses:
+  * `-m gpu`: each CUDA kernel is compared with its function here on the same seeded inputs;
+  * `-m "not gpu"`: `install(monkeypatch)` swaps these in for the native ops so that the HOST logic
+    of the product (layout plumbing, state machine, checkpoint handling) is checked end-to-end against
+    the oracle on CPU.  The product package itself never imports this file and has no CPU path.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _act(x, act):
+    if act == ACT_GELU:
+        return F.gelu(x)
+    if act == ACT_RELU:
+        return F.relu(x)
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(x)
+    return x
+
+
+def cc_label(mask_u8):
+    from oracle.sam2_oracle import connected_components_np
+    l, c = connected_components_np(mask_u8.cpu().numpy())
+    return torch.from_numpy(l).to(mask_u8.device), torch.from_numpy(c).to(mask_u8.device)
+
+
+def fill_holes(scores, max_area, thresh=0.0, fill_value=0.1):
+    lab, area = cc_label((scores <= thresh).to(torch.uint8))
+    hole = (lab > 0) & (area <= max_area)
+    return torch.where(hole, torch.full_like(scores, fill_value), scores)
+
+
+def layernorm(x, gamma, beta, eps, out_dtype=torch.float32, add=None, act=ACT_NONE):
+    h = x.float() if add is None else x.float() + add.float()
+    y = F.layer_norm(h, (h.shape[-1],), gamma.float(), beta.float(), eps)
+    return _act(y, act).to(out_dtype)
+
+
+def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, colscale=None, impl=0, out=None):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    y = _act(y, act)
+    if colscale is not None:
+        y = y * colscale
+    if residual is not None:
+        y = y + residual.reshape(y.shape)
+    y = y.to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def attention(q, k, v, heads, scale=None, impl=0):
+    B, Lq, HD = q.shape
+    D = HD // heads
+    sp = lambda t: t.float().reshape(B, t.shape[1], heads, D).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), scale=scale)
+    return o.transpose(1, 2).reshape(B, Lq, HD).to(q.dtype)
+
+
+def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool):
+    """Restates hieradet.py:58-83,136-159 + backbones/utils.py:16-62 on the qkv tensor: zero-padded
+    tokens are replaced by the qkv bias (= Linear(0))."""
+    C3 = 3 * heads * D
+    x = qkv.float().reshape(B, H, W, C3)
+    ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+    Hp, Wp = H + ph, W + pw
+    xp = qkv_bias.float().reshape(1, 1, 1, C3).expand(B, Hp, Wp, C3).clone()
+    xp[:, :H, :W] = x
+    xw = xp.view(B, Hp // ws, ws, Wp // ws, ws, C3).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, 3, heads, D)
+    q, k, v = xw.unbind(2)
+    w_out = ws
+    if qpool:
+        nW = q.shape[0]
+        q = q.reshape(nW, ws, ws, heads * D).permute(0, 3, 1, 2)
+        q = F.max_pool2d(q, 2, 2).permute(0, 2, 3, 1)
+        w_out = ws // 2
+        q = q.reshape(nW, w_out * w_out, heads, D)
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+    o = o.transpose(1, 2).reshape(-1, w_out, w_out, heads * D)
+    Ho, Wo = (H // 2, W // 2) if qpool else (H, W)
+    nwy, nwx = Hp // ws, Wp // ws
+    o = o.view(B, nwy, nwx, w_out, w_out, heads * D).permute(0, 1, 3, 2, 4, 5).reshape(B, nwy * w_out, nwx * w_out, -1)
+    return o[:, :Ho, :Wo].contiguous().to(qkv.dtype)
+
+
+def maxpool2x2(x):
+    return F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+
+
+def patch_embed(img, w, bias, pos):
+    y = F.conv2d(img, w, bias, stride=4, padding=3).permute(0, 2, 3, 1)
+    if pos is not None:
+        y = y + pos[None]
+    return y.contiguous()
+
+
+def axpby(x, a=1.0, z=None, b=1.0, c=0.0, out_dtype=torch.float32, out=None):
+    y = a * x.float()
+    if z is not None:
+        zz = z.float().reshape(-1)
+        y = (y.reshape(-1, zz.numel()) + b * zz).reshape(x.shape)
+    y = (y + c).to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def gate_rows(x, gate, fill):
+    g = gate.reshape(x.shape[0], *([1] * (x.dim() - 1)))
+    return torch.where(g > 0, x, torch.full_like(x, fill))
+
+
+def select_plane(x, idx):
+    B = x.shape[0]
+    return x[torch.arange(B, device=x.device), idx.long().clamp(0, x.shape[1] - 1)].unsqueeze(1).contiguous()
+
+
+def add_rowvec(x, v, s=1.0):
+    return x + s * v
+
+
+def cast(x, dtype):
+    return x.to(dtype)
+
+
+def activation(x, act):
+    return _act(x, act)
+
+
+def upsample2x_add_(fine, coarse):
+    up = coarse.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    fine.add_(up)
+    return fine
+
+
+def nhwc_to_nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def nchw_to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def rope_(x, B, rows, n_rope_rows, D, cos_t, sin_t, batch_stride=None, row_stride=None):
+    bs = batch_stride if batch_stride is not None else rows * D
+    rs = row_stride if row_stride is not None else D
+    v = torch.as_strided(x, (B, n_rope_rows, D // 2, 2), (bs, rs, 2, 1), x.storage_offset())
+    T = cos_t.shape[0]
+    pos = torch.arange(n_rope_rows, device=x.device) % T
+    c, s = cos_t[pos][None], sin_t[pos][None]
+    a, b = v[..., 0].float(), v[..., 1].float()
+    v[..., 0], v[..., 1] = (a * c - b * s).to(x.dtype), (a * s + b * c).to(x.dtype)
+    return x
+
+
+def im2col(x, k, stride, pad, out_dtype, pre=0, pre_scale=1.0, pre_bias=0.0):
+    B, H, W, Cin = x.shape
+    t = x.float()
+    if pre == 1:
+        t = torch.sigmoid(t)
+    elif pre == 2:
+        t = (t > 0).float()
+    if pre or pre_scale != 1.0 or pre_bias != 0.0:
+        t = t * pre_scale + pre_bias
+    u = F.unfold(t.permute(0, 3, 1, 2), k, padding=pad, stride=stride)       # [B, Cin*k*k, L] (ci,ky,kx)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    u = u.view(B, Cin, k * k, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(B, Ho, Wo, k * k * Cin)
+    return u.contiguous().to(out_dtype)
+
+
+def dwconv7x7(x, w, bias):
+    C = x.shape[-1]
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.view(C, 1, 7, 7), bias, padding=3, groups=C)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def pixel_shuffle_add(g, bias, skip, B, H, W, C, act=ACT_NONE):
+    y = g.view(B, H, W, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C)
+    if bias is not None:
+        y = y + bias
+    if skip is not None:
+        y = y + skip.reshape(y.shape)
+    return _act(y, act).contiguous()
+
+
+def hyper_mask(up, hyper):
+    return torch.einsum("bmc,bpc->bmp", hyper, up).contiguous()
+
+
+def resize_bilinear(x, size, antialias=False):
+    lead = x.shape[:-2]
+    y = F.interpolate(x.reshape(-1, 1, *x.shape[-2:]).float(), size=tuple(size), mode="bilinear",
+                      align_corners=False, antialias=bool(antialias))
+    return y.reshape(*lead, *size)
+
+
+def fourier_pe(coords01, gauss):
+    c = (2 * coords01 - 1) @ gauss
+    c = 2 * math.pi * c
+    return torch.cat([torch.sin(c), torch.cos(c)], dim=-1)
+
+
+def normalize_image(x):
+    if x.dtype == torch.uint8:
+        x = x.permute(0, 3, 1, 2).float()
+    mean = torch.tensor((0.485, 0.456, 0.406), device=x.device)[None, :, None, None]
+    std = torch.tensor((0.229, 0.224, 0.225), device=x.device)[None, :, None, None]
+    return (x.float() / 255.0 - mean) / std
+
+
+def mask_stability_counts(x, delta):
+    f = x.reshape(x.shape[0], -1)
+    return torch.stack([(f > delta).sum(-1), (f > -delta).sum(-1)], dim=1).to(torch.int32)
+
+
+_NAMES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("install",)]
+
+
+def install(monkeypatch):
+    """Swap the native ops for these statements (CPU host-logic tests only)."""
+    import medsam2_b200.ops as ops
+    for n in _NAMES:
+        if hasattr(ops, n):
+            monkeypatch.setattr(ops, n, globals()[n])

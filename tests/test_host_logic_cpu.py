@@ -1,0 +1,142 @@
+"""CPU: the product's HOST logic (module tree, layout plumbing, predictors' state machines, checkpoint
+handling) checked end-to-end against the golden fixtures of the real reference, with the native ops
+replaced by their plain-torch statements from tests/ref_ops.py (a test-only fake backend; the product
+package has no CPU path of its own)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_ops
+from oracle.config import get_config
+from oracle.weights import make_state_dict
+from synth_data import btcv_volume, fundus_images, random_image
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _close(a, b, tol, what):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, np.float32)
+    b = np.asarray(b, np.float32)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = float(np.abs(a - b).max()) if a.size else 0.0
+    assert err <= tol, f"{what}: max abs err {err} > {tol}"
+
+
+@pytest.fixture()
+def fake_backend(monkeypatch):
+    import medsam2_b200
+    ref_ops.install(monkeypatch)
+    with medsam2_b200.compute(torch.float32):
+        yield
+
+
+def _build(cfg, video, image_size=1024):
+    import medsam2_b200
+    fn = medsam2_b200.build_sam2_video_predictor if video else medsam2_b200.build_sam2
+    m = fn(cfg, device="cpu", hydra_overrides_extra=[f"++model.image_size={image_size}"])
+    m.load_state_dict(make_state_dict(get_config(cfg)), strict=True)
+    return m
+
+
+def test_image_predictor_config1(fake_backend):
+    from medsam2_b200 import SAM2ImagePredictor
+    z = np.load(f"{G}/image_hiera_t_1024.npz")
+    p = SAM2ImagePredictor(_build("sam2_hiera_t", video=False))
+    p.set_image(random_image(1024, 0))
+    _close(p._features["image_embed"][..., ::4, ::4], z["image_embed_sub"], 5e-4, "image_embed")
+    _close(p._features["high_res_feats"][0][..., ::16, ::16], z["high_res0_sub"], 5e-4, "hr0")
+    _close(p._features["high_res_feats"][1][..., ::8, ::8], z["high_res1_sub"], 5e-4, "hr1")
+    masks, ious, low = p.predict(point_coords=np.array([[512, 512]]), point_labels=np.array([1]),
+                                 multimask_output=True, return_logits=True)
+    _close(low, z["low_res"], 2e-4, "low_res")
+    _close(ious, z["ious"], 1e-5, "ious")
+    _close(masks[:, ::4, ::4], z["masks_sub"], 2e-4, "masks")
+    _, ious1, low1 = p.predict(box=np.array([300, 350, 700, 800]), multimask_output=False, return_logits=True)
+    _close(low1, z["box_low_res"], 2e-4, "box low_res")
+    _close(ious1, z["box_ious"], 1e-5, "box ious")
+
+
+def test_image_predictor_batch(fake_backend):
+    from medsam2_b200 import SAM2ImagePredictor
+    z = np.load(f"{G}/image_hiera_s_1024.npz")
+    p = SAM2ImagePredictor(_build("sam2_hiera_s", video=False))
+    imgs, pts = fundus_images(2, 1024, 0)
+    p.set_image_batch(imgs)
+    _close(p._features["image_embed"][..., ::4, ::4], z["image_embed_sub"], 5e-4, "image_embed")
+    masks, ious, low = p.predict_batch(pts, [np.array([1])] * 2, multimask_output=True, return_logits=True)
+    _close(np.stack(low), z["low_res"], 2e-4, "low_res")
+    _close(np.stack(ious), z["ious"], 1e-5, "ious")
+
+
+@pytest.mark.parametrize("case", ["s1", "t2"])
+def test_video_predictor(fake_backend, case):
+    if case == "s1":
+        cfg, size, T, n_obj, prompts, absent, seed, fname = "sam2_hiera_s", 512, 7, 1, (0, 2, 4), (), 1234, "video_hiera_s_512.npz"
+    else:
+        cfg, size, T, n_obj, prompts, absent, seed, fname = "sam2_hiera_t", 512, 6, 2, (0, 3), ((3, 1),), 77, "video_hiera_t_512_2obj.npz"
+    z = np.load(f"{G}/{fname}")
+    m = _build(cfg, video=True, image_size=size)
+    vol, boxes = btcv_volume(T, size, seed, n_obj)
+    st = m.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
+    for f in prompts:
+        for o in range(n_obj):
+            if (f, o) in absent:
+                m.train_add_new_mask(inference_state=st, frame_idx=f, obj_id=o + 1, mask=torch.zeros(size, size))
+            else:
+                m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=o + 1, bbox=torch.tensor(boxes[f][o]),
+                                     clear_old_points=False)
+    outs = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}
+    od = st["output_dict"]
+    for f in range(T):
+        o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+        _close(o["pred_masks"], z[f"pred_masks_{f}"], 3e-3, f"pred_masks frame {f}")
+        _close(o["obj_ptr"], z[f"obj_ptr_{f}"], 1e-3, f"obj_ptr frame {f}")
+        _close(o["maskmem_features"][..., ::4, ::4], z[f"maskmem_sub_{f}"], 1e-3, f"maskmem frame {f}")
+        _close(outs[f][..., ::4, ::4], z["video_res_masks_sub"][f], 3e-3, f"video masks frame {f}")
+
+
+def test_submodule_surface(fake_backend):
+    """func_2d-style direct calls against module-level golden answers."""
+    z = np.load(f"{G}/modules_hiera_t.npz")
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    g = torch.Generator().manual_seed(7)
+    B, HW = 2, 32 * 32
+    curr = torch.randn(HW, B, 256, generator=g)
+    curr_pos = torch.randn(HW, B, 256, generator=g)
+    Lk = 2 * HW + 8
+    memory = torch.randn(Lk, B, 64, generator=g)
+    memory_pos = torch.randn(Lk, B, 64, generator=g)
+    y = m.memory_attention(curr=[curr], curr_pos=[curr_pos], memory=memory, memory_pos=memory_pos, num_obj_ptr_tokens=8)
+    _close(y[::4], z["memattn_out_sub"], 3e-4, "memory_attention")
+    pix = torch.randn(HW, B, 256, generator=g)
+    hi = torch.randn(B, 1, 512, 512, generator=g) * 3
+    for flag in (False, True):
+        f, pe = m._encode_new_memory([pix], [(32, 32)], hi, is_mask_from_pts=flag)
+        _close(f, z[f"memenc_feat_{int(flag)}"], 3e-4, f"memory_encoder {flag}")
+    _close(pe[0][0], z["memenc_pos"], 1e-6, "memenc pos")
+    emb = torch.randn(B, 256, 32, 32, generator=g)
+    hr0 = torch.randn(B, 32, 128, 128, generator=g)
+    hr1 = torch.randn(B, 64, 64, 64, generator=g)
+    pts = {"point_coords": torch.tensor([[[100.0, 200.0], [300.0, 50.0]], [[10.0, 20.0], [400.0, 500.0]]]),
+           "point_labels": torch.tensor([[1, 0], [2, 3]], dtype=torch.int32)}
+    for mm in (False, True):
+        r = m._forward_sam_heads(emb, point_inputs=pts, high_res_features=[hr0, hr1], multimask_output=mm)
+        _close(r[0], z[f"heads_low_{int(mm)}"], 5e-4, "heads low")
+        _close(r[2], z[f"heads_ious_{int(mm)}"], 1e-5, "heads ious")
+        _close(r[5], z[f"heads_ptr_{int(mm)}"], 1e-4, "heads ptr")
+        _close(r[6], z[f"heads_obj_{int(mm)}"], 1e-4, "heads obj")
+    mask_in = (torch.rand(B, 1, 512, 512, generator=g) > 0.5).float()
+    r = m._use_mask_as_output(emb, [hr0, hr1], mask_in)
+    _close(r[0], z["maskout_low"], 1e-5, "mask-as-output low")
+    _close(r[5], z["maskout_ptr"], 1e-4, "mask-as-output ptr")
+    _close(m.sam_prompt_encoder.get_dense_pe(), z["dense_pe"], 1e-5, "dense pe")
+
+
+def test_product_refuses_cpu_without_backend():
+    """No fake backend installed -> the hot path must fail loudly on CPU tensors (no fallback)."""
+    from medsam2_b200 import ops
+    from medsam2_b200.native import NativeError
+    with pytest.raises(NativeError):
+        ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-6)
