@@ -208,11 +208,11 @@ size_t smem_bytes(int NB) { return (size_t)NB * 8 + (size_t)((NB + 3) & ~3); }
 extern "C" int ms2_cc_label(const uint8_t* mask, int32_t* labels, int32_t* counts, int32_t* workspace,
                             int N, int H, int W, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  MS2_CHECK_ARG(mask && labels && counts, "cc_label: null pointer");
   MS2_CHECK_ARG(N >= 0 && H > 0 && W > 0, "cc_label: bad shape");
   MS2_CHECK_ARG((H % 2) == 0, "height must be a even number");
   MS2_CHECK_ARG((W % 2) == 0, "width must be a even number");
   if (N == 0) return MS2_OK;
+  MS2_CHECK_ARG(mask && labels && counts, "cc_label: null pointer");
   const int NB = (H / 2) * (W / 2);
   if (NB <= kMaxSmemBlocks) {
     size_t sm = smem_bytes(NB);
@@ -236,10 +236,10 @@ extern "C" int ms2_cc_label(const uint8_t* mask, int32_t* labels, int32_t* count
 extern "C" int ms2_fill_holes(const float* in, float* out, int N, int H, int W, float thresh, int max_area,
                               float fill_value, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  MS2_CHECK_ARG(in && out, "fill_holes: null pointer");
   MS2_CHECK_ARG((H % 2) == 0 && (W % 2) == 0 && H > 0 && W > 0, "fill_holes: H, W must be even");
   MS2_CHECK_ARG(max_area > 0, "max_area must be positive");
   if (N == 0) return MS2_OK;
+  MS2_CHECK_ARG(in && out, "fill_holes: null pointer");
   const int NB = (H / 2) * (W / 2);
   MS2_CHECK_ARG(NB <= kMaxSmemBlocks, "fill_holes: %dx%d exceeds the shared-memory path", H, W);
   size_t sm = smem_bytes(NB);

@@ -1,0 +1,248 @@
+"""GPU: every C-ABI kernel against its plain-torch statement (tests/ref_ops.py) on seeded inputs, and
+connected components bit-exact against the oracle and the committed golden vectors.
+Tolerances: fp32 paths 1e-4 abs unless stated (fp32 accumulate, different summation order);
+bf16 operand paths are compared against the fp32 statement fed the SAME bf16-rounded operands."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_ops
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from medsam2_b200 import ops as o
+    return o
+
+
+def gen(seed=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=gen(seed)) * scale).cuda()
+
+
+def close(a, b, tol, what=""):
+    a, b = a.float(), b.float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert err <= tol, f"{what}: max abs err {err} > {tol}"
+
+
+# ------------------------------------------------------------------ connected components (bit-exact)
+def test_cc_golden_vectors(ops):
+    z = np.load(f"{G}/cc_cases.npz")
+    for i in range(int(z["n"])):
+        m = torch.from_numpy(z[f"mask_{i}"])[None, None].cuda()
+        l, c = ops.cc_label(m)
+        assert np.array_equal(l[0, 0].cpu().numpy(), z[f"labels_{i}"]), i
+        assert np.array_equal(c[0, 0].cpu().numpy(), z[f"counts_{i}"]), i
+
+
+@pytest.mark.parametrize("shape,density", [((3, 1, 256, 256), 0.5), ((2, 1, 256, 256), 0.9), ((1, 1, 256, 256), 0.02),
+                                           ((5, 1, 64, 48), 0.6), ((1, 1, 1024, 1024), 0.55), ((2, 1, 512, 640), 0.4),
+                                           ((0, 1, 16, 16), 0.5), ((1, 1, 2, 2), 1.0)])
+def test_cc_matches_oracle(ops, shape, density):
+    from oracle.sam2_oracle import connected_components_np
+    m = (torch.rand(shape, generator=gen(3)) < density).to(torch.uint8)
+    l, c = ops.cc_label(m.cuda())
+    lo, co = connected_components_np(m.numpy())
+    assert np.array_equal(l.cpu().numpy(), lo)
+    assert np.array_equal(c.cpu().numpy(), co)
+
+
+def test_cc_properties_full_size(ops):
+    """size-independent properties at 1024x1024: idempotent relabel, counts sum = #fg, labels constant
+    on 8-neighbours."""
+    m = (torch.rand((2, 1, 1024, 1024), generator=gen(9)) < 0.58).to(torch.uint8).cuda()
+    l, c = ops.cc_label(m)
+    fg = m.bool()
+    assert (l[~fg] == 0).all() and (c[~fg] == 0).all() and (l[fg] > 0).all()
+    for dy, dx in ((0, 1), (1, 0), (1, 1), (1, -1)):
+        a = l[..., : l.shape[-2] - dy, max(0, -dx): l.shape[-1] - max(0, dx)]
+        b = l[..., dy:, max(0, dx): l.shape[-1] - max(0, -dx)]
+        both = (a > 0) & (b > 0)
+        assert (a[both] == b[both]).all()
+    # every component's count equals its number of pixels
+    for n in range(2):
+        lab = l[n, 0][fg[n, 0]].long()
+        cnt = c[n, 0][fg[n, 0]].long()
+        hist = torch.bincount(lab)
+        assert (hist[lab] == cnt).all()
+
+
+def test_cc_entry_contract(ops):
+    from medsam2_b200 import _C
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros(1, 1, 4, 4, dtype=torch.uint8))           # CPU tensor
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros(1, 1, 4, 4, dtype=torch.float32).cuda())  # dtype
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros(1, 1, 5, 4, dtype=torch.uint8).cuda())    # odd H
+    out = _C.get_connected_componnets(torch.ones(1, 1, 4, 4, dtype=torch.uint8).cuda())
+    assert out[0].dtype == torch.int32 and (out[0] == 1).all() and (out[1] == 16).all()
+
+
+def test_fill_holes(ops):
+    x = rnd(3, 1, 256, 256, seed=4)
+    x = torch.where(torch.rand(x.shape, generator=gen(5)).cuda() < 0.03, -x.abs(), x.abs())   # sparse small holes
+    close(ops.fill_holes(x, 8), ref_ops.fill_holes(x, 8), 0.0, "fill_holes")
+
+
+# ------------------------------------------------------------------ norm / gemm
+@pytest.mark.parametrize("M,C", [(1000, 96), (333, 768), (4096, 256), (5000, 4), (777, 16), (129, 64), (9, 256)])
+def test_layernorm(ops, M, C):
+    x, a = rnd(M, C, seed=1, scale=2.0), rnd(M, C, seed=2)
+    g, b = rnd(C, seed=3), rnd(C, seed=4)
+    close(ops.layernorm(x, g, b, 1e-6), ref_ops.layernorm(x, g, b, 1e-6), 2e-5, "ln")
+    close(ops.layernorm(x, g, b, 1e-5, add=a, act=1), ref_ops.layernorm(x, g, b, 1e-5, add=a, act=1), 2e-5, "ln+add+gelu")
+    y = ops.layernorm(x, g, b, 1e-6, out_dtype=torch.bfloat16)
+    close(y, ref_ops.layernorm(x, g, b, 1e-6), 5e-2, "ln bf16")
+
+
+@pytest.mark.parametrize("M,N,K", [(65, 96, 96), (1000, 288, 96), (4096, 256, 64), (37, 4, 9), (513, 1024, 256),
+                                   (9, 256, 2048), (262144 // 64, 16, 36), (2, 32, 256)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_gemm_simt(ops, M, N, K, dt):
+    a = rnd(M, K, seed=1).to(dt)
+    w = (rnd(N, K, seed=2) / K ** 0.5).to(dt)
+    bias, cs, res = rnd(N, seed=3), rnd(N, seed=4), rnd(M, N, seed=5)
+    tol = 1e-4 if dt == torch.float32 else 2e-4
+    close(ops.gemm(a, w, bias, impl=1), ref_ops.gemm(a, w, bias), tol, "gemm")
+    close(ops.gemm(a, w, bias, act=1, residual=res, colscale=cs, impl=1),
+          ref_ops.gemm(a, w, bias, act=1, residual=res, colscale=cs), tol, "gemm epilogue")
+    close(ops.gemm(a, w, bias, act=2, out_dtype=torch.bfloat16, impl=1), ref_ops.gemm(a, w, bias, act=2), 3e-2, "gemm bf16 out")
+
+
+def test_gemm_strided_rows(ops):
+    x = rnd(4, 9, 256, seed=1)
+    w, b = rnd(32, 256, seed=2) / 16, rnd(32, seed=3)
+    a = x.view(36, 256)[3::9]
+    close(ops.gemm(a, w, b, impl=1), ref_ops.gemm(a, w, b), 1e-4, "strided A")
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(2, 8, 9, 9, 32), (2, 8, 9, 1024, 16), (2, 8, 1024, 9, 16), (1, 1, 1024, 2056, 256),
+                                         (1, 4, 1024, 1024, 96), (2, 1, 300, 77, 256), (1, 2, 5, 130, 64)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_attention_dense(ops, B, H, Lq, Lk, D, dt):
+    q, k, v = rnd(B, Lq, H * D, seed=1).to(dt), rnd(B, Lk, H * D, seed=2).to(dt), rnd(B, Lk, H * D, seed=3).to(dt)
+    tol = 2e-5 if dt == torch.float32 else 1.5e-2
+    close(ops.attention(q, k, v, H, impl=1), ref_ops.attention(q.float(), k.float(), v.float(), H), tol, "attention")
+
+
+def test_attention_strided_qkv(ops):
+    B, L, C = 2, 256, 256
+    qkv = rnd(B, L, 3 * C, seed=7)
+    o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], 1, impl=1)
+    r = ref_ops.attention(qkv[:, :, :C].contiguous(), qkv[:, :, C:2 * C].contiguous(), qkv[:, :, 2 * C:].contiguous(), 1)
+    close(o, r, 2e-5, "strided qkv")
+
+
+@pytest.mark.parametrize("H,W,heads,ws,qpool", [(64, 64, 1, 8, 0), (64, 64, 2, 8, 1), (32, 32, 2, 4, 0), (32, 32, 4, 4, 1),
+                                                (64, 64, 4, 14, 0), (64, 64, 8, 14, 1), (32, 32, 8, 7, 0), (20, 36, 2, 14, 0)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_window_attention(ops, H, W, heads, ws, qpool, dt):
+    B, D = 2, 96
+    qkv = rnd(B, H, W, 3 * heads * D, seed=1).to(dt)
+    bias = rnd(3 * heads * D, seed=2)
+    tol = 2e-5 if dt == torch.float32 else 1.5e-2
+    close(ops.window_attention(qkv, bias, B, H, W, heads, D, ws, qpool),
+          ref_ops.window_attention(qkv.float(), bias, B, H, W, heads, D, ws, qpool), tol, "window attention")
+
+
+# ------------------------------------------------------------------ conv-shaped / elementwise
+def test_patch_embed(ops):
+    img = rnd(2, 3, 256, 320, seed=1)
+    w, b, pos = rnd(96, 3, 7, 7, seed=2) / 12, rnd(96, seed=3), rnd(64, 80, 96, seed=4)
+    close(ops.patch_embed(img, w, b, pos), ref_ops.patch_embed(img, w, b, pos), 1e-4, "patch_embed")
+
+
+@pytest.mark.parametrize("k,s,p,Cin,pre", [(3, 2, 1, 1, 1), (3, 2, 1, 1, 2), (3, 2, 1, 4, 0), (3, 2, 1, 16, 0), (2, 2, 0, 1, 0),
+                                           (2, 2, 0, 4, 0), (4, 4, 0, 1, 0)])
+def test_im2col(ops, k, s, p, Cin, pre):
+    x = rnd(2, 64, 48, Cin, seed=1)
+    close(ops.im2col(x, k, s, p, torch.float32, pre, 20.0 if pre else 1.0, -10.0 if pre else 0.0),
+          ref_ops.im2col(x, k, s, p, torch.float32, pre, 20.0 if pre else 1.0, -10.0 if pre else 0.0), 1e-5, "im2col")
+
+
+def test_dwconv7x7(ops):
+    x, w, b = rnd(2, 64, 64, 256, seed=1), rnd(256, 49, seed=2) / 7, rnd(256, seed=3)
+    close(ops.dwconv7x7(x, w, b), ref_ops.dwconv7x7(x, w, b), 1e-4, "dwconv")
+
+
+def test_elementwise_family(ops):
+    x, z = rnd(3, 100, 64, seed=1), rnd(3, 100, 64, seed=2)
+    close(ops.axpby(x, 1.0, z, 0.1), ref_ops.axpby(x, 1.0, z, 0.1), 1e-6, "axpby")
+    close(ops.axpby(x, 20.0, None, 0.0, -10.0), ref_ops.axpby(x, 20.0, None, 0.0, -10.0), 1e-5, "axpby const")
+    close(ops.axpby(x, 1.0, z[0], 1.0), ref_ops.axpby(x, 1.0, z[0], 1.0), 1e-6, "axpby bcast")
+    close(ops.axpby(x, 1.0, z, 1.0, out_dtype=torch.bfloat16), ref_ops.axpby(x, 1.0, z, 1.0), 3e-2, "axpby bf16")
+    v = rnd(64, seed=3)
+    close(ops.add_rowvec(x, v), ref_ops.add_rowvec(x, v), 1e-6, "add_rowvec")
+    close(ops.cast(ops.cast(x, torch.bfloat16), torch.float32), x.bfloat16().float(), 0.0, "cast")
+    for act in (1, 2, 3):
+        close(ops.activation(x, act), ref_ops.activation(x, act), 1e-6, f"act {act}")
+    gate = torch.tensor([1.0, -1.0, 0.0]).cuda()
+    close(ops.gate_rows(x, gate, -1024.0), ref_ops.gate_rows(x, gate, -1024.0), 0.0, "gate_rows")
+    idx = torch.tensor([2, 0, 1], dtype=torch.int32).cuda()
+    xs = rnd(3, 4, 16, 16, seed=5)
+    close(ops.select_plane(xs, idx), ref_ops.select_plane(xs, idx), 0.0, "select_plane")
+    cnt = ops.mask_stability_counts(xs, 0.05)
+    assert torch.equal(cnt, ref_ops.mask_stability_counts(xs, 0.05))
+
+
+def test_layout_kernels(ops):
+    x = rnd(2, 32, 48, 96, seed=1)
+    close(ops.maxpool2x2(x), ref_ops.maxpool2x2(x), 0.0, "maxpool")
+    close(ops.nhwc_to_nchw(x), ref_ops.nhwc_to_nchw(x), 0.0, "nhwc->nchw")
+    y = rnd(2, 96, 32, 48, seed=2)
+    close(ops.nchw_to_nhwc(y), ref_ops.nchw_to_nhwc(y), 0.0, "nchw->nhwc")
+    fine, coarse = rnd(2, 32, 48, 96, seed=3), rnd(2, 16, 24, 96, seed=4)
+    close(ops.upsample2x_add_(fine.clone(), coarse), ref_ops.upsample2x_add_(fine.clone(), coarse), 0.0, "upsample2x_add")
+    g, bias, skip = rnd(2, 16, 16, 4 * 64, seed=5), rnd(64, seed=6), rnd(2, 32, 32, 64, seed=7)
+    close(ops.pixel_shuffle_add(g, bias, skip, 2, 16, 16, 64, act=1), ref_ops.pixel_shuffle_add(g, bias, skip, 2, 16, 16, 64, act=1),
+          1e-6, "pixel_shuffle_add")
+    up, hyper = rnd(2, 4096, 32, seed=8), rnd(2, 4, 32, seed=9)
+    close(ops.hyper_mask(up, hyper), ref_ops.hyper_mask(up, hyper), 1e-4, "hyper_mask")
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_rope(ops, dt):
+    from medsam2_b200.modeling.position_encoding import rope_table
+    cos, sin = rope_table(256, 16, 16, 10000.0, "cuda")
+    B, L, n_ptr = 2, 256 * 3 + 8, 8
+    x = rnd(B, L, 256, seed=1).to(dt)
+    r = ref_ops.rope_(x.clone(), B, L, L - n_ptr, 256, cos, sin)
+    y = ops.rope_(x.clone(), B, L, L - n_ptr, 256, cos, sin)
+    close(y, r, 1e-6 if dt == torch.float32 else 2e-2, "rope")
+    # strided (q slice of a fused qkv buffer)
+    qkv = rnd(B, 256, 768, seed=2)
+    r2 = qkv.clone()
+    r2[:, :, 256:512] = ref_ops.rope_(qkv[:, :, 256:512].contiguous(), B, 256, 256, 256, cos, sin)
+    y2 = qkv.clone()
+    ops.rope_(y2[:, :, 256:], B, 256, 256, 256, cos, sin, batch_stride=256 * 768, row_stride=768)
+    close(y2, r2, 1e-6, "rope strided")
+
+
+@pytest.mark.parametrize("size,out,aa", [((256, 256), (1024, 1024), 0), ((128, 128), (512, 512), 0), ((256, 256), (333, 517), 0),
+                                         ((1024, 1024), (256, 256), 1), ((700, 500), (256, 256), 1), ((1024, 1024), (256, 256), 0)])
+def test_resize(ops, size, out, aa):
+    x = rnd(3, *size, seed=1)
+    close(ops.resize_bilinear(x, out, aa), ref_ops.resize_bilinear(x, out, aa), 2e-5, "resize")
+
+
+def test_fourier_and_normalize(ops):
+    c, gm = torch.rand(5, 3, 2, generator=gen(1)).cuda(), rnd(2, 128, seed=2)
+    close(ops.fourier_pe(c, gm), ref_ops.fourier_pe(c, gm), 2e-5, "fourier_pe")
+    x = (torch.rand(2, 3, 64, 64, generator=gen(3)) * 255).cuda()
+    close(ops.normalize_image(x), ref_ops.normalize_image(x), 1e-5, "normalize f32")
+    u = (torch.rand(2, 64, 64, 3, generator=gen(4)) * 255).to(torch.uint8).cuda()
+    close(ops.normalize_image(u), ref_ops.normalize_image(u), 1e-5, "normalize u8")
