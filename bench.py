@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — slices/sec of SAM2VideoPredictor.propagate_in_video (hiera_s, 1024², bf16 operands).
+
+One "step" = one pass of the hot path over one synthetic BTCV-shaped volume (BASELINE.json configs[2]:
+96 slices, bbox prompt every 2 slices, num_maskmem=7, 1 object): val_init_state -> add_new_bbox on the
+prompted slices -> propagate_in_video over all slices.  `value` is measured with the volume resident in
+HBM; `e2e` runs the same public API from pinned HOST memory with the host->device copy of the volume and
+the device->host read-back of the binarised masks inside the timed region.  With N>1 (torchrun) every rank
+tracks its own volume (BASELINE.json configs[3]: sharded by volume, no data-path collective; weak scaling)
+and the time is the max over ranks.
+
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port, all host threads) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "medical-sam2_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "slices/sec propagate_in_video (hiera_s, 1024^2)"
+UNIT = "slices/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slices", type=int, default=96)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--prompt-every", type=int, default=2)
+    ap.add_argument("--config", default="sam2_hiera_s")
+    ap.add_argument("--cpu-sample-slices", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--feature-cache", type=int, default=0, help="0 = one entry per slice (no double encode)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ workload
+def prompt_frames(T, every):
+    return list(range(0, T, every))
+
+
+def run_volume(predictor, vol, boxes, size, every):
+    """The timed unit: func_3d/function.py:226-274's call order on one volume."""
+    st = predictor.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
+    for f in prompt_frames(vol.shape[0], every):
+        predictor.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]),
+                                     clear_old_points=False)
+    masks = [None] * vol.shape[0]
+    for f, _, m in predictor.propagate_in_video(st, start_frame_idx=0):
+        masks[f] = m
+    return masks
+
+
+def cpu_oracle_rate(args, n_slices, threads=None):
+    """Reference algorithm (oracle port) on the host CPU, fp32, bounded sample of the same workload."""
+    from oracle.config import get_config
+    from oracle.sam2_oracle import OracleSAM2, OracleVideoPredictor
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    torch.set_num_threads(threads or os.cpu_count())
+    cfg = get_config(args.config, image_size=args.size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg), device="cpu"))
+    vol, boxes = btcv_volume(n_slices, args.size, 1234, 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        st = vp.init_state(vol, args.size, args.size)
+        for f in prompt_frames(n_slices, args.prompt_every):
+            vp.add_new_bbox(st, f, 1, boxes[f][0], clear_old_points=False)
+        n = sum(1 for _ in vp.propagate_in_video(st, start_frame_idx=0))
+    dt = time.perf_counter() - t0
+    return n / dt, dt, torch.get_num_threads()
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_sample_slices
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(args, 2)
+    rates, secs, cores = [], [], os.cpu_count()
+    for _ in range(args.steps):
+        r, s, cores = cpu_oracle_rate(args, n)
+        rates.append(r)
+        secs.append(s)
+    value = n * args.steps / sum(secs)
+    sample = (f"first {n} slices of the config-3 volume (bbox every {args.prompt_every}), oracle port of the reference, "
+              f"fp32, {cores} host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2] sample: {n} slices {args.size}^2, {args.config}, CPU"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import medsam2_b200
+    from medsam2_b200 import native, ops
+    from oracle.config import get_config          # config table only (layout of the synthetic weights)
+    from oracle.weights import param_spec
+    from synth_data import btcv_volume, seeded_weights
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    medsam2_b200.set_compute_dtype(dtype)
+    T, S = args.slices, args.size
+    cache = args.feature_cache if args.feature_cache > 0 else T
+    model = medsam2_b200.build_sam2_video_predictor(
+        args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}"])
+    model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
+    vol, boxes = btcv_volume(T, S, 1234 + rank, 1)          # every rank tracks its own volume (config 4 sharding)
+    vol_host = vol.pin_memory()
+    vol_dev = vol.cuda()
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        l2_flush.zero_()
+        run_volume(model, vol_dev, boxes, S, args.prompt_every)
+
+    out_host = torch.empty((T, S, S), dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        l2_flush.zero_()
+        v = vol_host.to("cuda", non_blocking=True)
+        masks = run_volume(model, v, boxes, S, args.prompt_every)
+        res = torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8)
+        out_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = native.launch_count
+    ops.PROFILE.enable(("attention", "gemm", "window_attention"))
+    ms = timed(step_resident, args.steps)
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.disable()
+    launches = native.launch_count - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    roofline = None
+    if dom:
+        name, d = dom
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None, "launches": d["n"], "ms_per_launch": d["ms"] / max(d["n"], 1),
+                    "share_of_step": d["ms"] / ms, "peak_source": peak_src,
+                    "all": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0),
+                                "n": v["n"]} for k, v in prof.items()}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, secs, cores = cpu_oracle_rate(args, args.cpu_sample_slices)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {args.cpu_sample_slices} slices of the same volume (bbox every {args.prompt_every}), "
+                         f"oracle port, fp32, {secs:.1f} s"}
+    total_slices = T * args.steps * world
+    line = {"metric": METRIC, "value": total_slices / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: {args.config} SAM2VideoPredictor.propagate_in_video, one "
+                                   f"{T}-slice {S}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, "
+                                   f"num_maskmem=7, fill_hole_area=8",
+                       "sharding": "by volume, no collectives" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush buffer written before every step; per-step working set >> L2"},
+            "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel()},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -19,6 +19,49 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _EventProfiler:
+    """Optional per-launch CUDA-event timing of selected ops on the launching stream (bench.py's
+    roofline numbers).  Off by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.names = None
+        self.records = []
+
+    def enable(self, names):
+        self.names = set(names)
+        self.records = []
+
+    def disable(self):
+        self.names = None
+
+    def begin(self, name):
+        if self.names is None or name not in self.names:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, name, e0, flops):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((name, flops, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, e0, e1 in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["n"] += 1
+        return out
+
+
+PROFILE = _EventProfiler()
+
+
 def _chk(t, name, dtype=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise native.NativeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
@@ -87,9 +130,11 @@ def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, 
         a_ptr = _chk(a, "a")
     if out is None:
         out = torch.empty(a.shape[:-1] + (N,), dtype=out_dtype, device=a.device)
+    ev = PROFILE.begin("gemm")
     native.call("ms2_gemm", a_ptr, _DT[a.dtype], lda, _chk(w, "w"), _DT[w.dtype], _opt(bias, "bias"),
                 _opt(colscale, "colscale"), _opt(residual, "residual"), N, _chk(out, "out"), _DT[out.dtype], N,
                 M, N, K, act, impl, _st())
+    PROFILE.end("gemm", ev, 2.0 * M * N * K)
     return out
 
 
@@ -106,9 +151,11 @@ def attention(q, k, v, heads, scale=None, impl=0):
     o = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
     if scale is None:
         scale = 1.0 / math.sqrt(D)
+    ev = PROFILE.begin("attention")
     native.call("ms2_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
                 q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), D, v.stride(1),
                 o.stride(0), D, o.stride(1), B, heads, Lq, Lk, D, float(scale), impl, _st())
+    PROFILE.end("attention", ev, 4.0 * B * heads * Lq * Lk * D)
     return o
 
 
@@ -116,8 +163,12 @@ def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool):
     """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
     Ho, Wo = (H // 2, W // 2) if qpool else (H, W)
     out = torch.empty((B, Ho, Wo, heads * D), dtype=qkv.dtype, device=qkv.device)
+    ev = PROFILE.begin("window_attention")
     native.call("ms2_window_attention", _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias", torch.float32),
                 out.data_ptr(), _DT[qkv.dtype], B, H, W, heads, D, ws, int(bool(qpool)), 1.0 / math.sqrt(D), _st())
+    nwin = B * ((H + ws - 1) // ws) * ((W + ws - 1) // ws)
+    lq = (ws // 2) ** 2 if qpool else ws * ws
+    PROFILE.end("window_attention", ev, 4.0 * nwin * heads * lq * ws * ws * D)
     return out
 
 
