@@ -122,6 +122,30 @@ def test_gemm_simt(ops, M, N, K, dt):
     close(ops.gemm(a, w, bias, act=2, out_dtype=torch.bfloat16, impl=1), ref_ops.gemm(a, w, bias, act=2), 3e-2, "gemm bf16 out")
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (65, 96, 96), (1000, 288, 96), (4096, 256, 64),
+                                   (513, 1024, 256), (4096, 2048, 256), (4096, 256, 2048), (65536, 288, 96),
+                                   (16384, 576, 192), (4100, 1152, 384), (1024, 3072, 768), (300, 32, 256),
+                                   (777, 64, 264), (129, 8, 16), (64, 40, 72)])
+def test_gemm_tc(ops, M, N, K):
+    """tcgen05 path (impl=2) vs the fp32 statement on the same bf16-rounded operands."""
+    a = rnd(M, K, seed=1).to(torch.bfloat16)
+    w = (rnd(N, K, seed=2) / K ** 0.5).to(torch.bfloat16)
+    bias, cs, res = rnd(N, seed=3), rnd(N, seed=4), rnd(M, N, seed=5)
+    close(ops.gemm(a, w, bias, impl=2), ref_ops.gemm(a, w, bias), 3e-4, "gemm_tc")
+    close(ops.gemm(a, w, None, impl=2), ref_ops.gemm(a, w, None), 3e-4, "gemm_tc nobias")
+    close(ops.gemm(a, w, bias, act=1, residual=res, colscale=cs, impl=2),
+          ref_ops.gemm(a, w, bias, act=1, residual=res, colscale=cs), 3e-4, "gemm_tc epilogue")
+    close(ops.gemm(a, w, bias, act=2, out_dtype=torch.bfloat16, impl=2), ref_ops.gemm(a, w, bias, act=2), 3e-2,
+          "gemm_tc bf16 out")
+
+
+def test_gemm_tc_strided_rows(ops):
+    x = rnd(2, 4096, 768, seed=1).to(torch.bfloat16)
+    w, b = (rnd(256, 256, seed=2) / 16).to(torch.bfloat16), rnd(256, seed=3)
+    a = x.view(8192, 768)[:, 256:512]
+    close(ops.gemm(a, w, b, impl=2), ref_ops.gemm(a.contiguous(), w, b), 3e-4, "strided A (column slice)")
+
+
 def test_gemm_strided_rows(ops):
     x = rnd(4, 9, 256, seed=1)
     w, b = rnd(32, 256, seed=2) / 16, rnd(32, seed=3)
