@@ -73,6 +73,15 @@ int ms2_attention(const void* q, const void* k, const void* v, void* o, int dt,
                   long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts,
                   long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts,
                   int B, int Hh, int Lq, int Lk, int D, float scale, int impl, ms2_stream_t stream);
+/* same, with a caller-provided scratch buffer that lets the tcgen05 path split the keys over several
+ * CTAs per query tile (flash-decoding style) when B*Hh*ceil(Lq/128) alone cannot fill the SMs:
+ * workspace_bytes >= nsplit * B*Hh*Lq*(D+2)*4 enables up to nsplit splits (the kernel picks the count);
+ * impl: 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMA (bf16, D in {64,96,128,256}). */
+int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt,
+                     long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts,
+                     long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts,
+                     int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
+                     void* workspace, long workspace_bytes, ms2_stream_t stream);
 
 /* ---- Hiera windowed attention with window partition / zero-pad-as-bias-key / q max-pool /
  *      unpartition+crop folded into the loads and stores (hieradet.py:58-83,136-159,

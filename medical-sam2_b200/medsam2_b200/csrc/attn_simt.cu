@@ -198,19 +198,25 @@ int launch_t(const AttnP& p, int D, int nbatch, cudaStream_t st) {
 
 }  // namespace
 
-int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_ts, long k_ts, long v_ts,
-                            long o_ts, long q_bs, long k_bs, long v_bs, long o_bs, int B, int Lq, int Lk, int D,
-                            float scale, cudaStream_t st);
-bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_ts, long v_ts, long o_ts, int Hh, int Lq,
-                                int Lk, int D);
+int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts,
+                            long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
+                            long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
+                            cudaStream_t st);
+bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_ts, long v_hs, long v_ts, long o_hs,
+                                long o_ts, int Hh, int Lq, int Lk, int D);
 
-extern "C" int ms2_attention(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
-                             long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
-                             long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
-                             void* stream) {
+extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
+                                long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
+                                long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
+                                void* workspace, long workspace_bytes, void* stream) {
   MS2_CHECK_ARG(q && k && v && o, "attention: null pointer");
   MS2_CHECK_ARG(B >= 0 && Hh > 0 && Lq >= 0 && Lk > 0, "attention: bad shape");
   if (B == 0 || Lq == 0) return MS2_OK;
+  const bool tc_ok = ms2_attention_tc_supported(dt, q_hs, q_ts, k_hs, k_ts, v_hs, v_ts, o_hs, o_ts, Hh, Lq, Lk, D);
+  if (impl == 2) MS2_CHECK_ARG(tc_ok, "attention: tcgen05 path does not support this shape/dtype/stride");
+  if (impl == 2 || (impl == 0 && tc_ok))
+    return ms2_attention_tc_launch(q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B,
+                                   Hh, Lq, Lk, D, scale, workspace, workspace_bytes, (cudaStream_t)stream);
   AttnP p;
   memset(&p, 0, sizeof(p));
   p.q = q; p.k = k; p.v = v; p.o = o;
@@ -221,6 +227,14 @@ extern "C" int ms2_attention(const void* q, const void* k, const void* v, void* 
   p.B = B; p.Hh = Hh; p.Lq = Lq; p.Lk = Lk; p.scale = scale; p.win = 0;
   MS2_DISPATCH_DTYPE(dt, T, return launch_t<T>(p, D, B, (cudaStream_t)stream));
   return MS2_OK;
+}
+
+extern "C" int ms2_attention(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
+                             long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
+                             long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
+                             void* stream) {
+  return ms2_attention_ws(q, k, v, o, dt, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B, Hh,
+                          Lq, Lk, D, scale, impl, nullptr, 0, stream);
 }
 
 extern "C" int ms2_window_attention(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,

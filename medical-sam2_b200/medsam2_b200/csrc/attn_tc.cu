@@ -1,10 +1,457 @@
-// tcgen05 flash attention — placeholder until phase 2 lands.
-#include "common.cuh"
-bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_ts, long v_ts, long o_ts, int Hh, int Lq,
-                                int Lk, int D) { return false; }
-int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_ts, long k_ts, long v_ts,
-                            long o_ts, long q_bs, long k_bs, long v_bs, long o_bs, int B, int Lq, int Lk, int D,
-                            float scale, cudaStream_t st) {
-  ms2_set_error("attention_tc: not built");
+// tcgen05 / TMEM / TMA flash attention (no mask), bf16 operands, fp32 softmax statistics:
+//     O = softmax(scale * Q K^T) V          Q [B,Hh,Lq,D], K/V [B,Hh,Lk,D] through element strides
+// Replaces F.scaled_dot_product_attention at transformer.py:252-258,318 (memory self/cross attention,
+// one head of 256) and hieradet.py:72-76 (Hiera global blocks, heads of 96).  SURVEY §8(a) a2/a6.
+//
+// One CTA owns a 128-query tile and streams a contiguous range of key tiles (split-KV over gridDim.z so
+// that 32 query tiles still fill 148 SMs; partial (O, m, l) are merged by attn_combine_kernel):
+//   warp 0      TMA producer : Q once; K and V tiles (BKV keys) through two 2-deep rings, 128B-swizzled
+//   warp 1      MMA issuer   : S = Q K^T   (M=128, N=BKV, K=D, both operands K-major)   -> TMEM S[j&1]
+//                              O += P V    (M=128, N=D, K=BKV, P K-major from smem, V MN-major) -> TMEM O
+//   warps 2..5  softmax      : thread = query row; tcgen05.ld of its S row, online max/sum in the log2
+//                              domain with LAZY rescaling (O is only rescaled in TMEM when the running max
+//                              grows by > 2^8), P -> bf16 -> swizzled smem; final O/l -> global
+// QK^T of tile j+1 is issued before P V of tile j, so the tensor pipe works under the softmax.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BQ = 128;
+constexpr int NUM_THREADS = 192;
+constexpr float LAZY_TAU = 8.0f;
+
+struct AttnTcP {
+  void* o;
+  long o_bs, o_hs, o_ts;
+  float* opart;   // [nsplit][B*Hh][Lq][D] fp32 un-normalised partial outputs (nsplit > 1)
+  float* ml;      // [nsplit][B*Hh][Lq][2]  (running max in log2 units, row sum)
+  int B, Hh, Lq, Lk;
+  float c;        // scale * log2(e)
+  int ntiles, tiles_per_split, nsplit;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D, int BKV>
+struct Cfg {
+  static constexpr int DCH = (D + 63) / 64;             // 64-element (128 B) column chunks of Q/K/V
+  static constexpr int Q_BYTES = DCH * BQ * 128;
+  static constexpr int KV_BYTES = DCH * BKV * 128;      // one K (or V) stage
+  static constexpr int P_BYTES = (BKV / 64) * BQ * 128;
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int S_COL = 256;                     // TMEM: O at [0,D), S stages at 256 + st*BKV
+};
+
+template <int D, int BKV>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
+  using C = Cfg<D, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + C::Q_BYTES;
+  uint8_t* sV = sK + C::STAGES * C::KV_BYTES;
+  uint8_t* sP = sV + C::STAGES * C::KV_BYTES;
+  uint64_t* bars = (uint64_t*)(sP + C::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_empty = bars + 11;      // 2
+  uint64_t* p_full = bars + 13;       // 1
+  uint64_t* o_ready = bars + 14;      // 1
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int bh = blockIdx.y, b = bh / p.Hh, h = bh - b * p.Hh;
+  const int split = blockIdx.z;
+  const int t_begin = split * p.tiles_per_split;
+  int n = p.ntiles - t_begin;
+  if (n > p.tiles_per_split) n = p.tiles_per_split;     // >= 1 by construction on the host
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmK);
+    tc::prefetch_tmap(&tmV);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&k_full[s], 1);
+      tc::mbar_init(&k_empty[s], 1);
+      tc::mbar_init(&v_full[s], 1);
+      tc::mbar_init(&v_empty[s], 1);
+      tc::mbar_init(&s_full[s], 1);
+      tc::mbar_init(&s_empty[s], 4);
+    }
+    tc::mbar_init(p_full, 4);
+    tc::mbar_init(o_ready, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < C::DCH; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        const int key0 = (t_begin + j) * BKV;
+        tc::mbar_wait(&k_empty[st], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::DCH; ++c)
+          tc::tma_load_4d(sK + st * C::KV_BYTES + c * BKV * 128, &tmK, &k_full[st], c * 64, key0, h, b);
+        tc::mbar_wait(&v_empty[st], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::DCH; ++c)
+          tc::tma_load_4d(sV + st * C::KV_BYTES + c * BKV * 128, &tmV, &v_full[st], c * 64, key0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, D, 0, 1);
+    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+    const uint32_t tO = tmem_base, tS = tmem_base + C::S_COL;
+
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      tc::mbar_wait(&k_full[st], ph);
+      tc::mbar_wait(&s_empty[st], ph ^ 1);
+      tc::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (uint32_t)(kk >> 2) * 128u * 128u;   // 64-column chunk: rows * 128 B
+          const uint64_t da = tc::desc_kmajor_sw128(aQ + (kk >> 2) * BQ * 128 + (kk & 3) * 32);
+          const uint64_t db = tc::desc_kmajor_sw128(aK + st * C::KV_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
+          (void)off;
+          tc::umma_bf16(tS + st * BKV, da, db, idesc_qk, kk ? 1u : 0u);
+        }
+        tc::umma_commit(&k_empty[st]);
+        tc::umma_commit(&s_full[st]);
+      }
+      __syncwarp();
+    };
+
+    tc::mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n; ++j) {
+      if (j + 1 < n) issue_qk(j + 1);
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      tc::mbar_wait(&v_full[st], ph);
+      tc::mbar_wait(p_full, (uint32_t)j & 1u);
+      tc::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t da = tc::desc_kmajor_sw128(aP + (kk >> 2) * BQ * 128 + (kk & 3) * 32);
+          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * C::KV_BYTES + kk * 2048, BKV * 128);
+          tc::umma_bf16(tO, da, db, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+        tc::umma_commit(&v_empty[st]);
+        tc::umma_commit(o_ready);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..5) =====================
+    const int qtr = warp & 3;                       // TMEM lane quarter of this warp
+    const int row = qtr * 32 + lane;                // query row inside the tile
+    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+    const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + C::S_COL;
+    float m_used = 0.f, l = 0.f;
+    const int last_valid = p.Lk - (p.ntiles - 1) * BKV;   // valid keys of the globally last tile
+
+    for (int j = 0; j < n; ++j) {
+      const int st = j & 1;
+      tc::mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1u);
+      tc::tc_fence_after();
+      uint32_t r[BKV / 32][32];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) tc::tmem_ld32(tS + st * BKV + c * 32, r[c]);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_empty[st]);
+
+      float mx = -INFINITY;
+      const bool tail = (t_begin + j == p.ntiles - 1) && (last_valid < BKV);
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(r[c][i]) * p.c;
+          if (tail && (c * 32 + i >= last_valid)) t = -INFINITY;
+          r[c][i] = __float_as_uint(t);
+          mx = fmaxf(mx, t);
+        }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = mx > m_used + LAZY_TAU;
+        if (__any_sync(0xffffffffu, need)) {
+          tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);      // P V of tile j-1 has landed in O
+          tc::tc_fence_after();
+          float alpha = 1.f;
+          if (need) {
+            alpha = ex2(m_used - mx);
+            m_used = mx;
+            l *= alpha;
+          }
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld32(tO + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tO + c * 32, o);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      // p = 2^(t - m_used), row sum in fp32, pack to bf16 pairs
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(__uint_as_float(r[c][i]) - m_used);
+          const float p1 = ex2(__uint_as_float(r[c][i + 1]) - m_used);
+          l += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
+        }
+      if (j > 0) tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);   // P buffer free (and O stable)
+      // P tile, K-major SW128: chunk of 64 keys = [128 rows][128 B], 16-byte groups XOR (row & 7)
+#pragma unroll
+      for (int kc = 0; kc < BKV / 64; ++kc)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 v;
+          v.x = pk[kc * 32 + g * 4 + 0];
+          v.y = pk[kc * 32 + g * 4 + 1];
+          v.z = pk[kc * 32 + g * 4 + 2];
+          v.w = pk[kc * 32 + g * 4 + 3];
+          *(uint4*)(sP + kc * BQ * 128 + row * 128 + ((g ^ (row & 7)) << 4)) = v;
+        }
+      tc::fence_proxy_async();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+
+    // ---- epilogue
+    tc::mbar_wait(o_ready, (uint32_t)(n - 1) & 1u);
+    tc::tc_fence_after();
+    const int qi = q0 + row;
+    if (p.nsplit == 1) {
+      const float inv = 1.f / l;
+      bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(tO + c * 32, o);
+        tc::tmem_ld_wait();
+        if (qi < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv,
+                                                        __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
+              vv[i] = *(uint32_t*)&hh;
+            }
+            *(uint4*)(orow + c * 32 + g * 8) = v;
+          }
+        }
+      }
+    } else {
+      const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
+      float* orow = p.opart + rix * D;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(tO + c * 32, o);
+        tc::tmem_ld_wait();
+        if (qi < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *(float4*)(orow + c * 32 + g * 4) =
+                make_float4(__uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]), __uint_as_float(o[g * 4 + 2]),
+                            __uint_as_float(o[g * 4 + 3]));
+        }
+      }
+      if (qi < p.Lq) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// merge the split-KV partials: O = sum_s 2^(m_s - m*) O_s / sum_s 2^(m_s - m*) l_s
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_combine_kernel(const float* __restrict__ opart, const float* __restrict__ ml, bf16* __restrict__ o, long o_bs,
+                    long o_hs, long o_ts, int Hh, int Lq, int nsplit, long rows) {
+  constexpr int TPR = D / 8;                  // threads per row, 8 columns each
+  constexpr int RPB = 128 / TPR > 0 ? 128 / TPR : 1;
+  const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int cg = threadIdx.x % TPR;
+  if (threadIdx.x >= RPB * TPR || rix >= rows) return;
+  float mstar = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mstar = fmaxf(mstar, ml[((long)s * rows + rix) * 2]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float lsum = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float2 v = *(const float2*)(ml + ((long)s * rows + rix) * 2);
+    const float w = exp2f(v.x - mstar);
+    lsum += w * v.y;
+    const float4* src = (const float4*)(opart + ((long)s * rows + rix) * D + cg * 8);
+    const float4 a = src[0], bq = src[1];
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+  }
+  const float inv = 1.f / lsum;
+  const long bh = rix / Lq;
+  const int qi = (int)(rix - bh * Lq);
+  const int b = (int)(bh / Hh), h = (int)(bh - (long)b * Hh);
+  bf16* dst = o + (long)b * o_bs + (long)h * o_hs + (long)qi * o_ts + cg * 8;
+  uint4 v;
+  uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+    vv[i] = *(uint32_t*)&hh;
+  }
+  *(uint4*)dst = v;
+}
+
+int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long ws_bytes) {
+  const int sms = tc::sm_count();
+  if (qtiles_total >= 2 * sms || ntiles < 4) return 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 64 && s <= ntiles / 2; ++s) {
+    const int tps = (ntiles + s - 1) / s;
+    const int se = (ntiles + tps - 1) / tps;
+    if (se != s) continue;
+    if (s > 1 && (long)s * ws_rows_bytes_per_split > ws_bytes) break;
+    const long ctas = (long)qtiles_total * s;
+    const long waves = (ctas + sms - 1) / sms;
+    // time ~ waves * (tiles per CTA + fixed prologue/epilogue in tile units) (+ combine traffic)
+    const double cost = waves * (tps + 3.0) + (s > 1 ? 0.25 * s : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+template <int D, int BKV>
+int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts, long k_bs, long k_hs,
+           long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts, int B, int Hh, int Lq, int Lk,
+           float scale, void* ws, long ws_bytes, cudaStream_t st) {
+  using C = Cfg<D, BKV>;
+  static_assert(C::SMEM <= 227 * 1024, "attention tile does not fit shared memory");
+  CUtensorMap tmQ, tmK, tmV;
+  auto mk = [&](CUtensorMap* m, const void* base, long bs, long hs, long ts, int L, int rows) {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)L, (uint64_t)Hh, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ts, (uint64_t)(Hh > 1 ? hs : ts * (long)L), (uint64_t)(B > 1 ? bs : ts * (long)L * Hh)};
+    const uint32_t box[4] = {64, (uint32_t)rows, 1, 1};
+    return tc::make_tmap_bf16(m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  int rc;
+  if ((rc = mk(&tmQ, q, q_bs, q_hs, q_ts, Lq, BQ))) return rc;
+  if ((rc = mk(&tmK, k, k_bs, k_hs, k_ts, Lk, BKV))) return rc;
+  if ((rc = mk(&tmV, v, v_bs, v_hs, v_ts, Lk, BKV))) return rc;
+
+  AttnTcP p;
+  p.o = o; p.o_bs = o_bs; p.o_hs = o_hs; p.o_ts = o_ts;
+  p.B = B; p.Hh = Hh; p.Lq = Lq; p.Lk = Lk;
+  p.c = scale * 1.4426950408889634f;
+  p.ntiles = (Lk + BKV - 1) / BKV;
+  const int qtiles = (Lq + BQ - 1) / BQ;
+  const long rows = (long)B * Hh * Lq;
+  const long per_split = rows * (D + 2) * 4;
+  p.nsplit = ws ? pick_nsplit(qtiles * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
+  p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  p.opart = (float*)ws;
+  p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * D : nullptr;
+
+  auto kern = attn_tc_kernel<D, BKV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "attn_tc attr");
+    attr_set = true;
+  }
+  dim3 grid(qtiles, B * Hh, p.nsplit);
+  kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
+  MS2_CHECK_LAUNCH("attn_tc_kernel");
+  if (p.nsplit > 1) {
+    constexpr int TPR = D / 8, RPB = 128 / TPR;
+    attn_combine_kernel<D><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
+                                                                 p.nsplit, rows);
+    MS2_CHECK_LAUNCH("attn_combine_kernel");
+  }
+  return MS2_OK;
+}
+
+}  // namespace
+
+bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_ts, long v_hs, long v_ts, long o_hs,
+                                long o_ts, int Hh, int Lq, int Lk, int D) {
+  if (dt != MS2_BF16) return false;
+  if (!(D == 64 || D == 96 || D == 128 || D == 256)) return false;
+  if (Lq < 64 || Lk < 64) return false;
+  if ((q_ts | k_ts | v_ts | o_ts) % 8) return false;
+  if (Hh > 1 && ((q_hs | k_hs | v_hs | o_hs) % 8)) return false;
+  return true;
+}
+
+long ms2_attention_tc_workspace(int B, int Hh, int Lq, int D, int max_split) {
+  return (long)max_split * B * Hh * Lq * (D + 2) * 4;
+}
+
+int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts,
+                            long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
+                            long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
+                            cudaStream_t st) {
+  MS2_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                    ((uintptr_t)o % 16 == 0) && (!ws || (uintptr_t)ws % 16 == 0),
+                "attention_tc: pointers must be 16-byte aligned");
+  MS2_CHECK_ARG(B == 1 || ((q_bs | k_bs | v_bs | o_bs) % 8 == 0), "attention_tc: batch strides must be multiples of 8");
+#define MS2_ATTN_ARGS q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B, Hh, Lq, Lk, scale, ws, ws_bytes, st
+  switch (D) {
+    case 64: return launch<64, 128>(MS2_ATTN_ARGS);
+    case 96: return launch<96, 128>(MS2_ATTN_ARGS);
+    case 128: return launch<128, 128>(MS2_ATTN_ARGS);
+    case 256: return launch<256, 64>(MS2_ATTN_ARGS);
+  }
+#undef MS2_ATTN_ARGS
+  ms2_set_error("attention_tc: unsupported head dim %d", D);
   return MS2_ERR_UNSUPPORTED;
 }

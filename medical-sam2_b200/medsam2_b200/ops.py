@@ -13,6 +13,7 @@ from . import native
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
+_SMS = 148
 
 
 def _st():
@@ -151,10 +152,19 @@ def attention(q, k, v, heads, scale=None, impl=0):
     o = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
     if scale is None:
         scale = 1.0 / math.sqrt(D)
+    ws, ws_bytes = None, 0
+    if impl != 1 and q.dtype == torch.bfloat16 and D in (64, 96, 128, 256) and Lq >= 64 and Lk >= 512:
+        qtiles = B * heads * ((Lq + 127) // 128)
+        if qtiles < 2 * _SMS:                                   # too few query tiles to fill the SMs: split-KV scratch
+            per_split = B * heads * Lq * (D + 2) * 4
+            nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split))
+            ws_bytes = nsplit * per_split
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
     ev = PROFILE.begin("attention")
-    native.call("ms2_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
+    native.call("ms2_attention_ws", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
                 q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), D, v.stride(1),
-                o.stride(0), D, o.stride(1), B, heads, Lq, Lk, D, float(scale), impl, _st())
+                o.stride(0), D, o.stride(1), B, heads, Lq, Lk, D, float(scale), impl,
+                None if ws is None else ws.data_ptr(), ws_bytes, _st())
     PROFILE.end("attention", ev, 4.0 * B * heads * Lq * Lk * D)
     return o
 

@@ -163,6 +163,36 @@ def test_attention_dense(ops, B, H, Lq, Lk, D, dt):
     close(ops.attention(q, k, v, H, impl=1), ref_ops.attention(q.float(), k.float(), v.float(), H), tol, "attention")
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk,D,qs", [(1, 1, 128, 64, 256, 1.0), (1, 1, 256, 128, 64, 1.0), (1, 1, 128, 128, 128, 1.0),
+                                            (1, 1, 128, 128, 96, 1.0), (1, 1, 4096, 4096 + 37, 256, 1.0),
+                                            (1, 4, 4096, 4096, 96, 1.0), (2, 1, 300, 777, 256, 3.0),
+                                            (1, 2, 1024, 1024, 64, 2.0), (2, 2, 256, 640, 128, 1.0),
+                                            (1, 1, 4096, 28736, 256, 4.0), (3, 8, 200, 333, 96, 1.0)])
+def test_attention_tc(ops, B, H, Lq, Lk, D, qs):
+    """tcgen05 flash attention (impl=2, incl. split-KV + lazy rescale) vs the fp32 statement on the same
+    bf16-rounded operands.  Tolerance 1.5e-2 abs: bf16 P and bf16 output rounding of O(1) values."""
+    q = (rnd(B, Lq, H * D, seed=1) * qs).to(torch.bfloat16)
+    k, v = rnd(B, Lk, H * D, seed=2).to(torch.bfloat16), rnd(B, Lk, H * D, seed=3).to(torch.bfloat16)
+    o = ops.attention(q, k, v, H, impl=2)
+    r = ref_ops.attention(q.float(), k.float(), v.float(), H)
+    close(o, r, 1.5e-2, "attention_tc")
+    assert (o.float() - r).abs().mean().item() < 2e-3
+
+
+def test_attention_tc_strided_qkv(ops):
+    B, L, C = 2, 512, 256
+    qkv = rnd(B, L, 3 * C, seed=7).to(torch.bfloat16)
+    o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], 1, impl=2)
+    r = ref_ops.attention(qkv[:, :, :C].float().contiguous(), qkv[:, :, C:2 * C].float().contiguous(),
+                          qkv[:, :, 2 * C:].float().contiguous(), 1)
+    close(o, r, 1.5e-2, "strided qkv tc")
+    qkv = rnd(1, 1024, 3 * 384, seed=8).to(torch.bfloat16)      # Hiera global block layout: 4 heads of 96
+    o = ops.attention(qkv[:, :, :384], qkv[:, :, 384:768], qkv[:, :, 768:], 4, impl=2)
+    r = ref_ops.attention(qkv[:, :, :384].float().contiguous(), qkv[:, :, 384:768].float().contiguous(),
+                          qkv[:, :, 768:].float().contiguous(), 4)
+    close(o, r, 1.5e-2, "strided qkv tc d96")
+
+
 def test_attention_strided_qkv(ops):
     B, L, C = 2, 256, 256
     qkv = rnd(B, L, 3 * C, seed=7)
