@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--feature-cache", type=int, default=0, help="0 = one entry per slice (no double encode)")
+    ap.add_argument("--kernel-table", default="", help="write a CUPTI per-kernel time table of one extra step here")
+    ap.add_argument("--encode-batch", type=int, default=8, help="slices per image-encoder pass on a cache miss")
     return ap.parse_args()
 
 
@@ -177,7 +179,8 @@ def main_ours(args):
     T, S = args.slices, args.size
     cache = args.feature_cache if args.feature_cache > 0 else T
     model = medsam2_b200.build_sam2_video_predictor(
-        args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}"])
+        args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
+                                                      f"++model.feature_encode_batch={args.encode_batch}"])
     model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
     vol, boxes = btcv_volume(T, S, 1234 + rank, 1)          # every rank tracks its own volume (config 4 sharding)
     vol_host = vol.pin_memory()
@@ -231,6 +234,19 @@ def main_ours(args):
     ops.PROFILE.disable()
     launches = native.launch_count - n0
     ms_e2e = timed(step_e2e, args.steps)
+    if args.kernel_table and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_:
+            step_resident()
+            torch.cuda.synchronize()
+        rows = sorted(prof_.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(args.kernel_table, "w") as fh:
+            fh.write(f"# CUPTI kernel times of one step ({T} slices); total device time {tot / 1e3:.2f} ms\n")
+            fh.write("# share%   total_ms   calls   avg_us   kernel\n")
+            for e in rows[:60]:
+                fh.write(f"{100 * e.device_time_total / tot:6.2f} {e.device_time_total / 1e3:10.3f} {e.count:7d} "
+                         f"{e.device_time_total / max(e.count, 1):8.1f}   {e.key[:110]}\n")
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:

@@ -60,7 +60,8 @@ int ms2_layernorm(const float* x, const float* add, const float* gamma, const fl
  *      out[M,N] = residual + colscale * act(A[M,K] @ W[N,K]^T + bias)
  *      A dtype a_dt (row stride lda), W dtype w_dt (row stride K), bias/colscale fp32 [N] or NULL,
  *      residual fp32 (row stride ldr) or NULL, out dtype o_dt (row stride ldo).
- *      impl: 0 = auto, 1 = SIMT fp32-accumulate reference kernel, 2 = tcgen05/TMA (bf16 only). */
+ *      impl: 0 = auto, 1 = SIMT fp32-accumulate reference kernel, 2 = tcgen05/TMA (bf16 only),
+ *      3 = small-M (M <= 64) latency kernel for the decoder's token-side MLPs. */
 int ms2_gemm(const void* A, int a_dt, long lda, const void* W, int w_dt, const float* bias,
              const float* colscale, const float* residual, long ldr, void* out, int o_dt, long ldo,
              int M, int N, int K, int act, int impl, ms2_stream_t stream);
@@ -76,7 +77,8 @@ int ms2_attention(const void* q, const void* k, const void* v, void* o, int dt,
 /* same, with a caller-provided scratch buffer that lets the tcgen05 path split the keys over several
  * CTAs per query tile (flash-decoding style) when B*Hh*ceil(Lq/128) alone cannot fill the SMs:
  * workspace_bytes >= nsplit * B*Hh*Lq*(D+2)*4 enables up to nsplit splits (the kernel picks the count);
- * impl: 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMA (bf16, D in {64,96,128,256}). */
+ * impl: 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMA (bf16, D in {64,96,128,256}),
+ * 3 = small-shape kernels of the mask decoder (D in {16,32}; Lk <= 32 keys or Lq <= 16 queries). */
 int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt,
                      long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts,
                      long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts,
@@ -90,6 +92,10 @@ int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int d
  *      out [B,Ho,Wo,heads*D] dtype dt with Ho=H/(qpool?2:1).  ws = window size (on the input grid). */
 int ms2_window_attention(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
                          int heads, int D, int ws, int qpool, float scale, ms2_stream_t stream);
+/* same with an explicit implementation choice: 0 = auto, 1 = SIMT fp32-accumulate kernel,
+ * 2 = tcgen05 (bf16, D = 96, ws*ws <= 256: several windows packed per M=128 tile, block-diagonal mask). */
+int ms2_window_attention_impl(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
+                              int heads, int D, int ws, int qpool, float scale, int impl, ms2_stream_t stream);
 
 /* ---- 2x2 max pool, stride 2, NHWC fp32 (hieradet.py:23-34 on the shortcut). */
 int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int C, ms2_stream_t stream);

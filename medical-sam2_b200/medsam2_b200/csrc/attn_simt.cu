@@ -205,6 +205,10 @@ int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o
 bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_ts, long v_hs, long v_ts, long o_hs,
                                 long o_ts, int Hh, int Lq, int Lk, int D);
 
+int ms2_attention_small(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts,
+                        long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
+                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, cudaStream_t st);
+
 extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
                                 long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
                                 long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
@@ -214,6 +218,13 @@ extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, voi
   if (B == 0 || Lq == 0) return MS2_OK;
   const bool tc_ok = ms2_attention_tc_supported(dt, q_hs, q_ts, k_hs, k_ts, v_hs, v_ts, o_hs, o_ts, Hh, Lq, Lk, D);
   if (impl == 2) MS2_CHECK_ARG(tc_ok, "attention: tcgen05 path does not support this shape/dtype/stride");
+  if (impl == 0 || impl == 3) {
+    const int rc = ms2_attention_small(q, k, v, o, dt, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs,
+                                       o_ts, B, Hh, Lq, Lk, D, scale, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) return MS2_OK;
+    MS2_CHECK_ARG(impl != 3, "attention: small-shape path does not support this configuration");
+  }
   if (impl == 2 || (impl == 0 && tc_ok))
     return ms2_attention_tc_launch(q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B,
                                    Hh, Lq, Lk, D, scale, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -237,11 +248,20 @@ extern "C" int ms2_attention(const void* q, const void* k, const void* v, void* 
                           Lq, Lk, D, scale, impl, nullptr, 0, stream);
 }
 
-extern "C" int ms2_window_attention(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
-                                    int heads, int D, int ws, int qpool, float scale, void* stream) {
+bool ms2_window_attention_tc_supported(int dt, int heads, int D, int ws, int qpool);
+int ms2_window_attention_tc_launch(const void* qkv, const float* qkv_bias, void* out, int B, int H, int W, int heads,
+                                   int ws, int qpool, float scale, cudaStream_t st);
+
+extern "C" int ms2_window_attention_impl(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
+                                         int heads, int D, int ws, int qpool, float scale, int impl, void* stream) {
   MS2_CHECK_ARG(qkv && qkv_bias && out, "window_attention: null pointer");
   MS2_CHECK_ARG(ws > 0 && (!qpool || ws % 2 == 0), "window_attention: bad window %d", ws);
   MS2_CHECK_ARG(!qpool || (H % 2 == 0 && W % 2 == 0), "window_attention: q-pool needs even H,W");
+  if (B == 0) return MS2_OK;
+  const bool tc_ok = ms2_window_attention_tc_supported(dt, heads, D, ws, qpool);
+  if (impl == 2) MS2_CHECK_ARG(tc_ok, "window_attention: tcgen05 path does not support this configuration");
+  if (impl == 2 || (impl == 0 && tc_ok))
+    return ms2_window_attention_tc_launch(qkv, qkv_bias, out, B, H, W, heads, ws, qpool, scale, (cudaStream_t)stream);
   AttnP p;
   memset(&p, 0, sizeof(p));
   p.q = qkv; p.k = qkv; p.v = qkv; p.o = out; p.bias = qkv_bias;
@@ -255,4 +275,9 @@ extern "C" int ms2_window_attention(const void* qkv, const float* qkv_bias, void
   const int nbatch = B * p.nwy * p.nwx;
   MS2_DISPATCH_DTYPE(dt, T, return launch_t<T>(p, D, nbatch, (cudaStream_t)stream));
   return MS2_OK;
+}
+
+extern "C" int ms2_window_attention(const void* qkv, const float* qkv_bias, void* out, int dt, int B, int H, int W,
+                                    int heads, int D, int ws, int qpool, float scale, void* stream) {
+  return ms2_window_attention_impl(qkv, qkv_bias, out, dt, B, H, W, heads, D, ws, qpool, scale, 0, stream);
 }

@@ -8,6 +8,10 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
                        const float* residual, long ldr, void* out, int o_dt, long ldo, int M, int N, int K,
                        int act, cudaStream_t st);
 bool ms2_gemm_tc_supported(int a_dt, int w_dt, long lda, long ldo, int M, int N, int K);
+bool ms2_gemm_smallm_supported(int a_dt, int w_dt, const void* A, const void* W, long lda, int M, int N, int K);
+int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, const float* bias, const float* colscale,
+                           const float* residual, long ldr, void* out, int o_dt, long ldo, int M, int N, int K, int act,
+                           cudaStream_t st);
 
 namespace {
 
@@ -105,6 +109,10 @@ extern "C" int ms2_gemm(const void* A, int a_dt, long lda, const void* W, int w_
   if (impl == 2) MS2_CHECK_ARG(tc_ok, "gemm: tcgen05 path does not support this shape/dtype");
   if (impl == 2 || (impl == 0 && tc_ok))
     return ms2_gemm_tc_launch(A, lda, W, bias, colscale, residual, ldr, out, o_dt, ldo, M, N, K, act, st);
+  const bool sm_ok = ms2_gemm_smallm_supported(a_dt, w_dt, A, W, lda, M, N, K);
+  if (impl == 3) MS2_CHECK_ARG(sm_ok, "gemm: small-M path does not support this shape/dtype");
+  if (impl == 3 || (impl == 0 && sm_ok))
+    return ms2_gemm_smallm_launch(A, a_dt, lda, W, bias, colscale, residual, ldr, out, o_dt, ldo, M, N, K, act, st);
   if (a_dt == MS2_F32) {
     if (o_dt == MS2_F32) return launch<float, float>(A, lda, W, bias, colscale, residual, ldr, out, ldo, M, N, K, act, st);
     if (o_dt == MS2_BF16) return launch<float, bf16>(A, lda, W, bias, colscale, residual, ldr, out, ldo, M, N, K, act, st);

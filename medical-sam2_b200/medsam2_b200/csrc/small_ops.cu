@@ -1,0 +1,304 @@
+// Latency-oriented kernels for the token side of the SAM mask decoder ("many tiny
+// kernels on GPU, launch-bound"): these shapes have a handful of rows and cannot fill a tensor-core tile,
+// so they are HBM/L2-latency bound and are written as coalesced, vectorised SIMT kernels.
+//   * gemm_smallm : out[M<=16 per pass, N] = epilogue(A @ W^T); 8 lanes share one output column and split K
+//                   in 16-byte chunks, A rows come from L1 (a few KB), W streams once.
+//   * attn_fewk   : Lk <= 32 keys (image -> token attention, transformer.py:183-189): one thread per
+//                   (query, head), K/V of all heads staged in shared memory as fp32.
+//   * attn_fewq   : Lq <= 16 queries over any Lk that fits shared memory (token -> image attention,
+//                   transformer.py:167-181,110-116): one CTA per (head, batch); scores for all keys are
+//                   kept in shared memory (exact two-pass softmax), P V is reduced across 16 warps.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ small-M GEMM
+template <typename T> struct Vec8;
+template <> struct Vec8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&f)[8]) {
+    const uint4 u = *(const uint4*)p;
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = *(const float4*)p, b = *(const float4*)(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
+constexpr int SM_MT = 16;       // rows per pass
+constexpr int SM_WARPS = 4;     // 4 warps x 4 columns = 16 columns per CTA
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(SM_WARPS * 32)
+gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, const float* __restrict__ bias,
+                   const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
+                   TO* __restrict__ out, long ldo, int M, int N, int K, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = lane >> 3, kl = lane & 7;
+  const int n = (blockIdx.x * SM_WARPS + warp) * 4 + cg;
+  const bool n_ok = n < N;
+  const T* wrow = W + (long)(n_ok ? n : 0) * K;
+  for (int m0 = 0; m0 < M; m0 += SM_MT) {
+    const int mt = min(SM_MT, M - m0);
+    float acc[SM_MT];
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
+    for (int k = kl * 8; k < K; k += 64) {
+      float w[8];
+      Vec8<T>::load(wrow + k, w);
+#pragma unroll
+      for (int m = 0; m < SM_MT; ++m) {
+        if (m < mt) {
+          float a[8];
+          Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[i], acc[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) {
+      float v = acc[m];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      acc[m] = v;
+    }
+    if (kl == 0 && n_ok) {
+#pragma unroll
+      for (int m = 0; m < SM_MT; ++m) {
+        if (m < mt) {
+          float v = acc[m];
+          if (bias) v += bias[n];
+          if (act == 1) v = gelu_erf(v);
+          else if (act == 2) v = fmaxf(v, 0.f);
+          else if (act == 3) v = 1.f / (1.f + __expf(-v));
+          if (colscale) v *= colscale[n];
+          if (residual) v += residual[(long)(m0 + m) * ldr + n];
+          out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ attention, few keys
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+attn_fewk_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
+                 long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
+                 long o_bs, long o_hs, long o_ts, int Hh, int Lq, int Lk, float scale) {
+  extern __shared__ float smf[];
+  float* Ks = smf;                       // [Hh][Lk][D]
+  float* Vs = smf + Hh * Lk * D;
+  const int b = blockIdx.y;
+  for (int idx = threadIdx.x; idx < Hh * Lk * D; idx += blockDim.x) {
+    const int d = idx % D, j = (idx / D) % Lk, h = idx / (D * Lk);
+    Ks[idx] = to_f(k[b * k_bs + h * k_hs + (long)j * k_ts + d]);
+    Vs[idx] = to_f(v[b * v_bs + h * v_hs + (long)j * v_ts + d]);
+  }
+  __syncthreads();
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= Lq * Hh) return;
+  const int h = gid % Hh, qi = gid / Hh;
+  float qv[D];
+  const T* qp = q + b * q_bs + h * q_hs + (long)qi * q_ts;
+#pragma unroll
+  for (int d = 0; d < D; d += 8) {
+    float t[8];
+    Vec8<T>::load(qp + d, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[d + i] = t[i] * scale;
+  }
+  const float* kh = Ks + h * Lk * D;
+  const float* vh = Vs + h * Lk * D;
+  float mx = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < Lk; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) a = fmaf(qv[d], kh[j * D + d], a);
+    const float mn = fmaxf(mx, a);
+    const float corr = __expf(mx - mn), pj = __expf(a - mn);
+    mx = mn;
+    l = l * corr + pj;
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = fmaf(pj, vh[j * D + d], acc[d] * corr);
+  }
+  const float inv = 1.f / l;
+  T* op = o + b * o_bs + h * o_hs + (long)qi * o_ts;
+#pragma unroll
+  for (int d = 0; d < D; ++d) op[d] = from_f<T>(acc[d] * inv);
+}
+
+// ------------------------------------------------------------------ attention, few queries
+constexpr int FQ_THREADS = 512, FQ_WARPS = 16, FQ_MAXQ = 16;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(FQ_THREADS)
+attn_fewq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
+                 long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
+                 long o_bs, long o_hs, long o_ts, int Lq, int Lk, float scale) {
+  extern __shared__ float smf[];
+  float* S = smf;                                   // [Lq][Lk]
+  float* Qs = S + (long)Lq * Lk;                    // [Lq][D]
+  float* red = Qs + FQ_MAXQ * D;                    // [FQ_WARPS][Lq][D]
+  float* linv = red + FQ_WARPS * FQ_MAXQ * D;       // [Lq]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < Lq * D; idx += FQ_THREADS)
+    Qs[idx] = to_f(q[b * q_bs + h * q_hs + (long)(idx / D) * q_ts + idx % D]) * scale;
+  __syncthreads();
+  // pass 1: scores
+  const T* kb = k + b * k_bs + h * k_hs;
+  for (int j = tid; j < Lk; j += FQ_THREADS) {
+    float kv[D];
+#pragma unroll
+    for (int d = 0; d < D; d += 8) {
+      float t[8];
+      Vec8<T>::load(kb + (long)j * k_ts + d, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kv[d + i] = t[i];
+    }
+    for (int qi = 0; qi < Lq; ++qi) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) a = fmaf(Qs[qi * D + d], kv[d], a);
+      S[(long)qi * Lk + j] = a;
+    }
+  }
+  __syncthreads();
+  // pass 2: softmax numerators per query row (one warp per row)
+  for (int qi = warp; qi < Lq; qi += FQ_WARPS) {
+    float* row = S + (long)qi * Lk;
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float l = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float pj = __expf(row[j] - mx);
+      row[j] = pj;
+      l += pj;
+    }
+    l = warp_sum(l);
+    if (lane == 0) linv[qi] = 1.f / l;
+  }
+  __syncthreads();
+  // pass 3: O = P V ; lane -> (key slot within the warp's step, d)
+  constexpr int KPW = 32 / D;                        // keys per warp step (2 for D=16, 1 for D=32)
+  const int d = lane % D, sub = lane / D;
+  float acc[FQ_MAXQ];
+#pragma unroll
+  for (int qi = 0; qi < FQ_MAXQ; ++qi) acc[qi] = 0.f;
+  const T* vb = v + b * v_bs + h * v_hs;
+  for (int j = warp * KPW + sub; j < Lk; j += FQ_WARPS * KPW) {
+    const float vv = to_f(vb[(long)j * v_ts + d]);
+#pragma unroll
+    for (int qi = 0; qi < FQ_MAXQ; ++qi)
+      if (qi < Lq) acc[qi] = fmaf(S[(long)qi * Lk + j], vv, acc[qi]);
+  }
+#pragma unroll
+  for (int qi = 0; qi < FQ_MAXQ; ++qi) {
+    float a = acc[qi];
+    if (KPW == 2) a += __shfl_xor_sync(0xffffffffu, a, 16);
+    if (qi < Lq && sub == 0) red[(warp * FQ_MAXQ + qi) * D + d] = a;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Lq * D; idx += FQ_THREADS) {
+    const int qi = idx / D, dd = idx % D;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < FQ_WARPS; ++w) a += red[(w * FQ_MAXQ + qi) * D + dd];
+    o[b * o_bs + h * o_hs + (long)qi * o_ts + dd] = from_f<T>(a * linv[qi]);
+  }
+}
+
+size_t fewq_smem(int Lq, int Lk, int D) {
+  return sizeof(float) * ((size_t)Lq * Lk + FQ_MAXQ * D + FQ_WARPS * FQ_MAXQ * D + FQ_MAXQ);
+}
+
+}  // namespace
+
+// -------- dispatch helpers used by ms2_gemm / ms2_attention_ws
+bool ms2_gemm_smallm_supported(int a_dt, int w_dt, const void* A, const void* W, long lda, int M, int N, int K) {
+  if (a_dt != w_dt || M > 64) return false;
+  const int vb = a_dt == MS2_BF16 ? 8 : 4;          // 16-byte vectors
+  return K % 8 == 0 && lda % vb == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0);
+}
+
+int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, const float* bias, const float* colscale,
+                           const float* residual, long ldr, void* out, int o_dt, long ldo, int M, int N, int K, int act,
+                           cudaStream_t st) {
+  const int grid = ceil_div(N, SM_WARPS * 4);
+#define MS2_SMALLM(TA, TO)                                                                                          \
+  gemm_smallm_kernel<TA, TO><<<grid, SM_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, residual, \
+                                                             ldr, (TO*)out, ldo, M, N, K, act)
+  if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_SMALLM(bf16, bf16);
+  else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_SMALLM(bf16, float);
+  else if (a_dt == MS2_F32 && o_dt == MS2_BF16) MS2_SMALLM(float, bf16);
+  else if (a_dt == MS2_F32 && o_dt == MS2_F32) MS2_SMALLM(float, float);
+  else {
+    ms2_set_error("gemm_smallm: bad dtype");
+    return MS2_ERR_ARG;
+  }
+#undef MS2_SMALLM
+  MS2_CHECK_LAUNCH("gemm_smallm_kernel");
+  return MS2_OK;
+}
+
+// returns 1 if a small-shape kernel handled the call, 0 if not applicable, <0 on error
+int ms2_attention_small(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts,
+                        long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
+                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, cudaStream_t st) {
+  if (!(D == 16 || D == 32)) return 0;
+  const int vb = dt == MS2_BF16 ? 8 : 4;
+  const bool vec_ok = ((q_ts | k_ts | q_hs | k_hs | q_bs | k_bs) % vb == 0) && ((uintptr_t)q % 16 == 0) &&
+                      ((uintptr_t)k % 16 == 0);
+  if (!vec_ok) return 0;
+#define MS2_ARGS_T(T) (const T*)q, (const T*)k, (const T*)v, (T*)o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts
+  if (Lk <= 32 && (size_t)2 * Hh * Lk * D * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)2 * Hh * Lk * D * 4;
+    dim3 grid(ceil_div((long)Lq * Hh, 256), B);
+    if (dt == MS2_BF16 && D == 16) attn_fewk_kernel<bf16, 16><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
+    else if (dt == MS2_BF16 && D == 32) attn_fewk_kernel<bf16, 32><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
+    else if (dt == MS2_F32 && D == 16) attn_fewk_kernel<float, 16><<<grid, 256, smem, st>>>(MS2_ARGS_T(float), Hh, Lq, Lk, scale);
+    else if (dt == MS2_F32 && D == 32) attn_fewk_kernel<float, 32><<<grid, 256, smem, st>>>(MS2_ARGS_T(float), Hh, Lq, Lk, scale);
+    else return 0;
+    MS2_CHECK_LAUNCH("attn_fewk_kernel");
+    return 1;
+  }
+  if (Lq <= FQ_MAXQ && fewq_smem(Lq, Lk, D) <= 200 * 1024) {
+    const size_t smem = fewq_smem(Lq, Lk, D);
+    dim3 grid(Hh, B);
+#define MS2_FEWQ(T, DD)                                                                                         \
+  do {                                                                                                          \
+    auto kern = attn_fewq_kernel<T, DD>;                                                                        \
+    static size_t attr = 0;                                                                                     \
+    if (smem > attr) {                                                                                          \
+      MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "fewq attr"); \
+      attr = 200 * 1024;                                                                                        \
+    }                                                                                                           \
+    kern<<<grid, FQ_THREADS, smem, st>>>(MS2_ARGS_T(T), Lq, Lk, scale);                                         \
+  } while (0)
+    if (dt == MS2_BF16 && D == 16) MS2_FEWQ(bf16, 16);
+    else if (dt == MS2_BF16 && D == 32) MS2_FEWQ(bf16, 32);
+    else if (dt == MS2_F32 && D == 16) MS2_FEWQ(float, 16);
+    else if (dt == MS2_F32 && D == 32) MS2_FEWQ(float, 32);
+    else return 0;
+#undef MS2_FEWQ
+    MS2_CHECK_LAUNCH("attn_fewq_kernel");
+    return 1;
+  }
+#undef MS2_ARGS_T
+  return 0;
+}

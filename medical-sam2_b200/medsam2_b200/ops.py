@@ -14,6 +14,10 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 _SMS = 148
+# debugging aid: MS2_DISABLE=tc_gemm,small_gemm,tc_attn,small_attn,tc_win forces the fp32-accumulate SIMT
+# kernel for that family (still a CUDA kernel of this library - there is no non-native path)
+import os as _os
+_DISABLED = set(filter(None, _os.environ.get("MS2_DISABLE", "").split(",")))
 
 
 def _st():
@@ -131,6 +135,11 @@ def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, 
         a_ptr = _chk(a, "a")
     if out is None:
         out = torch.empty(a.shape[:-1] + (N,), dtype=out_dtype, device=a.device)
+    if impl == 0 and _DISABLED:
+        if M >= 64 and "tc_gemm" in _DISABLED:
+            impl = 1
+        if M < 64 and "small_gemm" in _DISABLED:
+            impl = 1
     ev = PROFILE.begin("gemm")
     native.call("ms2_gemm", a_ptr, _DT[a.dtype], lda, _chk(w, "w"), _DT[w.dtype], _opt(bias, "bias"),
                 _opt(colscale, "colscale"), _opt(residual, "residual"), N, _chk(out, "out"), _DT[out.dtype], N,
@@ -152,6 +161,11 @@ def attention(q, k, v, heads, scale=None, impl=0):
     o = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
     if scale is None:
         scale = 1.0 / math.sqrt(D)
+    if impl == 0 and _DISABLED:
+        if D in (16, 32) and "small_attn" in _DISABLED:
+            impl = 1
+        if D >= 64 and "tc_attn" in _DISABLED:
+            impl = 1
     ws, ws_bytes = None, 0
     if impl != 1 and q.dtype == torch.bfloat16 and D in (64, 96, 128, 256) and Lq >= 64 and Lk >= 512:
         qtiles = B * heads * ((Lq + 127) // 128)
@@ -169,13 +183,15 @@ def attention(q, k, v, heads, scale=None, impl=0):
     return o
 
 
-def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool):
+def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool, impl=0):
     """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
     Ho, Wo = (H // 2, W // 2) if qpool else (H, W)
     out = torch.empty((B, Ho, Wo, heads * D), dtype=qkv.dtype, device=qkv.device)
+    if impl == 0 and "tc_win" in _DISABLED:
+        impl = 1
     ev = PROFILE.begin("window_attention")
-    native.call("ms2_window_attention", _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias", torch.float32),
-                out.data_ptr(), _DT[qkv.dtype], B, H, W, heads, D, ws, int(bool(qpool)), 1.0 / math.sqrt(D), _st())
+    native.call("ms2_window_attention_impl", _chk(qkv, "qkv"), _chk(qkv_bias, "qkv_bias", torch.float32),
+                out.data_ptr(), _DT[qkv.dtype], B, H, W, heads, D, ws, int(bool(qpool)), 1.0 / math.sqrt(D), impl, _st())
     nwin = B * ((H + ws - 1) // ws) * ((W + ws - 1) // ws)
     lq = (ws // 2) ** 2 if qpool else ws * ws
     PROFILE.end("window_attention", ev, 4.0 * nwin * heads * lq * ws * ws * D)

@@ -4,6 +4,7 @@ operands (bf16 by default, fp32 = exact mode) and a cache of kernel-ready parame
 that `load_state_dict` / in-place updates invalidate them."""
 import contextlib
 import os
+import weakref
 
 import torch
 
@@ -43,11 +44,15 @@ class ParamCache:
         sig = tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
         k = (tuple(id(p) for p in params), key)
         hit = self._d.get(k)
-        if hit is not None and hit[0] == sig:
+        # id() and data_ptr() are both recycled once a model is freed: an entry is only valid while the very
+        # tensor objects it was derived from are still alive (weak references), not merely "same address".
+        if hit is not None and hit[0] == sig and all(r() is p for r, p in zip(hit[2], params)):
             return hit[1]
         with torch.no_grad():
             val = fn(*params)
-        self._d[k] = (sig, val)
+        if len(self._d) > 4096:                       # drop entries whose parameters are gone
+            self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
+        self._d[k] = (sig, val, tuple(weakref.ref(p) for p in params))
         return val
 
 

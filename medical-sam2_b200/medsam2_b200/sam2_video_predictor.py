@@ -22,13 +22,17 @@ def _new_frame_dict():
 
 class SAM2VideoPredictor(SAM2Base):
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
-                 clear_non_cond_mem_for_multi_obj=False, feature_cache_size=1, **kwargs):
+                 clear_non_cond_mem_for_multi_obj=False, feature_cache_size=1, feature_encode_batch=1, **kwargs):
         super().__init__(**kwargs)
         self.fill_hole_area = fill_hole_area
         self.non_overlap_masks = non_overlap_masks
         self.clear_non_cond_mem_around_input = clear_non_cond_mem_around_input
         self.clear_non_cond_mem_for_multi_obj = clear_non_cond_mem_for_multi_obj
         self.feature_cache_size = feature_cache_size
+        # slices encoded per image-encoder pass on a cache miss (the miss frame + the next ones in tracking
+        # order); per-slice results are bit-identical to one-at-a-time encoding, the GEMM/attention launches are
+        # just `feature_encode_batch` times larger.  Never exceeds the cache capacity.
+        self.feature_encode_batch = max(1, int(feature_encode_batch))
 
     # ------------------------------------------------------------------ state construction
     def _make_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):
@@ -345,6 +349,7 @@ class SAM2VideoPredictor(SAM2Base):
 
     # ------------------------------------------------------------------ propagation
     def _propagate(self, st, start_frame_idx, max_frame_num_to_track, reverse):
+        st["prefetch_reverse"] = bool(reverse)
         self._preflight(st)
         output_dict = st["output_dict"]
         cfi = st["consolidated_frame_inds"]
@@ -451,13 +456,28 @@ class SAM2VideoPredictor(SAM2Base):
         cache = st["cached_features"]
         hit = cache.get(frame_idx)
         if hit is None:
-            image = st["images"][frame_idx].to(st["device"]).float().unsqueeze(0)
-            backbone_out = self.forward_image(image)
-            if self.feature_cache_size <= 1:
+            cap = max(self.feature_cache_size, 1)
+            step = -1 if st.get("prefetch_reverse", False) else 1
+            frames = [frame_idx]
+            f = frame_idx + step
+            while len(frames) < min(self.feature_encode_batch, cap) and 0 <= f < st["num_frames"]:
+                if f not in cache:
+                    frames.append(f)
+                f += step
+            imgs = st["images"]
+            if len(frames) == 1:
+                images = imgs[frame_idx].to(st["device"]).float().unsqueeze(0)
+            else:
+                images = torch.stack([imgs[f] for f in frames]).to(st["device"]).float()
+            out = self.forward_image(images)
+            if cap <= 1:
                 cache.clear()
-            while len(cache) >= max(self.feature_cache_size, 1):
-                cache.popitem(last=False)
-            cache[frame_idx] = (image, backbone_out)
+            for i, f in enumerate(frames):
+                while len(cache) >= cap:
+                    cache.popitem(last=False)
+                cache[f] = (images[i:i + 1], {k: ([t[i:i + 1] for t in v] if isinstance(v, list) else v[i:i + 1])
+                                              for k, v in out.items()})
+            image, backbone_out = cache[frame_idx]
         else:
             image, backbone_out = hit
         expanded = {
