@@ -52,6 +52,34 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __flo
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// GELU with erf by Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 instead of
+// the ~25-instruction erff; used where the result is rounded to bf16 anyway (tensor-core GEMM epilogues).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);          // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+// GELU for bf16 outputs: erf(z) ~= tanh(z * P(z^2)) (fit error 1.3e-5 on |z| <= 4, clamped beyond) with the
+// single-instruction MUFU.TANH (rel. error 2^-11): total error is < 1/8 of the bf16 rounding of the result.
+__device__ __forceinline__ float gelu_erf_tanh(float x) {
+  float z = x * 0.70710678118654752440f;
+  z = fminf(fmaxf(z, -4.0f), 4.0f);
+  const float z2 = z * z;
+  float p = fmaf(-0.00015486571f, z2, -0.0010999786f);
+  p = fmaf(p, z2, 0.10336954f);
+  p = fmaf(p, z2, 1.1282882f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z * p));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,42 +5,61 @@
 //   warp 0      TMA producer  : A (128 x 64) and W (BN x 64) boxes, 128B-swizzled, ring of `stages`
 //   warp 1      MMA issuer    : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //                               TMEM accumulator stages; tcgen05.commit releases smem slots / signals epilogue
-//   warps 2..5  epilogue      : tcgen05.ld 32 lanes x 32 columns -> bias / act / colscale / residual ->
-//                               16-byte global stores (fp32 or bf16), overlapping the next tile's main loop
+//   warps 2..   epilogue      : 8 or 16 warps in groups of 4 (one warp per TMEM lane quarter); groups take
+//                               alternate 128-byte column chunks: tcgen05.ld -> bias / act / colscale / residual
+//                               -> private 128B-swizzled 4 KB staging buffer -> per-warp TMA store (coalesced,
+//                               M/N tails clipped by hardware), overlapping the next tile's main loop
 // Both operands are K-major, so no transposes exist anywhere; M/N/K tails are handled by TMA
-// out-of-bounds zero fill and masked stores.  BN (32..256) is a run-time choice per problem shape.
+// out-of-bounds zero fill / clipping.  BN (32..256) is a run-time choice per problem shape.
+// Most GEMMs of this model have K <= 384 and are HBM-bound: the epilogue, not the MMA loop, sets their speed.
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int BM = 128, BK = 64, MAX_STAGES = 8, ACC_STAGES = 2, TMEM_COLS = 512;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int SMEM_BUDGET = 200 * 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int MAX_EPI_WARPS = 16, EPI_BUF_BYTES = 32 * 128;     // per warp: one staging buffer of [32 rows][128 B]
+constexpr int MAX_THREADS = 64 + MAX_EPI_WARPS * 32;
+constexpr int SMEM_TOTAL = 226 * 1024;
 
 struct GemmP {
   const float* bias;
   const float* colscale;
   const float* residual;
   long ldr;
-  void* out;
-  long ldo;
-  int o_dt, M, N, K, act, BN, tiles_n, tiles, num_kb, stages;
+  int M, N, K, BN, tiles_n, tiles, num_kb, stages, epi_warps;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return gelu_erf(v);
-  if (act == 2) return fmaxf(v, 0.f);
-  if (act == 3) return 1.f / (1.f + __expf(-v));
+template <int ACT, bool F32OUT>
+__device__ __forceinline__ float apply_act(float v) {
+  if (ACT == 1) return F32OUT ? gelu_erf_fast(v) : gelu_erf_tanh(v);
+  if (ACT == 2) return fmaxf(v, 0.f);
+  if (ACT == 3) return 1.f / (1.f + __expf(-v));
   return v;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmP p) {
+// 32 fp32 values (bias or colscale) for columns [n, n+32), zero beyond N (N % 4 == 0); issued as 8 independent
+// 16-byte loads at the top of a chunk so their latency hides under the tcgen05.ld
+__device__ __forceinline__ void load_cols32(const float* __restrict__ src, int n, int N, float4 (&b)[8]) {
+  if (n + 32 <= N) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) b[g] = __ldg((const float4*)(src + n + g * 4));
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      b[g] = (n + g * 4 < N) ? __ldg((const float4*)(src + n + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool F32OUT, int ACT, bool RES>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;               // epi_warps x 4 KB, 1024-aligned
+  uint64_t* full = (uint64_t*)(staging + p.epi_warps * EPI_BUF_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* acc_full = empty + MAX_STAGES;
   uint64_t* acc_empty = acc_full + ACC_STAGES;
@@ -51,13 +70,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
+    tc::prefetch_tmap(&tmO);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       tc::mbar_init(&acc_full[s], 1);
-      tc::mbar_init(&acc_empty[s], 4);
+      tc::mbar_init(&acc_empty[s], p.epi_warps);
     }
     tc::fence_barrier_init();
   }
@@ -113,84 +133,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 .. 2+epi_warps) =====================
+    // Every warp owns the 32 accumulator rows of its TMEM lane quarter and a private 4 KB staging buffer, so
+    // the only synchronisation on this path is __syncwarp(): no CTA-level barrier, stores are per-warp TMA boxes.
+    // With a residual, the warp first copies the residual box into the staging buffer with coalesced 16-byte
+    // loads (4 rows x 128 B per instruction), then every lane updates its own row in place.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    int as = 0;
+    const int grp = (warp - 2) >> 2, ngrp = p.epi_warps >> 2;
+    constexpr int CPC = F32OUT ? 32 : 64;        // columns per 128-byte chunk
+    uint8_t* buf = staging + (warp - 2) * EPI_BUF_BYTES;
+    const uint32_t sbuf = tc::smem_u32(buf), srow = sbuf + lane * 128;
+    int as = 0, it = 0, rot = grp;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-      const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * p.BN;
-      const int row = m0 + q * 32 + lane;
+      const int m0 = (t / p.tiles_n) * BM + q * 32, n0 = (t % p.tiles_n) * p.BN;
+      int ncols = p.N - n0;
+      if (ncols > p.BN) ncols = p.BN;
+      const int nch = (ncols + CPC - 1) / CPC;
       tc::mbar_wait(&acc_full[as], aphase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(taddr + c, r);
-        tc::tmem_ld_wait();
-        const int nb = n0 + c;
-        if (row < p.M && nb < p.N) {
-          const float* res = p.residual ? p.residual + (long)row * p.ldr + nb : nullptr;
+      for (int c = rot; c < nch; c += ngrp, ++it) {   // groups rotate over tiles so odd chunk counts balance
+        if (it >= 1) {                              // the previous store of this warp has read the buffer
+          if (lane == 0) tc::tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        const int nb = n0 + c * CPC;
+        if (RES && p.residual) {
+          // residual box [32 rows][32 fp32] -> staging (only fp32 outputs carry a residual: CPC == 32)
+          uint4 rr[8];
 #pragma unroll
-          for (int g = 0; g < 32; g += 8) {
-            if (nb + g >= p.N) continue;
-            const bool second = nb + g + 4 < p.N;          // N % 4 == 0: groups of 4 are all-or-nothing
-            float v[8];
+          for (int i = 0; i < 8; ++i) {
+            const int rrow = i * 4 + (lane >> 3), cc = lane & 7;
+            const bool ok = (m0 + rrow < p.M) && (nb + cc * 4 < p.N);
+            rr[i] = ok ? *(const uint4*)(p.residual + (long)(m0 + rrow) * p.ldr + nb + cc * 4) : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g + j]);
-            if (p.bias) {
-              const float4 b0 = __ldg((const float4*)(p.bias + nb + g));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              if (second) {
-                const float4 b1 = __ldg((const float4*)(p.bias + nb + g + 4));
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-            }
-            if (p.act) {
+          for (int i = 0; i < 8; ++i) {
+            const int rrow = i * 4 + (lane >> 3), cc = lane & 7;
+            tc::sts128(sbuf + rrow * 128 + ((cc ^ (rrow & 7)) << 4), rr[i]);
+          }
+          __syncwarp();
+        }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+        for (int hlf = 0; hlf < CPC / 32; ++hlf) {
+          const int nh = nb + hlf * 32;
+          uint32_t acc[32];
+          tc::tmem_ld32(taddr + c * CPC + hlf * 32, acc);
+          float4 bb[8];
+          if (p.bias) load_cols32(p.bias, nh, p.N, bb);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float v[4] = {__uint_as_float(acc[g * 4]), __uint_as_float(acc[g * 4 + 1]), __uint_as_float(acc[g * 4 + 2]),
+                          __uint_as_float(acc[g * 4 + 3])};
+            if (p.bias) { v[0] += bb[g].x; v[1] += bb[g].y; v[2] += bb[g].z; v[3] += bb[g].w; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = apply_act<ACT, F32OUT>(v[j]);
+            if (RES && p.colscale && nh + g * 4 < p.N) {      // rare (layer-scale of the memory-encoder fuser)
+              const float4 cs = __ldg((const float4*)(p.colscale + nh + g * 4));
+              v[0] *= cs.x; v[1] *= cs.y; v[2] *= cs.z; v[3] *= cs.w;
             }
-            if (p.colscale) {
-              const float4 s0 = __ldg((const float4*)(p.colscale + nb + g));
-              v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-              if (second) {
-                const float4 s1 = __ldg((const float4*)(p.colscale + nb + g + 4));
-                v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+            if (F32OUT) {
+              const uint32_t slot = srow + ((g ^ (lane & 7)) << 4);
+              if (RES && p.residual) {
+                const float4 r4 = tc::lds128f(slot);
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
               }
-            }
-            if (res) {
-              const float4 r0 = *(const float4*)(res + g);
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-              if (second) {
-                const float4 r1 = *(const float4*)(res + g + 4);
-                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-              }
-            }
-            if (p.o_dt == MS2_F32) {
-              float* o = (float*)p.out + (long)row * p.ldo + nb + g;
-              *(float4*)o = make_float4(v[0], v[1], v[2], v[3]);
-              if (second) *(float4*)(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              tc::sts128f(slot, v[0], v[1], v[2], v[3]);
             } else {
-              bf16* o = (bf16*)p.out + (long)row * p.ldo + nb + g;
               __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-              if (second) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-                uint4 u;
-                u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
-                *(uint4*)o = u;
-              } else {
-                uint2 u;
-                u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1;
-                *(uint2*)o = u;
-              }
+              acc[g * 2] = *(uint32_t*)&h0;           // repack in place: 8 columns -> 4 words
+              acc[g * 2 + 1] = *(uint32_t*)&h1;
             }
           }
+          if (!F32OUT) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              tc::sts128(srow + (((hlf * 4 + g) ^ (lane & 7)) << 4), acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2],
+                         acc[g * 4 + 3]);
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && m0 < p.M) {
+          tc::tma_store_2d(&tmO, buf, nb, m0);
+          tc::tma_store_commit();
         }
       }
+      rot = (rot + 1 == ngrp) ? 0 : rot + 1;
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tc::tma_store_wait<0>();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -200,14 +237,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-int pick_bn(int M, int N, int K) {
+int pick_bn(int M, int N, int K, int o_dt) {
   const int sms = tc::sm_count();
   const long tm = (M + BM - 1) / BM;
   const long kb = (K + BK - 1) / BK;
-  int best = 32;
+  const int step = o_dt == MS2_BF16 ? 64 : 32;          // whole 128-byte output chunks per tile
+  int best = step;
   double best_cost = 1e30;
-  const int nmax = ((N + 31) / 32) * 32;
-  for (int bn = 32; bn <= 256 && bn <= (nmax < 32 ? 32 : nmax); bn += 32) {
+  const int nmax = ((N + step - 1) / step) * step;
+  for (int bn = step; bn <= 256 && bn <= nmax; bn += step) {
     const long tn = (N + bn - 1) / bn;
     const long waves = (tm * tn + sms - 1) / sms;
     const double per_tile = kb * (390.0 + 3.05 * bn) + 200.0 + 8.0 * bn;
@@ -220,7 +258,7 @@ int pick_bn(int M, int N, int K) {
 }  // namespace
 
 bool ms2_gemm_tc_supported(int a_dt, int w_dt, long lda, long ldo, int M, int N, int K) {
-  return a_dt == MS2_BF16 && w_dt == MS2_BF16 && M >= 64 && K % 8 == 0 && K >= 16 && lda % 8 == 0 && N % 8 == 0 &&
+  return a_dt == MS2_BF16 && w_dt == MS2_BF16 && M >= 64 && K % 8 == 0 && K >= 16 && lda % 8 == 0 && N % 4 == 0 &&
          ldo % 8 == 0;
 }
 
@@ -234,38 +272,72 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
   MS2_CHECK_ARG(!colscale || (uintptr_t)colscale % 16 == 0, "gemm_tc: colscale alignment");
   MS2_CHECK_ARG(o_dt == MS2_F32 || o_dt == MS2_BF16, "gemm_tc: bad output dtype");
   GemmP p;
-  p.bias = bias; p.colscale = colscale; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo; p.o_dt = o_dt;
-  p.M = M; p.N = N; p.K = K; p.act = act;
-  p.BN = pick_bn(M, N, K);
+  p.bias = bias; p.colscale = colscale; p.residual = residual; p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  p.BN = pick_bn(M, N, K, o_dt);
   p.tiles_n = (N + p.BN - 1) / p.BN;
   p.tiles = ((M + BM - 1) / BM) * p.tiles_n;
   p.num_kb = (K + BK - 1) / BK;
   const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-  p.stages = SMEM_BUDGET / stage_bytes;
+  // short-K problems are epilogue/HBM-bound: spend shared memory on 16 epilogue warps instead of pipeline depth
+  p.epi_warps = p.num_kb <= 8 ? 16 : 8;
+  const int stage_budget = SMEM_TOTAL - 1024 - 256 - p.epi_warps * EPI_BUF_BYTES;
+  p.stages = stage_budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)p.stages * stage_bytes + p.epi_warps * EPI_BUF_BYTES + 1024 + 256;
 
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO;
+  int rc;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)lda};
     const uint32_t box[2] = {BK, BM};
-    int rc = tc::make_tmap_bf16(&tmA, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    if ((rc = tc::make_tmap_bf16(&tmA, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K};
     const uint32_t box[2] = {BK, (uint32_t)p.BN};
-    int rc = tc::make_tmap_bf16(&tmW, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if ((rc = tc::make_tmap_bf16(&tmW, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldo};
+    if (o_dt == MS2_F32) {
+      const uint32_t box[2] = {32, 32};
+      rc = tc::make_tmap_f32(&tmO, out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      const uint32_t box[2] = {64, 32};
+      rc = tc::make_tmap_bf16(&tmO, out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MS2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048),
-             "gemm_tc attr");
-    attr_set = true;
-  }
   const int grid = p.tiles < tc::sm_count() ? p.tiles : tc::sm_count();
-  gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, p);
+  const bool res = residual || colscale;
+  MS2_CHECK_ARG(!residual || o_dt == MS2_F32, "gemm_tc: a residual needs an fp32 output");
+#define MS2_GEMM_TC(F, A, R)                                                                                   \
+  do {                                                                                                         \
+    auto kern = gemm_tc_kernel<F, A, R>;                                                                       \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL), "gemm_tc attr"); \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    kern<<<grid, 64 + p.epi_warps * 32, smem, st>>>(tmA, tmW, tmO, p);                                         \
+  } while (0)
+#define MS2_GEMM_TC_ACT(F, R)                                                                                  \
+  do {                                                                                                         \
+    if (act == 0) MS2_GEMM_TC(F, 0, R);                                                                        \
+    else if (act == 1) MS2_GEMM_TC(F, 1, R);                                                                   \
+    else if (act == 2) MS2_GEMM_TC(F, 2, R);                                                                   \
+    else MS2_GEMM_TC(F, 3, R);                                                                                 \
+  } while (0)
+  if (o_dt == MS2_F32) {
+    if (res) MS2_GEMM_TC_ACT(true, true);
+    else MS2_GEMM_TC_ACT(true, false);
+  } else {
+    if (res) MS2_GEMM_TC_ACT(false, true);
+    else MS2_GEMM_TC_ACT(false, false);
+  }
+#undef MS2_GEMM_TC_ACT
+#undef MS2_GEMM_TC
   MS2_CHECK_LAUNCH("gemm_tc_kernel");
   return MS2_OK;
 }

@@ -24,6 +24,21 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// explicit shared-window accesses: pointers carved out of the aligned dynamic smem buffer lose their address
+// space in the compiler (generic ST.E/LD.E with 64-bit address arithmetic), so hot paths use 32-bit addresses
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) { sts128(addr, v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -92,6 +107,23 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// smem (128B/64B-swizzled box) -> global tile; OOB parts of the box are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {      // <= N most recent groups may still read smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------ TMEM / tcgen05
@@ -194,9 +226,9 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 tensor of `rank` dims (dim 0 innermost, unit stride); strides in ELEMENTS for dims 1..rank-1.
-inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                          const uint32_t* box, CUtensorMapSwizzle swz) {
+// tensor of `rank` dims (dim 0 innermost, unit stride); strides in ELEMENTS for dims 1..rank-1.
+inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                     const uint32_t* box, CUtensorMapSwizzle swz, CUtensorMapDataType dtype, int esize) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     ms2_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -208,9 +240,9 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
     gd[i] = dims[i];
     bx[i] = box[i];
     es[i] = 1;
-    if (i > 0) gs[i - 1] = strides_el[i - 1] * 2;
+    if (i > 0) gs[i - 1] = strides_el[i - 1] * esize;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -220,6 +252,15 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
     return MS2_ERR_CUDA;
   }
   return MS2_OK;
+}
+
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                          const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap(m, base, rank, dims, strides_el, box, swz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                         const uint32_t* box, CUtensorMapSwizzle swz) {
+  return make_tmap(m, base, rank, dims, strides_el, box, swz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
 inline int sm_count() {
