@@ -207,7 +207,8 @@ bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_
 
 int ms2_attention_small(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts,
                         long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
-                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, cudaStream_t st);
+                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
+                        cudaStream_t st);
 
 extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
                                 long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
@@ -220,7 +221,7 @@ extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, voi
   if (impl == 2) MS2_CHECK_ARG(tc_ok, "attention: tcgen05 path does not support this shape/dtype/stride");
   if (impl == 0 || impl == 3) {
     const int rc = ms2_attention_small(q, k, v, o, dt, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs,
-                                       o_ts, B, Hh, Lq, Lk, D, scale, (cudaStream_t)stream);
+                                       o_ts, B, Hh, Lq, Lk, D, scale, workspace, workspace_bytes, (cudaStream_t)stream);
     if (rc < 0) return rc;
     if (rc == 1) return MS2_OK;
     MS2_CHECK_ARG(impl != 3, "attention: small-shape path does not support this configuration");

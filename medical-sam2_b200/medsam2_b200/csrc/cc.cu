@@ -233,6 +233,53 @@ extern "C" int ms2_cc_label(const uint8_t* mask, int32_t* labels, int32_t* count
   return MS2_OK;
 }
 
+namespace {
+// Hole filling only asks "is this background pixel in an 8-connected component of area <= max_area?".  For the
+// small areas used on the hot path (fill_hole_area = 8) that is a LOCAL question: a bounded flood fill from the
+// pixel either exhausts its component within max_area pixels (hole) or finds a (max_area+1)-th pixel (not a
+// hole).  One thread per pixel, at most (max_area+1)*8 neighbour probes out of L1/L2 - no union-find, no global
+// labels, and bit-identical to labelling the whole image (utils/misc.py:247-258).
+constexpr int kLocalMaxArea = 32;
+__global__ void __launch_bounds__(256)
+fill_holes_local_kernel(const float* __restrict__ in, float* __restrict__ out, long total, int H, int W, float thresh,
+                        int max_area, float fill_value) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int hw = H * W;
+  const long n = p / hw;
+  const int pix = (int)(p - n * hw), y0 = pix / W, x0 = pix - y0 * W;
+  const float* img = in + n * hw;
+  const float v = img[pix];
+  float res = v;
+  if (v <= thresh) {
+    int q[kLocalMaxArea];
+    q[0] = (y0 << 16) | x0;
+    int cnt = 1, head = 0;
+    bool small = true;
+    while (small && head < cnt) {
+      const int cy = q[head] >> 16, cx = q[head] & 0xffff;
+      ++head;
+#pragma unroll 1
+      for (int d = 0; d < 8 && small; ++d) {
+        const int dy = (d < 3) ? -1 : (d < 5 ? 0 : 1);
+        const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 1 || d == 6) ? 0 : 1);
+        const int ny = cy + dy, nx = cx + dx;
+        if (ny < 0 || ny >= H || nx < 0 || nx >= W) continue;
+        if (!(img[ny * W + nx] <= thresh)) continue;
+        const int key = (ny << 16) | nx;
+        bool seen = false;
+        for (int i = 0; i < cnt; ++i) seen |= (q[i] == key);
+        if (seen) continue;
+        if (cnt == max_area) { small = false; break; }
+        q[cnt++] = key;
+      }
+    }
+    if (small) res = fill_value;
+  }
+  out[p] = res;
+}
+}  // namespace
+
 extern "C" int ms2_fill_holes(const float* in, float* out, int N, int H, int W, float thresh, int max_area,
                               float fill_value, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -240,6 +287,12 @@ extern "C" int ms2_fill_holes(const float* in, float* out, int N, int H, int W, 
   MS2_CHECK_ARG(max_area > 0, "max_area must be positive");
   if (N == 0) return MS2_OK;
   MS2_CHECK_ARG(in && out, "fill_holes: null pointer");
+  if (max_area <= kLocalMaxArea && H < 65536 && W < 65536) {
+    const long total = (long)N * H * W;
+    fill_holes_local_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(in, out, total, H, W, thresh, max_area, fill_value);
+    MS2_CHECK_LAUNCH("fill_holes_local_kernel");
+    return MS2_OK;
+  }
   const int NB = (H / 2) * (W / 2);
   MS2_CHECK_ARG(NB <= kMaxSmemBlocks, "fill_holes: %dx%d exceeds the shared-memory path", H, W);
   size_t sm = smem_bytes(NB);

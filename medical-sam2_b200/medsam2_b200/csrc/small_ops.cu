@@ -223,6 +223,93 @@ attn_fewq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   }
 }
 
+// ---- few queries, many keys, split over key chunks (flash-decoding layout): grid (Hh, B, NS) x 128 threads;
+//      each CTA reduces its key chunk to (m, l, o[D]) per query, attn_fewq_combine_kernel merges the NS partials.
+constexpr int FS_THREADS = 128, FS_MAXCHUNK = 128;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(FS_THREADS)
+attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, float* __restrict__ part,
+                       long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
+                       int Lq, int Lk, int chunk, float scale) {
+  __shared__ float S[FQ_MAXQ][FS_MAXCHUNK];
+  __shared__ float Vs[FS_MAXCHUNK][D + 1];
+  __shared__ float Qs[FQ_MAXQ][D];
+  __shared__ float ms[FQ_MAXQ];
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, ns = gridDim.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j0 = sp * chunk;
+  const int nk = min(chunk, Lk - j0);                      // >= 1 by construction
+  for (int idx = tid; idx < Lq * D; idx += FS_THREADS)
+    Qs[idx / D][idx % D] = to_f(q[b * q_bs + h * q_hs + (long)(idx / D) * q_ts + idx % D]) * scale;
+  __syncthreads();
+  const T* kb = k + b * k_bs + h * k_hs;
+  const T* vb = v + b * v_bs + h * v_hs;
+  for (int j = tid; j < nk; j += FS_THREADS) {
+    float kv[D];
+#pragma unroll
+    for (int d = 0; d < D; d += 8) {
+      float t[8];
+      Vec8<T>::load(kb + (long)(j0 + j) * k_ts + d, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kv[d + i] = t[i];
+    }
+    for (int qi = 0; qi < Lq; ++qi) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) a = fmaf(Qs[qi][d], kv[d], a);
+      S[qi][j] = a;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) Vs[j][d] = to_f(vb[(long)(j0 + j) * v_ts + d]);
+  }
+  __syncthreads();
+  float* pbase = part + ((((long)b * gridDim.x + h) * ns + sp) * Lq) * (D + 2);
+  for (int qi = warp; qi < Lq; qi += FS_THREADS / 32) {
+    float mx = -INFINITY;
+    for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, S[qi][j]);
+    mx = warp_max(mx);
+    float l = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      const float pj = __expf(S[qi][j] - mx);
+      S[qi][j] = pj;
+      l += pj;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      pbase[qi * (D + 2) + D] = mx;
+      pbase[qi * (D + 2) + D + 1] = l;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Lq * D; idx += FS_THREADS) {
+    const int qi = idx / D, d = idx % D;
+    float a = 0.f;
+    for (int j = 0; j < nk; ++j) a = fmaf(S[qi][j], Vs[j][d], a);
+    pbase[qi * (D + 2) + d] = a;
+  }
+}
+
+template <typename T, int D>
+__global__ void attn_fewq_combine_kernel(const float* __restrict__ part, T* __restrict__ o, long o_bs, long o_hs, long o_ts,
+                                         int Hh, int Lq, int ns) {
+  const int bh = blockIdx.x, b = bh / Hh, h = bh - b * Hh;
+  for (int idx = threadIdx.x; idx < Lq * D; idx += blockDim.x) {
+    const int qi = idx / D, d = idx % D;
+    const float* pb = part + ((long)bh * ns * Lq + qi) * (D + 2);
+    const long sstride = (long)Lq * (D + 2);
+    float mstar = -INFINITY;
+    for (int s = 0; s < ns; ++s) mstar = fmaxf(mstar, pb[s * sstride + D]);
+    float acc = 0.f, l = 0.f;
+    for (int s = 0; s < ns; ++s) {
+      const float w = __expf(pb[s * sstride + D] - mstar);
+      acc = fmaf(w, pb[s * sstride + d], acc);
+      l = fmaf(w, pb[s * sstride + D + 1], l);
+    }
+    o[b * o_bs + h * o_hs + (long)qi * o_ts + d] = from_f<T>(acc / l);
+  }
+}
+
 size_t fewq_smem(int Lq, int Lk, int D) {
   return sizeof(float) * ((size_t)Lq * Lk + FQ_MAXQ * D + FQ_WARPS * FQ_MAXQ * D + FQ_MAXQ);
 }
@@ -259,7 +346,8 @@ int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, con
 // returns 1 if a small-shape kernel handled the call, 0 if not applicable, <0 on error
 int ms2_attention_small(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts,
                         long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
-                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, cudaStream_t st) {
+                        long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
+                        cudaStream_t st) {
   if (!(D == 16 || D == 32)) return 0;
   const int vb = dt == MS2_BF16 ? 8 : 4;
   const bool vec_ok = ((q_ts | k_ts | q_hs | k_hs | q_bs | k_bs) % vb == 0) && ((uintptr_t)q % 16 == 0) &&
@@ -276,6 +364,28 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
     else return 0;
     MS2_CHECK_LAUNCH("attn_fewk_kernel");
     return 1;
+  }
+  if (Lq <= FQ_MAXQ && Lk >= 512 && ws) {
+    const int chunk = FS_MAXCHUNK;
+    const int ns = (Lk + chunk - 1) / chunk;
+    const long need = (long)B * Hh * ns * Lq * (D + 2) * 4;
+    if (ns <= 64 && need <= ws_bytes) {
+      dim3 grid(Hh, B, ns);
+#define MS2_FEWQS(T, DD)                                                                                              \
+  do {                                                                                                                \
+    attn_fewq_split_kernel<T, DD><<<grid, FS_THREADS, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (float*)ws, q_bs, \
+                                                               q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, Lq, Lk, chunk, scale); \
+    attn_fewq_combine_kernel<T, DD><<<B * Hh, 256, 0, st>>>((const float*)ws, (T*)o, o_bs, o_hs, o_ts, Hh, Lq, ns);    \
+  } while (0)
+      if (dt == MS2_BF16 && D == 16) MS2_FEWQS(bf16, 16);
+      else if (dt == MS2_BF16 && D == 32) MS2_FEWQS(bf16, 32);
+      else if (dt == MS2_F32 && D == 16) MS2_FEWQS(float, 16);
+      else if (dt == MS2_F32 && D == 32) MS2_FEWQS(float, 32);
+      else return 0;
+#undef MS2_FEWQS
+      MS2_CHECK_LAUNCH("attn_fewq_split_kernel");
+      return 1;
+    }
   }
   if (Lq <= FQ_MAXQ && fewq_smem(Lq, Lk, D) <= 200 * 1024) {
     const size_t smem = fewq_smem(Lq, Lk, D);

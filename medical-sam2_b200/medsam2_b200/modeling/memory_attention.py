@@ -30,8 +30,9 @@ class MemoryAttentionLayer(nn.Module):
         self.pos_enc_at_cross_attn_queries = pos_enc_at_cross_attn_queries
         self.pos_enc_at_cross_attn_keys = pos_enc_at_cross_attn_keys
 
-    def forward_tokens(self, x, query_pos, mem_k_in, mem_v_in, num_k_exclude_rope):
-        """x fp32 [B,L,C]; mem_k_in / mem_v_in compute-dtype [B,Lk,64]."""
+    def forward_tokens(self, x, query_pos, mem_k_in, mem_v_in, num_k_exclude_rope, kv=None):
+        """x fp32 [B,L,C]; mem_k_in / mem_v_in compute-dtype [B,Lk,64], or kv = (K, V) already projected
+        (and rotated) [B,Lk,C] views of a MemoryBank."""
         cd = compute_dtype()
         L = x.shape[1]
         t = self.norm1(x, out_dtype=cd)
@@ -44,12 +45,47 @@ class MemoryAttentionLayer(nn.Module):
         if self.pos_enc_at_cross_attn_queries:
             t = ops.axpby(self.norm2(x), 1.0, query_pos, 1.0, out_dtype=cd)
         q = self.cross_attn_image.project_q(t)
-        k, v = self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
+        k, v = kv if kv is not None else self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
         o = ops.attention(q, k, v, self.cross_attn_image.num_heads)
         x = self.cross_attn_image.out_proj(o, out_dtype=torch.float32, residual=x)
         t = self.norm3(x, out_dtype=cd)
         h = self.linear1(t, out_dtype=cd, act=ops.ACT_RELU)
         return self.linear2(h, out_dtype=torch.float32, residual=x)
+
+
+class MemoryBank:
+    """Resident per-layer K (RoPE applied) / V of the memory bank of one tracking session.
+
+    Rows [0, n_static) hold the conditioning memories in arrival order; they are projected ONCE, because for a
+    conditioning frame neither the temporal slot (t_pos = 0), nor the spatial code, nor the RoPE phase (restarts
+    every frame) depends on the frame being tracked (reference sam2_base.py:566-580, memory_attention.py:73-79,
+    transformer.py:309-315).  Rows [n_static, n_static + n_dyn) are rewritten every frame with the
+    <= num_maskmem-1 recent memories and the object-pointer tokens.  Softmax is invariant to the key order, so this
+    layout is the reference's bank up to a permutation."""
+
+    def __init__(self):
+        self.keys, self.refs = [], []
+        self.K, self.V = [], []
+        self.cap = self.n_static = 0
+        self.B = self.device = self.dtype = None
+
+    def reset(self):
+        self.__init__()
+
+    def ensure(self, n_layers, B, rows, width, dtype, device):
+        if (self.B, self.device, self.dtype) != (B, device, dtype) or len(self.K) != n_layers:
+            self.reset()
+            self.B, self.device, self.dtype = B, device, dtype
+            self.K, self.V = [None] * n_layers, [None] * n_layers
+        if rows > self.cap:
+            cap = max(rows, int(self.cap * 1.5))
+            for l in range(n_layers):
+                for arr in (self.K, self.V):
+                    new = torch.empty((B, cap, width), dtype=dtype, device=device)
+                    if arr[l] is not None and self.n_static:
+                        new[:, : self.n_static] = arr[l][:, : self.n_static]
+                    arr[l] = new
+            self.cap = cap
 
 
 class MemoryAttention(nn.Module):
@@ -72,6 +108,67 @@ class MemoryAttention(nn.Module):
         mem_k_in = ops.axpby(memory, 1.0, memory_pos, 1.0, out_dtype=cd) if keys_at_pos else mem_v_in
         for layer in self.layers:
             x = layer.forward_tokens(x, curr_pos, mem_k_in, mem_v_in, num_obj_ptr_tokens)
+        return self.norm(x)
+
+    def _project_into_bank(self, bank, row0, mem, pos_flat, n_rope_rows, Lq):
+        """mem fp32 [B,n,Cm]; pos_flat: fp32 tensor broadcast over mem as pos.flatten()[i mod numel] (or None)
+        -> per layer K (RoPE on the first n_rope_rows rows, restarting every Lq rows) and V written at bank rows
+        [row0, row0+n)."""
+        cd = compute_dtype()
+        B, n, _ = mem.shape
+        v_in = to_compute(mem)
+        k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else v_in
+        for l, layer in enumerate(self.layers):
+            att = layer.cross_attn_image
+            D = att.internal_dim // att.num_heads
+            cos, sin = att._table(Lq, mem.device)
+            for b in range(B):
+                kd, vd = bank.K[l][b, row0: row0 + n], bank.V[l][b, row0: row0 + n]
+                att.k_proj(k_in[b], out_dtype=cd, out=kd)
+                att.v_proj(v_in[b], out_dtype=cd, out=vd)
+                if n_rope_rows > 0:
+                    for h in range(att.num_heads):
+                        ops.rope_(kd[:, h * D:], 1, n, n_rope_rows, D, cos, sin, batch_stride=n * att.internal_dim,
+                                  row_stride=att.internal_dim)
+
+    def forward_tokens_banked(self, curr, curr_pos, bank, cond, recent, ptrs, ptr_pos):
+        """Same result as forward_tokens on the concatenated bank (up to the key order), with the conditioning
+        memories' per-layer K/V taken from (or appended once to) `bank`.  cond / recent: lists of
+        (key, source tensor, feats [B,hw,Cm] fp32, pos table [hw,Cm]); ptrs / ptr_pos [B,n_tok,Cm] or None."""
+        cd = compute_dtype()
+        B, L, C = curr.shape
+        keys_at_pos = self.layers[0].pos_enc_at_cross_attn_keys
+        att0 = self.layers[0].cross_attn_image
+        hw = cond[0][2].shape[1] if cond else (recent[0][2].shape[1] if recent else L)
+        n_dyn = sum(e[2].shape[1] for e in recent) + (ptrs.shape[1] if ptrs is not None else 0)
+        keys = [e[0] for e in cond]
+        if bank.keys != keys[: len(bank.keys)] or bank.B not in (None, B):
+            bank.reset()
+        bank.ensure(len(self.layers), B, len(keys) * hw + n_dyn + 64, att0.internal_dim, cd, curr.device)
+        new = cond[len(bank.keys):]
+        if new:                                            # conditioning memories not yet resident: project once
+            mem = new[0][2] if len(new) == 1 else torch.cat([e[2] for e in new], dim=1)
+            same_pos = all(e[3] is new[0][3] for e in new)
+            pos = None
+            if keys_at_pos:
+                pos = new[0][3] if same_pos else torch.cat([e[3] for e in new], dim=0)
+            self._project_into_bank(bank, bank.n_static, mem.contiguous(), pos, mem.shape[1], L)
+            bank.n_static += mem.shape[1]
+            bank.keys = keys
+            bank.refs = [e[1] for e in cond]               # keep the sources alive: id() keys stay unique
+        row0 = bank.n_static
+        if n_dyn:
+            mems = [e[2] for e in recent] + ([ptrs] if ptrs is not None else [])
+            mem = mems[0] if len(mems) == 1 else torch.cat(mems, dim=1)
+            pos = None
+            if keys_at_pos:
+                poss = [e[3][None].expand(B, -1, -1) for e in recent] + ([ptr_pos] if ptrs is not None else [])
+                pos = (poss[0] if len(poss) == 1 else torch.cat(poss, dim=1)).contiguous()
+            self._project_into_bank(bank, row0, mem.contiguous(), pos, sum(e[2].shape[1] for e in recent), L)
+        Lk = row0 + n_dyn
+        x = ops.axpby(curr, 1.0, curr_pos, 0.1) if (self.pos_enc_at_input and curr_pos is not None) else curr
+        for l, layer in enumerate(self.layers):
+            x = layer.forward_tokens(x, curr_pos, None, None, 0, kv=(bank.K[l][:, :Lk], bank.V[l][:, :Lk]))
         return self.norm(x)
 
     def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0):

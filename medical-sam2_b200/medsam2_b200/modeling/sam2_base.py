@@ -53,6 +53,10 @@ class SAM2Base(nn.Module):
         if hasattr(self.memory_encoder, "out_proj") and hasattr(self.memory_encoder.out_proj, "weight"):
             self.mem_dim = self.memory_encoder.out_proj.weight.shape[0]
         self.num_maskmem = num_maskmem
+        # keep the per-layer projected K/V of conditioning memories resident between frames (eval only);
+        # MS2_MEMORY_BANK=0 selects the re-project-everything-per-frame path of the reference
+        import os
+        self.use_memory_bank_cache = os.environ.get("MS2_MEMORY_BANK", "1") != "0"
         self.maskmem_tpos_enc = nn.Parameter(torch.zeros(num_maskmem, 1, 1, self.mem_dim))
         trunc_normal_(self.maskmem_tpos_enc, std=0.02)
         self.no_mem_embed = nn.Parameter(torch.zeros(1, 1, self.hidden_dim))
@@ -245,14 +249,15 @@ class SAM2Base(nn.Module):
             return (t + tp[slot].float().reshape(1, -1)).contiguous()
         return CACHE.get(self.maskmem_tpos_enc, ("mem_pos", h, w, slot, str(device)), make)
 
-    def _gather_memory(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device):
-        """sam2_base.py:518-637 -> (memory [B,Lk,mem_dim] fp32, memory_pos, num_obj_ptr_tokens)."""
+    def _memory_entries(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device):
+        """sam2_base.py:518-637, un-concatenated: -> (cond, recent, ptrs, ptr_pos) where cond / recent are lists of
+        (key, feats [B,hw,mem_dim] fp32 token-major, pos table [hw,mem_dim]) for the conditioning memories
+        (t_pos = 0) and the <= num_maskmem-1 recent ones, and ptrs / ptr_pos are [B,n_tok,mem_dim] or None."""
         C = self.hidden_dim
-        mems, poss = [], []
         cond_outputs = output_dict["cond_frame_outputs"]
         assert len(cond_outputs) > 0
         selected, unselected = select_closest_cond_frames(frame_idx, cond_outputs, self.max_cond_frames_in_attn)
-        t_pos_and_prevs = [(0, out) for out in selected.values()]
+        t_pos_and_prevs = [(0, t, out) for t, out in selected.items()]
         r = self.memory_temporal_stride_for_eval
         for t_pos in range(1, self.num_maskmem):
             t_rel = self.num_maskmem - t_pos
@@ -265,15 +270,18 @@ class SAM2Base(nn.Module):
             out = output_dict["non_cond_frame_outputs"].get(prev_idx, None)
             if out is None:
                 out = unselected.get(prev_idx, None)
-            t_pos_and_prevs.append((t_pos, out))
-        for t_pos, prev in t_pos_and_prevs:
+            t_pos_and_prevs.append((t_pos, prev_idx, out))
+        cond, recent = [], []
+        for t_pos, t, prev in t_pos_and_prevs:
             if prev is None:
                 continue
-            feats = prev["maskmem_features"].to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
+            src = prev["maskmem_features"]
+            feats = src.to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
             h, w = feats.shape[-2:]
-            mems.append(as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim))
-            poss.append(self._mem_pos_table(h, w, self.num_maskmem - t_pos - 1, device)[None].expand(B, -1, -1))
-        n_ptr_tok = 0
+            item = ((t, id(src)), src, as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim),
+                    self._mem_pos_table(h, w, self.num_maskmem - t_pos - 1, device))
+            (cond if t_pos == 0 else recent).append(item)
+        ptrs = obj_pos = None
         if self.use_obj_ptrs_in_encoder:
             max_ptrs = min(num_frames, self.max_obj_ptrs_in_encoder)
             if not self.training and self.only_obj_ptrs_in_the_past_for_eval:
@@ -306,9 +314,18 @@ class SAM2Base(nn.Module):
                     rr = C // self.mem_dim
                     ptrs = ptrs.reshape(B, P * rr, self.mem_dim)
                     obj_pos = obj_pos.repeat_interleave(rr, dim=1)
-                mems.append(ptrs)
-                poss.append(obj_pos)
-                n_ptr_tok = ptrs.shape[1]
+        return cond, recent, ptrs, obj_pos
+
+    def _gather_memory(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device):
+        """sam2_base.py:518-637 -> (memory [B,Lk,mem_dim] fp32, memory_pos, num_obj_ptr_tokens)."""
+        cond, recent, ptrs, obj_pos = self._memory_entries(frame_idx, output_dict, num_frames, track_in_reverse, B, device)
+        mems = [e[2] for e in cond + recent]
+        poss = [e[3][None].expand(B, -1, -1) for e in cond + recent]
+        n_ptr_tok = 0
+        if ptrs is not None:
+            mems.append(ptrs)
+            poss.append(obj_pos)
+            n_ptr_tok = ptrs.shape[1]
         memory = torch.cat(mems, dim=1).contiguous()
         memory_pos = torch.cat(poss, dim=1).contiguous()
         return memory, memory_pos, n_ptr_tok
@@ -331,6 +348,18 @@ class SAM2Base(nn.Module):
             memory = p32(self.no_mem_embed).expand(B, 1, self.mem_dim).contiguous()
             memory_pos = p32(self.no_mem_pos_enc).expand(B, 1, self.mem_dim).contiguous()
             n_ptr_tok = 0
+        elif self.use_memory_bank_cache and not self.training:
+            # conditioning memories are frame-invariant after projection: keep their per-layer
+            # K (RoPE applied) / V resident and only project the <= 6 recent memories + object pointers per frame
+            cond, recent, ptrs, obj_pos = self._memory_entries(frame_idx, output_dict, num_frames, track_in_reverse,
+                                                               B, device)
+            bank = output_dict.get("_ms2_bank")
+            if bank is None:
+                from .memory_attention import MemoryBank
+                bank = output_dict["_ms2_bank"] = MemoryBank()
+            curr_pos = seq_to_tokens(current_vision_pos_embeds[-1].float())
+            out = self.memory_attention.forward_tokens_banked(curr, curr_pos, bank, cond, recent, ptrs, obj_pos)
+            return as_nchw_view(out.view(B, H, W, C))
         else:
             memory, memory_pos, n_ptr_tok = self._gather_memory(frame_idx, output_dict, num_frames, track_in_reverse,
                                                                 B, device)

@@ -11,9 +11,9 @@ from ..runtime import compute_dtype, w_c, p32
 class Linear(nn.Linear):
     """nn.Linear parameters; the contraction runs in ms2_gemm."""
 
-    def forward(self, x, out_dtype=torch.float32, act=ops.ACT_NONE, residual=None, colscale=None):
+    def forward(self, x, out_dtype=torch.float32, act=ops.ACT_NONE, residual=None, colscale=None, out=None):
         return ops.gemm(to_compute(x), w_c(self.weight), p32(self.bias), out_dtype=out_dtype, act=act,
-                        residual=residual, colscale=colscale)
+                        residual=residual, colscale=colscale, out=out)
 
 
 class LayerNorm(nn.LayerNorm):

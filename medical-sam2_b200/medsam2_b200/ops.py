@@ -174,6 +174,9 @@ def attention(q, k, v, heads, scale=None, impl=0):
             nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split))
             ws_bytes = nsplit * per_split
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    if impl in (0, 3) and D in (16, 32) and Lq <= 16 and Lk >= 512:
+        ws_bytes = B * heads * 64 * Lq * (D + 2) * 4             # decoder token->image attention: key-split partials
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
     ev = PROFILE.begin("attention")
     native.call("ms2_attention_ws", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
                 q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), D, v.stride(1),

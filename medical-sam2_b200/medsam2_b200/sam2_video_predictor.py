@@ -447,6 +447,7 @@ class SAM2VideoPredictor(SAM2Base):
         for d in (st["output_dict"], st["consolidated_frame_inds"]):
             d["cond_frame_outputs"].clear()
             d["non_cond_frame_outputs"].clear()
+        st["output_dict"].pop("_ms2_bank", None)
         st["tracking_has_started"] = False
         st["frames_already_tracked"].clear()
 

@@ -115,6 +115,27 @@ def test_video_predictor(case, dt):
     print("bf16 worst" if dt == torch.bfloat16 else "fp32", case, worst)
 
 
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_memory_bank_cache_matches_reprojection(dt, tol):
+    """resident per-layer K/V of the conditioning memories (MemoryBank) vs re-projecting the whole bank every
+    frame (the reference's data flow): same masks up to the summation order of the keys."""
+    import medsam2_b200
+    outs = {}
+    with medsam2_b200.compute(dt):
+        for cached in (True, False):
+            m = _build("sam2_hiera_t", video=True, image_size=512)
+            m.use_memory_bank_cache = cached
+            st, o = _run_video(m, 512, 6, 2, (0, 3), ((3, 1),), 77)
+            outs[cached] = {f: st["output_dict"]["cond_frame_outputs"].get(f) or st["output_dict"]["non_cond_frame_outputs"].get(f)
+                            for f in range(6)}
+            assert ("_ms2_bank" in st["output_dict"]) == cached
+    for f in range(6):
+        a, b = outs[True][f]["pred_masks"].float(), outs[False][f]["pred_masks"].float()
+        keep = ((a - 0.1).abs() > 1e-6) & ((b - 0.1).abs() > 1e-6)          # hole filling is discrete
+        assert (a - b)[keep].abs().max().item() <= tol, f
+        assert ((a > 0) == (b > 0)).float().mean().item() >= 0.998
+
+
 def test_full_size_properties_bf16():
     """Config-3 geometry (1024², hiera_s) through the public API: finite logits, deterministic re-run,
     hole filling idempotent on the outputs."""

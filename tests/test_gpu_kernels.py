@@ -105,6 +105,23 @@ def test_fill_holes(ops):
     close(ops.fill_holes(x, 8), ref_ops.fill_holes(x, 8), 0.0, "fill_holes")
 
 
+@pytest.mark.parametrize("density,area", [(0.03, 8), (0.2, 8), (0.45, 8), (0.6, 3), (0.5, 1), (0.5, 32), (0.4, 40)])
+def test_fill_holes_local_vs_labels(ops, density, area):
+    """the bounded-flood-fill path (max_area <= 32) and the union-find path (> 32) against the reference
+    statement (label everything, threshold the areas), incl. holes touching the border and the exact-area edge."""
+    x = rnd(2, 1, 128, 96, seed=11)
+    x = torch.where(torch.rand(x.shape, generator=gen(12)).cuda() < density, -x.abs(), x.abs())
+    x[0, 0, :3, :3] = -1.0            # a 9-pixel component in the corner
+    x[0, 0, 3, :4] = 1.0
+    x[0, 0, :4, 3] = 1.0
+    x[1, 0, 64, 10:18] = -1.0         # an exact 8-pixel bar ...
+    x[1, 0, 63, 9:19] = 1.0
+    x[1, 0, 65, 9:19] = 1.0
+    x[1, 0, 64, 9] = 1.0
+    x[1, 0, 64, 18] = 1.0
+    assert torch.equal(ops.fill_holes(x, area), ref_ops.fill_holes(x, area))
+
+
 # ------------------------------------------------------------------ norm / gemm
 @pytest.mark.parametrize("M,C", [(1000, 96), (333, 768), (4096, 256), (5000, 4), (777, 16), (129, 64), (9, 256)])
 def test_layernorm(ops, M, C):
