@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--feature-cache", type=int, default=0, help="0 = one entry per slice (no double encode)")
     ap.add_argument("--kernel-table", default="", help="write a CUPTI per-kernel time table of one extra step here")
+    ap.add_argument("--host-profile", default="", help="write a cProfile table of one extra step (host side) here")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     ap.add_argument("--encode-batch", type=int, default=8, help="slices per image-encoder pass on a cache miss")
     return ap.parse_args()
 
@@ -180,7 +182,8 @@ def main_ours(args):
     cache = args.feature_cache if args.feature_cache > 0 else T
     model = medsam2_b200.build_sam2_video_predictor(
         args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
-                                                      f"++model.feature_encode_batch={args.encode_batch}"])
+                                                      f"++model.feature_encode_batch={args.encode_batch}",
+                                                      f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}"])
     model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
     vol, boxes = btcv_volume(T, S, 1234 + rank, 1)          # every rank tracks its own volume (config 4 sharding)
     vol_host = vol.pin_memory()
@@ -234,6 +237,21 @@ def main_ours(args):
     ops.PROFILE.disable()
     launches = native.launch_count - n0
     ms_e2e = timed(step_e2e, args.steps)
+    if args.host_profile and rank == 0:
+        import cProfile, io, pstats
+        pr = cProfile.Profile()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.enable()
+        step_resident()
+        pr.disable()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        buf = io.StringIO()
+        buf.write(f"# host time to enqueue one step: {1e3 * (t1 - t0):.1f} ms (under cProfile); GPU drain after: {1e3 * (t2 - t1):.1f} ms\n")
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+        open(args.host_profile, "w").write(buf.getvalue())
     if args.kernel_table and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof_:

@@ -57,6 +57,11 @@ class SAM2Base(nn.Module):
         # MS2_MEMORY_BANK=0 selects the re-project-everything-per-frame path of the reference
         import os
         self.use_memory_bank_cache = os.environ.get("MS2_MEMORY_BANK", "1") != "0"
+        # replay the fixed-shape per-slice sub-pipelines (SAM heads, memory encoder, batched image encoder) as
+        # CUDA graphs (eval only; off by default, `++model.use_cuda_graphs=true` or MS2_CUDA_GRAPHS=1 turns it on)
+        self.use_cuda_graphs = os.environ.get("MS2_CUDA_GRAPHS", "0") == "1"
+        from ..runtime import GraphRunner
+        self._graphs = GraphRunner()
         self.maskmem_tpos_enc = nn.Parameter(torch.zeros(num_maskmem, 1, 1, self.mem_dim))
         trunc_normal_(self.maskmem_tpos_enc, std=0.02)
         self.no_mem_embed = nn.Parameter(torch.zeros(1, 1, self.hidden_dim))
@@ -130,11 +135,18 @@ class SAM2Base(nn.Module):
     # ------------------------------------------------------------------ image features
     def forward_image(self, img_batch):
         """sam2_base.py:464-476: encoder + conv_s0/conv_s1 on the two high-resolution levels."""
-        feats = self.image_encoder.forward_tokens(img_batch.float().contiguous())
-        if self.use_high_res_features_in_sam:
-            d = self.sam_mask_decoder
-            feats[0] = ops.gemm(to_compute(feats[0]), w_c(d.conv_s0.weight), p32(d.conv_s0.bias))
-            feats[1] = ops.gemm(to_compute(feats[1]), w_c(d.conv_s1.weight), p32(d.conv_s1.bias))
+        def encode(img):
+            fs = self.image_encoder.forward_tokens(img)
+            if self.use_high_res_features_in_sam:
+                d = self.sam_mask_decoder
+                fs[0] = ops.gemm(to_compute(fs[0]), w_c(d.conv_s0.weight), p32(d.conv_s0.bias))
+                fs[1] = ops.gemm(to_compute(fs[1]), w_c(d.conv_s1.weight), p32(d.conv_s1.bias))
+            return fs
+        img = img_batch.float().contiguous()
+        if self.use_cuda_graphs and not self.training and img.is_cuda and not torch.is_grad_enabled():
+            feats = self._graphs.run(("image_encoder",), encode, [img])
+        else:
+            feats = encode(img)
         pe = self.image_encoder.neck.position_encoding
         B = img_batch.shape[0]
         fpn = [as_nchw_view(f) for f in feats]
@@ -156,6 +168,23 @@ class SAM2Base(nn.Module):
     # ------------------------------------------------------------------ SAM heads
     def _forward_sam_heads(self, backbone_features, point_inputs=None, mask_inputs=None, high_res_features=None,
                            multimask_output=False):
+        """sam2_base.py:252-410; replayed as a CUDA graph per input signature when `use_cuda_graphs` is on."""
+        if not (self.use_cuda_graphs and not self.training and backbone_features.is_cuda and
+                not torch.is_grad_enabled()):
+            return self._forward_sam_heads_impl(backbone_features, point_inputs, mask_inputs, high_res_features,
+                                                multimask_output)
+        pc = point_inputs["point_coords"] if point_inputs is not None else None
+        pl = point_inputs["point_labels"] if point_inputs is not None else None
+        hr = list(high_res_features) if high_res_features is not None else []
+
+        def fn(bf, pc_, pl_, mi, *hr_):
+            return self._forward_sam_heads_impl(bf, None if pc_ is None else {"point_coords": pc_, "point_labels": pl_},
+                                                mi, list(hr_) if hr_ else None, multimask_output)
+        return self._graphs.run(("sam_heads", bool(multimask_output), len(hr)), fn,
+                                [backbone_features, pc, pl, mask_inputs] + hr)
+
+    def _forward_sam_heads_impl(self, backbone_features, point_inputs=None, mask_inputs=None, high_res_features=None,
+                                multimask_output=False):
         """sam2_base.py:252-410.  backbone_features NCHW-shaped [B,C,h,w]."""
         B = backbone_features.size(0)
         device = backbone_features.device
@@ -368,6 +397,18 @@ class SAM2Base(nn.Module):
         return as_nchw_view(out.view(B, H, W, C))
 
     def _encode_new_memory(self, current_vision_feats, feat_sizes, pred_masks_high_res, is_mask_from_pts):
+        """sam2_base.py:665-703; replayed as a CUDA graph per input signature when `use_cuda_graphs` is on."""
+        if not (self.use_cuda_graphs and not self.training and pred_masks_high_res.is_cuda and
+                not torch.is_grad_enabled()):
+            return self._encode_new_memory_impl(current_vision_feats, feat_sizes, pred_masks_high_res, is_mask_from_pts)
+        fs = [tuple(s) for s in feat_sizes]
+
+        def fn(feat, masks):
+            return self._encode_new_memory_impl([feat], fs, masks, is_mask_from_pts)
+        return self._graphs.run(("mem_enc", bool(is_mask_from_pts), tuple(fs[-1])), fn,
+                                [current_vision_feats[-1], pred_masks_high_res])
+
+    def _encode_new_memory_impl(self, current_vision_feats, feat_sizes, pred_masks_high_res, is_mask_from_pts):
         """sam2_base.py:665-703 -> (maskmem_features NCHW-shaped, [pos NCHW-shaped])."""
         B = current_vision_feats[-1].size(1)
         C = self.hidden_dim

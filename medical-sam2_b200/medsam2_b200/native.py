@@ -76,11 +76,16 @@ def lib():
     return _lib
 
 
+_fns = {}
+
+
 def call(name, *args):
     """Call an `int ms2_*` entry point; non-zero -> NativeError(ms2_last_error())."""
     global launch_count
-    l = lib()
-    rc = getattr(l, name)(*args)
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(lib(), name)
+    rc = fn(*args)
     launch_count += 1
     if rc != 0:
-        raise NativeError(f"{name} failed ({rc}): {l.ms2_last_error().decode()}")
+        raise NativeError(f"{name} failed ({rc}): {lib().ms2_last_error().decode()}")

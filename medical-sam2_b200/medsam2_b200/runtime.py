@@ -40,7 +40,19 @@ class ParamCache:
 
     def get(self, params, key, fn):
         if isinstance(params, torch.Tensor):
-            params = (params,)
+            # fast path (one parameter): id -> (version, data_ptr, weakref, value); ~1 us on the hot path
+            k = (id(params), key)
+            hit = self._d.get(k)
+            if hit is not None and hit[3] is not None:
+                if hit[0][0] == params._version and hit[0][1] == params.data_ptr() and hit[2][0]() is params:
+                    return hit[1]
+            with torch.no_grad():
+                val = fn(params)
+            if len(self._d) > 4096:
+                self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
+            self._d[k] = ((params._version, params.data_ptr(), params.dtype, str(params.device)), val,
+                          (weakref.ref(params),), True)
+            return val
         sig = tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
         k = (tuple(id(p) for p in params), key)
         hit = self._d.get(k)
@@ -52,7 +64,7 @@ class ParamCache:
             val = fn(*params)
         if len(self._d) > 4096:                       # drop entries whose parameters are gone
             self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
-        self._d[k] = (sig, val, tuple(weakref.ref(p) for p in params))
+        self._d[k] = (sig, val, tuple(weakref.ref(p) for p in params), None)
         return val
 
 
@@ -91,3 +103,65 @@ def cat_w_c(*ps):
 
 def cat_p32(*ps):
     return CACHE.get(ps, "cat32", lambda *ts: torch.cat([t.detach().float().reshape(-1) for t in ts], 0).contiguous())
+
+
+class GraphRunner:
+    """CUDA-graph replay of a fixed-shape sub-pipeline of native kernels (the mask decoder is
+    ~170 tiny launches per slice and launch-bound).  `run(key, fn, tensors, clone=True)` executes
+    `fn(*tensors)`: the first `warmup` calls per key run eagerly (parameter caches, tables and kernel
+    attributes get initialised outside any capture), then the call is captured once on static copies of the
+    inputs and replayed afterwards.  Inputs keep their strides (NCHW-shaped views of NHWC memory stay views);
+    outputs live in the graph's private pool and are cloned out unless the caller consumes them immediately.
+    Only shapes/strides/dtypes and `key` select a graph - values never do, so the kernels must not read host
+    state that changes between calls."""
+
+    def __init__(self, warmup=2):
+        self.warmup = warmup
+        self._seen = {}
+        self._graphs = {}
+        self.replays = 0
+
+    @staticmethod
+    def _sig(t):
+        return None if t is None else (tuple(t.shape), tuple(t.stride()), t.dtype)
+
+    def run(self, key, fn, tensors, clone=True):
+        from . import native
+        full_key = (key, tuple(self._sig(t) for t in tensors))
+        entry = self._graphs.get(full_key)
+        if entry is None:
+            n = self._seen.get(full_key, 0)
+            self._seen[full_key] = n + 1
+            if n < self.warmup or not torch.cuda.is_available():
+                return fn(*tensors)
+            # empty_like keeps the strides of dense (permuted) views and densifies expanded (stride-0) ones
+            static_in = [None if t is None else torch.empty_like(t) for t in tensors]
+            for s, t in zip(static_in, tensors):
+                if s is not None:
+                    s.copy_(t)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = native.launch_count
+            with torch.cuda.graph(graph):
+                static_out = fn(*static_in)
+            entry = self._graphs[full_key] = (graph, static_in, static_out, native.launch_count - n0)
+        graph, static_in, static_out, launches = entry
+        for s, t in zip(static_in, tensors):
+            if s is not None:
+                s.copy_(t)
+        graph.replay()
+        self.replays += 1
+        native.launch_count += launches            # kernels of this library executed by the replay
+        if not clone:
+            return static_out
+        return _clone_tree(static_out)
+
+
+def _clone_tree(x):
+    if isinstance(x, torch.Tensor):
+        return x.clone()
+    if isinstance(x, (list, tuple)):
+        return type(x)(_clone_tree(v) for v in x)
+    if isinstance(x, dict):
+        return {k: _clone_tree(v) for k, v in x.items()}
+    return x

@@ -22,7 +22,8 @@ def _new_frame_dict():
 
 class SAM2VideoPredictor(SAM2Base):
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
-                 clear_non_cond_mem_for_multi_obj=False, feature_cache_size=1, feature_encode_batch=1, **kwargs):
+                 clear_non_cond_mem_for_multi_obj=False, feature_cache_size=1, feature_encode_batch=1,
+                 use_cuda_graphs=None, **kwargs):
         super().__init__(**kwargs)
         self.fill_hole_area = fill_hole_area
         self.non_overlap_masks = non_overlap_masks
@@ -33,6 +34,8 @@ class SAM2VideoPredictor(SAM2Base):
         # order); per-slice results are bit-identical to one-at-a-time encoding, the GEMM/attention launches are
         # just `feature_encode_batch` times larger.  Never exceeds the cache capacity.
         self.feature_encode_batch = max(1, int(feature_encode_batch))
+        if use_cuda_graphs is not None:
+            self.use_cuda_graphs = bool(use_cuda_graphs)
 
     # ------------------------------------------------------------------ state construction
     def _make_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):

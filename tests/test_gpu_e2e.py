@@ -136,6 +136,27 @@ def test_memory_bank_cache_matches_reprojection(dt, tol):
         assert ((a > 0) == (b > 0)).float().mean().item() >= 0.998
 
 
+def test_cuda_graph_replay_is_bit_identical():
+    """CUDA-graph replay of the SAM heads / memory encoder / batched image encoder launches exactly the kernels of
+    the eager path: outputs must be bit-identical (2 objects, mask prompt, 8 frames so that replays happen)."""
+    import medsam2_b200
+    res = {}
+    for graphs in (False, True):
+        m = _build("sam2_hiera_t", video=True, image_size=512)
+        m.use_cuda_graphs = graphs
+        m.feature_cache_size, m.feature_encode_batch = 16, 2
+        st, o = _run_video(m, 512, 10, 2, (0, 3, 6), ((3, 1),), 77)
+        res[graphs] = (st, o)
+        if graphs:
+            assert m._graphs.replays > 10, m._graphs.replays
+    for f in range(10):
+        assert torch.equal(res[False][1][f], res[True][1][f]), f"graph replay differs on frame {f}"
+    for kind in ("cond_frame_outputs", "non_cond_frame_outputs"):
+        for f, o in res[False][0]["output_dict"][kind].items():
+            g = res[True][0]["output_dict"][kind][f]
+            assert torch.equal(o["obj_ptr"], g["obj_ptr"]) and torch.equal(o["maskmem_features"], g["maskmem_features"]), f
+
+
 def test_full_size_properties_bf16():
     """Config-3 geometry (1024², hiera_s) through the public API: finite logits, deterministic re-run,
     hole filling idempotent on the outputs."""
