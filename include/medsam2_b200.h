@@ -85,6 +85,16 @@ int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int d
                      int B, int Hh, int Lq, int Lk, int D, float scale, int impl,
                      void* workspace, long workspace_bytes, ms2_stream_t stream);
 
+/* memory cross-attention with un-projected values (tcgen05 only): q,k head dim D = 256, v/o head dim DV = 64.
+ * Because softmax rows sum to one, softmax(QK^T)(M Wv^T + b) = (softmax(QK^T) M) Wv^T + b, so the kernel attends
+ * over the raw 64-d memory values M and the caller applies v_proj to the 64-d result (memory_attention.py:73-79,
+ * transformer.py:292-294,318): 4x less P.V work, V traffic and tensor memory. */
+int ms2_attention_dv(const void* q, const void* k, const void* v, void* o, int dt,
+                     long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts,
+                     long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts,
+                     int B, int Hh, int Lq, int Lk, int D, int DV, float scale,
+                     void* workspace, long workspace_bytes, ms2_stream_t stream);
+
 /* ---- Hiera windowed attention with window partition / zero-pad-as-bias-key / q max-pool /
  *      unpartition+crop folded into the loads and stores (hieradet.py:58-83,136-159,
  *      backbones/utils.py:16-62).  qkv [B,H,W,3,heads,D] dtype dt (the qkv Linear output on the

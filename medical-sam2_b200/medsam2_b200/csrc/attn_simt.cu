@@ -200,15 +200,28 @@ int launch_t(const AttnP& p, int D, int nbatch, cudaStream_t st) {
 
 int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts,
                             long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
-                            long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
-                            cudaStream_t st);
+                            long o_ts, int B, int Hh, int Lq, int Lk, int D, int DV, float scale, void* ws,
+                            long ws_bytes, cudaStream_t st);
 bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_ts, long v_hs, long v_ts, long o_hs,
-                                long o_ts, int Hh, int Lq, int Lk, int D);
+                                long o_ts, int Hh, int Lq, int Lk, int D, int DV);
 
 int ms2_attention_small(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts,
                         long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
                         long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
                         cudaStream_t st);
+
+extern "C" int ms2_attention_dv(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
+                                long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
+                                long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, int DV, float scale,
+                                void* workspace, long workspace_bytes, void* stream) {
+  MS2_CHECK_ARG(q && k && v && o, "attention: null pointer");
+  MS2_CHECK_ARG(B >= 0 && Hh > 0 && Lq >= 0 && Lk > 0, "attention: bad shape");
+  if (B == 0 || Lq == 0) return MS2_OK;
+  MS2_CHECK_ARG(ms2_attention_tc_supported(dt, q_hs, q_ts, k_hs, k_ts, v_hs, v_ts, o_hs, o_ts, Hh, Lq, Lk, D, DV),
+                "attention_dv: unsupported shape/dtype/stride (bf16, D=256, DV=64, Lq,Lk >= 64)");
+  return ms2_attention_tc_launch(q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B, Hh,
+                                 Lq, Lk, D, DV, scale, workspace, workspace_bytes, (cudaStream_t)stream);
+}
 
 extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
                                 long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
@@ -217,7 +230,7 @@ extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, voi
   MS2_CHECK_ARG(q && k && v && o, "attention: null pointer");
   MS2_CHECK_ARG(B >= 0 && Hh > 0 && Lq >= 0 && Lk > 0, "attention: bad shape");
   if (B == 0 || Lq == 0) return MS2_OK;
-  const bool tc_ok = ms2_attention_tc_supported(dt, q_hs, q_ts, k_hs, k_ts, v_hs, v_ts, o_hs, o_ts, Hh, Lq, Lk, D);
+  const bool tc_ok = ms2_attention_tc_supported(dt, q_hs, q_ts, k_hs, k_ts, v_hs, v_ts, o_hs, o_ts, Hh, Lq, Lk, D, D);
   if (impl == 2) MS2_CHECK_ARG(tc_ok, "attention: tcgen05 path does not support this shape/dtype/stride");
   if (impl == 0 || impl == 3) {
     const int rc = ms2_attention_small(q, k, v, o, dt, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs,
@@ -228,7 +241,7 @@ extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, voi
   }
   if (impl == 2 || (impl == 0 && tc_ok))
     return ms2_attention_tc_launch(q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B,
-                                   Hh, Lq, Lk, D, scale, workspace, workspace_bytes, (cudaStream_t)stream);
+                                   Hh, Lq, Lk, D, D, scale, workspace, workspace_bytes, (cudaStream_t)stream);
   AttnP p;
   memset(&p, 0, sizeof(p));
   p.q = q; p.k = k; p.v = v; p.o = o;

@@ -7,17 +7,19 @@
 // that 32 query tiles still fill 148 SMs; partial (O, m, l) are merged by attn_combine_kernel):
 //   warp 0      TMA producer : Q once; K and V tiles (BKV keys) through two 2-deep rings, 128B-swizzled
 //   warp 1      MMA issuer   : S = Q K^T   (M=128, N=BKV, K=D, both operands K-major)   -> TMEM S[j&1]
-//                              O += P V    (M=128, N=D, K=BKV, P K-major from smem, V MN-major) -> TMEM O
-//   warps 2..5  softmax      : thread = query row; tcgen05.ld of its S row, online max/sum in the log2
+//                              O += P V    (M=128, N=D, K=BKV, P from TENSOR MEMORY, V MN-major smem) -> TMEM O
+//   warps 2..9  softmax      : two warps per TMEM lane quarter split the S columns of their 32 query rows;
+//                              thread = (row, column half): tcgen05.ld of its S slice, online max/sum in the log2
 //                              domain with LAZY rescaling (O is only rescaled in TMEM when the running max
-//                              grows by > 2^8), P -> bf16 -> swizzled smem; final O/l -> global
+//                              grows by > 2^8), P -> bf16 pairs -> tcgen05.st over the S columns it came from
+//                              (no shared-memory round trip, no proxy fence); final O/l -> global
 // QK^T of tile j+1 is issued before P V of tile j, so the tensor pipe works under the softmax.
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int BQ = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
 constexpr float LAZY_TAU = 8.0f;
 
 struct AttnTcP {
@@ -36,39 +38,42 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int D, int BKV>
+// D = head dim of Q/K, DV = head dim of V/O (DV < D: attention over un-projected 64-d memory values, the value
+// projection is applied to the 64-d result afterwards - softmax rows sum to 1), BKV = keys per
+// tile, KST = depth of the K ring (V ring: 2).
+template <int D, int DV, int BKV, int KST>
 struct Cfg {
-  static constexpr int DCH = (D + 63) / 64;             // 64-element (128 B) column chunks of Q/K/V
+  static constexpr int DCH = (D + 63) / 64;             // 64-element (128 B) column chunks of Q/K
+  static constexpr int DCHV = (DV + 63) / 64;           // ... of V
   static constexpr int Q_BYTES = DCH * BQ * 128;
-  static constexpr int KV_BYTES = DCH * BKV * 128;      // one K (or V) stage
-  static constexpr int P_BYTES = (BKV / 64) * BQ * 128;
-  static constexpr int STAGES = 2;
-  static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int S_COL = 256;                     // TMEM: O at [0,D), S stages at 256 + st*BKV
+  static constexpr int K_BYTES = DCH * BKV * 128;       // one K stage
+  static constexpr int V_BYTES = DCHV * BKV * 128;      // one V stage
+  static constexpr int SMEM = Q_BYTES + KST * K_BYTES + 2 * V_BYTES + 1024 /*align*/ + 4096 /*barriers, max/sum exchange*/;
+  static constexpr int S_COL = 256;                     // TMEM: O at [0,DV), S stages at 256 + st*BKV
 };
 
-template <int D, int BKV>
+template <int D, int DV, int BKV, int KST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
-  using C = Cfg<D, BKV>;
+  using C = Cfg<D, DV, BKV, KST>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + C::Q_BYTES;
-  uint8_t* sV = sK + C::STAGES * C::KV_BYTES;
-  uint8_t* sP = sV + C::STAGES * C::KV_BYTES;
-  uint64_t* bars = (uint64_t*)(sP + C::P_BYTES);
+  uint8_t* sV = sK + KST * C::K_BYTES;
+  uint64_t* bars = (uint64_t*)(sV + 2 * C::V_BYTES);
   uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 2
-  uint64_t* k_empty = bars + 3;       // 2
-  uint64_t* v_full = bars + 5;        // 2
-  uint64_t* v_empty = bars + 7;       // 2
-  uint64_t* s_full = bars + 9;        // 2
-  uint64_t* s_empty = bars + 11;      // 2
-  uint64_t* p_full = bars + 13;       // 1
-  uint64_t* o_ready = bars + 14;      // 1
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 15);
+  uint64_t* k_full = bars + 1;        // <= 4
+  uint64_t* k_empty = bars + 5;       // <= 4
+  uint64_t* v_full = bars + 9;        // 2
+  uint64_t* v_empty = bars + 11;      // 2
+  uint64_t* s_full = bars + 13;       // 2
+  uint64_t* p_full = bars + 15;       // 1
+  uint64_t* o_ready = bars + 16;      // 1
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 17);
+  float* mxbuf = (float*)(bars + 18);    // [tile parity][half][128 rows] row-max exchange
+  float* lbuf = mxbuf + 512;             // [half][128 rows] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -83,15 +88,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc::prefetch_tmap(&tmK);
     tc::prefetch_tmap(&tmV);
     tc::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KST; ++s) {
       tc::mbar_init(&k_full[s], 1);
       tc::mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&v_full[s], 1);
       tc::mbar_init(&v_empty[s], 1);
       tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&s_empty[s], 4);
     }
-    tc::mbar_init(p_full, 4);
+    tc::mbar_init(p_full, 8);
     tc::mbar_init(o_ready, 1);
     tc::fence_barrier_init();
   }
@@ -107,45 +113,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < C::DCH; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
+      // K runs KST-1 tiles ahead of V: the K ring is deeper, and S = Q K^T of tile j+1 is issued before P V of j
+      auto load_k = [&](int j) {
+        const int ks = j % KST;
+        tc::mbar_wait(&k_empty[ks], ((uint32_t)(j / KST) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(&k_full[ks], C::K_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::DCH; ++c)
+          tc::tma_load_4d(sK + ks * C::K_BYTES + c * BKV * 128, &tmK, &k_full[ks], c * 64, (t_begin + j) * BKV, h, b);
+      };
+      for (int j = 0; j < KST - 1 && j < n; ++j) load_k(j);
       for (int j = 0; j < n; ++j) {
+        if (j + KST - 1 < n) load_k(j + KST - 1);
         const int st = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        const int key0 = (t_begin + j) * BKV;
-        tc::mbar_wait(&k_empty[st], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
+        tc::mbar_wait(&v_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(&v_full[st], C::V_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::DCH; ++c)
-          tc::tma_load_4d(sK + st * C::KV_BYTES + c * BKV * 128, &tmK, &k_full[st], c * 64, key0, h, b);
-        tc::mbar_wait(&v_empty[st], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
-#pragma unroll
-        for (int c = 0; c < C::DCH; ++c)
-          tc::tma_load_4d(sV + st * C::KV_BYTES + c * BKV * 128, &tmV, &v_full[st], c * 64, key0, h, b);
+        for (int c = 0; c < C::DCHV; ++c)
+          tc::tma_load_4d(sV + st * C::V_BYTES + c * BKV * 128, &tmV, &v_full[st], c * 64, (t_begin + j) * BKV, h, b);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
-    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, D, 0, 1);
-    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
+    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
     const uint32_t tO = tmem_base, tS = tmem_base + C::S_COL;
 
     auto issue_qk = [&](int j) {
-      const int st = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      tc::mbar_wait(&k_full[st], ph);
-      tc::mbar_wait(&s_empty[st], ph ^ 1);
+      const int st = j & 1, ks = j % KST;
+      // S[st] (whose first BKV/2 columns hold P of tile j-2) is overwritten only after P V of tile j-2, which
+      // this thread issued earlier: tcgen05.mma instructions of one thread execute in issue order
+      tc::mbar_wait(&k_full[ks], (uint32_t)(j / KST) & 1u);
       tc::tc_fence_after();
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 2) * 128u * 128u;   // 64-column chunk: rows * 128 B
           const uint64_t da = tc::desc_kmajor_sw128(aQ + (kk >> 2) * BQ * 128 + (kk & 3) * 32);
-          const uint64_t db = tc::desc_kmajor_sw128(aK + st * C::KV_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
-          (void)off;
+          const uint64_t db = tc::desc_kmajor_sw128(aK + ks * C::K_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
           tc::umma_bf16(tS + st * BKV, da, db, idesc_qk, kk ? 1u : 0u);
         }
-        tc::umma_commit(&k_empty[st]);
+        tc::umma_commit(&k_empty[ks]);
         tc::umma_commit(&s_full[st]);
       }
       __syncwarp();
@@ -163,9 +171,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t da = tc::desc_kmajor_sw128(aP + (kk >> 2) * BQ * 128 + (kk & 3) * 32);
-          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * C::KV_BYTES + kk * 2048, BKV * 128);
-          tc::umma_bf16(tO, da, db, idesc_pv, (j | kk) ? 1u : 0u);
+          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * C::V_BYTES + kk * 2048, BKV * 128);
+          tc::umma_bf16_ts(tO, tS + st * BKV + kk * 8, db, idesc_pv, (j | kk) ? 1u : 0u);   // 16 keys = 8 columns of P
         }
         tc::umma_commit(&v_empty[st]);
         tc::umma_commit(o_ready);
@@ -173,8 +180,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // ===================== softmax / correction / epilogue (warps 2..5) =====================
-    const int qtr = warp & 3;                       // TMEM lane quarter of this warp
+    // ===================== softmax / correction / epilogue (warps 2..9) =====================
+    // Two warps share each TMEM lane quarter (= 32 query rows) and split the S columns of a tile, so every SM
+    // sub-partition has two softmax warps to overlap MUFU/FMA latency; the row maximum is exchanged through shared
+    // memory with a 64-thread named barrier, the row sums are merged once at the end.
+    constexpr int HC = BKV / 2;                     // S columns per warp
+    const int qtr = warp & 3, half = (warp - 2) >> 2;
     const int row = qtr * 32 + lane;                // query row inside the tile
     const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
     const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + C::S_COL;
@@ -185,25 +196,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int st = j & 1;
       tc::mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1u);
       tc::tc_fence_after();
-      uint32_t r[BKV / 32][32];
+      uint32_t r[HC / 32][32];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tc::tmem_ld32(tS + st * BKV + c * 32, r[c]);
+      for (int c = 0; c < HC / 32; ++c) tc::tmem_ld32(tS + st * BKV + half * HC + c * 32, r[c]);
       tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_empty[st]);
 
       float mx = -INFINITY;
-      const bool tail = (t_begin + j == p.ntiles - 1) && (last_valid < BKV);
+      if ((t_begin + j == p.ntiles - 1) && (last_valid < BKV)) {
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c)
+        for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(r[c][i]) * p.c;
-          if (tail && (c * 32 + i >= last_valid)) t = -INFINITY;
-          r[c][i] = __float_as_uint(t);
-          mx = fmaxf(mx, t);
-        }
+          for (int i = 0; i < 32; ++i)
+            if (half * HC + c * 32 + i >= last_valid) r[c][i] = 0xff800000u;     // -inf: key beyond Lk
+      }
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+      mx *= p.c;                                      // p.c > 0: max commutes with the scaling
+      float* mslot = mxbuf + (j & 1) * 256;
+      mslot[half * 128 + row] = mx;
+      tc::named_bar_sync(1 + qtr, 64);
+      mx = fmaxf(mx, mslot[(half ^ 1) * 128 + row]);
       if (j == 0) {
         m_used = mx;
       } else {
@@ -218,7 +232,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             l *= alpha;
           }
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = half; c < DV / 32; c += 2) {             // the two warps of a quarter split the O columns
             uint32_t o[32];
             tc::tmem_ld32(tO + c * 32, o);
             tc::tmem_ld_wait();
@@ -229,38 +243,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc::tmem_st_wait();
         }
       }
-      // p = 2^(t - m_used), row sum in fp32, pack to bf16 pairs
-      uint32_t pk[BKV / 2];
+      // p = 2^(s*c - m_used), row sum in fp32, pack to bf16 pairs
+      uint32_t pk[HC / 2];
+      const float nm = -m_used;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c)
+      for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(__uint_as_float(r[c][i]) - m_used);
-          const float p1 = ex2(__uint_as_float(r[c][i + 1]) - m_used);
+          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
+          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
           l += p0 + p1;
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
         }
-      if (j > 0) tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);   // P buffer free (and O stable)
-      // P tile, K-major SW128: chunk of 64 keys = [128 rows][128 B], 16-byte groups XOR (row & 7)
+      // P overwrites the first BKV/2 columns of this S stage: row = lane, two bf16 keys per 32-bit column
 #pragma unroll
-      for (int kc = 0; kc < BKV / 64; ++kc)
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint4 v;
-          v.x = pk[kc * 32 + g * 4 + 0];
-          v.y = pk[kc * 32 + g * 4 + 1];
-          v.z = pk[kc * 32 + g * 4 + 2];
-          v.w = pk[kc * 32 + g * 4 + 3];
-          *(uint4*)(sP + kc * BQ * 128 + row * 128 + ((g ^ (row & 7)) << 4)) = v;
-        }
-      tc::fence_proxy_async();
+      for (int c = 0; c < HC / 32; ++c) tc::tmem_st16(tS + st * BKV + half * (HC / 2) + c * 16, &pk[c * 16]);
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_full);
     }
 
-    // ---- epilogue
+    // ---- epilogue: merge the two partial row sums, then each warp writes its share of the O columns
+    lbuf[half * 128 + row] = l;
+    tc::named_bar_sync(1 + qtr, 64);
+    l += lbuf[(half ^ 1) * 128 + row];
     tc::mbar_wait(o_ready, (uint32_t)(n - 1) & 1u);
     tc::tc_fence_after();
     const int qi = q0 + row;
@@ -268,7 +276,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float inv = 1.f / l;
       bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half; c < DV / 32; c += 2) {
         uint32_t o[32];
         tc::tmem_ld32(tO + c * 32, o);
         tc::tmem_ld_wait();
@@ -289,9 +297,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     } else {
       const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
-      float* orow = p.opart + rix * D;
+      float* orow = p.opart + rix * DV;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half; c < DV / 32; c += 2) {
         uint32_t o[32];
         tc::tmem_ld32(tO + c * 32, o);
         tc::tmem_ld_wait();
@@ -303,7 +311,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             __uint_as_float(o[g * 4 + 3]));
         }
       }
-      if (qi < p.Lq) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
+      if (qi < p.Lq && half == 0) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
     }
     tc::tc_fence_before();
   }
@@ -371,23 +379,24 @@ int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long
   return best;
 }
 
-template <int D, int BKV>
+template <int D, int DV, int BKV, int KST>
 int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts, long k_bs, long k_hs,
            long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts, int B, int Hh, int Lq, int Lk,
            float scale, void* ws, long ws_bytes, cudaStream_t st) {
-  using C = Cfg<D, BKV>;
+  using C = Cfg<D, DV, BKV, KST>;
   static_assert(C::SMEM <= 227 * 1024, "attention tile does not fit shared memory");
+  static_assert(KST >= 2 && KST <= 4, "K ring depth");
   CUtensorMap tmQ, tmK, tmV;
-  auto mk = [&](CUtensorMap* m, const void* base, long bs, long hs, long ts, int L, int rows) {
-    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)L, (uint64_t)Hh, (uint64_t)B};
+  auto mk = [&](CUtensorMap* m, const void* base, long bs, long hs, long ts, int L, int rows, int width) {
+    const uint64_t dims[4] = {(uint64_t)width, (uint64_t)L, (uint64_t)Hh, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)ts, (uint64_t)(Hh > 1 ? hs : ts * (long)L), (uint64_t)(B > 1 ? bs : ts * (long)L * Hh)};
     const uint32_t box[4] = {64, (uint32_t)rows, 1, 1};
     return tc::make_tmap_bf16(m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   };
   int rc;
-  if ((rc = mk(&tmQ, q, q_bs, q_hs, q_ts, Lq, BQ))) return rc;
-  if ((rc = mk(&tmK, k, k_bs, k_hs, k_ts, Lk, BKV))) return rc;
-  if ((rc = mk(&tmV, v, v_bs, v_hs, v_ts, Lk, BKV))) return rc;
+  if ((rc = mk(&tmQ, q, q_bs, q_hs, q_ts, Lq, BQ, D))) return rc;
+  if ((rc = mk(&tmK, k, k_bs, k_hs, k_ts, Lk, BKV, D))) return rc;
+  if ((rc = mk(&tmV, v, v_bs, v_hs, v_ts, Lk, BKV, DV))) return rc;
 
   AttnTcP p;
   p.o = o; p.o_bs = o_bs; p.o_hs = o_hs; p.o_ts = o_ts;
@@ -396,13 +405,13 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   p.ntiles = (Lk + BKV - 1) / BKV;
   const int qtiles = (Lq + BQ - 1) / BQ;
   const long rows = (long)B * Hh * Lq;
-  const long per_split = rows * (D + 2) * 4;
+  const long per_split = rows * (DV + 2) * 4;
   p.nsplit = ws ? pick_nsplit(qtiles * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
   p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
   p.opart = (float*)ws;
-  p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * D : nullptr;
+  p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
 
-  auto kern = attn_tc_kernel<D, BKV>;
+  auto kern = attn_tc_kernel<D, DV, BKV, KST>;
   static bool attr_set = false;
   if (!attr_set) {
     MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "attn_tc attr");
@@ -412,8 +421,8 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
   MS2_CHECK_LAUNCH("attn_tc_kernel");
   if (p.nsplit > 1) {
-    constexpr int TPR = D / 8, RPB = 128 / TPR;
-    attn_combine_kernel<D><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
+    constexpr int TPR = DV / 8, RPB = 128 / TPR;
+    attn_combine_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
                                                                  p.nsplit, rows);
     MS2_CHECK_LAUNCH("attn_combine_kernel");
   }
@@ -423,35 +432,34 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
 }  // namespace
 
 bool ms2_attention_tc_supported(int dt, long q_hs, long q_ts, long k_hs, long k_ts, long v_hs, long v_ts, long o_hs,
-                                long o_ts, int Hh, int Lq, int Lk, int D) {
+                                long o_ts, int Hh, int Lq, int Lk, int D, int DV) {
   if (dt != MS2_BF16) return false;
-  if (!(D == 64 || D == 96 || D == 128 || D == 256)) return false;
+  if (!(((D == 64 || D == 96 || D == 128 || D == 256) && DV == D) || (D == 256 && DV == 64))) return false;
   if (Lq < 64 || Lk < 64) return false;
   if ((q_ts | k_ts | v_ts | o_ts) % 8) return false;
   if (Hh > 1 && ((q_hs | k_hs | v_hs | o_hs) % 8)) return false;
   return true;
 }
 
-long ms2_attention_tc_workspace(int B, int Hh, int Lq, int D, int max_split) {
-  return (long)max_split * B * Hh * Lq * (D + 2) * 4;
-}
-
 int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts,
                             long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs,
-                            long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, void* ws, long ws_bytes,
-                            cudaStream_t st) {
+                            long o_ts, int B, int Hh, int Lq, int Lk, int D, int DV, float scale, void* ws,
+                            long ws_bytes, cudaStream_t st) {
   MS2_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                     ((uintptr_t)o % 16 == 0) && (!ws || (uintptr_t)ws % 16 == 0),
                 "attention_tc: pointers must be 16-byte aligned");
   MS2_CHECK_ARG(B == 1 || ((q_bs | k_bs | v_bs | o_bs) % 8 == 0), "attention_tc: batch strides must be multiples of 8");
 #define MS2_ATTN_ARGS q, k, v, o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts, B, Hh, Lq, Lk, scale, ws, ws_bytes, st
-  switch (D) {
-    case 64: return launch<64, 128>(MS2_ATTN_ARGS);
-    case 96: return launch<96, 128>(MS2_ATTN_ARGS);
-    case 128: return launch<128, 128>(MS2_ATTN_ARGS);
-    case 256: return launch<256, 64>(MS2_ATTN_ARGS);
+  if (D == 256 && DV == 64) return launch<256, 64, 64, 4>(MS2_ATTN_ARGS);
+  if (DV == D) {
+    switch (D) {
+      case 64: return launch<64, 64, 128, 2>(MS2_ATTN_ARGS);
+      case 96: return launch<96, 96, 128, 2>(MS2_ATTN_ARGS);
+      case 128: return launch<128, 128, 128, 2>(MS2_ATTN_ARGS);
+      case 256: return launch<256, 256, 64, 2>(MS2_ATTN_ARGS);
+    }
   }
 #undef MS2_ATTN_ARGS
-  ms2_set_error("attention_tc: unsupported head dim %d", D);
+  ms2_set_error("attention_tc: unsupported head dims %d/%d", D, DV);
   return MS2_ERR_UNSUPPORTED;
 }

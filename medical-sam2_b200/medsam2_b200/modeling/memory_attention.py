@@ -32,7 +32,7 @@ class MemoryAttentionLayer(nn.Module):
 
     def forward_tokens(self, x, query_pos, mem_k_in, mem_v_in, num_k_exclude_rope, kv=None):
         """x fp32 [B,L,C]; mem_k_in / mem_v_in compute-dtype [B,Lk,64], or kv = (K, V) already projected
-        (and rotated) [B,Lk,C] views of a MemoryBank."""
+        (and rotated) views of a MemoryBank: (K [B,Lk,C], V [B,Lk,C], False) or (K, raw memory [B,Lk,Cm], True)."""
         cd = compute_dtype()
         L = x.shape[1]
         t = self.norm1(x, out_dtype=cd)
@@ -45,8 +45,11 @@ class MemoryAttentionLayer(nn.Module):
         if self.pos_enc_at_cross_attn_queries:
             t = ops.axpby(self.norm2(x), 1.0, query_pos, 1.0, out_dtype=cd)
         q = self.cross_attn_image.project_q(t)
-        k, v = kv if kv is not None else self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
-        o = ops.attention(q, k, v, self.cross_attn_image.num_heads)
+        if kv is not None and kv[2]:
+            o = self.cross_attn_image.v_proj(ops.attention_dv(q, kv[0], kv[1]), out_dtype=cd)   # deferred value projection
+        else:
+            k, v = kv[:2] if kv is not None else self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
+            o = ops.attention(q, k, v, self.cross_attn_image.num_heads)
         x = self.cross_attn_image.out_proj(o, out_dtype=torch.float32, residual=x)
         t = self.norm3(x, out_dtype=cd)
         h = self.linear1(t, out_dtype=cd, act=ops.ACT_RELU)
@@ -66,25 +69,33 @@ class MemoryBank:
     def __init__(self):
         self.keys, self.refs = [], []
         self.K, self.V = [], []
+        self.M = None                # raw memory values [B,cap,Cm] (compute dtype) when the value projection is deferred
+        self.raw_v = False
         self.cap = self.n_static = 0
         self.B = self.device = self.dtype = None
 
     def reset(self):
         self.__init__()
 
-    def ensure(self, n_layers, B, rows, width, dtype, device):
-        if (self.B, self.device, self.dtype) != (B, device, dtype) or len(self.K) != n_layers:
+    def ensure(self, n_layers, B, rows, width, mem_width, raw_v, dtype, device):
+        if (self.B, self.device, self.dtype, self.raw_v) != (B, device, dtype, raw_v) or len(self.K) != n_layers:
             self.reset()
-            self.B, self.device, self.dtype = B, device, dtype
+            self.B, self.device, self.dtype, self.raw_v = B, device, dtype, raw_v
             self.K, self.V = [None] * n_layers, [None] * n_layers
         if rows > self.cap:
             cap = max(rows, int(self.cap * 1.5))
+
+            def grow(old, w):
+                new = torch.empty((B, cap, w), dtype=dtype, device=device)
+                if old is not None and self.n_static:
+                    new[:, : self.n_static] = old[:, : self.n_static]
+                return new
             for l in range(n_layers):
-                for arr in (self.K, self.V):
-                    new = torch.empty((B, cap, width), dtype=dtype, device=device)
-                    if arr[l] is not None and self.n_static:
-                        new[:, : self.n_static] = arr[l][:, : self.n_static]
-                    arr[l] = new
+                self.K[l] = grow(self.K[l], width)
+                if not raw_v:
+                    self.V[l] = grow(self.V[l], width)
+            if raw_v:
+                self.M = grow(self.M, mem_width)
             self.cap = cap
 
 
@@ -116,16 +127,23 @@ class MemoryAttention(nn.Module):
         [row0, row0+n)."""
         cd = compute_dtype()
         B, n, _ = mem.shape
-        v_in = to_compute(mem)
-        k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else v_in
+        if bank.raw_v:
+            for b in range(B):
+                ops.cast_into(mem[b], bank.M[b, row0: row0 + n])
+            v_in = None
+            k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else to_compute(mem)
+        else:
+            v_in = to_compute(mem)
+            k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else v_in
         for l, layer in enumerate(self.layers):
             att = layer.cross_attn_image
             D = att.internal_dim // att.num_heads
             cos, sin = att._table(Lq, mem.device)
             for b in range(B):
-                kd, vd = bank.K[l][b, row0: row0 + n], bank.V[l][b, row0: row0 + n]
+                kd = bank.K[l][b, row0: row0 + n]
                 att.k_proj(k_in[b], out_dtype=cd, out=kd)
-                att.v_proj(v_in[b], out_dtype=cd, out=vd)
+                if not bank.raw_v:
+                    att.v_proj(v_in[b], out_dtype=cd, out=bank.V[l][b, row0: row0 + n])
                 if n_rope_rows > 0:
                     for h in range(att.num_heads):
                         ops.rope_(kd[:, h * D:], 1, n, n_rope_rows, D, cos, sin, batch_stride=n * att.internal_dim,
@@ -144,7 +162,13 @@ class MemoryAttention(nn.Module):
         keys = [e[0] for e in cond]
         if bank.keys != keys[: len(bank.keys)] or bank.B not in (None, B):
             bank.reset()
-        bank.ensure(len(self.layers), B, len(keys) * hw + n_dyn + 64, att0.internal_dim, cd, curr.device)
+        # bf16 + one head of 256 over 64-d memories (the shipped configuration): keep the raw memory values once
+        # instead of a projected V per layer and attend over them (ms2_attention_dv); v_proj then runs on the
+        # [L,64] attention result
+        raw_v = (cd == torch.bfloat16 and att0.num_heads == 1 and att0.internal_dim == 256 and att0.kv_in_dim == 64
+                 and L >= 64)
+        bank.ensure(len(self.layers), B, len(keys) * hw + n_dyn + 64, att0.internal_dim, att0.kv_in_dim, raw_v, cd,
+                    curr.device)
         new = cond[len(bank.keys):]
         if new:                                            # conditioning memories not yet resident: project once
             mem = new[0][2] if len(new) == 1 else torch.cat([e[2] for e in new], dim=1)
@@ -168,7 +192,8 @@ class MemoryAttention(nn.Module):
         Lk = row0 + n_dyn
         x = ops.axpby(curr, 1.0, curr_pos, 0.1) if (self.pos_enc_at_input and curr_pos is not None) else curr
         for l, layer in enumerate(self.layers):
-            x = layer.forward_tokens(x, curr_pos, None, None, 0, kv=(bank.K[l][:, :Lk], bank.V[l][:, :Lk]))
+            kv = (bank.K[l][:, :Lk], bank.M[:, :Lk], True) if bank.raw_v else (bank.K[l][:, :Lk], bank.V[l][:, :Lk], False)
+            x = layer.forward_tokens(x, curr_pos, None, None, 0, kv=kv)
         return self.norm(x)
 
     def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0):

@@ -190,6 +190,33 @@ def attention(q, k, v, heads, scale=None, impl=0):
     return o
 
 
+def attention_dv(q, k, v, scale=None):
+    """single-head attention with a narrower value: q [B,Lq,D], k [B,Lk,D], v [B,Lk,DV] -> o [B,Lq,DV]
+    (tcgen05 only; D=256, DV=64: memory cross-attention over un-projected memory values)."""
+    B, Lq, D = q.shape
+    Lk, DV = k.shape[1], v.shape[2]
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.stride(-1) != 1 or t.dtype != torch.bfloat16:
+            raise native.NativeError(f"attention_dv: {n} must be a bf16 CUDA tensor with unit inner stride")
+    o = torch.empty((B, Lq, DV), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    ws, ws_bytes = None, 0
+    qtiles = B * ((Lq + 127) // 128)
+    if qtiles < 2 * _SMS and Lk >= 512:
+        per_split = B * Lq * (DV + 2) * 4
+        nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split))
+        ws_bytes = nsplit * per_split
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    ev = PROFILE.begin("attention")
+    native.call("ms2_attention_dv", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
+                q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), DV, v.stride(1),
+                o.stride(0), DV, o.stride(1), B, 1, Lq, Lk, D, DV, float(scale),
+                None if ws is None else ws.data_ptr(), ws_bytes, _st())
+    PROFILE.end("attention", ev, 2.0 * B * Lq * Lk * (D + DV))
+    return o
+
+
 def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool, impl=0):
     """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
     Ho, Wo = (H // 2, W // 2) if qpool else (H, W)
@@ -264,6 +291,14 @@ def cast(x, dtype):
     y = torch.empty(x.shape, dtype=dtype, device=x.device)
     native.call("ms2_cast", _chk(x, "x"), _DT[x.dtype], y.data_ptr(), _DT[dtype], x.numel(), _st())
     return y
+
+
+def cast_into(x, out):
+    """dtype cast of contiguous x into the (contiguous) pre-allocated `out`."""
+    if x.numel() != out.numel():
+        raise native.NativeError("cast_into: size mismatch")
+    native.call("ms2_cast", _chk(x, "x"), _DT[x.dtype], _chk(out, "out"), _DT[out.dtype], x.numel(), _st())
+    return out
 
 
 def activation(x, act):

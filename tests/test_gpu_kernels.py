@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import ref_ops
 
@@ -232,6 +233,17 @@ def test_attention_tc(ops, B, H, Lq, Lk, D, qs):
     o = ops.attention(q, k, v, H, impl=2)
     r = ref_ops.attention(q.float(), k.float(), v.float(), H)
     close_rel(o, r, 1e-2, 8e-3, "attention_tc")
+    assert (o.float() - r).abs().mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,Lq,Lk,qs", [(1, 128, 64, 1.0), (1, 4096, 4096 + 37, 1.0), (2, 300, 777, 3.0), (1, 4096, 28736, 4.0)])
+def test_attention_dv(ops, B, Lq, Lk, qs):
+    """D=256 queries/keys over 64-d values (memory cross-attention with un-projected memory values)."""
+    q = (rnd(B, Lq, 256, seed=1) * qs).to(torch.bfloat16)
+    k, v = rnd(B, Lk, 256, seed=2).to(torch.bfloat16), rnd(B, Lk, 64, seed=3).to(torch.bfloat16)
+    o = ops.attention_dv(q, k, v)
+    r = F.scaled_dot_product_attention(q.float()[:, None], k.float()[:, None], v.float()[:, None])[:, 0]
+    close_rel(o, r, 1e-2, 8e-3, "attention_dv")
     assert (o.float() - r).abs().mean().item() < 2e-3
 
 
