@@ -6,7 +6,10 @@
 // One CTA owns a 128-query tile and streams a contiguous range of key tiles (split-KV over gridDim.z so
 // that 32 query tiles still fill 148 SMs; partial (O, m, l) are merged by attn_combine_kernel):
 //   warp 0      TMA producer : Q once; K and V tiles (BKV keys) through two 2-deep rings, 128B-swizzled
-//   warp 1      MMA issuer   : S = Q K^T   (M=128, N=BKV, K=D, both operands K-major)   -> TMEM S[j&1]
+//   warp 1      MMA issuer   : S = Q K^T   (M=128, N=BKV, K=D; Q is copied ONCE from smem into TENSOR MEMORY and
+//                              used as the A operand from there: with both operands in smem the 128x16 Q slice
+//                              would be re-read for every instruction and the ~56 B/clk operand fetch, not the
+//                              tensor pipe, would set the pace)                                  -> TMEM S[j&1]
 //                              O += P V    (M=128, N=D, K=BKV, P from TENSOR MEMORY, V MN-major smem) -> TMEM O
 //   warps 2..9  softmax      : two warps per TMEM lane quarter split the S columns of their 32 query rows;
 //                              thread = (row, column half): tcgen05.ld of its S slice, online max/sum in the log2
@@ -15,6 +18,7 @@
 //                              (no shared-memory round trip, no proxy fence); final O/l -> global
 // QK^T of tile j+1 is issued before P V of tile j, so the tensor pipe works under the softmax.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -30,6 +34,7 @@ struct AttnTcP {
   int B, Hh, Lq, Lk;
   float c;        // scale * log2(e)
   int ntiles, tiles_per_split, nsplit;
+  float tau;      // lazy-rescale threshold (log2 units)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -50,6 +55,7 @@ struct Cfg {
   static constexpr int V_BYTES = DCHV * BKV * 128;      // one V stage
   static constexpr int SMEM = Q_BYTES + KST * K_BYTES + 2 * V_BYTES + 1024 /*align*/ + 4096 /*barriers, max/sum exchange*/;
   static constexpr int S_COL = 256;                     // TMEM: O at [0,DV), S stages at 256 + st*BKV
+  static constexpr int Q_COL = D == 256 ? 384 : 128;    // Q (A operand of S = Q K^T) resident in TMEM, D/2 columns
 };
 
 template <int D, int DV, int BKV, int KST>
@@ -71,8 +77,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* s_full = bars + 13;       // 2
   uint64_t* p_full = bars + 15;       // 1
   uint64_t* o_ready = bars + 16;      // 1
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 17);
-  float* mxbuf = (float*)(bars + 18);    // [tile parity][half][128 rows] row-max exchange
+  uint64_t* q_tmem = bars + 17;       // 1: Q copied into tensor memory
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 18);
+  float* mxbuf = (float*)(bars + 19);    // [tile parity][half][128 rows] row-max exchange
   float* lbuf = mxbuf + 512;             // [half][128 rows] row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,6 +106,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     tc::mbar_init(p_full, 8);
     tc::mbar_init(o_ready, 1);
+    tc::mbar_init(q_tmem, 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -109,7 +117,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < C::DCH; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
@@ -137,21 +145,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
-    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
-    const uint32_t tO = tmem_base, tS = tmem_base + C::S_COL;
+    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
+    const uint32_t tO = tmem_base, tS = tmem_base + C::S_COL, tQ = tmem_base + C::Q_COL;
 
     auto issue_qk = [&](int j) {
       const int st = j & 1, ks = j % KST;
-      // S[st] (whose first BKV/2 columns hold P of tile j-2) is overwritten only after P V of tile j-2, which
-      // this thread issued earlier: tcgen05.mma instructions of one thread execute in issue order
+      // S[st] still holds P of tile j-2 in its first BKV/2 columns: P V of tile j-2 must have finished READING it
+      // before this S = Q K^T starts writing (back-to-back independent MMAs overlap in the tensor pipe, so issue
+      // order alone does not protect the operand read)
+      if (j >= 2) tc::mbar_wait(o_ready, (uint32_t)(j - 2) & 1u);
       tc::mbar_wait(&k_full[ks], (uint32_t)(j / KST) & 1u);
       tc::tc_fence_after();
-      if (lane == 0) {
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t da = tc::desc_kmajor_sw128(aQ + (kk >> 2) * BQ * 128 + (kk & 3) * 32);
           const uint64_t db = tc::desc_kmajor_sw128(aK + ks * C::K_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
-          tc::umma_bf16(tS + st * BKV, da, db, idesc_qk, kk ? 1u : 0u);
+          tc::umma_bf16_ts(tS + st * BKV, tQ + kk * 8, db, idesc_qk, kk ? 1u : 0u);   // 16 dims = 8 columns of Q
         }
         tc::umma_commit(&k_empty[ks]);
         tc::umma_commit(&s_full[st]);
@@ -159,7 +168,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
     };
 
-    tc::mbar_wait(q_full, 0);
+    tc::mbar_wait(q_tmem, 0);
+    tc::tc_fence_after();
     issue_qk(0);
     for (int j = 0; j < n; ++j) {
       if (j + 1 < n) issue_qk(j + 1);
@@ -168,7 +178,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_wait(&v_full[st], ph);
       tc::mbar_wait(p_full, (uint32_t)j & 1u);
       tc::tc_fence_after();
-      if (lane == 0) {
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t db = tc::desc_mnmajor_sw128(aV + st * C::V_BYTES + kk * 2048, BKV * 128);
@@ -191,6 +201,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + C::S_COL;
     float m_used = 0.f, l = 0.f;
     const int last_valid = p.Lk - (p.ntiles - 1) * BKV;   // valid keys of the globally last tile
+
+    // ---- Q: swizzled smem tile (TMA) -> tensor memory, row = lane, two bf16 per 32-bit column; the two warps of a
+    //      lane quarter take alternate 16-byte pieces-groups (32-column blocks of the packed row)
+    {
+      tc::mbar_wait(q_full, 0);
+      const uint32_t aQ = tc::smem_u32(sQ);
+      constexpr int QW = D / 2;                         // packed words per row
+#pragma unroll
+      for (int blk = 0; blk < (QW + 15) / 16; ++blk) {  // 16 words = 32 bf16 = 4 pieces of 16 bytes
+        if ((blk & 1) != half) continue;
+        const int ch = blk >> 1, g0 = (blk & 1) * 4;    // 64-column chunk, first piece inside it
+        uint32_t w[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 v = tc::lds128(aQ + ch * BQ * 128 + row * 128 + (((g0 + g) ^ (row & 7)) << 4));
+          w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+        }
+        tc::tmem_st16(tmem_base + lane_addr + C::Q_COL + blk * 16, w);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(q_tmem);
+    }
 
     for (int j = 0; j < n; ++j) {
       const int st = j & 1;
@@ -221,7 +255,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (j == 0) {
         m_used = mx;
       } else {
-        const bool need = mx > m_used + LAZY_TAU;
+        const bool need = mx > m_used + p.tau;
         if (__any_sync(0xffffffffu, need)) {
           tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);      // P V of tile j-1 has landed in O
           tc::tc_fence_after();
@@ -256,6 +290,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
         }
+      // Every warp observes EVERY phase of o_ready (one per tile): an mbarrier only carries a phase parity, and a
+      // waiter that skips phases (the rescale above is rare) can no longer tell phase j-1 from j-3.  P V of tile
+      // j-1 was issued a whole softmax ago, so this wait is normally already satisfied.
+      if (j > 0) tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);
       // P overwrites the first BKV/2 columns of this S stage: row = lane, two bf16 keys per 32-bit column
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c) tc::tmem_st16(tS + st * BKV + half * (HC / 2) + c * 16, &pk[c * 16]);
@@ -402,6 +440,10 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   p.o = o; p.o_bs = o_bs; p.o_hs = o_hs; p.o_ts = o_ts;
   p.B = B; p.Hh = Hh; p.Lq = Lq; p.Lk = Lk;
   p.c = scale * 1.4426950408889634f;
+  {
+    static const float tau = []() { const char* e = getenv("MS2_LAZY_TAU"); return e ? (float)atof(e) : LAZY_TAU; }();
+    p.tau = tau;
+  }
   p.ntiles = (Lk + BKV - 1) / BKV;
   const int qtiles = (Lq + BQ - 1) / BQ;
   const long rows = (long)B * Hh * Lq;

@@ -89,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
@@ -116,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < p.num_kb; ++kb) {
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
@@ -155,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       for (int c = rot; c < nch; c += ngrp, ++it) {   // groups rotate over tiles so odd chunk counts balance
         if (it >= 1) {                              // the previous store of this warp has read the buffer
-          if (lane == 0) tc::tma_store_wait_read<0>();
+          if (tc::elect_one()) tc::tma_store_wait_read<0>();
           __syncwarp();
         }
         const int nb = n0 + c * CPC;
@@ -216,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && m0 < p.M) {
+        if (m0 < p.M && tc::elect_one()) {
           tc::tma_store_2d(&tmO, buf, nb, m0);
           tc::tma_store_commit();
         }
@@ -227,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
-    if (lane == 0) tc::tma_store_wait<0>();
+    if (tc::elect_one()) tc::tma_store_wait<0>();
   }
   tc::tc_fence_before();
   __syncthreads();

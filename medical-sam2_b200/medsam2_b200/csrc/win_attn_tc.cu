@@ -140,7 +140,7 @@ win_attn_tc_kernel(const WinP p) {
   __syncthreads();
 
   const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)p.o_col;
-  if (tid == 0) {
+  if (warp == 0 && tc::elect_one()) {
     tc::tc_fence_after();
     const uint32_t idesc = tc::make_idesc_bf16(128, p.NK, 0, 0);
     const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK);
@@ -212,7 +212,7 @@ win_attn_tc_kernel(const WinP p) {
     tc::tc_fence_before();
   }
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0 && tc::elect_one()) {
     tc::tc_fence_after();
     const uint32_t idesc = tc::make_idesc_bf16(128, WD, 0, 1);
     const uint32_t aP = tc::smem_u32(sP), aV = tc::smem_u32(sV);

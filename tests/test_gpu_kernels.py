@@ -224,7 +224,9 @@ def test_attention_dense(ops, B, H, Lq, Lk, D, dt):
                                             (1, 1, 128, 128, 96, 1.0), (1, 1, 4096, 4096 + 37, 256, 1.0),
                                             (1, 4, 4096, 4096, 96, 1.0), (2, 1, 300, 777, 256, 3.0),
                                             (1, 2, 1024, 1024, 64, 2.0), (2, 2, 256, 640, 128, 1.0),
-                                            (1, 1, 4096, 28736, 256, 4.0), (3, 8, 200, 333, 96, 1.0)])
+                                            (1, 1, 4096, 28736, 256, 4.0), (3, 8, 200, 333, 96, 1.0),
+                                            (1, 1, 128, 448, 256, 4.0), (1, 1, 256, 448, 256, 4.0), (1, 1, 300, 777, 256, 3.0),
+                                            (1, 2, 640, 1200, 128, 4.0), (2, 4, 500, 900, 96, 5.0), (1, 1, 256, 4096, 64, 6.0)])
 def test_attention_tc(ops, B, H, Lq, Lk, D, qs):
     """tcgen05 flash attention (impl=2, incl. split-KV + lazy rescale) vs the fp32 statement on the same
     bf16-rounded operands.  Tolerance 1.5e-2 abs: bf16 P and bf16 output rounding of O(1) values."""
@@ -245,6 +247,24 @@ def test_attention_dv(ops, B, Lq, Lk, qs):
     r = F.scaled_dot_product_attention(q.float()[:, None], k.float()[:, None], v.float()[:, None])[:, 0]
     close_rel(o, r, 1e-2, 8e-3, "attention_dv")
     assert (o.float() - r).abs().mean().item() < 2e-3
+
+
+def test_attention_tc_rescale_every_tile(ops, monkeypatch):
+    """MS2_LAZY_TAU=0 forces the in-TMEM rescale of O whenever a row maximum grows (normally only beyond 2^8):
+    exercises the softmax <-> MMA hand-shake of that rare path on every tile."""
+    import subprocess, sys, os
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from medsam2_b200 import ops; import ref_ops\n"
+        "g = torch.Generator().manual_seed(5)\n"
+        "for (B,H,Lq,Lk,D,qs) in [(1,1,300,777,256,3.0),(1,1,4096,28736,256,4.0),(2,4,500,900,96,4.0)]:\n"
+        "    q=(torch.randn(B,Lq,H*D,generator=g)*qs).cuda().bfloat16(); k=torch.randn(B,Lk,H*D,generator=g).cuda().bfloat16(); v=torch.randn(B,Lk,H*D,generator=g).cuda().bfloat16()\n"
+        "    o=ops.attention(q,k,v,H,impl=2); r=ref_ops.attention(q.float(),k.float(),v.float(),H)\n"
+        "    e=((o.float()-r).abs()-8e-3*r.abs()).max().item(); assert e<=1e-2,(B,H,Lq,Lk,D,e)\n"
+        "print('ok')\n") % (os.path.join(os.path.dirname(__file__), "..", "medical-sam2_b200"), os.path.dirname(__file__))
+    env = dict(os.environ, MS2_LAZY_TAU="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_attention_tc_strided_qkv(ops):
