@@ -36,12 +36,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"],
+                    help="ours = this library; reference = the reference algorithm on the host CPU (oracle port); "
+                         "torch-gpu = the same oracle in torch eager (cuBLAS/SDPA, bf16 autocast) on cuda:0, informative")
     ap.add_argument("--slices", type=int, default=96)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--prompt-every", type=int, default=2)
     ap.add_argument("--config", default="sam2_hiera_s")
-    ap.add_argument("--cpu-sample-slices", type=int, default=6)
+    ap.add_argument("--cpu-sample-slices", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--feature-cache", type=int, default=0, help="0 = one entry per slice (no double encode)")
@@ -135,6 +137,41 @@ def cpu_oracle_rate(args, n_slices, threads=None):
         n = sum(1 for _ in vp.propagate_in_video(st, start_frame_idx=0))
     dt = time.perf_counter() - t0
     return n / dt, dt, torch.get_num_threads()
+
+
+def main_torch_gpu(args):
+    """Informative: the oracle port (plain torch modules' math: cuBLAS, SDPA, cuDNN) on one B200 with bf16
+    autocast, as train_3d.py:28,57 runs the reference - the GPU number a user of the reference sees today."""
+    from oracle.config import get_config
+    from oracle.sam2_oracle import OracleSAM2, OracleVideoPredictor
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cfg = get_config(args.config, image_size=args.size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg), device="cuda"))
+    vol, boxes = btcv_volume(args.slices, args.size, 1234, 1)
+    vol = vol.cuda()
+
+    def run():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            st = vp.init_state(vol, args.size, args.size)
+            for f in prompt_frames(args.slices, args.prompt_every):
+                vp.add_new_bbox(st, f, 1, boxes[f][0], clear_old_points=False)
+            return sum(1 for _ in vp.propagate_in_video(st, start_frame_idx=0))
+    for _ in range(max(1, args.warmup)):
+        run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n = run()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    print(json.dumps({"impl": "torch_eager_gpu", "metric": METRIC, "value": n / dt, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+                      "dtype": "bf16 autocast", "data": "synthetic",
+                      "config": {"workload": f"BASELINE configs[2]: {args.config}, {args.slices} slices {args.size}^2, oracle port in "
+                                             f"torch eager on cuda:0 (feature cache 1 as the reference: prompted slices encoded twice)"}}))
 
 
 def main_reference(args):
@@ -231,12 +268,15 @@ def main_ours(args):
     if rank == 0:
         clocks.start()
     n0 = native.launch_count
-    ops.PROFILE.enable(("attention", "gemm", "window_attention"))
     ms = timed(step_resident, args.steps)
-    prof = ops.PROFILE.summary()
-    ops.PROFILE.disable()
     launches = native.launch_count - n0
     ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    # per-kernel-family CUDA-event timing of ONE extra step (outside the timed region: two events per launch)
+    ops.PROFILE.enable(("mem_cross_attention", "attention", "gemm", "window_attention"))
+    ms_prof = timed(step_resident, 1)
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.disable()
     if args.host_profile and rank == 0:
         import cProfile, io, pstats
         pr = cProfile.Profile()
@@ -283,9 +323,18 @@ def main_ours(args):
     if dom:
         name, d = dom
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "launches": d["n"], "ms_per_launch": d["ms"] / max(d["n"], 1),
-                    "share_of_step": d["ms"] / ms, "peak_source": peak_src,
+        # memory cross-attention executes 2*Lq*Lk*(256+64) FLOP per launch (values stay 64-d); the
+        # reference's formulation of the same attention is 4*Lq*Lk*256 (SURVEY §8(d) "canonical")
+        canon = achieved * (512.0 / 320.0) if name == "mem_cross_attention" else achieved
+        roofline = {"bound": "tensor", "kernel": "attn_tc_kernel<256,64,64,4> (memory cross-attention)" if name == "mem_cross_attention" else name,
+                    "achieved": achieved, "achieved_canonical_flops": canon, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf,
+                    "traffic": 156.05e6 if name == "mem_cross_attention" else None,
+                    "traffic_note": "dram read+write of one launch at Lk=209120 (profiles/r1_attn_dv_ncu.txt); algorithmic "
+                                    "bytes of that launch: K 107.1 MB + M 26.8 MB + Q/O 2.6 MB",
+                    "launches": d["n"], "ms_per_launch": d["ms"] / max(d["n"], 1),
+                    "share_of_step": d["ms"] / ms_prof, "peak_source": peak_src,
+                    "profiled_step_ms": ms_prof,
                     "all": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0),
                                 "n": v["n"]} for k, v in prof.items()}}
     cpu = None
@@ -302,6 +351,7 @@ def main_ours(args):
                                    f"{T}-slice {S}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, "
                                    f"num_maskmem=7, fill_hole_area=8",
                        "sharding": "by volume, no collectives" if world > 1 else "single GPU",
+                       "encode_batch": args.encode_batch, "cuda_graphs": not args.no_graphs,
                        "l2": "256 MiB flush buffer written before every step; per-step working set >> L2"},
             "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel()},
@@ -315,5 +365,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         main_reference(a)
+    elif a.impl == "torch-gpu":
+        main_torch_gpu(a)
     else:
         main_ours(a)

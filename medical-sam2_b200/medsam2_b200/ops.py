@@ -208,12 +208,12 @@ def attention_dv(q, k, v, scale=None):
         nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split))
         ws_bytes = nsplit * per_split
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
-    ev = PROFILE.begin("attention")
+    ev = PROFILE.begin("mem_cross_attention")
     native.call("ms2_attention_dv", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _DT[q.dtype],
                 q.stride(0), D, q.stride(1), k.stride(0), D, k.stride(1), v.stride(0), DV, v.stride(1),
                 o.stride(0), DV, o.stride(1), B, 1, Lq, Lk, D, DV, float(scale),
                 None if ws is None else ws.data_ptr(), ws_bytes, _st())
-    PROFILE.end("attention", ev, 2.0 * B * Lq * Lk * (D + DV))
+    PROFILE.end("mem_cross_attention", ev, 2.0 * B * Lq * Lk * (D + DV))
     return o
 
 

@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing of the hot path; one process per GPU, `torch.distributed` (NCCL on GPUs,
+gloo in the CPU tests).
+
+* Volumes are independent: `shard_volumes` deals them round-robin to ranks - no data-path collective (configs 3/4).
+* Within ONE volume only the slice encoder shards (config 5): `encode_volume_sharded` lets every rank encode a
+  contiguous block of slices and all-gathers the feature pyramid (fpn levels `[32,256,256] + [64,128,128] +
+  [256,64,64]` per slice; the position encodings are constant tables and are never sent), filling the predictor's
+  per-slice feature cache on every rank.  Propagation stays sequential in t on the rank that tracks the volume.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_volumes(n_volumes, rank=None, world=None):
+    """indices of the volumes rank `rank` tracks (round-robin: equal counts +-1, no exchange needed)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    return list(range(rank, n_volumes, world))
+
+
+def slice_block(num_frames, rank, world):
+    """contiguous block [lo, hi) of slices encoded by `rank`; blocks have equal length `per` except the tail."""
+    per = int(math.ceil(num_frames / world))
+    lo = min(rank * per, num_frames)
+    return lo, min(lo + per, num_frames), per
+
+
+@torch.no_grad()
+def encode_volume_sharded(predictor, inference_state, group=None):
+    """Encode all slices of the volume held by `inference_state`, each rank a contiguous block, then all-gather the
+    pyramid so that every rank's `cached_features` holds every slice.  Results are identical to encoding locally
+    (the per-slice encoder output does not depend on how slices are batched).  Returns the number of slices this
+    rank encoded."""
+    st = inference_state
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    T = st["num_frames"]
+    if getattr(predictor, "feature_cache_size", T) < T:
+        raise ValueError(f"feature_cache_size ({predictor.feature_cache_size}) must hold all {T} slices")
+    lo, hi, per = slice_block(T, rank, world)
+    nb = max(1, int(getattr(predictor, "feature_encode_batch", 1)))
+    imgs = st["images"]
+    dev = st["device"]
+    levels, pos, kept_images = None, None, {}
+    for f0 in range(lo, hi, nb):
+        f1 = min(f0 + nb, hi)
+        batch = torch.stack([imgs[f] for f in range(f0, f1)]).to(dev).float()
+        out = predictor.forward_image(batch)
+        fpn = [t.permute(0, 2, 3, 1) for t in out["backbone_fpn"]]          # NHWC memory of the channels-last views
+        fpn = [t if t.is_contiguous() else t.contiguous() for t in fpn]
+        if levels is None:
+            levels = [torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in fpn]
+            pos = [p[:1] for p in out["vision_pos_enc"]]
+        for lvl, t in zip(levels, fpn):
+            lvl[f0 - lo: f1 - lo] = t
+        for i, f in enumerate(range(f0, f1)):
+            kept_images[f] = batch[i: i + 1]
+    if levels is None:                                    # this rank has no slices: learn the shapes from slice 0
+        out = predictor.forward_image(imgs[0].to(dev).float().unsqueeze(0))
+        fpn = [t.permute(0, 2, 3, 1) for t in out["backbone_fpn"]]
+        levels = [torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in fpn]
+        pos = [p[:1] for p in out["vision_pos_enc"]]
+    if world > 1:
+        gathered = []
+        for lvl in levels:
+            parts = [torch.empty_like(lvl) for _ in range(world)]
+            dist.all_gather(parts, lvl, group=group)                        # the one exchange step of this path
+            gathered.append(parts)
+    else:
+        gathered = [[lvl] for lvl in levels]
+    cache = st["cached_features"]
+    cache.clear()
+    for f in range(T):
+        owner, idx = divmod(f, per)
+        fpn = [gathered[l][owner][idx: idx + 1].permute(0, 3, 1, 2) for l in range(len(levels))]
+        image = kept_images.get(f)
+        if image is None:
+            image = imgs[f].to(dev).float().unsqueeze(0)
+        cache[f] = (image, {"vision_features": fpn[-1], "vision_pos_enc": pos, "backbone_fpn": fpn})
+    return hi - lo
