@@ -66,6 +66,14 @@ int ms2_gemm(const void* A, int a_dt, long lda, const void* W, int w_dt, const f
              const float* colscale, const float* residual, long ldr, void* out, int o_dt, long ldo,
              int M, int N, int K, int act, int impl, ms2_stream_t stream);
 
+/* up to 8 independent small-M GEMMs (same M <= 64, same K, per-group N / activation) in one launch:
+ * out_g[M,N_g] = act_g(A_g[M,K] @ W_g[N_g,K]^T + bias_g).  h_* are HOST arrays of `groups` entries holding device
+ * pointers / strides; used for the six 3-layer head MLPs of the mask decoder (mask_decoder.py:75-92,238-267). */
+int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const long* h_lda, const void* const* h_W,
+                            const float* const* h_bias, void* const* h_out, const long* h_ldo,
+                            const int* h_N, const int* h_act, int a_dt, int o_dt, int M, int K,
+                            ms2_stream_t stream);
+
 /* ---- scaled-dot-product attention, no mask (F.scaled_dot_product_attention call sites:
  *      hieradet.py:72-76, transformer.py:252-258, :318).  Dense mode:
  *      q [B,Hh,Lq,D] / k,v [B,Hh,Lk,D] / o [B,Hh,Lq,D] addressed through element strides
@@ -115,6 +123,11 @@ int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int C, ms2_str
  *      w fp32 [Cout,3,7,7]. */
 int ms2_patch_embed(const float* img, const float* w, const float* bias, const float* pos, float* out,
                     int B, int Hin, int Win, int Cout, ms2_stream_t stream);
+
+/* bf16 path of the same conv: NCHW fp32 image -> bf16 im2col rows [B*Ho*Wo, ldk] (taps in (ky,kx,c) order, zero
+ * beyond 147; ldk a multiple of 8 >= 152); the contraction then runs in ms2_gemm against the weight re-laid-out to
+ * [Cout, ldk], with bias and the pos-embed table as the epilogue residual. */
+int ms2_patch_im2col(const float* img, void* cols, int B, int Hin, int Win, int ldk, ms2_stream_t stream);
 
 /* ---- elementwise family (fp32 unless noted) */
 /* y = a*x + b*z + c; x fp32 [n]; z fp32 [zn] or NULL, broadcast as z[i mod zn] (zn divides n);

@@ -109,42 +109,103 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ cols,
 }
 
 // ------------------------------------------------------------------ depth-wise 7x7
-__global__ void __launch_bounds__(256)
+// HBM-bound (2 x 4 B x pixels x C): an 8x8 output tile x 32 channels per CTA; the 14x14 input halo tile is staged
+// once in shared memory ([row][col][channel]: channel = bank, conflict-free) and each thread slides a 7-tap window
+// along one output row of one channel, so every input value is read from HBM once (+ halo) instead of 49 times.
+constexpr int DW_T = 8, DW_C = 32, DW_IN = DW_T + 6;
+__global__ void __launch_bounds__(DW_T * DW_C)
 dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y, int B, int H, int W, int C) {
-  __shared__ float ws[49][64];
-  const int c0 = blockIdx.y * 64;
-  const int cl = threadIdx.x & 63, pl = threadIdx.x >> 6;
-  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) {
-    int c = i / 49, tap = i - c * 49;
+  __shared__ float tile[DW_IN][DW_IN][DW_C];
+  __shared__ float ws[49][DW_C];
+  const int tilesx = (W + DW_T - 1) / DW_T;
+  const int tx0 = (blockIdx.x % tilesx) * DW_T, ty0 = (blockIdx.x / tilesx) * DW_T;
+  const int c0 = blockIdx.y * DW_C, b = blockIdx.z;
+  const int cl = threadIdx.x % DW_C, ty = threadIdx.x / DW_C;
+  for (int i = threadIdx.x; i < 49 * DW_C; i += blockDim.x) {
+    const int c = i % DW_C, tap = i / DW_C;
     ws[tap][c] = (c0 + c < C) ? w[(long)(c0 + c) * 49 + tap] : 0.f;
+  }
+  for (int i = threadIdx.x; i < DW_IN * DW_IN * DW_C; i += blockDim.x) {
+    const int c = i % DW_C, col = (i / DW_C) % DW_IN, row = i / (DW_C * DW_IN);
+    const int sy = ty0 + row - 3, sx = tx0 + col - 3;
+    float v = 0.f;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W && c0 + c < C) v = x[(((long)b * H + sy) * W + sx) * C + c0 + c];
+    tile[row][col][c] = v;
   }
   __syncthreads();
   const int c = c0 + cl;
-  if (c >= C) return;
-  const long npix = (long)B * H * W;
-  for (long p = (long)blockIdx.x * 4 + pl; p < npix; p += (long)gridDim.x * 4) {
-    int xx = p % W;
-    long t = p / W;
-    int yy = t % H;
-    int b = t / H;
-    float acc = bias ? bias[c] : 0.f;
+  float acc[DW_T];
+  const float bv = (bias && c < C) ? bias[c] : 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 7; ++ky) {
-      int sy = yy + ky - 3;
-      if (sy < 0 || sy >= H) continue;
+  for (int i = 0; i < DW_T; ++i) acc[i] = bv;
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        int sx = xx + kx - 3;
-        if (sx < 0 || sx >= W) continue;
-        acc = fmaf(x[(((long)b * H + sy) * W + sx) * C + c], ws[ky * 7 + kx][cl], acc);
-      }
+  for (int ky = 0; ky < 7; ++ky) {
+    float in[DW_IN];
+#pragma unroll
+    for (int i = 0; i < DW_IN; ++i) in[i] = tile[ty + ky][i][cl];
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float wv = ws[ky * 7 + kx][cl];
+#pragma unroll
+      for (int i = 0; i < DW_T; ++i) acc[i] = fmaf(in[i + kx], wv, acc[i]);
     }
-    y[p * C + c] = acc;
+  }
+  const int oy = ty0 + ty;
+  if (c < C && oy < H) {
+#pragma unroll
+    for (int i = 0; i < DW_T; ++i)
+      if (tx0 + i < W) y[(((long)b * H + oy) * W + tx0 + i) * C + c] = acc[i];
   }
 }
 
+// ------------------------------------------------------------------ patch-embed im2col (bf16 path)
+// NCHW fp32 image -> bf16 rows [B*Ho*Wo, ldk] of the 7x7/s4/p3 taps in (ky, kx, c) order, zero beyond 147; the
+// contraction itself then runs on the tensor-core GEMM (K = 147 padded to a 16-byte multiple).  One thread = one
+// 16-byte chunk of a row: coalesced stores, gathers served from L1.
+__global__ void __launch_bounds__(256)
+patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ cols, long total_chunks, int Hin, int Win, int Ho,
+                    int Wo, int chunks) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_chunks) return;
+  const int ch = (int)(t % chunks);
+  const long row = t / chunks;
+  const int ox = (int)(row % Wo);
+  const long r2 = row / Wo;
+  const int oy = (int)(r2 % Ho), b = (int)(r2 / Ho);
+  const float* base = img + (long)b * 3 * Hin * Win;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int idx = ch * 8 + e;
+    float val = 0.f;
+    if (idx < 147) {
+      const int ky = idx / 21, r = idx - ky * 21, kx = r / 3, c = r - kx * 3;
+      const int sy = oy * 4 + ky - 3, sx = ox * 4 + kx - 3;
+      if (sy >= 0 && sy < Hin && sx >= 0 && sx < Win) val = __ldg(base + ((long)c * Hin + sy) * Win + sx);
+    }
+    v[e] = val;
+  }
+  uint4 u;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
+  *(uint4*)(cols + t * 8) = u;
+}
+
 }  // namespace
+
+extern "C" int ms2_patch_im2col(const float* img, void* cols, int B, int Hin, int Win, int ldk, void* stream) {
+  MS2_CHECK_ARG(img && cols, "patch_im2col: null pointer");
+  MS2_CHECK_ARG(ldk >= 152 && ldk % 8 == 0 && ((uintptr_t)cols % 16 == 0), "patch_im2col: ldk must be a multiple of 8 >= 152");
+  const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
+  const long total = (long)B * Ho * Wo * (ldk / 8);
+  if (!total) return MS2_OK;
+  patch_im2col_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (bf16*)cols, total, Hin, Win, Ho, Wo,
+                                                                               ldk / 8);
+  MS2_CHECK_LAUNCH("patch_im2col_kernel");
+  return MS2_OK;
+}
 
 extern "C" int ms2_patch_embed(const float* img, const float* w, const float* bias, const float* pos, float* out,
                                int B, int Hin, int Win, int Cout, void* stream) {
@@ -180,10 +241,8 @@ extern "C" int ms2_dwconv7x7(const float* x, const float* w, const float* bias, 
   MS2_CHECK_ARG(x && w && y, "dwconv7x7: null pointer");
   long npix = (long)B * H * W;
   if (!npix) return MS2_OK;
-  long gx = (npix + 3) / 4;
-  if (gx > 148L * 8) gx = 148L * 8;
-  dim3 grid((int)gx, ceil_div(C, 64));
-  dwconv7x7_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C);
+  dim3 grid(ceil_div(W, DW_T) * ceil_div(H, DW_T), ceil_div(C, DW_C), B);
+  dwconv7x7_kernel<<<grid, DW_T * DW_C, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C);
   MS2_CHECK_LAUNCH("dwconv7x7");
   return MS2_OK;
 }

@@ -44,10 +44,84 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
   }
 }
 
+// Vectorised variant for C % 4 == 0, C <= 1024 (every LayerNorm of the encoder / memory attention / decoder image
+// side): one warp per row, the row is read from HBM ONCE as float4 into registers (VPT float4 per lane), statistics by
+// shuffles, 8- or 16-byte stores.  Same two-pass formula as above, so results are bit-identical to it.
+template <typename TO, int VPT>
+__global__ void __launch_bounds__(256)
+layernorm_vec_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, TO* __restrict__ y, long M, int C, float eps, int act) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  const int nv = C >> 2;
+  const float4* xr = (const float4*)(x + row * (long)C);
+  const float4* ar = add ? (const float4*)(add + row * (long)C) : nullptr;
+  float4 v[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      v[i] = xr[c];
+      if (ar) { const float4 a = ar[c]; v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    if (lane + i * 32 < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c2 * c2 + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  TO* yr = y + row * (long)C;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 g = __ldg((const float4*)gamma + c), bb = __ldg((const float4*)beta + c);
+      float o[4] = {(v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                    (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (act == 1) o[j] = gelu_erf(o[j]);
+        else if (act == 2) o[j] = fmaxf(o[j], 0.f);
+      }
+      if (sizeof(TO) == 4) {
+        *(float4*)((float*)yr + c * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 u;
+        u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1;
+        *(uint2*)((bf16*)yr + c * 4) = u;
+      }
+    }
+  }
+}
+
 template <typename TO>
 int launch_ln(const float* x, const float* add, const float* gamma, const float* beta, TO* y, long M, int C,
               float eps, int act, cudaStream_t st) {
   const int threads = 256;
+  const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!add || (uintptr_t)add % 16 == 0) &&
+                       ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0);
+  if (C % 4 == 0 && C >= 32 && C <= 1024 && aligned) {
+    const int vpt = (C / 4 + 31) / 32;
+    const int grid = ceil_div(M * 32, threads);
+#define LN_VEC(V) layernorm_vec_kernel<TO, V><<<grid, threads, 0, st>>>(x, add, gamma, beta, y, M, C, eps, act)
+    if (vpt == 1) LN_VEC(1);
+    else if (vpt == 2) LN_VEC(2);
+    else if (vpt <= 4) LN_VEC(4);
+    else LN_VEC(8);
+#undef LN_VEC
+    MS2_CHECK_LAUNCH("layernorm_vec_kernel");
+    return MS2_OK;
+  }
 #define LN_LAUNCH(G)                                                                            \
   layernorm_kernel<TO, G><<<ceil_div(M * G, threads), threads, 0, st>>>(x, add, gamma, beta, y, M, C, eps, act)
   if (C <= 4) LN_LAUNCH(4);

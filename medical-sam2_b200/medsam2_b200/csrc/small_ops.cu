@@ -90,6 +90,79 @@ gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, c
   }
 }
 
+// ---- grouped variant: up to 8 independent small-M GEMMs of the same M and K in ONE launch (blockIdx.y = group):
+//      the 6 three-layer head MLPs of the mask decoder (4 hyper-networks, IoU, object score; mask_decoder.py:75-92,
+//      238-267) run layer by layer as 3 launches instead of 18.
+constexpr int SM_MAXG = 8;
+template <typename T>
+struct GroupedP {
+  const T* A[SM_MAXG];
+  const T* W[SM_MAXG];
+  const float* bias[SM_MAXG];
+  void* out[SM_MAXG];
+  long lda[SM_MAXG], ldo[SM_MAXG];
+  int N[SM_MAXG], act[SM_MAXG];
+};
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(SM_WARPS * 32)
+gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K) {
+  const int g = blockIdx.y;
+  const int N = p.N[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = lane >> 3, kl = lane & 7;
+  const int n = (blockIdx.x * SM_WARPS + warp) * 4 + cg;
+  if ((int)(blockIdx.x * SM_WARPS * 4) >= N) return;
+  const bool n_ok = n < N;
+  const T* A = p.A[g];
+  const long lda = p.lda[g];
+  const T* wrow = p.W[g] + (long)(n_ok ? n : 0) * K;
+  const float* bias = p.bias[g];
+  TO* out = (TO*)p.out[g];
+  const long ldo = p.ldo[g];
+  const int act = p.act[g];
+  for (int m0 = 0; m0 < M; m0 += SM_MT) {
+    const int mt = min(SM_MT, M - m0);
+    float acc[SM_MT];
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
+    for (int k = kl * 8; k < K; k += 64) {
+      float w[8];
+      Vec8<T>::load(wrow + k, w);
+#pragma unroll
+      for (int m = 0; m < SM_MT; ++m) {
+        if (m < mt) {
+          float a[8];
+          Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[i], acc[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) {
+      float v = acc[m];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      acc[m] = v;
+    }
+    if (kl == 0 && n_ok) {
+#pragma unroll
+      for (int m = 0; m < SM_MT; ++m) {
+        if (m < mt) {
+          float v = acc[m];
+          if (bias) v += bias[n];
+          if (act == 1) v = gelu_erf(v);
+          else if (act == 2) v = fmaxf(v, 0.f);
+          else if (act == 3) v = 1.f / (1.f + __expf(-v));
+          out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ attention, few keys
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
@@ -340,6 +413,46 @@ int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, con
   }
 #undef MS2_SMALLM
   MS2_CHECK_LAUNCH("gemm_smallm_kernel");
+  return MS2_OK;
+}
+
+extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const long* h_lda, const void* const* h_W,
+                                       const float* const* h_bias, void* const* h_out, const long* h_ldo,
+                                       const int* h_N, const int* h_act, int a_dt, int o_dt, int M, int K,
+                                       void* stream) {
+  MS2_CHECK_ARG(groups >= 1 && groups <= SM_MAXG, "gemm_smallm_grouped: 1..%d groups", SM_MAXG);
+  MS2_CHECK_ARG(M >= 1 && M <= 64 && K > 0 && K % 8 == 0, "gemm_smallm_grouped: M in 1..64, K %% 8 == 0");
+  int nmax = 0;
+  const int vb = a_dt == MS2_BF16 ? 8 : 4;
+  for (int g = 0; g < groups; ++g) {
+    MS2_CHECK_ARG(h_A[g] && h_W[g] && h_out[g] && h_N[g] > 0, "gemm_smallm_grouped: bad group %d", g);
+    MS2_CHECK_ARG(h_lda[g] % vb == 0 && ((uintptr_t)h_A[g] % 16 == 0) && ((uintptr_t)h_W[g] % 16 == 0),
+                  "gemm_smallm_grouped: group %d operands must be 16-byte aligned", g);
+    nmax = h_N[g] > nmax ? h_N[g] : nmax;
+  }
+  dim3 grid(ceil_div(nmax, SM_WARPS * 4), groups);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MS2_GROUPED(TA, TO)                                                                        \
+  do {                                                                                             \
+    GroupedP<TA> p;                                                                                \
+    memset(&p, 0, sizeof(p));                                                                      \
+    for (int g = 0; g < groups; ++g) {                                                             \
+      p.A[g] = (const TA*)h_A[g]; p.W[g] = (const TA*)h_W[g]; p.bias[g] = h_bias ? h_bias[g] : nullptr; \
+      p.out[g] = h_out[g]; p.lda[g] = h_lda[g]; p.ldo[g] = h_ldo[g]; p.N[g] = h_N[g];              \
+      p.act[g] = h_act ? h_act[g] : 0;                                                             \
+    }                                                                                              \
+    gemm_smallm_grouped_kernel<TA, TO><<<grid, SM_WARPS * 32, 0, st>>>(p, M, K);                   \
+  } while (0)
+  if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_GROUPED(bf16, bf16);
+  else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_GROUPED(bf16, float);
+  else if (a_dt == MS2_F32 && o_dt == MS2_BF16) MS2_GROUPED(float, bf16);
+  else if (a_dt == MS2_F32 && o_dt == MS2_F32) MS2_GROUPED(float, float);
+  else {
+    ms2_set_error("gemm_smallm_grouped: bad dtype");
+    return MS2_ERR_ARG;
+  }
+#undef MS2_GROUPED
+  MS2_CHECK_LAUNCH("gemm_smallm_grouped_kernel");
   return MS2_OK;
 }
 

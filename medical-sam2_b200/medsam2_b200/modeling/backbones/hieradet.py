@@ -23,8 +23,22 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
 
     def forward(self, x, pos=None):
-        """x fp32 NCHW -> NHWC tokens (+pos table)."""
-        return ops.patch_embed(x, p32(self.proj.weight), p32(self.proj.bias), pos)
+        """x fp32 NCHW -> NHWC tokens (+pos table).  bf16 mode: im2col -> tensor-core GEMM (bias and the pos-embed
+        table ride in the epilogue); fp32 mode: the direct fp32 conv kernel."""
+        if compute_dtype() != torch.bfloat16:
+            return ops.patch_embed(x, p32(self.proj.weight), p32(self.proj.bias), pos)
+        B, _, Hin, Win = x.shape
+        Ho, Wo = (Hin + 6 - 7) // 4 + 1, (Win + 6 - 7) // 4 + 1
+        E = self.proj.weight.shape[0]
+        w = CACHE.get(self.proj.weight, "patch_w152",
+                      lambda t: torch.nn.functional.pad(t.detach().permute(0, 2, 3, 1).reshape(t.shape[0], -1), (0, 5))
+                      .to(torch.bfloat16).contiguous())
+        cols = ops.patch_im2col(x)
+        out = torch.empty((B, Ho, Wo, E), dtype=torch.float32, device=x.device)
+        res = None if pos is None else pos.reshape(Ho * Wo, E)
+        for b in range(B):
+            ops.gemm(cols[b], w, p32(self.proj.bias), residual=res, out=out[b].view(Ho * Wo, E))
+        return out
 
 
 class MultiScaleAttention(nn.Module):

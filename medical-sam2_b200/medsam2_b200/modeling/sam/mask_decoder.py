@@ -85,20 +85,47 @@ class MaskDecoder(nn.Module):
         g2 = ops.gemm(u1, convT_w_c(dc2.weight), None, out_dtype=torch.float32)                   # [B,4hw,4*C/8]
         up = ops.pixel_shuffle_add(g2, p32(dc2.bias), feat_s0, B, 2 * h, 2 * w, C // 8, act=ops.ACT_GELU)
         hyper = torch.empty((B, self.num_mask_tokens, C // 8), dtype=torch.float32, device=src.device)
+        heads = list(self.output_hypernetworks_mlps) + [self.iou_prediction_head]
+        rows = [hs2[s + 1 + i:: Nt] for i in range(self.num_mask_tokens)] + [hs2[s:: Nt]]     # row-strided [B, C] views
+        obj = None
+        if self.pred_obj_scores and isinstance(self.pred_obj_score_head, MLP):
+            heads.append(self.pred_obj_score_head)
+            rows.append(hs2[0:: Nt])
+        outs = self._grouped_mlps(heads, rows) if B <= 64 and len(heads) <= 8 else None
+        if outs is None:
+            outs = [m(r) for m, r in zip(heads, rows)]
         for i in range(self.num_mask_tokens):
-            tok_i = hs2[s + 1 + i:: Nt]                         # row-strided view [B, C]
-            hyper[:, i, :] = self.output_hypernetworks_mlps[i](tok_i)
+            hyper[:, i, :] = outs[i]
         masks = ops.hyper_mask(up.view(B, 16 * HW, C // 8), hyper).view(B, self.num_mask_tokens, 4 * h, 4 * w)
-        iou_pred = self.iou_prediction_head(hs2[s:: Nt])
+        iou_pred = outs[self.num_mask_tokens]
         if self.pred_obj_scores:
             head = self.pred_obj_score_head
             if isinstance(head, MLP):
-                obj = head(hs2[0:: Nt])
+                obj = outs[self.num_mask_tokens + 1]
             else:
                 obj = ops.gemm(to_compute(hs2[0:: Nt].contiguous()), w_c(head.weight), p32(head.bias))
         else:
             obj = 10.0 * iou_pred.new_ones(B, 1)
         return masks, iou_pred, mask_tokens_out, obj
+
+    @staticmethod
+    def _grouped_mlps(mlps, rows):
+        """the head MLPs (4 hyper-networks, IoU, object score) share depth and input width: run them layer by layer
+        as ONE grouped small-M launch per layer (3 launches instead of 18).  None if they are not uniform."""
+        depth = mlps[0].num_layers
+        if any(m.num_layers != depth or m.act != mlps[0].act for m in mlps):
+            return None
+        cd = compute_dtype()
+        xs = list(rows)
+        for li in range(depth):
+            layers = [m.layers[li] for m in mlps]
+            if len({l.weight.shape[1] for l in layers}) != 1 or layers[0].weight.shape[1] % 8:
+                return None
+            last = li == depth - 1
+            acts = [(ops.ACT_SIGMOID if (last and m.sigmoid_output) else ops.ACT_NONE) if last else m.act for m in mlps]
+            xs = ops.gemm_grouped(xs, [w_c(l.weight) for l in layers], [p32(l.bias) for l in layers],
+                                  out_dtype=torch.float32 if last else cd, acts=acts)
+        return xs
 
     def select_outputs(self, masks, iou_pred, mask_tokens_out, multimask_output):
         """mask_decoder.py:150-175 without host synchronisation."""

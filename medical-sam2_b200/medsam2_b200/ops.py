@@ -152,6 +152,27 @@ def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, 
     return out
 
 
+def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None):
+    """len(a_list) <= 8 independent small-M GEMMs in one launch: out_g = act_g(a_g[M,K] @ w_g[N_g,K]^T + bias_g).
+    a_g may be row-strided 2-D views (token rows of [B,Nt,C]); all share M, K and dtype."""
+    import ctypes
+    G = len(a_list)
+    M, K = a_list[0].shape
+    outs, A, W, Bs, O, lda, ldo, Ns = [], [], [], [], [], [], [], []
+    for a, w, b in zip(a_list, w_list, bias_list):
+        if a.shape != (M, K) or w.shape[1] != K or a.stride(1) != 1 or not a.is_cuda or a.dtype != a_list[0].dtype:
+            raise native.NativeError("gemm_grouped: operands must share M, K, dtype and be CUDA with unit inner stride")
+        o = torch.empty((M, w.shape[0]), dtype=out_dtype, device=a.device)
+        outs.append(o)
+        A.append(a.data_ptr()); W.append(_chk(w, "w")); Bs.append(0 if b is None else _chk(b, "bias", torch.float32))
+        O.append(o.data_ptr()); lda.append(a.stride(0)); ldo.append(w.shape[0]); Ns.append(w.shape[0])
+    acts = list(acts) if acts is not None else [ACT_NONE] * G
+    vp, lp, ip = ctypes.c_void_p * G, ctypes.c_long * G, ctypes.c_int * G
+    native.call("ms2_gemm_smallm_grouped", G, vp(*A), lp(*lda), vp(*W), vp(*Bs), vp(*O), lp(*ldo), ip(*Ns), ip(*acts),
+                _DT[a_list[0].dtype], _DT[out_dtype], M, K, _st())
+    return outs
+
+
 # ------------------------------------------------------------------ attention
 def attention(q, k, v, heads, scale=None, impl=0):
     """q [B,Lq,heads*D], k/v [B,Lk,heads*D] (token-major, possibly column slices of a wider
@@ -248,6 +269,15 @@ def patch_embed(img, w, bias, pos):
     native.call("ms2_patch_embed", _chk(img, "img", torch.float32), _chk(w, "w", torch.float32),
                 _chk(bias, "bias", torch.float32), _opt(pos, "pos"), out.data_ptr(), B, Hin, Win, Cout, _st())
     return out
+
+
+def patch_im2col(img, ldk=152):
+    """fp32 NCHW image [B,3,H,W] -> bf16 [B, Ho*Wo, ldk] rows of 7x7/s4/p3 taps ((ky,kx,c) order, zero padded)."""
+    B, _, Hin, Win = img.shape
+    Ho, Wo = (Hin + 6 - 7) // 4 + 1, (Win + 6 - 7) // 4 + 1
+    cols = torch.empty((B, Ho * Wo, ldk), dtype=torch.bfloat16, device=img.device)
+    native.call("ms2_patch_im2col", _chk(img, "img", torch.float32), cols.data_ptr(), B, Hin, Win, ldk, _st())
+    return cols
 
 
 def axpby(x, a=1.0, z=None, b=1.0, c=0.0, out_dtype=torch.float32, out=None):

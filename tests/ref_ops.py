@@ -224,6 +224,29 @@ def mask_stability_counts(x, delta):
     return torch.stack([(f > delta).sum(-1), (f > -delta).sum(-1)], dim=1).to(torch.int32)
 
 
+def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None):
+    acts = acts or [ACT_NONE] * len(a_list)
+    return [gemm(a, w, b, out_dtype=out_dtype, act=act) for a, w, b, act in zip(a_list, w_list, bias_list, acts)]
+
+
+def attention_dv(q, k, v, scale=None):
+    o = F.scaled_dot_product_attention(q.float()[:, None], k.float()[:, None], v.float()[:, None], scale=scale)[:, 0]
+    return o.to(q.dtype)
+
+
+def patch_im2col(img, ldk=152):
+    B, _, H, W = img.shape
+    cols = F.unfold(img.float(), 7, stride=4, padding=3)                      # [B, 3*49, L] in (c, ky, kx) order
+    L = cols.shape[-1]
+    cols = cols.view(B, 3, 49, L).permute(0, 3, 2, 1).reshape(B, L, 147)       # -> (ky, kx, c)
+    return F.pad(cols, (0, ldk - 147)).to(torch.bfloat16)
+
+
+def cast_into(x, out):
+    out.copy_(x.reshape(out.shape))
+    return out
+
+
 _NAMES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("install",)]
 
 

@@ -186,6 +186,19 @@ def test_gemm_smallm(ops, M, N, K, dt):
     close(ops.gemm(a, w, bias, act=3, out_dtype=torch.bfloat16, impl=3), ref_ops.gemm(a, w, bias, act=3), 3e-2, "smallm bf16 out")
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_gemm_grouped(ops, dt):
+    """6 small-M GEMMs (different N / activation, row-strided A) in one launch == 6 separate statements."""
+    x = rnd(3, 9, 256, seed=1).to(dt)
+    a = [x.view(27, 256)[i::9] for i in range(6)]
+    Ns, acts = [256, 256, 32, 4, 1, 40], [2, 0, 2, 3, 0, 1]
+    ws = [(rnd(n, 256, seed=10 + i) / 16).to(dt) for i, n in enumerate(Ns)]
+    bs = [rnd(n, seed=20 + i) for i, n in enumerate(Ns)]
+    outs = ops.gemm_grouped(a, ws, bs, out_dtype=torch.float32, acts=acts)
+    for o, ai, w, b, act in zip(outs, a, ws, bs, acts):
+        close(o, ref_ops.gemm(ai.contiguous(), w, b, act=act), 1e-4 if dt == torch.float32 else 2e-4, "grouped")
+
+
 def test_gemm_smallm_strided_rows(ops):
     x = rnd(4, 9, 256, seed=1).to(torch.bfloat16)
     w, b = (rnd(32, 256, seed=2) / 16).to(torch.bfloat16), rnd(32, seed=3)
@@ -331,9 +344,22 @@ def test_im2col(ops, k, s, p, Cin, pre):
           ref_ops.im2col(x, k, s, p, torch.float32, pre, 20.0 if pre else 1.0, -10.0 if pre else 0.0), 1e-5, "im2col")
 
 
-def test_dwconv7x7(ops):
-    x, w, b = rnd(2, 64, 64, 256, seed=1), rnd(256, 49, seed=2) / 7, rnd(256, seed=3)
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 256), (1, 13, 21, 40), (3, 8, 8, 32), (1, 5, 70, 96)])
+def test_dwconv7x7(ops, B, H, W, C):
+    x, w, b = rnd(B, H, W, C, seed=1), rnd(C, 49, seed=2) / 7, rnd(C, seed=3)
     close(ops.dwconv7x7(x, w, b), ref_ops.dwconv7x7(x, w, b), 1e-4, "dwconv")
+    close(ops.dwconv7x7(x, w, None), ref_ops.dwconv7x7(x, w, None), 1e-4, "dwconv nobias")
+
+
+def test_patch_im2col_gemm_matches_conv(ops):
+    """bf16 patch-embed path: im2col rows x re-laid-out weight == conv 7x7/s4/p3 on the same bf16-rounded operands."""
+    img = rnd(2, 3, 96, 128, seed=1)
+    w, b = rnd(96, 3, 7, 7, seed=2) / 12, rnd(96, seed=3)
+    cols = ops.patch_im2col(img)
+    w152 = F.pad(w.permute(0, 2, 3, 1).reshape(96, -1), (0, 5)).to(torch.bfloat16).contiguous()
+    y = ops.gemm(cols, w152, b)
+    ref = F.conv2d(img.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b, stride=4, padding=3).permute(0, 2, 3, 1)
+    close(y.view(2, 24, 32, 96), ref, 3e-4, "patch im2col+gemm")
 
 
 def test_elementwise_family(ops):
