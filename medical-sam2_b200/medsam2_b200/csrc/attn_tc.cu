@@ -360,6 +360,306 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Memory cross-attention, TWO query tiles per CTA (D = 256 keys, DV = 64 un-projected values, 64-key tiles).
+// With one 128-query tile per CTA the 32 query tiles of a frame each stream the whole K bank: ~6 TB/s of L2->SM
+// traffic at 0.96 PFLOP/s, i.e. the L2, not the tensor pipe, sets the pace (profiles/r1_attn_dv_ncu.txt).  Here a
+// CTA owns 256 queries as two independent 128-row streams a/b that share every K/V tile (half the operand traffic
+// per FLOP) and ping-pong on the tensor pipe: while one stream's softmax runs, the other stream's S = Q K^T or
+// O += P V executes.
+//   warp 0      TMA producer : Q_a, Q_b (through one 64 KB staging buffer), K ring (4 x 32 KB), V ring (2 x 8 KB)
+//   warp 1      MMA issuer   : order  P V_a(j), S_a(j+1), P V_b(j), S_b(j+1)  (Q and P operands in tensor memory)
+//   warps 2..5  softmax of stream a (one warp per TMEM lane quarter, a thread owns a full 64-column S row)
+//   warps 6..9  softmax of stream b
+// TMEM: O_a [0,64) O_b [64,128) S_a [128,192) S_b [192,256) Q_a [256,384) Q_b [384,512); P overwrites S in place,
+// so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
+constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64;
+constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
+constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
+  constexpr int BKV = T2_BKV, KST = T2_KST, DV = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + T2_Q_BYTES;
+  uint8_t* sV = sK + KST * T2_K_BYTES;
+  uint64_t* bars = (uint64_t*)(sV + 2 * T2_V_BYTES);
+  uint64_t* q_full = bars;            // 2 (stream a, b)
+  uint64_t* q_tmem = bars + 2;        // 2: Q_x copied into tensor memory (4 warps each)
+  uint64_t* k_full = bars + 4;        // 4
+  uint64_t* k_empty = bars + 8;       // 4
+  uint64_t* v_full = bars + 12;       // 2
+  uint64_t* v_empty = bars + 14;      // 2
+  uint64_t* s_full = bars + 16;       // 2 (stream)
+  uint64_t* p_full = bars + 18;       // 2 (stream), 4 warps each
+  uint64_t* o_ready = bars + 20;      // 2 (stream)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * BQ;
+  const int bh = blockIdx.y, b = bh / p.Hh, h = bh - b * p.Hh;
+  const int split = blockIdx.z;
+  const int t_begin = split * p.tiles_per_split;
+  int n = p.ntiles - t_begin;
+  if (n > p.tiles_per_split) n = p.tiles_per_split;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmK);
+    tc::prefetch_tmap(&tmV);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&q_full[s], 1);
+      tc::mbar_init(&q_tmem[s], 4);
+      tc::mbar_init(&v_full[s], 1);
+      tc::mbar_init(&v_empty[s], 1);
+      tc::mbar_init(&s_full[s], 1);
+      tc::mbar_init(&p_full[s], 4);
+      tc::mbar_init(&o_ready[s], 1);
+    }
+    for (int s = 0; s < KST; ++s) {
+      tc::mbar_init(&k_full[s], 1);
+      tc::mbar_init(&k_empty[s], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(&q_full[0], T2_Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, &q_full[0], c * 64, q0, h, b);
+      auto load_k = [&](int j) {
+        const int ks = j % KST;
+        tc::mbar_wait(&k_empty[ks], ((uint32_t)(j / KST) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(&k_full[ks], T2_K_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tc::tma_load_4d(sK + ks * T2_K_BYTES + c * BKV * 128, &tmK, &k_full[ks], c * 64, (t_begin + j) * BKV, h, b);
+      };
+      for (int j = 0; j < KST - 1 && j < n; ++j) load_k(j);
+      // Q_b reuses the staging buffer once stream a's warps have moved Q_a into tensor memory
+      tc::mbar_wait(&q_tmem[0], 0);
+      tc::mbar_arrive_expect_tx(&q_full[1], T2_Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, &q_full[1], c * 64, q0 + BQ, h, b);
+      for (int j = 0; j < n; ++j) {
+        if (j + KST - 1 < n) load_k(j + KST - 1);
+        const int st = j & 1;
+        tc::mbar_wait(&v_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(&v_full[st], T2_V_BYTES);
+        tc::tma_load_4d(sV + st * T2_V_BYTES, &tmV, &v_full[st], 0, (t_begin + j) * BKV, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
+    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
+    auto issue_qk = [&](int x, int j) {          // stream x, tile j: S_x = Q_x K_j^T
+      const int ks = j % KST;
+      if (x == 0) tc::mbar_wait(&k_full[ks], (uint32_t)(j / KST) & 1u);
+      if (j >= 1) tc::mbar_wait(&o_ready[x], (uint32_t)(j - 1) & 1u);     // P V_x(j-1) has finished reading P_x
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t tS = tmem_base + 128 + x * 64, tQ = tmem_base + 256 + x * 128;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint64_t db = tc::desc_kmajor_sw128(aK + ks * T2_K_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
+          tc::umma_bf16_ts(tS, tQ + kk * 8, db, idesc_qk, kk ? 1u : 0u);
+        }
+        tc::umma_commit(&s_full[x]);
+        if (x == 1) tc::umma_commit(&k_empty[ks]);                         // both streams have consumed K_j
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int j) {
+      const int st = j & 1;
+      if (x == 0) tc::mbar_wait(&v_full[st], (uint32_t)(j >> 1) & 1u);
+      tc::mbar_wait(&p_full[x], (uint32_t)j & 1u);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t tO = tmem_base + x * 64, tP = tmem_base + 128 + x * 64;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * T2_V_BYTES + kk * 2048, BKV * 128);
+          tc::umma_bf16_ts(tO, tP + kk * 8, db, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+        tc::umma_commit(&o_ready[x]);
+        if (x == 1) tc::umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    };
+    tc::mbar_wait(&q_tmem[0], 0);
+    tc::tc_fence_after();
+    issue_qk(0, 0);
+    tc::mbar_wait(&q_tmem[1], 0);
+    tc::tc_fence_after();
+    issue_qk(1, 0);
+    for (int j = 0; j < n; ++j) {
+      issue_pv(0, j);
+      if (j + 1 < n) issue_qk(0, j + 1);
+      issue_pv(1, j);
+      if (j + 1 < n) issue_qk(1, j + 1);
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: warps 2..5 stream a, 6..9 stream b =====================
+    const int x = (warp - 2) >> 2;                  // stream
+    const int qtr = warp & 3;
+    const int row = qtr * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+    const uint32_t tO = tmem_base + lane_addr + x * 64, tS = tmem_base + lane_addr + 128 + x * 64;
+    const uint32_t tQ = tmem_base + lane_addr + 256 + x * 128;
+    float m_used = 0.f, l = 0.f;
+    const int last_valid = p.Lk - (p.ntiles - 1) * BKV;
+
+    {  // Q_x: swizzled staging tile -> tensor memory (row = lane, two bf16 per column)
+      tc::mbar_wait(&q_full[x], 0);
+      const uint32_t aQ = tc::smem_u32(sQ);
+#pragma unroll
+      for (int blk = 0; blk < 8; ++blk) {
+        const int ch = blk >> 1, g0 = (blk & 1) * 4;
+        uint32_t w[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 v = tc::lds128(aQ + ch * BQ * 128 + row * 128 + (((g0 + g) ^ (row & 7)) << 4));
+          w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+        }
+        tc::tmem_st16(tQ + blk * 16, w);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&q_tmem[x]);
+    }
+
+    for (int j = 0; j < n; ++j) {
+      tc::mbar_wait(&s_full[x], (uint32_t)j & 1u);
+      tc::tc_fence_after();
+      uint32_t r[2][32];
+      tc::tmem_ld32(tS, r[0]);
+      tc::tmem_ld32(tS + 32, r[1]);
+      tc::tmem_ld_wait();
+      if ((t_begin + j == p.ntiles - 1) && (last_valid < BKV)) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+      mx *= p.c;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = mx > m_used + p.tau;
+        if (__any_sync(0xffffffffu, need)) {
+          tc::mbar_wait(&o_ready[x], (uint32_t)(j - 1) & 1u);
+          tc::tc_fence_after();
+          float alpha = 1.f;
+          if (need) {
+            alpha = ex2(m_used - mx);
+            m_used = mx;
+            l *= alpha;
+          }
+#pragma unroll 1
+          for (int c = 0; c < DV / 32; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld32(tO + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tO + c * 32, o);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      uint32_t pk[32];
+      const float nm = -m_used;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
+          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
+          l += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
+        }
+      if (j > 0) tc::mbar_wait(&o_ready[x], (uint32_t)(j - 1) & 1u);      // observe every phase (see attn_tc_kernel)
+      tc::tmem_st16(tS, &pk[0]);
+      tc::tmem_st16(tS + 16, &pk[16]);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[x]);
+    }
+
+    tc::mbar_wait(&o_ready[x], (uint32_t)(n - 1) & 1u);
+    tc::tc_fence_after();
+    const int qi = q0 + x * BQ + row;
+    if (p.nsplit == 1) {
+      const float inv = 1.f / l;
+      bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
+#pragma unroll 1
+      for (int c = 0; c < DV / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(tO + c * 32, o);
+        tc::tmem_ld_wait();
+        if (qi < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv,
+                                                        __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
+              vv[i] = *(uint32_t*)&hh;
+            }
+            *(uint4*)(orow + c * 32 + g * 8) = v;
+          }
+        }
+      }
+    } else {
+      const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
+      float* orow = p.opart + rix * DV;
+#pragma unroll 1
+      for (int c = 0; c < DV / 32; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(tO + c * 32, o);
+        tc::tmem_ld_wait();
+        if (qi < p.Lq) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *(float4*)(orow + c * 32 + g * 4) =
+                make_float4(__uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]), __uint_as_float(o[g * 4 + 2]),
+                            __uint_as_float(o[g * 4 + 3]));
+        }
+      }
+      if (qi < p.Lq) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // merge the split-KV partials: O = sum_s 2^(m_s - m*) O_s / sum_s 2^(m_s - m*) l_s
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -453,15 +753,32 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   p.opart = (float*)ws;
   p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
 
-  auto kern = attn_tc_kernel<D, DV, BKV, KST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "attn_tc attr");
-    attr_set = true;
+  static const bool two_tiles_ok = []() { const char* e = getenv("MS2_ATTN_TWO_TILES"); return !e || atoi(e) != 0; }();
+  if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
+    // two query tiles per CTA share every K/V tile (half the L2->SM operand traffic per FLOP)
+    const int qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);
+    p.nsplit = ws ? pick_nsplit(qpairs * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
+    p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
+    p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
+    static bool attr2 = false;
+    if (!attr2) {
+      MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr");
+      attr2 = true;
+    }
+    dim3 grid2(qpairs, B * Hh, p.nsplit);
+    attn_tc2_kernel<<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p);
+    MS2_CHECK_LAUNCH("attn_tc2_kernel");
+  } else {
+    auto kern = attn_tc_kernel<D, DV, BKV, KST>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "attn_tc attr");
+      attr_set = true;
+    }
+    dim3 grid(qtiles, B * Hh, p.nsplit);
+    kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
+    MS2_CHECK_LAUNCH("attn_tc_kernel");
   }
-  dim3 grid(qtiles, B * Hh, p.nsplit);
-  kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
-  MS2_CHECK_LAUNCH("attn_tc_kernel");
   if (p.nsplit > 1) {
     constexpr int TPR = DV / 8, RPB = 128 / TPR;
     attn_combine_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
