@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--kernel-table", default="", help="write a CUPTI per-kernel time table of one extra step here")
     ap.add_argument("--host-profile", default="", help="write a cProfile table of one extra step (host side) here")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
+    ap.add_argument("--shard-encode", action="store_true",
+                    help="config 5: ONE volume; slice encoding sharded over the ranks + NCCL all-gather of the pyramid, "
+                         "rank 0 propagates (strong scaling; default is one volume per rank, no collectives)")
     ap.add_argument("--encode-batch", type=int, default=8, help="slices per image-encoder pass on a cache miss")
     return ap.parse_args()
 
@@ -222,7 +225,9 @@ def main_ours(args):
                                                       f"++model.feature_encode_batch={args.encode_batch}",
                                                       f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}"])
     model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
-    vol, boxes = btcv_volume(T, S, 1234 + rank, 1)          # every rank tracks its own volume (config 4 sharding)
+    shard_encode = args.shard_encode and world > 1
+    # default: every rank tracks its own volume (config 4 sharding); --shard-encode: all ranks hold the same volume
+    vol, boxes = btcv_volume(T, S, 1234 + (0 if shard_encode else rank), 1)
     vol_host = vol.pin_memory()
     vol_dev = vol.cuda()
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -248,18 +253,35 @@ def main_ours(args):
             ms = float(t.item())
         return ms
 
+    def run_sharded(v):
+        from medsam2_b200.parallel import encode_volume_sharded
+        st = model.val_init_state(imgs_tensor=v, video_height=S, video_width=S)
+        encode_volume_sharded(model, st)                     # NCCL all-gather of the feature pyramid
+        masks = [None] * T
+        if rank == 0:                                        # propagation is sequential in t: one rank runs it
+            for f in prompt_frames(T, args.prompt_every):
+                model.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]),
+                                         clear_old_points=False)
+            for f, _, m in model.propagate_in_video(st, start_frame_idx=0):
+                masks[f] = m
+        return masks
+
     def step_resident():
         l2_flush.zero_()
-        run_volume(model, vol_dev, boxes, S, args.prompt_every)
+        if shard_encode:
+            run_sharded(vol_dev)
+        else:
+            run_volume(model, vol_dev, boxes, S, args.prompt_every)
 
     out_host = torch.empty((T, S, S), dtype=torch.uint8).pin_memory()
 
     def step_e2e():
         l2_flush.zero_()
         v = vol_host.to("cuda", non_blocking=True)
-        masks = run_volume(model, v, boxes, S, args.prompt_every)
-        res = torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8)
-        out_host.copy_(res, non_blocking=True)
+        masks = run_sharded(v) if shard_encode else run_volume(model, v, boxes, S, args.prompt_every)
+        if masks[0] is not None:
+            res = torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8)
+            out_host.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(args.warmup):
@@ -343,14 +365,15 @@ def main_ours(args):
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {args.cpu_sample_slices} slices of the same volume (bbox every {args.prompt_every}), "
                          f"oracle port, fp32, {secs:.1f} s"}
-    total_slices = T * args.steps * world
+    total_slices = T * args.steps * (1 if shard_encode else world)
     line = {"metric": METRIC, "value": total_slices / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if shard_encode else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"BASELINE configs[2]: {args.config} SAM2VideoPredictor.propagate_in_video, one "
                                    f"{T}-slice {S}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, "
                                    f"num_maskmem=7, fill_hole_area=8",
-                       "sharding": "by volume, no collectives" if world > 1 else "single GPU",
+                       "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid, rank 0 propagates"
+                                    if shard_encode else "by volume, no collectives" if world > 1 else "single GPU"),
                        "encode_batch": args.encode_batch, "cuda_graphs": not args.no_graphs,
                        "l2": "256 MiB flush buffer written before every step; per-step working set >> L2"},
             "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host.numel() * 4,

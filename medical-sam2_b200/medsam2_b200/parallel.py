@@ -32,8 +32,8 @@ def slice_block(num_frames, rank, world):
 @torch.no_grad()
 def encode_volume_sharded(predictor, inference_state, group=None):
     """Encode all slices of the volume held by `inference_state`, each rank a contiguous block, then all-gather the
-    pyramid so that every rank's `cached_features` holds every slice.  Results are identical to encoding locally
-    (the per-slice encoder output does not depend on how slices are batched).  Returns the number of slices this
+    pyramid so that every rank's `cached_features` holds every slice.  Results equal a local encode with the same slice batches bit for bit
+    (a different batching may change the split-KV factor of the global-attention blocks, i.e. the summation order).  Returns the number of slices this
     rank encoded."""
     st = inference_state
     on = dist.is_available() and dist.is_initialized()

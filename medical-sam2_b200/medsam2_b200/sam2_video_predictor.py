@@ -31,8 +31,8 @@ class SAM2VideoPredictor(SAM2Base):
         self.clear_non_cond_mem_for_multi_obj = clear_non_cond_mem_for_multi_obj
         self.feature_cache_size = feature_cache_size
         # slices encoded per image-encoder pass on a cache miss (the miss frame + the next ones in tracking
-        # order); per-slice results are bit-identical to one-at-a-time encoding, the GEMM/attention launches are
-        # just `feature_encode_batch` times larger.  Never exceeds the cache capacity.
+        # order); per-slice results equal one-at-a-time encoding up to the summation order of the split-KV global-attention
+        # blocks; the GEMM/attention launches are just `feature_encode_batch` times larger.  Never exceeds the cache capacity.
         self.feature_encode_batch = max(1, int(feature_encode_batch))
         if use_cuda_graphs is not None:
             self.use_cuda_graphs = bool(use_cuda_graphs)
