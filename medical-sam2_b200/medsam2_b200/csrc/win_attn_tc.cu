@@ -5,13 +5,15 @@
 // or re-ordered copy of the tokens ever exists in HBM.
 //
 // One CTA = one group of G windows of one head packed into a single M=128 tile (block-diagonal mask):
-//   all warps : gather Q (<=128 rows, optional 2x2 max-pool), K, V (NK <= 256 key slots) -> SW128 smem
-//   thread 0  : S = Q K^T  (tcgen05.mma M=128, N=NK, K=96)                       -> TMEM
-//   warps 0-3 : row softmax restricted to the row's own window -> P (bf16, swizzled smem, aliases Q/K)
-//   thread 0  : O = P V    (M=128, N=96, K=NK; V is MN-major)                    -> TMEM
-//   warps 0-3 : O / l -> bf16 -> scatter to [B,Ho,Wo,heads*D]
-// Windows of 196 tokens (stage 3) use two query tiles per window.  Small-window configurations need
-// <= 113 KB of shared memory and 256 TMEM columns, so two CTAs share an SM and overlap each other's phases.
+//   all warps : K, V (NK <= 256 key slots) gathered ONCE -> SW128 smem; per query tile: Q (<=128 rows, optional
+//               2x2 max-pool) -> SW128 smem.  Row -> token offsets come from a small table built once per row.
+//   1 thread  : S = Q K^T  (tcgen05.mma M=128, N=NK, K=96)                       -> TMEM
+//   warps 0-7 : row softmax restricted to the row's own window; two warps per TMEM lane quarter split the
+//               column chunks their rows can touch; P (bf16 pairs) overwrites S in tensor memory
+//   1 thread  : O = P V    (M=128, N=96, K=NK; P from tensor memory, V MN-major) -> TMEM
+//   warps 0-7 : O / l -> bf16 -> scatter to [B,Ho,Wo,heads*D]
+// Windows of 196 tokens (stage 3) run their two query tiles in the same CTA, sharing the gathered K/V.  Small-window
+// configurations need <= 113 KB of shared memory and 256 TMEM columns, so two CTAs share an SM and overlap phases.
 #include "tc_common.cuh"
 
 namespace {
@@ -47,7 +49,10 @@ __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
   return r;
 }
 
-__global__ void __launch_bounds__(NT)
+// MAXC = column chunks (of 32) a warp half may own: 2 when NK <= 128 (<= 128 registers/thread, two CTAs per SM),
+// 4 for the 196-key windows.
+template <int MAXC>
+__global__ void __launch_bounds__(NT, MAXC == 2 ? 2 : 1)
 win_attn_tc_kernel(const WinP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -55,20 +60,22 @@ win_attn_tc_kernel(const WinP p) {
   uint8_t* sQ = smem;                               // 2 x [128][128 B]
   uint8_t* sK = sQ + WDCH * 128 * 128;              // 2 x [NK][128 B]
   uint8_t* sV = sK + kv_bytes;
-  uint8_t* sP = smem;                               // aliases Q (+K): ceil(NK/64) x [128][128 B]
   uint8_t* tail = sV + kv_bytes;
   uint4* sBias = (uint4*)tail;                      // [3][12] 16-byte chunks of the bf16 bias of this head
-  uint64_t* bar_s = (uint64_t*)(tail + 3 * WCH16 * 16);
+  int* rowtab = (int*)(tail + 3 * WCH16 * 16);      // [128*4 + 256] token element offsets (-1 pad -> bias, -2 none)
+  float* mxs = (float*)(rowtab + 128 * 4 + 256);    // [2 halves][128 rows] row-max / row-sum exchange
+  uint64_t* bar_s = (uint64_t*)(mxs + 256);
   uint64_t* bar_o = bar_s + 1;
   uint32_t* tmem_ptr = (uint32_t*)(bar_o + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = blockIdx.x / p.q_tiles, qt = blockIdx.x - grp * p.q_tiles;
+  const int grp = blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int nwin = p.nwx * p.nwy;
   const int w0 = grp * p.G;
   const long C3 = 3L * p.dim_out;
-  const bf16* base = p.qkv + (long)b * p.H * p.W * C3;
+  const bf16* base = p.qkv + (long)b * p.H * p.W * C3 + h * WD;
+  const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
 
   if (tid == 0) {
     tc::mbar_init(bar_s, 1);
@@ -85,150 +92,196 @@ win_attn_tc_kernel(const WinP p) {
     for (int i = 0; i < 4; ++i) pv[i] = __floats2bfloat162_rn(bs[2 * i], bs[2 * i + 1]);
     sBias[tid] = v;
   }
+  // K/V row table: key slot -> element offset of its token (the divisions happen once per row, not per chunk)
+  for (int r = tid; r < p.NK; r += NT) {
+    const int wl = r / p.lk_w, j = r - wl * p.lk_w, w = w0 + wl;
+    int off = -2;
+    if (wl < p.G && w < nwin) {
+      const int wy = w / p.nwx, wx = w - wy * p.nwx;
+      const int y = wy * p.ws + j / p.ws, x = wx * p.ws + j % p.ws;
+      off = (y < p.H && x < p.W) ? (int)(((long)y * p.W + x) * C3) : -1;
+    }
+    rowtab[512 + r] = off;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)p.o_col;
 
-  // value of q/k/v (which) chunk ch at padded-grid position (y,x): pad -> bias
-  auto tok = [&](int which, int y, int x, int ch) -> uint4 {
-    if (y < p.H && x < p.W)
-      return __ldg((const uint4*)(base + ((long)y * p.W + x) * C3 + which * p.dim_out + h * WD + ch * 8));
-    return sBias[which * WCH16 + ch];
-  };
-  auto swz = [](uint8_t* chunk0, int rows, int row, int ch) -> uint4* {
-    return (uint4*)(chunk0 + (ch >> 3) * rows * 128 + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
-  };
-
-  // ---- gather Q
-  for (int idx = tid; idx < 128 * WCH16; idx += NT) {
-    const int r = idx / WCH16, ch = idx - r * WCH16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    int wl, i;
-    if (p.q_tiles > 1) { wl = 0; i = qt * 128 + r; }
-    else { wl = r / p.lq_w; i = r - wl * p.lq_w; }
-    const int w = w0 + wl;
-    if (wl < p.G && w < nwin && i < p.lq_w) {
-      const int wy = w / p.nwx, wx = w - wy * p.nwx;
-      if (!p.qpool) {
-        v = tok(0, wy * p.ws + i / p.ws, wx * p.ws + i % p.ws, ch);
-      } else {
-        const int hw = p.ws >> 1;
-        const int y = wy * p.ws + 2 * (i / hw), x = wx * p.ws + 2 * (i % hw);
-        v = max_bf16x8(max_bf16x8(tok(0, y, x, ch), tok(0, y, x + 1, ch)),
-                       max_bf16x8(tok(0, y + 1, x, ch), tok(0, y + 1, x + 1, ch)));
-      }
-    }
-    *swz(sQ, 128, r, ch) = v;
-  }
-  // ---- gather K, V
+  // ---- gather K, V once per CTA (shared by all query tiles of the window group)
   for (int idx = tid; idx < p.NK * WCH16; idx += NT) {
     const int r = idx / WCH16, ch = idx - r * WCH16;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    const int wl = r / p.lk_w, j = r - wl * p.lk_w;
-    const int w = w0 + wl;
-    if (wl < p.G && w < nwin) {
-      const int wy = w / p.nwx, wx = w - wy * p.nwx;
-      const int y = wy * p.ws + j / p.ws, x = wx * p.ws + j % p.ws;
-      kv = tok(1, y, x, ch);
-      vv = tok(2, y, x, ch);
+    const int off = rowtab[512 + r];
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+    if (off >= 0) {
+      kv = __ldg((const uint4*)(base + off + p.dim_out + ch * 8));
+      vv = __ldg((const uint4*)(base + off + 2 * p.dim_out + ch * 8));
+    } else if (off == -1) {
+      kv = sBias[WCH16 + ch];
+      vv = sBias[2 * WCH16 + ch];
     }
-    *swz(sK, p.NK, r, ch) = kv;
-    *swz(sV, p.NK, r, ch) = vv;
+    const uint32_t so = (ch >> 3) * p.NK * 128 + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+    tc::sts128(aK + so, kv);
+    tc::sts128(aV + so, vv);
   }
-  tc::fence_proxy_async();
-  __syncthreads();
 
-  const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)p.o_col;
-  if (warp == 0 && tc::elect_one()) {
-    tc::tc_fence_after();
-    const uint32_t idesc = tc::make_idesc_bf16(128, p.NK, 0, 0);
-    const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK);
+  const int qtr = warp & 3, half = warp >> 2;       // TMEM lane quarter / column half handled by this warp
+  const int r = qtr * 32 + lane;                    // query row inside the tile
+  const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+  // column chunks this warp's 32 rows can touch (their windows' key slots), split between the two halves
+  int clo, chi;
+  if (p.q_tiles > 1) { clo = 0; chi = (p.NK + 31) >> 5; }
+  else {
+    const int wlo = (qtr * 32) / p.lq_w;
+    int whi = (qtr * 32 + 31) / p.lq_w;
+    if (whi > p.G - 1) whi = p.G - 1;
+    clo = (wlo * p.lk_w) >> 5;
+    chi = wlo > whi ? clo : (min((whi + 1) * p.lk_w, p.NK) + 31) >> 5;
+  }
+  const int cmid = clo + ((chi - clo + 1) >> 1);
+  const int cb = half ? cmid : clo, ce = half ? chi : cmid;          // my chunks [cb, ce), at most 4
+  const int nchunks = (p.NK + 31) >> 5;
+
+  for (int qt = 0; qt < p.q_tiles; ++qt) {
+    const uint32_t ph = (uint32_t)qt & 1u;
+    // ---- Q row table (4 source positions with the 2x2 max-pool, 1 without) and gather
+    if (tid < 128) {
+      int wl, i;
+      if (p.q_tiles > 1) { wl = 0; i = qt * 128 + tid; }
+      else { wl = tid / p.lq_w; i = tid - wl * p.lq_w; }
+      const int w = w0 + wl;
+      int o4[4] = {-2, -2, -2, -2};
+      if (wl < p.G && w < nwin && i < p.lq_w) {
+        const int wy = w / p.nwx, wx = w - wy * p.nwx;
+        if (!p.qpool) {
+          const int y = wy * p.ws + i / p.ws, x = wx * p.ws + i % p.ws;
+          o4[0] = (y < p.H && x < p.W) ? (int)(((long)y * p.W + x) * C3) : -1;
+        } else {
+          const int hw = p.ws >> 1;
+          const int y = wy * p.ws + 2 * (i / hw), x = wx * p.ws + 2 * (i % hw);
 #pragma unroll
-    for (int kk = 0; kk < WD / 16; ++kk)
-      tc::umma_bf16(tS, tc::desc_kmajor_sw128(aQ + (kk >> 2) * 128 * 128 + (kk & 3) * 32),
-                    tc::desc_kmajor_sw128(aK + (kk >> 2) * p.NK * 128 + (kk & 3) * 32), idesc, kk ? 1u : 0u);
-    tc::umma_commit(bar_s);
-  }
+          for (int q = 0; q < 4; ++q) {
+            const int yy = y + (q >> 1), xx = x + (q & 1);
+            o4[q] = (yy < p.H && xx < p.W) ? (int)(((long)yy * p.W + xx) * C3) : -1;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rowtab[tid * 4 + q] = o4[q];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 128 * WCH16; idx += NT) {
+      const int rr = idx / WCH16, ch = idx - rr * WCH16;
+      auto ldq = [&](int off) -> uint4 {
+        return off >= 0 ? __ldg((const uint4*)(base + off + ch * 8)) : sBias[ch];
+      };
+      const int o0 = rowtab[rr * 4];
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (o0 != -2) {
+        v = ldq(o0);
+        if (p.qpool)
+          v = max_bf16x8(max_bf16x8(v, ldq(rowtab[rr * 4 + 1])), max_bf16x8(ldq(rowtab[rr * 4 + 2]), ldq(rowtab[rr * 4 + 3])));
+      }
+      tc::sts128(aQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4), v);
+    }
+    tc::fence_proxy_async();
+    __syncthreads();
 
-  float l = 0.f;
-  int out_y = -1, out_x = -1;
-  if (warp < 4) {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    if (warp == 0 && tc::elect_one()) {
+      tc::tc_fence_after();
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.NK, 0, 0);
+#pragma unroll
+      for (int kk = 0; kk < WD / 16; ++kk)
+        tc::umma_bf16(tS, tc::desc_kmajor_sw128(aQ + (kk >> 2) * 128 * 128 + (kk & 3) * 32),
+                      tc::desc_kmajor_sw128(aK + (kk >> 2) * p.NK * 128 + (kk & 3) * 32), idesc, kk ? 1u : 0u);
+      tc::umma_commit(bar_s);
+    }
+
+    // ---- softmax: all 8 warps; a thread owns row r and the column chunks [cb, ce) of it
     int wl, i;
     if (p.q_tiles > 1) { wl = 0; i = qt * 128 + r; }
     else { wl = r / p.lq_w; i = r - wl * p.lq_w; }
     const int w = w0 + wl;
     const bool valid = wl < p.G && w < nwin && i < p.lq_w;
     const int k0 = wl * p.lk_w, k1 = valid ? k0 + p.lk_w : k0;     // this row's key slots
+    int out_y = -1, out_x = -1;
     if (valid) {
       const int wy = w / p.nwx, wx = w - wy * p.nwx;
       const int wo = p.qpool ? (p.ws >> 1) : p.ws;
       const int y = wy * wo + i / wo, x = wx * wo + i % wo;
       if (y < p.Ho && x < p.Wo) { out_y = y; out_x = x; }
     }
-    tc::mbar_wait(bar_s, 0);
+    tc::mbar_wait(bar_s, ph);
     tc::tc_fence_after();
-    // pass 1: row max over own window
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < p.NK; c0 += 32) {
-      uint32_t s[32];
-      tc::tmem_ld32(tS + lane_addr + c0, s);
+    for (int c = cb; c < ce; ++c) {
+      uint32_t sv[32];
+      tc::tmem_ld32(tS + lane_addr + c * 32, sv);
       tc::tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int col = c0 + e;
-        if (col >= k0 && col < k1) mx = fmaxf(mx, __uint_as_float(s[e]) * p.c);
+        const int col = c * 32 + e;
+        if (col >= k0 && col < k1) mx = fmaxf(mx, __uint_as_float(sv[e]));
       }
     }
-    // pass 2: p = 2^(s*c - mx) on own window, 0 elsewhere -> swizzled P (K-major, chunks of 64 keys)
-    for (int c0 = 0; c0 < p.NK; c0 += 32) {
-      uint32_t s[32];
-      tc::tmem_ld32(tS + lane_addr + c0, s);
-      tc::tmem_ld_wait();
-      uint32_t pk[16];
+    mx *= p.c;
+    mxs[half * 128 + r] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, mxs[(half ^ 1) * 128 + r]);
+    // p = 2^(s*c - mx) on the row's own window, 0 elsewhere, kept in registers until BOTH halves have read S
+    uint32_t pk[MAXC][16];
+    float l = 0.f;
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const int col = c0 + e;
-        float p0 = 0.f, p1 = 0.f;
-        if (col >= k0 && col < k1) p0 = ex2w(__uint_as_float(s[e]) * p.c - mx);
-        if (col + 1 >= k0 && col + 1 < k1) p1 = ex2w(__uint_as_float(s[e + 1]) * p.c - mx);
-        l += p0 + p1;
-        __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-        pk[e >> 1] = *(uint32_t*)&hh;
-      }
+    for (int cc = 0; cc < MAXC; ++cc) {
+      const int c = cb + cc;
+      if (c < ce) {
+        uint32_t sv[32];
+        tc::tmem_ld32(tS + lane_addr + c * 32, sv);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = c0 + g * 8;
-        if (col < p.NK) {
-          const int kc = col >> 6, gg = (col & 63) >> 3;
-          *(uint4*)(sP + kc * 128 * 128 + r * 128 + ((gg ^ (r & 7)) << 4)) =
-              make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        for (int e = 0; e < 32; e += 2) {
+          const int col = c * 32 + e;
+          float p0 = 0.f, p1 = 0.f;
+          if (col >= k0 && col < k1) p0 = ex2w(fmaf(__uint_as_float(sv[e]), p.c, -mx));
+          if (col + 1 >= k0 && col + 1 < k1) p1 = ex2w(fmaf(__uint_as_float(sv[e + 1]), p.c, -mx));
+          l += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[cc][e >> 1] = *(uint32_t*)&hh;
         }
       }
     }
-    tc::fence_proxy_async();
+    __syncthreads();                                 // every S column has been read: P may overwrite S in place
+    mxs[half * 128 + r] = l;
+    // P (bf16 pairs) over the first NK/2 columns of S; chunks outside this warp pair's range are zero for these rows
+    {
+      uint32_t zero[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) zero[e] = 0;
+      for (int c = half; c < nchunks; c += 2)
+        if (c < clo || c >= chi) tc::tmem_st16(tS + lane_addr + c * 16, zero);
+#pragma unroll
+      for (int cc = 0; cc < MAXC; ++cc)
+        if (cb + cc < ce) tc::tmem_st16(tS + lane_addr + (cb + cc) * 16, pk[cc]);
+    }
+    tc::tmem_st_wait();
     tc::tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 0 && tc::elect_one()) {
-    tc::tc_fence_after();
-    const uint32_t idesc = tc::make_idesc_bf16(128, WD, 0, 1);
-    const uint32_t aP = tc::smem_u32(sP), aV = tc::smem_u32(sV);
-    for (int kk = 0; kk < p.NK / 16; ++kk)
-      tc::umma_bf16(tO, tc::desc_kmajor_sw128(aP + (kk >> 2) * 128 * 128 + (kk & 3) * 32),
-                    tc::desc_mnmajor_sw128(aV + kk * 2048, (uint32_t)p.NK * 128), idesc, kk ? 1u : 0u);
-    tc::umma_commit(bar_o);
-  }
-  if (warp < 4) {
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    tc::mbar_wait(bar_o, 0);
+    __syncthreads();
+    l += mxs[(half ^ 1) * 128 + r];
+    if (warp == 0 && tc::elect_one()) {
+      tc::tc_fence_after();
+      const uint32_t idesc = tc::make_idesc_bf16(128, WD, 0, 1);
+      for (int kk = 0; kk < p.NK / 16; ++kk)
+        tc::umma_bf16_ts(tO, tS + kk * 8, tc::desc_mnmajor_sw128(aV + kk * 2048, (uint32_t)p.NK * 128), idesc, kk ? 1u : 0u);
+      tc::umma_commit(bar_o);
+    }
+    // ---- epilogue: O / l -> bf16 -> scatter; the two halves take alternate 32-column chunks
+    tc::mbar_wait(bar_o, ph);
     tc::tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
     bf16* orow = p.out + (((long)b * p.Ho + (out_y < 0 ? 0 : out_y)) * p.Wo + (out_x < 0 ? 0 : out_x)) * p.dim_out + h * WD;
 #pragma unroll 1
-    for (int c = 0; c < WD / 32; ++c) {
+    for (int c = half; c < WD / 32; c += 2) {
       uint32_t o[32];
       tc::tmem_ld32(tO + lane_addr + c * 32, o);
       tc::tmem_ld_wait();
@@ -248,12 +301,10 @@ win_attn_tc_kernel(const WinP p) {
       }
     }
     tc::tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
+    __syncthreads();                                 // S / O / Q smem are reused by the next query tile
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 }  // namespace
@@ -289,17 +340,28 @@ int ms2_window_attention_tc_launch(const void* qkv, const float* qkv_bias, void*
   p.groups = (nwin + p.G - 1) / p.G;
   p.tmem_cols = p.NK <= 128 ? 256 : 512;
   p.o_col = p.NK <= 128 ? 128 : 256;
-  const int pch = (p.NK + 63) / 64;
-  MS2_CHECK_ARG(pch * 128 * 128 <= WDCH * 128 * 128 + WDCH * p.NK * 128, "window_attention_tc: P does not fit");
-  const size_t smem = (size_t)WDCH * 128 * 128 + 2 * (size_t)WDCH * p.NK * 128 + 3 * WCH16 * 16 + 64 + 1024;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    MS2_CUDA(cudaFuncSetAttribute(win_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-             "win_attn_tc attr");
-    attr_smem = smem;
+  MS2_CHECK_ARG(((long)H * W * 3 * p.dim_out) < (1L << 31), "window_attention_tc: token offsets must fit 31 bits");
+  MS2_CHECK_ARG((p.NK + 31) / 32 <= 8, "window_attention_tc: at most 256 key slots per tile");
+  const size_t smem = (size_t)WDCH * 128 * 128 + 2 * (size_t)WDCH * p.NK * 128 + 3 * WCH16 * 16 + (128 * 4 + 256) * 4 +
+                      256 * 4 + 64 + 1024;
+  dim3 grid(p.groups, heads, B);
+  if (p.NK <= 128) {
+    static size_t attr2 = 0;
+    if (smem > attr2) {
+      MS2_CUDA(cudaFuncSetAttribute(win_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "win_attn_tc attr");
+      attr2 = smem;
+    }
+    win_attn_tc_kernel<2><<<grid, NT, smem, st>>>(p);
+  } else {
+    static size_t attr4 = 0;
+    if (smem > attr4) {
+      MS2_CUDA(cudaFuncSetAttribute(win_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "win_attn_tc attr");
+      attr4 = smem;
+    }
+    win_attn_tc_kernel<4><<<grid, NT, smem, st>>>(p);
   }
-  dim3 grid(p.groups * p.q_tiles, heads, B);
-  win_attn_tc_kernel<<<grid, NT, smem, st>>>(p);
   MS2_CHECK_LAUNCH("win_attn_tc_kernel");
   return MS2_OK;
 }
