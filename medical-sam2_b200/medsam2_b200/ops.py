@@ -421,8 +421,8 @@ def fourier_pe(coords01, gauss):
     return out
 
 
-def normalize_image(x):
-    """fp32 [B,3,H,W] in 0..255 or uint8 [B,H,W,3] -> fp32 NCHW (x/255-mean)/std."""
+def normalize_image(x, out=None):
+    """fp32 [B,3,H,W] in 0..255 or uint8 [B,H,W,3] -> fp32 NCHW (x/255-mean)/std (optionally into `out`)."""
     if x.dtype == torch.uint8:
         B, H, W, _ = x.shape
         layout = 1
@@ -430,8 +430,11 @@ def normalize_image(x):
         B, _, H, W = x.shape
         layout = 0
         _chk(x, "x", torch.float32)
-    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
-    native.call("ms2_normalize_image", _chk(x, "x"), layout, out.data_ptr(), B, H, W, _st())
+    if out is None:
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (B, 3, H, W):
+        raise native.NativeError("normalize_image: bad `out` shape")
+    native.call("ms2_normalize_image", _chk(x, "x"), layout, _chk(out, "out", torch.float32), B, H, W, _st())
     return out
 
 

@@ -47,11 +47,78 @@ def mask_to_box(masks):
     return torch.stack((min_xs, min_ys, max_xs, max_ys), dim=-1)
 
 
+_UPLOAD_STREAMS = {}
+
+
+def _upload_stream(device):
+    """one long-lived copy stream per device (a fresh stream per volume would give the caching allocator a fresh,
+    empty pool every time: cudaMalloc in the timed path)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    s = _UPLOAD_STREAMS.get(key)
+    if s is None:
+        s = _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=key)
+    return s
+
+
+class StreamedFrames:
+    """Frames of a HOST tensor uploaded and normalised chunk by chunk on a side stream (the counterpart of the
+    reference's AsyncVideoFrameLoader, utils/misc.py:92-160, for frames that are already decoded): indexing a frame
+    makes the consumer's stream wait for the CUDA event of its chunk, so the host->device copy of later slices
+    overlaps the encoding / tracking of earlier ones instead of preceding it."""
+
+    def __init__(self, host, device, chunk=8):
+        assert not host.is_cuda and host.dim() == 4
+        self.T = host.shape[0]
+        self.chunk = max(1, int(chunk))
+        layout_u8 = host.dtype == torch.uint8
+        H, W = (host.shape[1], host.shape[2]) if layout_u8 else (host.shape[2], host.shape[3])
+        self.out = torch.empty((self.T, 3, H, W), dtype=torch.float32, device=device)
+        self.stream = _upload_stream(device)
+        self.out.record_stream(self.stream)
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+        self.events, self.waited = [], []
+        src = host if (layout_u8 or host.dtype == torch.float32) else host.float()
+        with torch.cuda.stream(self.stream):
+            for c0 in range(0, self.T, self.chunk):
+                c1 = min(c0 + self.chunk, self.T)
+                raw = src[c0:c1].to(device, non_blocking=True)
+                ops.normalize_image(raw.contiguous(), out=self.out[c0:c1])
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.events.append(ev)
+                self.waited.append(False)
+
+    def _wait(self, c):
+        if not self.waited[c]:
+            torch.cuda.current_stream(self.out.device).wait_event(self.events[c])
+            self.waited[c] = True
+
+    def __len__(self):
+        return self.T
+
+    @property
+    def shape(self):
+        return self.out.shape
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            lo, hi, _ = idx.indices(self.T)
+            for c in range(lo // self.chunk, (max(hi, lo + 1) - 1) // self.chunk + 1):
+                self._wait(c)
+        else:
+            i = int(idx) % self.T
+            self._wait(i // self.chunk)
+        return self.out[idx]
+
+
 def load_video_frames_from_data(imgs_tensor, offload_video_to_cpu=False, img_mean=(0.485, 0.456, 0.406),
                                 img_std=(0.229, 0.224, 0.225), async_loading_frames=False, device="cuda"):
-    """utils/misc.py:215-244: [T,3,S,S] in 0..255 -> normalised fp32 frames, one fused kernel on device."""
+    """utils/misc.py:215-244: [T,3,S,S] in 0..255 -> normalised fp32 frames, one fused kernel on device.
+    `async_loading_frames=True` with a host tensor streams the upload (StreamedFrames)."""
     assert tuple(img_mean) == (0.485, 0.456, 0.406) and tuple(img_std) == (0.229, 0.224, 0.225)
     x = imgs_tensor
+    if async_loading_frames and not x.is_cuda and not offload_video_to_cpu and torch.cuda.is_available():
+        return StreamedFrames(x, device)
     if not x.is_cuda:
         x = x.to(device, non_blocking=True)
     images = ops.normalize_image(x.float().contiguous() if x.dtype != torch.uint8 else x.contiguous())

@@ -157,6 +157,23 @@ def test_cuda_graph_replay_is_bit_identical():
             assert torch.equal(o["obj_ptr"], g["obj_ptr"]) and torch.equal(o["maskmem_features"], g["maskmem_features"]), f
 
 
+def test_streamed_host_upload_matches_resident_volume():
+    """`async_loading_frames=True` on a pinned host tensor (chunked H2D + normalisation on a side stream, consumers
+    wait per chunk) must give exactly the masks of a device-resident volume."""
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    m.feature_cache_size, m.feature_encode_batch = 16, 4
+    vol, boxes = btcv_volume(9, 512, 21, 1)
+    outs = []
+    for v, flag in ((vol.cuda(), False), (vol.pin_memory(), True)):
+        st = m.val_init_state(imgs_tensor=v, video_height=512, video_width=512, async_loading_frames=flag)
+        for f in (0, 4):
+            m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+        outs.append({f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)})
+    assert type(st["images"]).__name__ == "StreamedFrames"
+    for f in range(9):
+        assert torch.equal(outs[0][f], outs[1][f]), f
+
+
 def test_full_size_properties_bf16():
     """Config-3 geometry (1024², hiera_s) through the public API: finite logits, deterministic re-run,
     hole filling idempotent on the outputs."""
