@@ -165,6 +165,13 @@ int ms2_rope(void* x, int dt, long batch_stride, long row_stride, int B, int row
 int ms2_im2col(const float* x, void* cols, int dt, int B, int H, int W, int Cin, int k, int stride, int pad,
                int pre, float pre_scale, float pre_bias, ms2_stream_t stream);
 
+/* ---- fused conv 3x3 stride 2 pad 1 + LayerNorm2d + GELU for the thin first layers of the mask down-sampler
+ *      (memory_encoder.py:38-58; Cin->Cout in {1->4, 4->16, 16->64}): x fp32 NHWC [B,H,W,Cin], w fp32 [Cout,Cin,3,3],
+ *      y dtype y_dt NHWC [B,Ho,Wo,Cout]; `pre` as in ms2_im2col. */
+int ms2_conv3x3s2_ln_gelu(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                          void* y, int y_dt, int B, int H, int W, int Cin, int Cout, float eps, int pre,
+                          float pre_scale, float pre_bias, ms2_stream_t stream);
+
 /* ---- depthwise conv 7x7 pad 3, NHWC fp32, w fp32 [C,7,7] (memory_encoder.py:84-90). */
 int ms2_dwconv7x7(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int C,
                   ms2_stream_t stream);

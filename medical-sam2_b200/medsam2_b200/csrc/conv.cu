@@ -108,6 +108,95 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ cols,
   }
 }
 
+// vectorised im2col for Cin % 8 == 0: one thread = 8 consecutive channels of one tap (16-byte bf16 store)
+__global__ void __launch_bounds__(256)
+im2col_vec8_kernel(const float* __restrict__ x, bf16* __restrict__ cols, long total, int H, int W, int Cin, int k,
+                   int stride, int pad, int Ho, int Wo) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = Cin >> 3;
+  const int cc = (int)(t % c8);
+  long r = t / c8;
+  const int tap = (int)(r % (k * k));
+  r /= (k * k);
+  const int xo = (int)(r % Wo);
+  r /= Wo;
+  const int yo = (int)(r % Ho), b = (int)(r / Ho);
+  const int ky = tap / k, kx = tap - ky * k;
+  const int y = yo * stride - pad + ky, xx = xo * stride - pad + kx;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (y >= 0 && y < H && xx >= 0 && xx < W) {
+    const float4* src = (const float4*)(x + (((long)b * H + y) * W + xx) * Cin + cc * 8);
+    const float4 a = src[0], c = src[1];
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+    u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
+  }
+  *(uint4*)(cols + t * 8) = u;
+}
+
+// ------------------------------------------------------------------ fused conv3x3/s2/p1 + LayerNorm2d + GELU
+// The first layers of the mask down-sampler (memory_encoder.py:38-58: 1->4->16->64 channels) are far too thin for
+// a GEMM: one thread computes ALL output channels of one output pixel (weights broadcast from shared memory),
+// applies the channel LayerNorm and GELU in registers and writes the NHWC row - replacing im2col + GEMM + LN.
+// pre: 0 none, 1 sigmoid, 2 (x > 0); then x*pre_scale + pre_bias on in-range inputs (sam2_base.py:686-696).
+template <int CIN, int COUT, typename TO>
+__global__ void __launch_bounds__(128)
+conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, TO* __restrict__ y, int B,
+                         int H, int W, int Ho, int Wo, float eps, int pre, float pre_scale, float pre_bias) {
+  __shared__ float ws[9 * CIN * COUT];                 // [tap][ci][co]
+  __shared__ float sb[3 * COUT];
+  for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
+    ws[i] = w[((long)co * CIN + ci) * 9 + tap];       // conv weight [Cout, Cin, 3, 3]
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    sb[i] = bias[i];
+    sb[COUT + i] = gamma[i];
+    sb[2 * COUT + i] = beta[i];
+  }
+  __syncthreads();
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long)B * Ho * Wo) return;
+  const int xo = (int)(p % Wo);
+  const long r = p / Wo;
+  const int yo = (int)(r % Ho), b = (int)(r / Ho);
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yo * 2 - 1 + tap / 3, xx = xo * 2 - 1 + tap % 3;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* src = x + (((long)b * H + yy) * W + xx) * CIN;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float v = src[ci];
+      if (pre == 1) v = 1.f / (1.f + expf(-v));
+      else if (pre == 2) v = v > 0.f ? 1.f : 0.f;
+      if (pre) v = v * pre_scale + pre_bias;
+      const float* wr = ws + (tap * CIN + ci) * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+    }
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) mean += acc[c];
+  mean *= (1.f / COUT);
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    const float d = acc[c] - mean;
+    var = fmaf(d, d, var);
+  }
+  const float rstd = rsqrtf(var * (1.f / COUT) + eps);
+  TO* dst = y + p * COUT;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) dst[c] = from_f<TO>(gelu_erf((acc[c] - mean) * rstd * sb[COUT + c] + sb[2 * COUT + c]));
+}
+
 // ------------------------------------------------------------------ depth-wise 7x7
 // HBM-bound (2 x 4 B x pixels x C): an 8x8 output tile x 32 channels per CTA; the 14x14 input halo tile is staged
 // once in shared memory ([row][col][channel]: channel = bank, conflict-free) and each thread slides a 7-tap window
@@ -195,6 +284,36 @@ patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ cols, long
 
 }  // namespace
 
+extern "C" int ms2_conv3x3s2_ln_gelu(const float* x, const float* w, const float* bias, const float* gamma,
+                                     const float* beta, void* y, int y_dt, int B, int H, int W, int Cin, int Cout,
+                                     float eps, int pre, float pre_scale, float pre_bias, void* stream) {
+  MS2_CHECK_ARG(x && w && bias && gamma && beta && y, "conv3x3s2_ln_gelu: null pointer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long np = (long)B * Ho * Wo;
+  if (!np) return MS2_OK;
+  const int grid = ceil_div(np, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MS2_C3(CI, CO)                                                                                               \
+  do {                                                                                                               \
+    if (y_dt == MS2_F32)                                                                                             \
+      conv3x3s2_ln_gelu_kernel<CI, CO, float><<<grid, 128, 0, st>>>(x, w, bias, gamma, beta, (float*)y, B, H, W, Ho, Wo, \
+                                                                    eps, pre, pre_scale, pre_bias);                  \
+    else                                                                                                             \
+      conv3x3s2_ln_gelu_kernel<CI, CO, bf16><<<grid, 128, 0, st>>>(x, w, bias, gamma, beta, (bf16*)y, B, H, W, Ho, Wo,  \
+                                                                   eps, pre, pre_scale, pre_bias);                   \
+  } while (0)
+  if (Cin == 1 && Cout == 4) MS2_C3(1, 4);
+  else if (Cin == 4 && Cout == 16) MS2_C3(4, 16);
+  else if (Cin == 16 && Cout == 64) MS2_C3(16, 64);
+  else {
+    ms2_set_error("conv3x3s2_ln_gelu: only (1->4), (4->16), (16->64) are instantiated (got %d->%d)", Cin, Cout);
+    return MS2_ERR_UNSUPPORTED;
+  }
+#undef MS2_C3
+  MS2_CHECK_LAUNCH("conv3x3s2_ln_gelu_kernel");
+  return MS2_OK;
+}
+
 extern "C" int ms2_patch_im2col(const float* img, void* cols, int B, int Hin, int Win, int ldk, void* stream) {
   MS2_CHECK_ARG(img && cols, "patch_im2col: null pointer");
   MS2_CHECK_ARG(ldk >= 152 && ldk % 8 == 0 && ((uintptr_t)cols % 16 == 0), "patch_im2col: ldk must be a multiple of 8 >= 152");
@@ -228,6 +347,13 @@ extern "C" int ms2_im2col(const float* x, void* cols, int dt, int B, int H, int 
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   long n = (long)B * Ho * Wo * k * k * Cin;
   if (!n) return MS2_OK;
+  if (dt == MS2_BF16 && pre == 0 && Cin % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)cols % 16 == 0)) {
+    const long total = n / 8;
+    im2col_vec8_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)cols, total, H, W, Cin, k, stride,
+                                                                               pad, Ho, Wo);
+    MS2_CHECK_LAUNCH("im2col_vec8");
+    return MS2_OK;
+  }
   long blocks = (n + 255) / 256;
   int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
   MS2_DISPATCH_DTYPE(dt, T, (im2col_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(

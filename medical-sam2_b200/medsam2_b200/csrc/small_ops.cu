@@ -34,16 +34,21 @@ template <> struct Vec8<float> {
 };
 
 constexpr int SM_MT = 16;       // rows per pass
-constexpr int SM_WARPS = 4;     // 4 warps x 4 columns = 16 columns per CTA
+constexpr int SM_WARPS = 4;     // grouped kernel: 4 warps x 4 columns = 16 columns per CTA
 
-template <typename T, typename TO>
-__global__ void __launch_bounds__(SM_WARPS * 32)
+// KL lanes share one output column and split K in 16-byte chunks (KL = 8: 4 columns per warp; KL = 32: one column
+// per warp, for K >= 1024 where 8 lanes would each walk 128+ elements serially).  Two warps per CTA so that even
+// N = 256 gives 32..128 CTAs: these GEMMs are pure latency (W is 0.1-1 MB, A a few KB).
+constexpr int SMK_WARPS = 2;
+template <typename T, typename TO, int KL>
+__global__ void __launch_bounds__(SMK_WARPS * 32)
 gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, const float* __restrict__ bias,
                    const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
                    TO* __restrict__ out, long ldo, int M, int N, int K, int act) {
+  constexpr int CPW = 32 / KL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cg = lane >> 3, kl = lane & 7;
-  const int n = (blockIdx.x * SM_WARPS + warp) * 4 + cg;
+  const int cg = lane / KL, kl = lane % KL;
+  const int n = (blockIdx.x * SMK_WARPS + warp) * CPW + cg;
   const bool n_ok = n < N;
   const T* wrow = W + (long)(n_ok ? n : 0) * K;
   for (int m0 = 0; m0 < M; m0 += SM_MT) {
@@ -51,7 +56,7 @@ gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, c
     float acc[SM_MT];
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
-    for (int k = kl * 8; k < K; k += 64) {
+    for (int k = kl * 8; k < K; k += KL * 8) {
       float w[8];
       Vec8<T>::load(wrow + k, w);
 #pragma unroll
@@ -67,9 +72,8 @@ gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, c
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) {
       float v = acc[m];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+      for (int o = KL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       acc[m] = v;
     }
     if (kl == 0 && n_ok) {
@@ -308,7 +312,6 @@ attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
   __shared__ float S[FQ_MAXQ][FS_MAXCHUNK];
   __shared__ float Vs[FS_MAXCHUNK][D + 1];
   __shared__ float Qs[FQ_MAXQ][D];
-  __shared__ float ms[FQ_MAXQ];
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, ns = gridDim.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j0 = sp * chunk;
@@ -399,10 +402,17 @@ bool ms2_gemm_smallm_supported(int a_dt, int w_dt, const void* A, const void* W,
 int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, const float* bias, const float* colscale,
                            const float* residual, long ldr, void* out, int o_dt, long ldo, int M, int N, int K, int act,
                            cudaStream_t st) {
-  const int grid = ceil_div(N, SM_WARPS * 4);
+  const bool wide = K >= 1024;                       // one column per warp, 32 lanes split K
+  const int grid = ceil_div(N, SMK_WARPS * (wide ? 1 : 4));
 #define MS2_SMALLM(TA, TO)                                                                                          \
-  gemm_smallm_kernel<TA, TO><<<grid, SM_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, residual, \
-                                                             ldr, (TO*)out, ldo, M, N, K, act)
+  do {                                                                                                              \
+    if (wide)                                                                                                       \
+      gemm_smallm_kernel<TA, TO, 32><<<grid, SMK_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                      residual, ldr, (TO*)out, ldo, M, N, K, act);  \
+    else                                                                                                            \
+      gemm_smallm_kernel<TA, TO, 8><<<grid, SMK_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                     residual, ldr, (TO*)out, ldo, M, N, K, act);   \
+  } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_SMALLM(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_SMALLM(bf16, float);
   else if (a_dt == MS2_F32 && o_dt == MS2_BF16) MS2_SMALLM(float, bf16);

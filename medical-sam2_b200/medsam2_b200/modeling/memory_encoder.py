@@ -38,10 +38,17 @@ class MaskDownSampler(nn.Module):
         x = x_nhwc
         for j in range(self.num_layers):
             conv, norm = self.encoder[3 * j], self.encoder[3 * j + 1]
+            last = j == self.num_layers - 1
+            if (self.kernel_size, self.stride, self.padding) == (3, 2, 1) and \
+                    (conv.in_channels, conv.out_channels) in ((1, 4), (4, 16), (16, 64)):
+                # thin layers: one fused direct-conv + LN2d + GELU kernel instead of im2col + GEMM + LN
+                x = ops.conv3x3s2_ln_gelu(x, p32(conv.weight), p32(conv.bias), p32(norm.weight), p32(norm.bias), norm.eps,
+                                          out_dtype=cd if last else torch.float32, pre=pre if j == 0 else 0,
+                                          pre_scale=pre_scale if j == 0 else 1.0, pre_bias=pre_bias if j == 0 else 0.0)
+                continue
             cols = ops.im2col(x, self.kernel_size, self.stride, self.padding, cd,
                               pre if j == 0 else 0, pre_scale if j == 0 else 1.0, pre_bias if j == 0 else 0.0)
             y = ops.gemm(cols, conv_w_c(conv.weight), p32(conv.bias), out_dtype=torch.float32)
-            last = j == self.num_layers - 1
             x = norm(y, out_dtype=cd if last else torch.float32, act=ops.ACT_GELU)
         fin = self.encoder[3 * self.num_layers]
         return ops.gemm(x, w_c(fin.weight), p32(fin.bias), out_dtype=torch.float32)

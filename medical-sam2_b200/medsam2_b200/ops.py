@@ -377,6 +377,18 @@ def im2col(x, k, stride, pad, out_dtype, pre=0, pre_scale=1.0, pre_bias=0.0):
     return cols
 
 
+def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
+    """fused conv3x3/s2/p1 + LayerNorm2d + GELU on NHWC fp32 x [B,H,W,Cin]; w fp32 [Cout,Cin,3,3]."""
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
+    native.call("ms2_conv3x3s2_ln_gelu", _chk(x, "x", torch.float32), _chk(w, "w", torch.float32),
+                _chk(bias, "bias", torch.float32), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32),
+                y.data_ptr(), _DT[out_dtype], B, H, W, Cin, Cout, float(eps), pre, float(pre_scale), float(pre_bias), _st())
+    return y
+
+
 def dwconv7x7(x, w, bias):
     B, H, W, C = x.shape
     y = torch.empty_like(x)

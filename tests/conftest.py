@@ -12,7 +12,15 @@ for p in (ROOT, PKG):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _true_fp32_references():
+    """the torch statements the kernels are checked against must run in real fp32 (cuDNN convs default to TF32)."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def pytest_configure(config):
+    _true_fp32_references()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 

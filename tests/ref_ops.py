@@ -224,6 +224,19 @@ def mask_stability_counts(x, delta):
     return torch.stack([(f > delta).sum(-1), (f > -delta).sum(-1)], dim=1).to(torch.int32)
 
 
+def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
+    xi = x.float()
+    if pre == 1:
+        xi = torch.sigmoid(xi)
+    elif pre == 2:
+        xi = (xi > 0).float()
+    if pre:
+        xi = xi * pre_scale + pre_bias
+    y = F.conv2d(xi.permute(0, 3, 1, 2), w.float(), bias.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    y = F.layer_norm(y, (y.shape[-1],), gamma.float(), beta.float(), eps)
+    return F.gelu(y).to(out_dtype).contiguous()
+
+
 def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None):
     acts = acts or [ACT_NONE] * len(a_list)
     return [gemm(a, w, b, out_dtype=out_dtype, act=act) for a, w, b, act in zip(a_list, w_list, bias_list, acts)]

@@ -351,6 +351,23 @@ def test_dwconv7x7(ops, B, H, W, C):
     close(ops.dwconv7x7(x, w, None), ref_ops.dwconv7x7(x, w, None), 1e-4, "dwconv nobias")
 
 
+@pytest.mark.parametrize("cin,cout,pre", [(1, 4, 1), (1, 4, 2), (4, 16, 0), (16, 64, 0)])
+def test_conv3x3s2_ln_gelu(ops, cin, cout, pre):
+    x = rnd(2, 36, 50, cin, seed=1)
+    w, b = rnd(cout, cin, 3, 3, seed=2) / 3, rnd(cout, seed=3)
+    g, be = rnd(cout, seed=4), rnd(cout, seed=5)
+    ps, pb = (20.0, -10.0) if pre else (1.0, 0.0)
+    close(ops.conv3x3s2_ln_gelu(x, w, b, g, be, 1e-6, pre=pre, pre_scale=ps, pre_bias=pb),
+          ref_ops.conv3x3s2_ln_gelu(x, w, b, g, be, 1e-6, pre=pre, pre_scale=ps, pre_bias=pb), 2e-4, "conv3x3s2+ln+gelu")
+    close(ops.conv3x3s2_ln_gelu(x, w, b, g, be, 1e-6, out_dtype=torch.bfloat16),
+          ref_ops.conv3x3s2_ln_gelu(x, w, b, g, be, 1e-6), 3e-2, "conv3x3s2+ln+gelu bf16")
+
+
+def test_im2col_vec8(ops):
+    x = rnd(2, 32, 24, 64, seed=1)
+    close(ops.im2col(x, 3, 2, 1, torch.bfloat16), ref_ops.im2col(x, 3, 2, 1, torch.bfloat16), 1e-6, "im2col vec8")
+
+
 def test_patch_im2col_gemm_matches_conv(ops):
     """bf16 patch-embed path: im2col rows x re-laid-out weight == conv 7x7/s4/p3 on the same bf16-rounded operands."""
     img = rnd(2, 3, 96, 128, seed=1)
