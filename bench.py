@@ -391,12 +391,15 @@ def main_ours(args):
         # memory cross-attention executes 2*Lq*Lk*(256+64) FLOP per launch (values stay 64-d); the
         # reference's formulation of the same attention is 4*Lq*Lk*256 (SURVEY §8(d) "canonical")
         canon = achieved * (512.0 / 320.0) if name == "mem_cross_attention" else achieved
-        roofline = {"bound": "tensor", "kernel": "attn_tc_kernel<256,64,64,4> (memory cross-attention)" if name == "mem_cross_attention" else name,
+        meta = {}
+        try:      # kernel name + dram traffic of the dominant kernel from the committed ncu capture
+            meta = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json"))).get(name, {})
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": meta.get("kernel", name),
                     "achieved": achieved, "achieved_canonical_flops": canon, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
-                    "traffic": 156.05e6 if name == "mem_cross_attention" else None,
-                    "traffic_note": "dram read+write of one launch at Lk=209120 (profiles/r1_attn_dv_ncu.txt); algorithmic "
-                                    "bytes of that launch: K 107.1 MB + M 26.8 MB + Q/O 2.6 MB",
+                    "traffic": meta.get("traffic"), "traffic_note": meta.get("traffic_note"),
                     "launches": d["n"], "ms_per_launch": d["ms"] / max(d["n"], 1),
                     "share_of_step": d["ms"] / ms_prof, "peak_source": peak_src,
                     "profiled_step_ms": ms_prof,

@@ -13,6 +13,7 @@
 // out-of-bounds zero fill / clipping.  BN (32..256) is a run-time choice per problem shape.
 // Most GEMMs of this model have K <= 384 and are HBM-bound: the epilogue, not the MMA loop, sets their speed.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -27,7 +28,7 @@ struct GemmP {
   const float* colscale;
   const float* residual;
   long ldr;
-  int M, N, K, BN, tiles_n, tiles, num_kb, stages, epi_warps;
+  int M, N, K, BN, tiles_n, tiles, num_kb, stages, epi_warps, epi_bufs;
 };
 
 template <int ACT, bool F32OUT>
@@ -58,8 +59,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;               // epi_warps x 4 KB, 1024-aligned
-  uint64_t* full = (uint64_t*)(staging + p.epi_warps * EPI_BUF_BYTES);
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;               // epi_warps x epi_bufs x 4 KB, 1024-aligned
+  uint64_t* full = (uint64_t*)(staging + p.epi_warps * p.epi_bufs * EPI_BUF_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* acc_full = empty + MAX_STAGES;
   uint64_t* acc_empty = acc_full + ACC_STAGES;
@@ -141,40 +142,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2, ngrp = p.epi_warps >> 2;
     constexpr int CPC = F32OUT ? 32 : 64;        // columns per 128-byte chunk
-    uint8_t* buf = staging + (warp - 2) * EPI_BUF_BYTES;
-    const uint32_t sbuf = tc::smem_u32(buf), srow = sbuf + lane * 128;
+    const int nbuf = p.epi_bufs;                 // staging buffers of this warp (2: stores / residual fetches overlap)
+    const uint32_t sbuf0 = tc::smem_u32(staging + (warp - 2) * nbuf * EPI_BUF_BYTES);
+    auto tile_nch = [&](int t) {
+      int ncols = p.N - (t % p.tiles_n) * p.BN;
+      if (ncols > p.BN) ncols = p.BN;
+      return (ncols + CPC - 1) / CPC;
+    };
+    // residual box [32 rows][32 fp32] of chunk c of tile t -> staging buffer, as asynchronous 16-byte global->shared
+    // copies (4 rows x 128 B per instruction, coalesced); only fp32 outputs carry a residual (CPC == 32)
+    auto fetch_residual = [&](int t, int c, uint32_t sb) {
+      const int m0 = (t / p.tiles_n) * BM + q * 32, nb = (t % p.tiles_n) * p.BN + c * CPC;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rrow = i * 4 + (lane >> 3), cc = lane & 7;
+        const uint32_t dst = sb + rrow * 128 + ((cc ^ (rrow & 7)) << 4);
+        if ((m0 + rrow < p.M) && (nb + cc * 4 < p.N))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                       "l"(p.residual + (long)(m0 + rrow) * p.ldr + nb + cc * 4) : "memory");
+        else
+          tc::sts128(dst, make_uint4(0, 0, 0, 0));
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // the chunk this warp handles after (t, c): same tile, or the first one of a later tile (groups rotate per tile)
+    auto next_chunk = [&](int t, int c, int rot, int& tn, int& cn) -> bool {
+      tn = t; cn = c + ngrp;
+      while (cn >= tile_nch(tn)) {
+        tn += gridDim.x;
+        if (tn >= p.tiles) return false;
+        rot = (rot + 1 == ngrp) ? 0 : rot + 1;
+        cn = rot;
+      }
+      return true;
+    };
+    const bool has_res = RES && p.residual;
     int as = 0, it = 0, rot = grp;
     uint32_t aphase = 0;
+    bool fetched = false;                          // the residual of the upcoming chunk is already on its way
+    if (has_res && nbuf > 1) {
+      int t0 = blockIdx.x, c0 = rot - ngrp, tn, cn;   // "chunk before the first": next_chunk finds the first one
+      if (t0 < p.tiles && next_chunk(t0, c0, rot, tn, cn)) { fetch_residual(tn, cn, sbuf0); fetched = true; }
+    }
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       const int m0 = (t / p.tiles_n) * BM + q * 32, n0 = (t % p.tiles_n) * p.BN;
-      int ncols = p.N - n0;
-      if (ncols > p.BN) ncols = p.BN;
-      const int nch = (ncols + CPC - 1) / CPC;
-      tc::mbar_wait(&acc_full[as], aphase);
-      tc::tc_fence_after();
+      const int nch = tile_nch(t);
+      bool waited = false;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       for (int c = rot; c < nch; c += ngrp, ++it) {   // groups rotate over tiles so odd chunk counts balance
-        if (it >= 1) {                              // the previous store of this warp has read the buffer
-          if (tc::elect_one()) tc::tma_store_wait_read<0>();
-          __syncwarp();
+        const uint32_t sbuf = sbuf0 + (nbuf > 1 ? (it & 1) * EPI_BUF_BYTES : 0), srow = sbuf + lane * 128;
+        if (nbuf > 1) {
+          // the OTHER buffer is about to be refilled (residual of the next chunk) / this one was last read by the
+          // store two chunks ago: at most the most recent store may still be reading
+          if (it >= 1) {
+            if (tc::elect_one()) {
+              if (has_res) tc::tma_store_wait_read<0>();
+              else tc::tma_store_wait_read<1>();
+            }
+            __syncwarp();
+          }
+          if (has_res) {
+            if (!fetched) fetch_residual(t, c, sbuf);          // (only when the look-ahead found nothing)
+            int tn, cn;
+            const bool more = next_chunk(t, c, rot, tn, cn);
+            if (more) {
+              fetch_residual(tn, cn, sbuf0 + ((it + 1) & 1) * EPI_BUF_BYTES);
+              asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+              asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            fetched = more;
+            __syncwarp();
+          }
+        } else {
+          if (it >= 1) {                              // the previous store of this warp has read the buffer
+            if (tc::elect_one()) tc::tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          if (has_res) {
+            fetch_residual(t, c, sbuf);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+          }
+        }
+        if (!waited) {
+          tc::mbar_wait(&acc_full[as], aphase);
+          tc::tc_fence_after();
+          waited = true;
         }
         const int nb = n0 + c * CPC;
-        if (RES && p.residual) {
-          // residual box [32 rows][32 fp32] -> staging (only fp32 outputs carry a residual: CPC == 32)
-          uint4 rr[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rrow = i * 4 + (lane >> 3), cc = lane & 7;
-            const bool ok = (m0 + rrow < p.M) && (nb + cc * 4 < p.N);
-            rr[i] = ok ? *(const uint4*)(p.residual + (long)(m0 + rrow) * p.ldr + nb + cc * 4) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rrow = i * 4 + (lane >> 3), cc = lane & 7;
-            tc::sts128(sbuf + rrow * 128 + ((cc ^ (rrow & 7)) << 4), rr[i]);
-          }
-          __syncwarp();
-        }
 #pragma unroll
         for (int hlf = 0; hlf < CPC / 32; ++hlf) {
           const int nh = nb + hlf * 32;
@@ -196,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (F32OUT) {
               const uint32_t slot = srow + ((g ^ (lane & 7)) << 4);
-              if (RES && p.residual) {
+              if (has_res) {
                 const float4 r4 = tc::lds128f(slot);
                 v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
               }
@@ -217,11 +273,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::fence_proxy_async();
         __syncwarp();
         if (m0 < p.M && tc::elect_one()) {
-          tc::tma_store_2d(&tmO, buf, nb, m0);
+          tc::tma_store_2d(&tmO, (const void*)(staging + (sbuf - tc::smem_u32(staging))), nb, m0);
           tc::tma_store_commit();
         }
       }
       rot = (rot + 1 == ngrp) ? 0 : rot + 1;
+      if (!waited) {                                 // no chunk of this tile was mine: still observe the phase
+        tc::mbar_wait(&acc_full[as], aphase);
+      }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
@@ -281,10 +340,18 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
   const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
   // short-K problems are epilogue/HBM-bound: spend shared memory on 16 epilogue warps instead of pipeline depth
   p.epi_warps = p.num_kb <= 8 ? 16 : 8;
-  const int stage_budget = SMEM_TOTAL - 1024 - 256 - p.epi_warps * EPI_BUF_BYTES;
+  // two staging buffers per epilogue warp (the TMA store of one chunk and the residual fetch of the next overlap the
+  // arithmetic of the current one) as long as >= 3 pipeline stages still fit
+  static const int bufs_env = []() { const char* e = getenv("MS2_GEMM_EPI_BUFS"); return e ? atoi(e) : 1; }();
+  p.epi_bufs = bufs_env >= 2 ? 2 : 1;
+  if (p.epi_bufs == 2 && (SMEM_TOTAL - 1024 - 256 - p.epi_warps * 2 * EPI_BUF_BYTES) / stage_bytes < 3) {
+    if (p.epi_warps == 16 && (SMEM_TOTAL - 1024 - 256 - 8 * 2 * EPI_BUF_BYTES) / stage_bytes >= 3) p.epi_warps = 8;
+    else p.epi_bufs = 1;
+  }
+  const int stage_budget = SMEM_TOTAL - 1024 - 256 - p.epi_warps * p.epi_bufs * EPI_BUF_BYTES;
   p.stages = stage_budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const size_t smem = (size_t)p.stages * stage_bytes + p.epi_warps * EPI_BUF_BYTES + 1024 + 256;
+  const size_t smem = (size_t)p.stages * stage_bytes + p.epi_warps * p.epi_bufs * EPI_BUF_BYTES + 1024 + 256;
 
   CUtensorMap tmA, tmW, tmO;
   int rc;

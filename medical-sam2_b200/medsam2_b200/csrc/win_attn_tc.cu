@@ -49,6 +49,13 @@ __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
   return r;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // MAXC = column chunks (of 32) a warp half may own: 2 when NK <= 128 (<= 128 registers/thread, two CTAs per SM),
 // 4 for the 196-key windows.
 template <int MAXC>
@@ -57,13 +64,13 @@ win_attn_tc_kernel(const WinP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int kv_bytes = WDCH * p.NK * 128;
-  uint8_t* sQ = smem;                               // 2 x [128][128 B]
-  uint8_t* sK = sQ + WDCH * 128 * 128;              // 2 x [NK][128 B]
+  uint8_t* sQ = smem;                               // q_tiles x 2 x [128][128 B]
+  uint8_t* sK = sQ + p.q_tiles * WDCH * 128 * 128;  // 2 x [NK][128 B]
   uint8_t* sV = sK + kv_bytes;
   uint8_t* tail = sV + kv_bytes;
   uint4* sBias = (uint4*)tail;                      // [3][12] 16-byte chunks of the bf16 bias of this head
-  int* rowtab = (int*)(tail + 3 * WCH16 * 16);      // [128*4 + 256] token element offsets (-1 pad -> bias, -2 none)
-  float* mxs = (float*)(rowtab + 128 * 4 + 256);    // [2 halves][128 rows] row-max / row-sum exchange
+  int* rowtab = (int*)(tail + 3 * WCH16 * 16);      // [2*128*4 + 256] token element offsets (-1 pad -> bias, -2 none)
+  float* mxs = (float*)(rowtab + 2 * 128 * 4 + 256);  // [2 halves][128 rows] row-max / row-sum exchange
   uint64_t* bar_s = (uint64_t*)(mxs + 256);
   uint64_t* bar_o = bar_s + 1;
   uint32_t* tmem_ptr = (uint32_t*)(bar_o + 1);
@@ -101,7 +108,7 @@ win_attn_tc_kernel(const WinP p) {
       const int y = wy * p.ws + j / p.ws, x = wx * p.ws + j % p.ws;
       off = (y < p.H && x < p.W) ? (int)(((long)y * p.W + x) * C3) : -1;
     }
-    rowtab[512 + r] = off;
+    rowtab[1024 + r] = off;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -109,43 +116,8 @@ win_attn_tc_kernel(const WinP p) {
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)p.o_col;
 
-  // ---- gather K, V once per CTA (shared by all query tiles of the window group)
-  for (int idx = tid; idx < p.NK * WCH16; idx += NT) {
-    const int r = idx / WCH16, ch = idx - r * WCH16;
-    const int off = rowtab[512 + r];
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-    if (off >= 0) {
-      kv = __ldg((const uint4*)(base + off + p.dim_out + ch * 8));
-      vv = __ldg((const uint4*)(base + off + 2 * p.dim_out + ch * 8));
-    } else if (off == -1) {
-      kv = sBias[WCH16 + ch];
-      vv = sBias[2 * WCH16 + ch];
-    }
-    const uint32_t so = (ch >> 3) * p.NK * 128 + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
-    tc::sts128(aK + so, kv);
-    tc::sts128(aV + so, vv);
-  }
-
-  const int qtr = warp & 3, half = warp >> 2;       // TMEM lane quarter / column half handled by this warp
-  const int r = qtr * 32 + lane;                    // query row inside the tile
-  const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
-  // column chunks this warp's 32 rows can touch (their windows' key slots), split between the two halves
-  int clo, chi;
-  if (p.q_tiles > 1) { clo = 0; chi = (p.NK + 31) >> 5; }
-  else {
-    const int wlo = (qtr * 32) / p.lq_w;
-    int whi = (qtr * 32 + 31) / p.lq_w;
-    if (whi > p.G - 1) whi = p.G - 1;
-    clo = (wlo * p.lk_w) >> 5;
-    chi = wlo > whi ? clo : (min((whi + 1) * p.lk_w, p.NK) + 31) >> 5;
-  }
-  const int cmid = clo + ((chi - clo + 1) >> 1);
-  const int cb = half ? cmid : clo, ce = half ? chi : cmid;          // my chunks [cb, ce), at most 4
-  const int nchunks = (p.NK + 31) >> 5;
-
-  for (int qt = 0; qt < p.q_tiles; ++qt) {
-    const uint32_t ph = (uint32_t)qt & 1u;
-    // ---- Q row table (4 source positions with the 2x2 max-pool, 1 without) and gather
+  // Q row table of query tile qt (4 source positions with the 2x2 max-pool, 1 without)
+  auto build_q_rowtab = [&](int qt) {
     if (tid < 128) {
       int wl, i;
       if (p.q_tiles > 1) { wl = 0; i = qt * 128 + tid; }
@@ -168,32 +140,91 @@ win_attn_tc_kernel(const WinP p) {
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rowtab[tid * 4 + q] = o4[q];
+      for (int q = 0; q < 4; ++q) rowtab[(qt & 1) * 512 + tid * 4 + q] = o4[q];
     }
-    __syncthreads();
+  };
+  // Q tile qt -> sQ[qt]: without pooling every 16-byte piece is an asynchronous global->shared copy (no register
+  // staging, all pieces of a thread in flight at once); with the 2x2 max-pool the four source rows go through registers
+  auto gather_q = [&](int qt) {
+    const int* rt = rowtab + (qt & 1) * 512;
+    const uint32_t dstQ = aQ + (uint32_t)qt * (WDCH * 128 * 128);
     for (int idx = tid; idx < 128 * WCH16; idx += NT) {
       const int rr = idx / WCH16, ch = idx - rr * WCH16;
-      auto ldq = [&](int off) -> uint4 {
-        return off >= 0 ? __ldg((const uint4*)(base + off + ch * 8)) : sBias[ch];
-      };
-      const int o0 = rowtab[rr * 4];
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (o0 != -2) {
-        v = ldq(o0);
-        if (p.qpool)
-          v = max_bf16x8(max_bf16x8(v, ldq(rowtab[rr * 4 + 1])), max_bf16x8(ldq(rowtab[rr * 4 + 2]), ldq(rowtab[rr * 4 + 3])));
+      const uint32_t dst = dstQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4);
+      const int o0 = rt[rr * 4];
+      if (!p.qpool) {
+        if (o0 >= 0) cp_async16(dst, base + o0 + ch * 8);
+        else tc::sts128(dst, o0 == -1 ? sBias[ch] : make_uint4(0, 0, 0, 0));
+      } else {
+        auto ldq = [&](int off) -> uint4 {
+          return off >= 0 ? __ldg((const uint4*)(base + off + ch * 8)) : sBias[ch];
+        };
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (o0 != -2)
+          v = max_bf16x8(max_bf16x8(ldq(o0), ldq(rt[rr * 4 + 1])), max_bf16x8(ldq(rt[rr * 4 + 2]), ldq(rt[rr * 4 + 3])));
+        tc::sts128(dst, v);
       }
-      tc::sts128(aQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4), v);
+    }
+  };
+
+  // ---- gather K, V once per CTA (shared by all query tiles of the window group): asynchronous 16-byte copies, so
+  //      a thread has all of its pieces in flight instead of paying one global-memory latency per piece
+  build_q_rowtab(0);
+  for (int idx = tid; idx < p.NK * WCH16; idx += NT) {
+    const int r = idx / WCH16, ch = idx - r * WCH16;
+    const int off = rowtab[1024 + r];
+    const uint32_t so = (ch >> 3) * p.NK * 128 + r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+    if (off >= 0) {
+      cp_async16(aK + so, base + off + p.dim_out + ch * 8);
+      cp_async16(aV + so, base + off + 2 * p.dim_out + ch * 8);
+    } else {
+      tc::sts128(aK + so, off == -1 ? sBias[WCH16 + ch] : make_uint4(0, 0, 0, 0));
+      tc::sts128(aV + so, off == -1 ? sBias[2 * WCH16 + ch] : make_uint4(0, 0, 0, 0));
+    }
+  }
+  __syncthreads();                                    // Q row table of tile 0
+  gather_q(0);
+  cp_async_commit();                                  // group: K, V, Q tile 0
+
+  const int qtr = warp & 3, half = warp >> 2;       // TMEM lane quarter / column half handled by this warp
+  const int r = qtr * 32 + lane;                    // query row inside the tile
+  const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+  // column chunks this warp's 32 rows can touch (their windows' key slots), split between the two halves
+  int clo, chi;
+  if (p.q_tiles > 1) { clo = 0; chi = (p.NK + 31) >> 5; }
+  else {
+    const int wlo = (qtr * 32) / p.lq_w;
+    int whi = (qtr * 32 + 31) / p.lq_w;
+    if (whi > p.G - 1) whi = p.G - 1;
+    clo = (wlo * p.lk_w) >> 5;
+    chi = wlo > whi ? clo : (min((whi + 1) * p.lk_w, p.NK) + 31) >> 5;
+  }
+  const int cmid = clo + ((chi - clo + 1) >> 1);
+  const int cb = half ? cmid : clo, ce = half ? chi : cmid;          // my chunks [cb, ce), at most 4
+  const int nchunks = (p.NK + 31) >> 5;
+
+  for (int qt = 0; qt < p.q_tiles; ++qt) {
+    const uint32_t ph = (uint32_t)qt & 1u;
+    // ---- the next query tile's Q is fetched under this tile's MMAs and softmax
+    if (qt + 1 < p.q_tiles) {
+      build_q_rowtab(qt + 1);
+      __syncthreads();
+      gather_q(qt + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     tc::fence_proxy_async();
     __syncthreads();
+    const uint32_t aQt = aQ + (uint32_t)qt * (WDCH * 128 * 128);
 
     if (warp == 0 && tc::elect_one()) {
       tc::tc_fence_after();
       const uint32_t idesc = tc::make_idesc_bf16(128, p.NK, 0, 0);
 #pragma unroll
       for (int kk = 0; kk < WD / 16; ++kk)
-        tc::umma_bf16(tS, tc::desc_kmajor_sw128(aQ + (kk >> 2) * 128 * 128 + (kk & 3) * 32),
+        tc::umma_bf16(tS, tc::desc_kmajor_sw128(aQt + (kk >> 2) * 128 * 128 + (kk & 3) * 32),
                       tc::desc_kmajor_sw128(aK + (kk >> 2) * p.NK * 128 + (kk & 3) * 32), idesc, kk ? 1u : 0u);
       tc::umma_commit(bar_s);
     }
@@ -301,7 +332,7 @@ win_attn_tc_kernel(const WinP p) {
       }
     }
     tc::tc_fence_before();
-    __syncthreads();                                 // S / O / Q smem are reused by the next query tile
+    __syncthreads();                                 // S / O are reused by the next query tile
     tc::tc_fence_after();
   }
   if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -342,7 +373,7 @@ int ms2_window_attention_tc_launch(const void* qkv, const float* qkv_bias, void*
   p.o_col = p.NK <= 128 ? 128 : 256;
   MS2_CHECK_ARG(((long)H * W * 3 * p.dim_out) < (1L << 31), "window_attention_tc: token offsets must fit 31 bits");
   MS2_CHECK_ARG((p.NK + 31) / 32 <= 8, "window_attention_tc: at most 256 key slots per tile");
-  const size_t smem = (size_t)WDCH * 128 * 128 + 2 * (size_t)WDCH * p.NK * 128 + 3 * WCH16 * 16 + (128 * 4 + 256) * 4 +
+  const size_t smem = (size_t)p.q_tiles * WDCH * 128 * 128 + 2 * (size_t)WDCH * p.NK * 128 + 3 * WCH16 * 16 + (2 * 128 * 4 + 256) * 4 +
                       256 * 4 + 64 + 1024;
   dim3 grid(p.groups, heads, B);
   if (p.NK <= 128) {
