@@ -57,6 +57,8 @@ def parse():
                     help="config 5: ONE volume; slice encoding sharded over the ranks + NCCL all-gather of the pyramid, "
                          "rank 0 propagates (strong scaling; default is one volume per rank, no collectives)")
     ap.add_argument("--encode-batch", type=int, default=8, help="slices per image-encoder pass on a cache miss")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="encode slices on demand on the tracking stream (no side-stream encoding ahead of need)")
     return ap.parse_args()
 
 
@@ -264,7 +266,8 @@ def main_ours(args):
     model = medsam2_b200.build_sam2_video_predictor(
         args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
                                                       f"++model.feature_encode_batch={args.encode_batch}",
-                                                      f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}"])
+                                                      f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}",
+                                                      f"++model.feature_prefetch={'false' if args.no_prefetch else 'true'}"])
     model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
     shard_encode = args.shard_encode and world > 1
     # default: every rank tracks its own volume (config 4 sharding); --shard-encode: all ranks hold the same volume
@@ -421,6 +424,7 @@ def main_ours(args):
                        "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid, rank 0 propagates"
                                     if shard_encode else "by volume, no collectives" if world > 1 else "single GPU"),
                        "encode_batch": args.encode_batch, "cuda_graphs": not args.no_graphs,
+                       "encode_prefetch": not args.no_prefetch,
                        "l2": "256 MiB flush buffer written before every step; per-step working set >> L2"},
             "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel()},

@@ -36,6 +36,42 @@ template <> struct Vec8<float> {
 constexpr int SM_MT = 16;       // rows per pass
 constexpr int SM_WARPS = 4;     // grouped kernel: 4 warps x 4 columns = 16 columns per CTA
 
+// acc[m] += sum_k A[m0+m, k] * wrow[k] over this lane's 16-byte chunks (chunk stride KL*8 elements).  Four chunks per
+// pass: their weight loads (and the activation loads behind them) are all issued before the first FMA, so a
+// K = 256 column costs one global-memory round trip instead of four dependent ones.
+template <typename T, int KL>
+__device__ __forceinline__ void smallm_accumulate(const T* __restrict__ A, long lda, const T* __restrict__ wrow, int K,
+                                                  int kl, int m0, int mt, float (&acc)[SM_MT]) {
+  constexpr int U = 4;
+  for (int k0 = kl * 8; k0 < K; k0 += KL * 8 * U) {
+    float w[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * KL * 8;
+      if (k < K) Vec8<T>::load(wrow + k, w[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) {
+      if (m < mt) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = k0 + u * KL * 8;
+          if (k < K) {
+            float a[8];
+            Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[u][i], acc[m]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // KL lanes share one output column and split K in 16-byte chunks (KL = 8: 4 columns per warp; KL = 32: one column
 // per warp, for K >= 1024 where 8 lanes would each walk 128+ elements serially).  Two warps per CTA so that even
 // N = 256 gives 32..128 CTAs: these GEMMs are pure latency (W is 0.1-1 MB, A a few KB).
@@ -56,19 +92,7 @@ gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, c
     float acc[SM_MT];
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
-    for (int k = kl * 8; k < K; k += KL * 8) {
-      float w[8];
-      Vec8<T>::load(wrow + k, w);
-#pragma unroll
-      for (int m = 0; m < SM_MT; ++m) {
-        if (m < mt) {
-          float a[8];
-          Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[i], acc[m]);
-        }
-      }
-    }
+    smallm_accumulate<T, KL>(A, lda, wrow, K, kl, m0, mt, acc);
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) {
       float v = acc[m];
@@ -130,19 +154,7 @@ gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K) {
     float acc[SM_MT];
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
-    for (int k = kl * 8; k < K; k += 64) {
-      float w[8];
-      Vec8<T>::load(wrow + k, w);
-#pragma unroll
-      for (int m = 0; m < SM_MT; ++m) {
-        if (m < mt) {
-          float a[8];
-          Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[i], acc[m]);
-        }
-      }
-    }
+    smallm_accumulate<T, 8>(A, lda, wrow, K, kl, m0, mt, acc);
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) {
       float v = acc[m];

@@ -148,21 +148,49 @@ win_attn_tc_kernel(const WinP p) {
   auto gather_q = [&](int qt) {
     const int* rt = rowtab + (qt & 1) * 512;
     const uint32_t dstQ = aQ + (uint32_t)qt * (WDCH * 128 * 128);
-    for (int idx = tid; idx < 128 * WCH16; idx += NT) {
-      const int rr = idx / WCH16, ch = idx - rr * WCH16;
-      const uint32_t dst = dstQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4);
-      const int o0 = rt[rr * 4];
-      if (!p.qpool) {
+    if (!p.qpool) {
+      for (int idx = tid; idx < 128 * WCH16; idx += NT) {
+        const int rr = idx / WCH16, ch = idx - rr * WCH16;
+        const uint32_t dst = dstQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4);
+        const int o0 = rt[rr * 4];
         if (o0 >= 0) cp_async16(dst, base + o0 + ch * 8);
         else tc::sts128(dst, o0 == -1 ? sBias[ch] : make_uint4(0, 0, 0, 0));
-      } else {
-        auto ldq = [&](int off) -> uint4 {
-          return off >= 0 ? __ldg((const uint4*)(base + off + ch * 8)) : sBias[ch];
-        };
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (o0 != -2)
-          v = max_bf16x8(max_bf16x8(ldq(o0), ldq(rt[rr * 4 + 1])), max_bf16x8(ldq(rt[rr * 4 + 2]), ldq(rt[rr * 4 + 3])));
-        tc::sts128(dst, v);
+      }
+    } else {
+      // valid (pooled) query rows are the first nv rows of the tile; two pieces per thread and pass, so that eight
+      // independent 16-byte loads are in flight before the first max
+      int nv = 128;
+      if (p.q_tiles == 1) {
+        int nw = nwin - w0;
+        if (nw > p.G) nw = p.G;
+        nv = nw * p.lq_w;
+      }
+      auto dst_of = [&](int rr, int ch) { return dstQ + (ch >> 3) * 128 * 128 + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4); };
+      for (int idx = tid + nv * WCH16; idx < 128 * WCH16; idx += NT)          // rows without a query: zeros
+        tc::sts128(dst_of(idx / WCH16, idx % WCH16), make_uint4(0, 0, 0, 0));
+      for (int i0 = tid; i0 < nv * WCH16; i0 += 2 * NT) {
+        uint4 v[2][4];
+        int rrs[2], chs[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = i0 + u * NT;
+          on[u] = idx < nv * WCH16;
+          rrs[u] = on[u] ? idx / WCH16 : 0;
+          chs[u] = on[u] ? idx - rrs[u] * WCH16 : 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int off = on[u] ? rt[rrs[u] * 4 + q] : -2;
+            v[u][q] = off >= 0 ? __ldg((const uint4*)(base + off + chs[u] * 8)) : (off == -1 ? sBias[chs[u]] : make_uint4(0, 0, 0, 0));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (on[u]) {
+            const bool none = rt[rrs[u] * 4] == -2;
+            const uint4 r = max_bf16x8(max_bf16x8(v[u][0], v[u][1]), max_bf16x8(v[u][2], v[u][3]));
+            tc::sts128(dst_of(rrs[u], chs[u]), none ? make_uint4(0, 0, 0, 0) : r);
+          }
       }
     }
   };

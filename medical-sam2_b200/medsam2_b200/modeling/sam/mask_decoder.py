@@ -91,11 +91,13 @@ class MaskDecoder(nn.Module):
         if self.pred_obj_scores and isinstance(self.pred_obj_score_head, MLP):
             heads.append(self.pred_obj_score_head)
             rows.append(hs2[0:: Nt])
-        outs = self._grouped_mlps(heads, rows) if B <= 64 and len(heads) <= 8 else None
+        # the hyper-network outputs land directly in their rows of `hyper`
+        dst = [hyper[:, i, :] for i in range(self.num_mask_tokens)] + [None] * (len(heads) - self.num_mask_tokens)
+        outs = self._grouped_mlps(heads, rows, dst) if B <= 64 and len(heads) <= 8 else None
         if outs is None:
             outs = [m(r) for m, r in zip(heads, rows)]
-        for i in range(self.num_mask_tokens):
-            hyper[:, i, :] = outs[i]
+            for i in range(self.num_mask_tokens):
+                hyper[:, i, :] = outs[i]
         masks = ops.hyper_mask(up.view(B, 16 * HW, C // 8), hyper).view(B, self.num_mask_tokens, 4 * h, 4 * w)
         iou_pred = outs[self.num_mask_tokens]
         if self.pred_obj_scores:
@@ -109,7 +111,7 @@ class MaskDecoder(nn.Module):
         return masks, iou_pred, mask_tokens_out, obj
 
     @staticmethod
-    def _grouped_mlps(mlps, rows):
+    def _grouped_mlps(mlps, rows, dst=None):
         """the head MLPs (4 hyper-networks, IoU, object score) share depth and input width: run them layer by layer
         as ONE grouped small-M launch per layer (3 launches instead of 18).  None if they are not uniform."""
         depth = mlps[0].num_layers
@@ -124,7 +126,7 @@ class MaskDecoder(nn.Module):
             last = li == depth - 1
             acts = [(ops.ACT_SIGMOID if (last and m.sigmoid_output) else ops.ACT_NONE) if last else m.act for m in mlps]
             xs = ops.gemm_grouped(xs, [w_c(l.weight) for l in layers], [p32(l.bias) for l in layers],
-                                  out_dtype=torch.float32 if last else cd, acts=acts)
+                                  out_dtype=torch.float32 if last else cd, acts=acts, outs=dst if last else None)
         return xs
 
     def select_outputs(self, masks, iou_pred, mask_tokens_out, multimask_output):

@@ -33,9 +33,26 @@ class Attention(nn.Module):
     def forward(self, q, k, v, residual=None):
         """q [B,Lq,C], k/v [B,Lk,Ckv] (fp32 or compute dtype) -> fp32 [B,Lq,C] (+ residual)."""
         cd = compute_dtype()
-        qp = self.q_proj(q, out_dtype=cd)
-        kp = self.k_proj(k, out_dtype=cd)
-        vp = self.v_proj(v, out_dtype=cd)
+        qp = kp = vp = None
+        # token-side projections (a handful of rows: pure launch latency) share one grouped small-M launch
+        B, Lk = k.shape[0], k.shape[1]
+        if B * Lk <= 64 and k.shape == v.shape:
+            kc, vc = to_compute(k).reshape(B * Lk, -1), to_compute(v).reshape(B * Lk, -1)
+            xs, ls = [kc, vc], [self.k_proj, self.v_proj]
+            if q.shape == k.shape and self.q_proj.weight.shape[1] == self.k_proj.weight.shape[1]:
+                xs.insert(0, to_compute(q).reshape(B * Lk, -1))
+                ls.insert(0, self.q_proj)
+            if all(x.shape[1] % 8 == 0 for x in xs):
+                outs = ops.gemm_grouped(xs, [w_c(l.weight) for l in ls], [p32(l.bias) for l in ls], out_dtype=cd)
+                outs = [o.view(B, Lk, -1) for o in outs]
+                kp, vp = outs[-2], outs[-1]
+                if len(outs) == 3:
+                    qp = outs[0]
+        if qp is None:
+            qp = self.q_proj(q, out_dtype=cd)
+        if kp is None:
+            kp = self.k_proj(k, out_dtype=cd)
+            vp = self.v_proj(v, out_dtype=cd)
         o = ops.attention(qp, kp, vp, self.num_heads)
         return self.out_proj(o, out_dtype=torch.float32, residual=residual)
 
@@ -64,9 +81,13 @@ class RoPEAttention(Attention):
         qkv = ops.gemm(t, w, b, out_dtype=cd)                       # [B,L,3*Ci]
         cos, sin = self._table(L, t.device)
         D = Ci // self.num_heads
-        for part in (0, 1):
-            for h in range(self.num_heads):
-                ops.rope_(qkv[:, :, part * Ci + h * D:], B, L, L, D, cos, sin, batch_stride=L * 3 * Ci, row_stride=3 * Ci)
+        if B == 1 and self.num_heads == 1:
+            # q and k of the fused projection in one launch: "batch" 0 = q columns, 1 = k columns of the same rows
+            ops.rope_(qkv, 2, L, L, D, cos, sin, batch_stride=Ci, row_stride=3 * Ci)
+        else:
+            for part in (0, 1):
+                for h in range(self.num_heads):
+                    ops.rope_(qkv[:, :, part * Ci + h * D:], B, L, L, D, cos, sin, batch_stride=L * 3 * Ci, row_stride=3 * Ci)
         o = ops.attention(qkv[:, :, :Ci], qkv[:, :, Ci:2 * Ci], qkv[:, :, 2 * Ci:], self.num_heads)
         return self.out_proj(o, out_dtype=torch.float32, residual=residual)
 

@@ -152,20 +152,25 @@ def gemm(a, w, bias=None, out_dtype=torch.float32, act=ACT_NONE, residual=None, 
     return out
 
 
-def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None):
+def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None, outs=None):
     """len(a_list) <= 8 independent small-M GEMMs in one launch: out_g = act_g(a_g[M,K] @ w_g[N_g,K]^T + bias_g).
-    a_g may be row-strided 2-D views (token rows of [B,Nt,C]); all share M, K and dtype."""
+    a_g may be row-strided 2-D views (token rows of [B,Nt,C]); all share M, K and dtype.  `outs`: optional
+    destinations (row-strided [M,N_g] views of `out_dtype`, None entries are allocated)."""
     import ctypes
     G = len(a_list)
     M, K = a_list[0].shape
+    dst = list(outs) if outs is not None else [None] * G
     outs, A, W, Bs, O, lda, ldo, Ns = [], [], [], [], [], [], [], []
-    for a, w, b in zip(a_list, w_list, bias_list):
+    for a, w, b, o in zip(a_list, w_list, bias_list, dst):
         if a.shape != (M, K) or w.shape[1] != K or a.stride(1) != 1 or not a.is_cuda or a.dtype != a_list[0].dtype:
             raise native.NativeError("gemm_grouped: operands must share M, K, dtype and be CUDA with unit inner stride")
-        o = torch.empty((M, w.shape[0]), dtype=out_dtype, device=a.device)
+        if o is None:
+            o = torch.empty((M, w.shape[0]), dtype=out_dtype, device=a.device)
+        elif tuple(o.shape) != (M, w.shape[0]) or o.dtype != out_dtype or o.stride(1) != 1 or not o.is_cuda:
+            raise native.NativeError("gemm_grouped: bad destination view")
         outs.append(o)
         A.append(a.data_ptr()); W.append(_chk(w, "w")); Bs.append(0 if b is None else _chk(b, "bias", torch.float32))
-        O.append(o.data_ptr()); lda.append(a.stride(0)); ldo.append(w.shape[0]); Ns.append(w.shape[0])
+        O.append(o.data_ptr()); lda.append(a.stride(0)); ldo.append(o.stride(0)); Ns.append(w.shape[0])
     acts = list(acts) if acts is not None else [ACT_NONE] * G
     vp, lp, ip = ctypes.c_void_p * G, ctypes.c_long * G, ctypes.c_int * G
     native.call("ms2_gemm_smallm_grouped", G, vp(*A), lp(*lda), vp(*W), vp(*Bs), vp(*O), lp(*ldo), ip(*Ns), ip(*acts),

@@ -16,6 +16,19 @@ from .modeling.sam2_base import NO_OBJ_SCORE, SAM2Base
 from .utils.misc import concat_points, fill_holes_in_mask_scores, load_video_frames, load_video_frames_from_data
 
 
+_ENCODE_STREAMS = {}
+
+
+def _encode_stream(device):
+    """one long-lived slice-encoding stream per device (a fresh stream per volume would start with an empty
+    allocator pool: cudaMalloc in the timed path)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    s = _ENCODE_STREAMS.get(key)
+    if s is None:
+        s = _ENCODE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return s
+
+
 def _new_frame_dict():
     return {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
 
@@ -23,7 +36,7 @@ def _new_frame_dict():
 class SAM2VideoPredictor(SAM2Base):
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, feature_cache_size=1, feature_encode_batch=1,
-                 use_cuda_graphs=None, **kwargs):
+                 use_cuda_graphs=None, feature_prefetch=None, **kwargs):
         super().__init__(**kwargs)
         self.fill_hole_area = fill_hole_area
         self.non_overlap_masks = non_overlap_masks
@@ -34,6 +47,11 @@ class SAM2VideoPredictor(SAM2Base):
         # order); per-slice results equal one-at-a-time encoding up to the summation order of the split-KV global-attention
         # blocks; the GEMM/attention launches are just `feature_encode_batch` times larger.  Never exceeds the cache capacity.
         self.feature_encode_batch = max(1, int(feature_encode_batch))
+        # Slice encoding ahead of need on a side stream (None = automatic: on when the cache holds the whole volume and
+        # slices are encoded in batches).  The request stride is learnt from the calls (prompts every k slices, then
+        # the tracked slices in between), so the encoder batches of the slices the tracker will need next run
+        # concurrently with the latency-bound per-slice tracking kernels instead of in front of them.
+        self.feature_prefetch = feature_prefetch
         if use_cuda_graphs is not None:
             self.use_cuda_graphs = bool(use_cuda_graphs)
 
@@ -251,7 +269,7 @@ class SAM2VideoPredictor(SAM2Base):
         return any_res_masks, video_res_masks
 
     def _consolidate_temp_output_across_obj(self, inference_state, frame_idx, is_cond, run_mem_encoder,
-                                            consolidate_at_video_res=False):
+                                            consolidate_at_video_res=False, deferred_mem_enc=None):
         st = inference_state
         batch_size = self._get_obj_num(st)
         key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
@@ -291,10 +309,36 @@ class SAM2VideoPredictor(SAM2Base):
                                                  (self.image_size, self.image_size))
             if self.non_overlap_masks_for_mem_enc:
                 high_res_masks = self._apply_non_overlapping_constraints(high_res_masks)
-            cons["maskmem_features"], cons["maskmem_pos_enc"] = self._run_memory_encoder(
-                inference_state=st, frame_idx=frame_idx, batch_size=batch_size, high_res_masks=high_res_masks,
-                is_mask_from_pts=True)
+            if deferred_mem_enc is not None:      # preflight: the memory encoder runs on several frames at once
+                deferred_mem_enc.append((frame_idx, cons, high_res_masks))
+            else:
+                cons["maskmem_features"], cons["maskmem_pos_enc"] = self._run_memory_encoder(
+                    inference_state=st, frame_idx=frame_idx, batch_size=batch_size, high_res_masks=high_res_masks,
+                    is_mask_from_pts=True)
         return cons
+
+    def _run_memory_encoder_frames(self, st, pending, batch_size):
+        """Memory encoder of the prompted frames of the preflight (`pending`: (frame, consolidated output, 1024^2
+        masks)), several frames per pass: the frames are independent, and one frame alone (4096 tokens) leaves most of
+        the GPU idle.  Per-sample arithmetic is that of `_run_memory_encoder`."""
+        per = max(1, self.feature_encode_batch // max(batch_size, 1))
+        for c0 in range(0, len(pending), per):
+            chunk = pending[c0: c0 + per]
+            if len(chunk) == 1:
+                f, cons, hr = chunk[0]
+                cons["maskmem_features"], cons["maskmem_pos_enc"] = self._run_memory_encoder(
+                    inference_state=st, frame_idx=f, batch_size=batch_size, high_res_masks=hr, is_mask_from_pts=True)
+                continue
+            got = [self._get_image_feature(st, f, batch_size) for f, _, _ in chunk]
+            sizes = got[0][4]
+            feat = torch.cat([g[2][-1] for g in got], dim=1)                       # [HW, frames*B, C]
+            masks = torch.cat([hr for _, _, hr in chunk], dim=0)
+            mf, pe = self._encode_new_memory(current_vision_feats=[feat], feat_sizes=sizes, pred_masks_high_res=masks,
+                                             is_mask_from_pts=True)
+            for i, (f, cons, _) in enumerate(chunk):
+                sl = slice(i * batch_size, (i + 1) * batch_size)
+                cons["maskmem_features"] = mf[sl].to(st["storage_device"], non_blocking=True)
+                cons["maskmem_pos_enc"] = self._get_maskmem_pos_enc(st, {"maskmem_pos_enc": [p[sl] for p in pe]})
 
     def _get_empty_mask_ptr(self, inference_state, frame_idx):
         st = inference_state
@@ -318,8 +362,12 @@ class SAM2VideoPredictor(SAM2Base):
             for t in temp.values():
                 frames.update(t[key].keys())
             cfi[key].update(frames)
+            pending = []
             for frame_idx in sorted(frames):
-                cons = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond=is_cond, run_mem_encoder=True)
+                self._consolidate_temp_output_across_obj(st, frame_idx, is_cond=is_cond, run_mem_encoder=True,
+                                                         deferred_mem_enc=pending)
+            self._run_memory_encoder_frames(st, pending, batch_size)
+            for frame_idx, cons, _ in pending:
                 output_dict[key][frame_idx] = cons
                 self._add_output_per_object(st, frame_idx, cons, key)
                 if self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or batch_size <= 1):
@@ -353,6 +401,15 @@ class SAM2VideoPredictor(SAM2Base):
     # ------------------------------------------------------------------ propagation
     def _propagate(self, st, start_frame_idx, max_frame_num_to_track, reverse):
         st["prefetch_reverse"] = bool(reverse)
+        if self._prefetch_enabled(st):
+            # the first un-encoded slices in tracking order start encoding now, under the (latency-bound) preflight
+            first = start_frame_idx
+            if first is None:
+                prompted = [f for d in (st["point_inputs_per_obj"], st["mask_inputs_per_obj"]) for v in d.values() for f in v]
+                first = min(prompted) if prompted else 0
+            ahead = self._plan_frames(st, first, -1 if reverse else 1)
+            if ahead:
+                self._encode_frames(st, ahead, side=True)
         self._preflight(st)
         output_dict = st["output_dict"]
         cfi = st["consolidated_frame_inds"]
@@ -455,35 +512,100 @@ class SAM2VideoPredictor(SAM2Base):
         st["frames_already_tracked"].clear()
 
     # ------------------------------------------------------------------ per-frame execution
+    def _prefetch_enabled(self, st):
+        if self.feature_prefetch is False or st["device"].type != "cuda":
+            return False
+        whole = self.feature_cache_size >= st["num_frames"] and self.feature_encode_batch > 1
+        return whole if self.feature_prefetch is None else (whole and bool(self.feature_prefetch))
+
+    def _encode_frames(self, st, frames, side):
+        """Encode `frames` in one image-encoder pass and put them into the cache.  side=True: on the encode stream,
+        cache entries carry the CUDA event their consumers must wait for."""
+        cache = st["cached_features"]
+        cap = max(self.feature_cache_size, 1)
+        imgs = st["images"]
+        dev = st["device"]
+
+        def run():
+            if len(frames) == 1:
+                images = imgs[frames[0]].to(dev).float().unsqueeze(0)
+            else:
+                images = torch.stack([imgs[f] for f in frames]).to(dev).float()
+            return images, self.forward_image(images)
+
+        ev = None
+        if side:
+            main = torch.cuda.current_stream(dev)
+            enc = _encode_stream(dev)
+            enc.wait_stream(main)            # frames / parameter caches written by work already queued on this stream
+            with torch.cuda.stream(enc):
+                images, out = run()
+                ev = torch.cuda.Event()
+                ev.record(enc)
+            for t in [images] + [x for v in out.values() for x in (v if isinstance(v, list) else [v])]:
+                t.record_stream(main)        # allocated on the encode stream, consumed on the caller's stream
+        else:
+            images, out = run()
+        if cap <= 1:
+            cache.clear()
+        for i, f in enumerate(frames):
+            while len(cache) >= cap:
+                cache.popitem(last=False)
+            cache[f] = (images[i:i + 1], {k: ([t[i:i + 1] for t in v] if isinstance(v, list) else v[i:i + 1])
+                                          for k, v in out.items()}, ev)
+
+    def _plan_frames(self, st, first, stride, need_within=None):
+        """The next `feature_encode_batch` un-cached frames on the predicted request path first, first+stride, ...;
+        with `need_within`, nothing unless the first of them is at most that many requests away."""
+        cache, T = st["cached_features"], st["num_frames"]
+        frames, f, k = [], first, 0
+        while 0 <= f < T and len(frames) < self.feature_encode_batch:
+            if f not in cache:
+                if need_within is not None and not frames and k > need_within:
+                    return []
+                frames.append(f)
+            f += stride
+            k += 1
+        return frames
+
     def _get_image_feature(self, inference_state, frame_idx, batch_size):
         st = inference_state
         cache = st["cached_features"]
+        prefetch = self._prefetch_enabled(st)
+        direction = -1 if st.get("prefetch_reverse", False) else 1
+        stride = direction
+        if prefetch:
+            # request stride: prompts arrive every k slices, then the tracker asks for the slices in between
+            last = st.get("_last_feature_request")
+            stride = st.get("_feature_stride", direction)
+            if last is not None and frame_idx != last:
+                d = frame_idx - last
+                stride = d if 1 <= abs(d) <= self.feature_encode_batch else direction
+            st["_last_feature_request"], st["_feature_stride"] = frame_idx, stride
         hit = cache.get(frame_idx)
         if hit is None:
             cap = max(self.feature_cache_size, 1)
-            step = -1 if st.get("prefetch_reverse", False) else 1
-            frames = [frame_idx]
-            f = frame_idx + step
-            while len(frames) < min(self.feature_encode_batch, cap) and 0 <= f < st["num_frames"]:
-                if f not in cache:
-                    frames.append(f)
-                f += step
-            imgs = st["images"]
-            if len(frames) == 1:
-                images = imgs[frame_idx].to(st["device"]).float().unsqueeze(0)
+            if prefetch:
+                frames = self._plan_frames(st, frame_idx, stride)
             else:
-                images = torch.stack([imgs[f] for f in frames]).to(st["device"]).float()
-            out = self.forward_image(images)
-            if cap <= 1:
-                cache.clear()
-            for i, f in enumerate(frames):
-                while len(cache) >= cap:
-                    cache.popitem(last=False)
-                cache[f] = (images[i:i + 1], {k: ([t[i:i + 1] for t in v] if isinstance(v, list) else v[i:i + 1])
-                                              for k, v in out.items()})
-            image, backbone_out = cache[frame_idx]
-        else:
-            image, backbone_out = hit
+                frames = [frame_idx]
+                f = frame_idx + direction
+                while len(frames) < min(self.feature_encode_batch, cap) and 0 <= f < st["num_frames"]:
+                    if f not in cache:
+                        frames.append(f)
+                    f += direction
+            self._encode_frames(st, frames, side=prefetch)
+            hit = cache[frame_idx]
+        if len(hit) > 2 and hit[2] is not None:             # encoded on the side stream: order this stream after it
+            torch.cuda.current_stream(st["device"]).wait_event(hit[2])
+            for f, e in list(cache.items()):
+                if len(e) > 2 and e[2] is hit[2]:
+                    cache[f] = (e[0], e[1], None)
+        image, backbone_out = hit[0], hit[1]
+        if prefetch:
+            ahead = self._plan_frames(st, frame_idx + stride, stride, need_within=self.feature_encode_batch)
+            if ahead:
+                self._encode_frames(st, ahead, side=True)
         expanded = {
             "backbone_fpn": [f.expand(batch_size, -1, -1, -1) for f in backbone_out["backbone_fpn"]],
             "vision_pos_enc": [p.expand(batch_size, -1, -1, -1) for p in backbone_out["vision_pos_enc"]],

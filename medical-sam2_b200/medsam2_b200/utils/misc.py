@@ -89,9 +89,12 @@ class StreamedFrames:
                 self.waited.append(False)
 
     def _wait(self, c):
-        if not self.waited[c]:
-            torch.cuda.current_stream(self.out.device).wait_event(self.events[c])
-            self.waited[c] = True
+        cur = torch.cuda.current_stream(self.out.device)
+        if self.waited[c] is False:
+            self.waited[c] = set()
+        if cur.cuda_stream not in self.waited[c]:          # per consumer stream (tracking / slice-encoding streams)
+            cur.wait_event(self.events[c])
+            self.waited[c].add(cur.cuda_stream)
 
     def __len__(self):
         return self.T

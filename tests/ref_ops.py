@@ -237,9 +237,15 @@ def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre
     return F.gelu(y).to(out_dtype).contiguous()
 
 
-def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None):
+def gemm_grouped(a_list, w_list, bias_list, out_dtype=torch.float32, acts=None, outs=None):
     acts = acts or [ACT_NONE] * len(a_list)
-    return [gemm(a, w, b, out_dtype=out_dtype, act=act) for a, w, b, act in zip(a_list, w_list, bias_list, acts)]
+    res = [gemm(a, w, b, out_dtype=out_dtype, act=act) for a, w, b, act in zip(a_list, w_list, bias_list, acts)]
+    if outs is not None:
+        for i, o in enumerate(outs):
+            if o is not None:
+                o.copy_(res[i])
+                res[i] = o
+    return res
 
 
 def attention_dv(q, k, v, scale=None):

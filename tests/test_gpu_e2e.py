@@ -157,6 +157,31 @@ def test_cuda_graph_replay_is_bit_identical():
             assert torch.equal(o["obj_ptr"], g["obj_ptr"]) and torch.equal(o["maskmem_features"], g["maskmem_features"]), f
 
 
+def test_encode_prefetch_matches_on_demand_and_is_deterministic():
+    """Slice encoding ahead of need on the side stream (stride learnt from the requests) against on-demand
+    encoding on the tracking stream: same masks (up to the split-KV summation order of differently composed
+    encoder batches), identical from run to run (a missing stream dependency would show up as noise), and every
+    slice encoded exactly once."""
+    res = {}
+    for mode in (True, True, False):
+        m = _build("sam2_hiera_t", video=True, image_size=512)
+        m.feature_cache_size, m.feature_encode_batch, m.feature_prefetch = 14, 4, mode
+        calls = []
+        enc = m._encode_frames
+        m._encode_frames = lambda st, frames, side: (calls.append((tuple(frames), side)), enc(st, frames, side))[1]
+        st, o = _run_video(m, 512, 14, 1, (0, 2, 4, 6, 8, 10, 12), (), 99)
+        res.setdefault(mode, []).append(o)
+        assert sorted(f for fr, _ in calls for f in fr) == list(range(14)), calls
+        assert all(side == mode for _, side in calls), calls
+        if mode:
+            assert any(fr[1] - fr[0] == 2 for fr, _ in calls if len(fr) > 1), calls     # strided batches were planned
+    for f in range(14):
+        assert torch.equal(res[True][0][f], res[True][1][f]), f"prefetch run-to-run mismatch on frame {f}"
+        a, b = res[True][0][f].float(), res[False][0][f].float()
+        assert (a - b).abs().max().item() <= 3e-2, f
+        assert ((a > 0) == (b > 0)).float().mean().item() >= 0.998
+
+
 def test_streamed_host_upload_matches_resident_volume():
     """`async_loading_frames=True` on a pinned host tensor (chunked H2D + normalisation on a side stream, consumers
     wait per chunk) must give exactly the masks of a device-resident volume."""

@@ -78,6 +78,9 @@ def test_video_predictor(fake_backend, case):
         cfg, size, T, n_obj, prompts, absent, seed, fname = "sam2_hiera_t", 512, 6, 2, (0, 3), ((3, 1),), 77, "video_hiera_t_512_2obj.npz"
     z = np.load(f"{G}/{fname}")
     m = _build(cfg, video=True, image_size=size)
+    # batched slice encoding + preflight memory encoder over several prompted frames per pass (golden answers are from
+    # the reference's frame-at-a-time flow)
+    m.feature_cache_size, m.feature_encode_batch = 8, 4
     vol, boxes = btcv_volume(T, size, seed, n_obj)
     st = m.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
     for f in prompts:
@@ -140,3 +143,52 @@ def test_product_refuses_cpu_without_backend():
     from medsam2_b200.native import NativeError
     with pytest.raises(NativeError):
         ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-6)
+
+
+def test_slice_encode_prefetch_planner():
+    """Request-stride learning of the slice-encoding prefetcher (host logic only: the encoder is stubbed).  Config-3
+    call order on 96 slices, batches of 8: prompts on the even slices, then tracking of the odd ones.  Every slice is
+    encoded exactly once, in full batches, the odd slices are only encoded during tracking, and each batch is
+    requested at least one request before its first slice is needed (after the very first one)."""
+    from medsam2_b200.sam2_video_predictor import SAM2VideoPredictor
+
+    class Stub:
+        feature_cache_size, feature_encode_batch, feature_prefetch = 96, 8, True
+        _prefetch_enabled = lambda self, st: True
+        _plan_frames = SAM2VideoPredictor._plan_frames
+        _get_image_feature = SAM2VideoPredictor._get_image_feature
+
+        def __init__(self):
+            self.batches = []
+
+        def _encode_frames(self, st, frames, side):
+            assert side and frames and all(f not in st["cached_features"] for f in frames)
+            self.batches.append((st["_last_feature_request"], tuple(frames)))
+            for f in frames:
+                st["cached_features"][f] = (torch.zeros(1, 3, 4, 4), {"backbone_fpn": [torch.zeros(1, 2, 4, 4)],
+                                                                     "vision_pos_enc": [torch.zeros(1, 2, 4, 4)]}, None)
+
+        def _prepare_backbone_features(self, d):
+            return d, None, None, None
+
+    p = Stub()
+    st = {"cached_features": {}, "num_frames": 96, "device": torch.device("cpu")}
+    p._get_image_feature(st, 0, 1)                       # init_state warm-up
+    for f in range(0, 96, 2):                            # add_new_bbox on every other slice
+        p._get_image_feature(st, f, 1)
+    n_phase1 = len(p.batches)
+    assert all(f % 2 == 0 or f < 16 for _, fr in p.batches for f in fr), p.batches
+    for f in range(0, 96, 2):                            # preflight: memory encoder on the prompted slices
+        p._get_image_feature(st, f, 1)
+    assert len(p.batches) == n_phase1
+    for f in range(1, 96, 2):                            # tracking: only the un-prompted slices ask for features
+        p._get_image_feature(st, f, 1)
+    enc = [f for _, fr in p.batches for f in fr]
+    assert sorted(enc) == list(range(96)) and len(p.batches) == 12 and all(len(fr) == 8 for _, fr in p.batches)
+    for at, fr in p.batches[1:]:
+        assert at != fr[0], (at, fr)                     # launched ahead of the request that needs it
+    # reverse tracking plans downwards
+    p2 = Stub()
+    st2 = {"cached_features": {}, "num_frames": 20, "device": torch.device("cpu"), "prefetch_reverse": True}
+    p2._get_image_feature(st2, 19, 1)
+    assert p2.batches[0][1] == tuple(range(19, 11, -1)), p2.batches

@@ -9,7 +9,8 @@ from oracle.weights import param_spec
 from synth_data import btcv_volume, seeded_weights
 T, S = 96, 1024
 m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_s", device="cuda", hydra_overrides_extra=[
-    f"++model.image_size={S}", f"++model.feature_cache_size={T}", "++model.feature_encode_batch=8", "++model.use_cuda_graphs=true"])
+    f"++model.image_size={S}", f"++model.feature_cache_size={T}", "++model.feature_encode_batch=8", "++model.use_cuda_graphs=true",
+    "++model.feature_prefetch=" + os.environ.get("PREFETCH", "false")])
 m.load_state_dict(seeded_weights(param_spec(get_config("sam2_hiera_s"))), strict=True)
 vol, boxes = btcv_volume(T, S, 1234, 1)
 vol = vol.cuda()
