@@ -144,17 +144,23 @@ class GraphRunner:
             n0 = native.launch_count
             with torch.cuda.graph(graph):
                 static_out = fn(*static_in)
-            entry = self._graphs[full_key] = (graph, static_in, static_out, native.launch_count - n0)
-        graph, static_in, static_out, launches = entry
+            entry = self._graphs[full_key] = [graph, static_in, static_out, native.launch_count - n0, None]
+        graph, static_in, static_out, launches, last = entry
+        cur = torch.cuda.current_stream()
+        if last is not None and last[0] != cur.cuda_stream:
+            # the previous replay ran on another stream (slice encoding ahead of need): the static buffers are shared
+            cur.wait_event(last[1])
         for s, t in zip(static_in, tensors):
             if s is not None:
                 s.copy_(t)
         graph.replay()
         self.replays += 1
         native.launch_count += launches            # kernels of this library executed by the replay
-        if not clone:
-            return static_out
-        return _clone_tree(static_out)
+        out = static_out if not clone else _clone_tree(static_out)
+        ev = last[1] if last is not None else torch.cuda.Event()
+        ev.record(cur)
+        entry[4] = (cur.cuda_stream, ev)
+        return out
 
 
 def _clone_tree(x):
