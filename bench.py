@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--shard-encode", action="store_true",
                     help="config 5: ONE volume; slice encoding sharded over the ranks + NCCL all-gather of the pyramid, "
                          "rank 0 propagates (strong scaling; default is one volume per rank, no collectives)")
+    ap.add_argument("--shard-attention", action="store_true",
+                    help="with --shard-encode: also deal the memory bank to the ranks (split-KV memory cross-attention, "
+                         "partials all-gathered per layer); all ranks track the volume in lockstep")
     ap.add_argument("--encode-batch", type=int, default=8, help="slices per image-encoder pass on a cache miss")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="encode slices on demand on the tracking stream (no side-stream encoding ahead of need)")
@@ -267,9 +270,13 @@ def main_ours(args):
         args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
                                                       f"++model.feature_encode_batch={args.encode_batch}",
                                                       f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}",
-                                                      f"++model.feature_prefetch={'false' if args.no_prefetch else 'true'}"])
+                                                      f"++model.feature_prefetch={'false' if (args.no_prefetch or args.shard_encode) else 'true'}"])
     model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
     shard_encode = args.shard_encode and world > 1
+    shard_attention = shard_encode and args.shard_attention
+    if shard_attention:
+        from medsam2_b200.parallel import shard_memory_attention
+        shard_memory_attention(model)
     # default: every rank tracks its own volume (config 4 sharding); --shard-encode: all ranks hold the same volume
     vol, boxes = btcv_volume(T, S, 1234 + (0 if shard_encode else rank), 1)
     vol_host = vol.pin_memory()
@@ -302,7 +309,8 @@ def main_ours(args):
         st = model.val_init_state(imgs_tensor=v, video_height=S, video_width=S)
         encode_volume_sharded(model, st)                     # NCCL all-gather of the feature pyramid
         masks = [None] * T
-        if rank == 0:                                        # propagation is sequential in t: one rank runs it
+        if rank == 0 or shard_attention:                     # propagation is sequential in t: one rank runs it (or all
+                                                             # ranks in lockstep, each attending over its share of the bank)
             for f in prompt_frames(T, args.prompt_every):
                 model.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]),
                                          clear_old_points=False)
@@ -427,7 +435,10 @@ def main_ours(args):
             "config": {"workload": f"BASELINE configs[2]: {args.config} SAM2VideoPredictor.propagate_in_video, one "
                                    f"{T}-slice {S}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, "
                                    f"num_maskmem=7, fill_hole_area=8",
-                       "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid, rank 0 propagates"
+                       "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid; memory bank dealt to the ranks "
+                                    "(split-KV cross-attention, partials all-gathered per layer), all ranks propagate in lockstep"
+                                    if shard_attention else
+                                    "one volume: slice encoding sharded + NCCL all-gather of the pyramid, rank 0 propagates"
                                     if shard_encode else "by volume, no collectives" if world > 1 else "single GPU"),
                        "encode_batch": args.encode_batch, "cuda_graphs": not args.no_graphs,
                        "encode_prefetch": not args.no_prefetch,

@@ -103,6 +103,19 @@ int ms2_attention_dv(const void* q, const void* k, const void* v, void* o, int d
                      int B, int Hh, int Lq, int Lk, int D, int DV, float scale,
                      void* workspace, long workspace_bytes, ms2_stream_t stream);
 
+/* Split-KV memory cross-attention over several GPUs (the reference has no counterpart: it attends
+ * over the whole bank on one GPU, memory_attention.py:73-79 -> transformer.py:288-331).  Every rank attends over its own
+ * share of the bank and emits ONE un-normalised partial per query row:
+ *   part_o [B*Lq, DV] fp32 = sum_j 2^(s_j - m) v_j,   part_ml [B*Lq, 2] fp32 = (m = row max of s in log2 units, l = sum_j 2^(s_j - m)).
+ * ms2_attention_merge combines `nparts` partials (part r at parts_o + r*part_stride and parts_ml + r*part_stride, in
+ * floats; an empty share is (0, -inf, 0)) into the softmax-normalised o [B,Lq,DV]. */
+int ms2_attention_dv_partial(const void* q, const void* k, const void* v, float* part_o, float* part_ml, int dt,
+                             long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts,
+                             int B, int Lq, int Lk, int D, int DV, float scale,
+                             void* workspace, long workspace_bytes, ms2_stream_t stream);
+int ms2_attention_merge(const float* parts_o, const float* parts_ml, long part_stride, void* o, int dt,
+                        long o_bs, long o_ts, int B, int Lq, int DV, int nparts, ms2_stream_t stream);
+
 /* ---- Hiera windowed attention with window partition / zero-pad-as-bias-key / q max-pool /
  *      unpartition+crop folded into the loads and stores (hieradet.py:58-83,136-159,
  *      backbones/utils.py:16-62).  qkv [B,H,W,3,heads,D] dtype dt (the qkv Linear output on the

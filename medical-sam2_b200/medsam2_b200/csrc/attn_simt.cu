@@ -223,6 +223,33 @@ extern "C" int ms2_attention_dv(const void* q, const void* k, const void* v, voi
                                  Lq, Lk, D, DV, scale, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int ms2_attention_dv_partial_launch(const void* q, const void* k, const void* v, float* part_o, float* part_ml, long q_bs,
+                                    long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk,
+                                    float scale, void* ws, long ws_bytes, cudaStream_t st);
+int ms2_attention_merge_launch(const float* parts_o, const float* parts_ml, long part_stride, void* o, long o_bs, long o_ts,
+                               int B, int Lq, int nparts, cudaStream_t st);
+
+extern "C" int ms2_attention_dv_partial(const void* q, const void* k, const void* v, float* part_o, float* part_ml, int dt,
+                                        long q_bs, long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, int B, int Lq,
+                                        int Lk, int D, int DV, float scale, void* workspace, long workspace_bytes,
+                                        void* stream) {
+  MS2_CHECK_ARG(q && k && v && part_o && part_ml, "attention_dv_partial: null pointer");
+  MS2_CHECK_ARG(B > 0 && Lq > 0 && Lk > 0, "attention_dv_partial: bad shape");
+  MS2_CHECK_ARG(ms2_attention_tc_supported(dt, 256, q_ts, 256, k_ts, 64, v_ts, 64, 64, 1, Lq, Lk, D, DV) && D == 256 &&
+                    DV == 64,
+                "attention_dv_partial: unsupported shape/dtype/stride (bf16, D=256, DV=64, Lq,Lk >= 64)");
+  return ms2_attention_dv_partial_launch(q, k, v, part_o, part_ml, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, Lq, Lk, scale,
+                                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ms2_attention_merge(const float* parts_o, const float* parts_ml, long part_stride, void* o, int dt,
+                                   long o_bs, long o_ts, int B, int Lq, int DV, int nparts, void* stream) {
+  MS2_CHECK_ARG(parts_o && parts_ml && o && nparts >= 1, "attention_merge: bad args");
+  MS2_CHECK_ARG(dt == MS2_BF16 && DV == 64, "attention_merge: bf16 output with DV = 64 only");
+  if (B == 0 || Lq == 0) return MS2_OK;
+  return ms2_attention_merge_launch(parts_o, parts_ml, part_stride, o, o_bs, o_ts, B, Lq, nparts, (cudaStream_t)stream);
+}
+
 extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
                                 long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
                                 long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,

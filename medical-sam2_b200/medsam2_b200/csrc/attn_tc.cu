@@ -35,6 +35,7 @@ struct AttnTcP {
   float c;        // scale * log2(e)
   int ntiles, tiles_per_split, nsplit;
   float tau;      // lazy-rescale threshold (log2 units)
+  int force_part; // write the un-normalised partial (opart, ml) even when nsplit == 1 (split-KV across GPUs)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -310,7 +311,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc::mbar_wait(o_ready, (uint32_t)(n - 1) & 1u);
     tc::tc_fence_after();
     const int qi = q0 + row;
-    if (p.nsplit == 1) {
+    if (p.nsplit == 1 && !p.force_part) {
       const float inv = 1.f / l;
       bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
 #pragma unroll 1
@@ -610,7 +611,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc::mbar_wait(&o_ready[x], (uint32_t)(n - 1) & 1u);
     tc::tc_fence_after();
     const int qi = q0 + x * BQ + row;
-    if (p.nsplit == 1) {
+    if (p.nsplit == 1 && !p.force_part) {
       const float inv = 1.f / l;
       bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
 #pragma unroll 1
@@ -698,6 +699,74 @@ attn_combine_kernel(const float* __restrict__ opart, const float* __restrict__ m
   *(uint4*)dst = v;
 }
 
+// ---- split-KV across GPUs: every rank attends over its own share of the memory bank and
+//      hands out ONE un-normalised partial per query row; the partials of all ranks are merged exactly as the
+//      split-KV partials of one GPU are.
+// local splits -> one partial:  m* = max_s m_s,  O* = sum_s 2^(m_s - m*) O_s,  l* = sum_s 2^(m_s - m*) l_s
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_reduce_partials_kernel(const float* __restrict__ opart, const float* __restrict__ ml, float* __restrict__ out_o,
+                            float* __restrict__ out_ml, int nsplit, long rows) {
+  constexpr int TPR = D / 8, RPB = 128 / TPR;
+  const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int cg = threadIdx.x % TPR;
+  if (rix >= rows) return;
+  float mstar = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mstar = fmaxf(mstar, ml[((long)s * rows + rix) * 2]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float lsum = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float2 v = *(const float2*)(ml + ((long)s * rows + rix) * 2);
+    const float w = exp2f(v.x - mstar);
+    lsum += w * v.y;
+    const float4* src = (const float4*)(opart + ((long)s * rows + rix) * D + cg * 8);
+    const float4 a = src[0], bq = src[1];
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+  }
+  float4* dst = (float4*)(out_o + rix * D + cg * 8);
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  if (cg == 0) *(float2*)(out_ml + rix * 2) = make_float2(mstar, lsum);
+}
+
+// partials of `nparts` ranks (part r at parts_o + r*part_stride / parts_ml + r*part_stride; an empty share is
+// (0, -inf, 0)) -> softmax-normalised bf16 rows
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_merge_kernel(const float* __restrict__ parts_o, const float* __restrict__ parts_ml, long part_stride,
+                  bf16* __restrict__ o, long o_bs, long o_ts, int Lq, int nparts, long rows) {
+  constexpr int TPR = D / 8, RPB = 128 / TPR;
+  const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int cg = threadIdx.x % TPR;
+  if (rix >= rows) return;
+  float mstar = -INFINITY;
+  for (int r = 0; r < nparts; ++r) mstar = fmaxf(mstar, parts_ml[(long)r * part_stride + rix * 2]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float lsum = 0.f;
+  for (int r = 0; r < nparts; ++r) {
+    const float2 v = *(const float2*)(parts_ml + (long)r * part_stride + rix * 2);
+    if (v.y <= 0.f) continue;                                  // empty share
+    const float w = exp2f(v.x - mstar);
+    lsum += w * v.y;
+    const float4* src = (const float4*)(parts_o + (long)r * part_stride + rix * D + cg * 8);
+    const float4 a = src[0], bq = src[1];
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+  }
+  const float inv = 1.f / lsum;
+  const long b = rix / Lq;
+  const int qi = (int)(rix - b * Lq);
+  uint4 v;
+  uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+    vv[i] = *(uint32_t*)&hh;
+  }
+  *(uint4*)(o + b * o_bs + (long)qi * o_ts + cg * 8) = v;
+}
+
 int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long ws_bytes) {
   const int sms = tc::sm_count();
   if (qtiles_total >= 2 * sms || ntiles < 4) return 1;
@@ -720,7 +789,7 @@ int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long
 template <int D, int DV, int BKV, int KST>
 int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts, long k_bs, long k_hs,
            long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts, int B, int Hh, int Lq, int Lk,
-           float scale, void* ws, long ws_bytes, cudaStream_t st) {
+           float scale, void* ws, long ws_bytes, cudaStream_t st, float* part_o = nullptr, float* part_ml = nullptr) {
   using C = Cfg<D, DV, BKV, KST>;
   static_assert(C::SMEM <= 227 * 1024, "attention tile does not fit shared memory");
   static_assert(KST >= 2 && KST <= 4, "K ring depth");
@@ -752,6 +821,7 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
   p.opart = (float*)ws;
   p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
+  p.force_part = part_o ? 1 : 0;
 
   static const bool two_tiles_ok = []() { const char* e = getenv("MS2_ATTN_TWO_TILES"); return !e || atoi(e) != 0; }();
   if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
@@ -760,6 +830,7 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.nsplit = ws ? pick_nsplit(qpairs * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
+    if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
     static bool attr2 = false;
     if (!attr2) {
       MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr");
@@ -769,6 +840,7 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     attn_tc2_kernel<<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p);
     MS2_CHECK_LAUNCH("attn_tc2_kernel");
   } else {
+    if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
     auto kern = attn_tc_kernel<D, DV, BKV, KST>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -779,7 +851,13 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
     MS2_CHECK_LAUNCH("attn_tc_kernel");
   }
-  if (p.nsplit > 1) {
+  if (part_o) {
+    if (p.nsplit > 1) {
+      constexpr int TPR = DV / 8, RPB = 128 / TPR;
+      attn_reduce_partials_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, part_o, part_ml, p.nsplit, rows);
+      MS2_CHECK_LAUNCH("attn_reduce_partials_kernel");
+    }
+  } else if (p.nsplit > 1) {
     constexpr int TPR = DV / 8, RPB = 128 / TPR;
     attn_combine_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
                                                                  p.nsplit, rows);
@@ -821,4 +899,28 @@ int ms2_attention_tc_launch(const void* q, const void* k, const void* v, void* o
 #undef MS2_ATTN_ARGS
   ms2_set_error("attention_tc: unsupported head dims %d/%d", D, DV);
   return MS2_ERR_UNSUPPORTED;
+}
+
+// ---- split-KV across GPUs: partial attention over this rank's keys / merge of all ranks' partials (D=256, DV=64)
+int ms2_attention_dv_partial_launch(const void* q, const void* k, const void* v, float* part_o, float* part_ml, long q_bs,
+                                    long q_ts, long k_bs, long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk,
+                                    float scale, void* ws, long ws_bytes, cudaStream_t st) {
+  MS2_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                    ((uintptr_t)part_o % 16 == 0) && ((uintptr_t)part_ml % 8 == 0) && (!ws || (uintptr_t)ws % 16 == 0),
+                "attention_dv_partial: pointers must be 16-byte aligned");
+  return launch<256, 64, 64, 4>(q, k, v, nullptr, q_bs, 256, q_ts, k_bs, 256, k_ts, v_bs, 64, v_ts, 0, 0, 0, B, 1, Lq, Lk,
+                                scale, ws, ws_bytes, st, part_o, part_ml);
+}
+
+int ms2_attention_merge_launch(const float* parts_o, const float* parts_ml, long part_stride, void* o, long o_bs, long o_ts,
+                               int B, int Lq, int nparts, cudaStream_t st) {
+  MS2_CHECK_ARG(((uintptr_t)parts_o % 16 == 0) && ((uintptr_t)parts_ml % 8 == 0) && ((uintptr_t)o % 16 == 0) &&
+                    part_stride % 4 == 0 && o_ts % 8 == 0 && (B == 1 || o_bs % 8 == 0),
+                "attention_merge: alignment");
+  const long rows = (long)B * Lq;
+  constexpr int DV = 64, TPR = DV / 8, RPB = 128 / TPR;
+  attn_merge_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(parts_o, parts_ml, part_stride, (bf16*)o, o_bs, o_ts, Lq,
+                                                             nparts, rows);
+  MS2_CHECK_LAUNCH("attn_merge_kernel");
+  return MS2_OK;
 }

@@ -46,7 +46,8 @@ class MemoryAttentionLayer(nn.Module):
             t = ops.axpby(self.norm2(x), 1.0, query_pos, 1.0, out_dtype=cd)
         q = self.cross_attn_image.project_q(t)
         if kv is not None and kv[2]:
-            o = self.cross_attn_image.v_proj(ops.attention_dv(q, kv[0], kv[1]), out_dtype=cd)   # deferred value projection
+            attend = kv[3] if len(kv) > 3 else ops.attention_dv          # kv[3]: split-KV over several GPUs (KVShard.attend)
+            o = self.cross_attn_image.v_proj(attend(q, kv[0], kv[1]), out_dtype=cd)             # deferred value projection
         else:
             k, v = kv[:2] if kv is not None else self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
             o = ops.attention(q, k, v, self.cross_attn_image.num_heads)
@@ -109,6 +110,7 @@ class MemoryAttention(nn.Module):
         self.norm = LayerNorm(d_model)
         self.pos_enc_at_input = pos_enc_at_input
         self.batch_first = batch_first
+        self.kv_shard = None          # parallel.KVShard: the bank's keys are dealt to several GPUs (split-KV attention)
 
     def forward_tokens(self, curr, curr_pos, memory, memory_pos, num_obj_ptr_tokens=0):
         """batch-first fp32: curr/curr_pos [B,L,C], memory/memory_pos [B,Lk,Cm] -> fp32 [B,L,C]."""
@@ -157,6 +159,15 @@ class MemoryAttention(nn.Module):
         B, L, C = curr.shape
         keys_at_pos = self.layers[0].pos_enc_at_cross_attn_keys
         att0 = self.layers[0].cross_attn_image
+        shard = self.kv_shard
+        if shard is not None:
+            # this rank's share of the bank: conditioning memories i = rank (mod world), recent memories rotated, the
+            # pointer tokens with the first recent memory; softmax partials are merged across ranks per layer
+            n_cond, n_recent = len(cond), len(recent)
+            cond = [e for i, e in enumerate(cond) if shard.owns_cond(i)]
+            recent = [e for j, e in enumerate(recent) if shard.owns_recent(j, n_cond)]
+            if not shard.owns_pointers(n_recent, n_cond):
+                ptrs = ptr_pos = None
         hw = cond[0][2].shape[1] if cond else (recent[0][2].shape[1] if recent else L)
         n_dyn = sum(e[2].shape[1] for e in recent) + (ptrs.shape[1] if ptrs is not None else 0)
         keys = [e[0] for e in cond]
@@ -167,6 +178,8 @@ class MemoryAttention(nn.Module):
         # [L,64] attention result
         raw_v = (cd == torch.bfloat16 and att0.num_heads == 1 and att0.internal_dim == 256 and att0.kv_in_dim == 64
                  and L >= 64)
+        if shard is not None and not raw_v:
+            raise RuntimeError("split-KV memory attention needs the bf16 single-head 256/64 configuration")
         bank.ensure(len(self.layers), B, len(keys) * hw + n_dyn + 64, att0.internal_dim, att0.kv_in_dim, raw_v, cd,
                     curr.device)
         new = cond[len(bank.keys):]
@@ -192,7 +205,12 @@ class MemoryAttention(nn.Module):
         Lk = row0 + n_dyn
         x = ops.axpby(curr, 1.0, curr_pos, 0.1) if (self.pos_enc_at_input and curr_pos is not None) else curr
         for l, layer in enumerate(self.layers):
-            kv = (bank.K[l][:, :Lk], bank.M[:, :Lk], True) if bank.raw_v else (bank.K[l][:, :Lk], bank.V[l][:, :Lk], False)
+            if shard is not None:
+                kv = (bank.K[l][:, :Lk] if Lk else None, bank.M[:, :Lk] if Lk else None, True, shard.attend)
+            elif bank.raw_v:
+                kv = (bank.K[l][:, :Lk], bank.M[:, :Lk], True)
+            else:
+                kv = (bank.K[l][:, :Lk], bank.V[l][:, :Lk], False)
             x = layer.forward_tokens(x, curr_pos, None, None, 0, kv=kv)
         return self.norm(x)
 

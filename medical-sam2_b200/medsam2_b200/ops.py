@@ -243,6 +243,55 @@ def attention_dv(q, k, v, scale=None):
     return o
 
 
+def attention_dv_partial(q, k, v, out=None, scale=None):
+    """this rank's share of a split-KV memory cross-attention: q [B,Lq,256], k [B,Lk,256], v [B,Lk,64] (bf16) ->
+    packed fp32 partial [B*Lq*(64+2)]: B*Lq*64 un-normalised outputs followed by B*Lq (row max in log2 units, row sum)
+    pairs.  k = None or Lk == 0 gives the empty partial (0, -inf, 0)."""
+    B, Lq, D = q.shape
+    DV = 64
+    rows = B * Lq
+    if out is None:
+        out = torch.empty(rows * (DV + 2), dtype=torch.float32, device=q.device)
+    part_o, part_ml = out[: rows * DV], out[rows * DV:]
+    Lk = 0 if k is None else k.shape[1]
+    if Lk == 0:
+        part_o.zero_()
+        ml = part_ml.view(rows, 2)
+        ml[:, 0] = float("-inf")
+        ml[:, 1] = 0.0
+        return out
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.stride(-1) != 1 or t.dtype != torch.bfloat16:
+            raise native.NativeError(f"attention_dv_partial: {n} must be a bf16 CUDA tensor with unit inner stride")
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    ws, ws_bytes = None, 0
+    qtiles = B * ((Lq + 127) // 128)
+    if qtiles < 2 * _SMS and Lk >= 512:
+        per_split = rows * (DV + 2) * 4
+        nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split))
+        ws_bytes = nsplit * per_split
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    ev = PROFILE.begin("mem_cross_attention")
+    native.call("ms2_attention_dv_partial", q.data_ptr(), k.data_ptr(), v.data_ptr(), part_o.data_ptr(), part_ml.data_ptr(),
+                _DT[q.dtype], q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), B, Lq, Lk, D,
+                v.shape[2], float(scale), None if ws is None else ws.data_ptr(), ws_bytes, _st())
+    PROFILE.end("mem_cross_attention", ev, 2.0 * B * Lq * Lk * (D + DV))
+    return out
+
+
+def attention_merge(parts, B, Lq, DV=64):
+    """parts fp32 [nparts, B*Lq*(DV+2)] (packed partials of attention_dv_partial, one per rank) -> o bf16 [B,Lq,DV]."""
+    nparts = parts.shape[0]
+    rows = B * Lq
+    _chk(parts, "parts", torch.float32)
+    assert parts.shape[1] == rows * (DV + 2)
+    o = torch.empty((B, Lq, DV), dtype=torch.bfloat16, device=parts.device)
+    native.call("ms2_attention_merge", parts.data_ptr(), parts.data_ptr() + rows * DV * 4, parts.stride(0), o.data_ptr(),
+                _DT[o.dtype], o.stride(0), o.stride(1), B, Lq, DV, nparts, _st())
+    return o
+
+
 def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool, impl=0):
     """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
     Ho, Wo = (H // 2, W // 2) if qpool else (H, W)

@@ -6,6 +6,10 @@ gloo in the CPU tests).
   contiguous block of slices and all-gathers the feature pyramid (fpn levels `[32,256,256] + [64,128,128] +
   [256,64,64]` per slice; the position encodings are constant tables and are never sent), filling the predictor's
   per-slice feature cache on every rank.  Propagation stays sequential in t on the rank that tracks the volume.
+* Split-KV memory cross-attention: `shard_memory_attention` deals the conditioning memories of
+  the bank (and the recent memories) round-robin to the ranks; all ranks run the tracking loop in lockstep, every rank
+  attends over its own keys (`ms2_attention_dv_partial`), one all-gather of the 1 MiB per-rank partial (O, m, l) per
+  layer is the exchange step, and `ms2_attention_merge` gives every rank the same softmax-normalised result.
 """
 import math
 
@@ -83,3 +87,50 @@ def encode_volume_sharded(predictor, inference_state, group=None):
             image = imgs[f].to(dev).float().unsqueeze(0)
         cache[f] = (image, {"vision_features": fpn[-1], "vision_pos_enc": pos, "backbone_fpn": fpn})
     return hi - lo
+
+
+class KVShard:
+    """Placement of the memory bank's keys over the ranks of `group` and the exchange of the attention partials."""
+
+    def __init__(self, rank, world, group=None):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.exchanges = 0
+
+    def owns_cond(self, i):
+        """conditioning memory number i (arrival order) lives on rank i mod world (rank 0 always owns the first)."""
+        return i % self.world == self.rank
+
+    def owns_recent(self, j, n_cond):
+        """recent memory j of the current frame; the rotation by the number of conditioning memories evens the load."""
+        return (j + n_cond) % self.world == self.rank
+
+    def owns_pointers(self, n_recent, n_cond):
+        """the object-pointer tokens (<= 64 rows) travel with the first recent memory, or with the first conditioning
+        memory when there is none, so that no rank ends up with a few rows only."""
+        return self.owns_recent(0, n_cond) if n_recent else self.rank == 0
+
+    def attend(self, q, k, v):
+        """q [B,L,256] (identical on all ranks), k/v: this rank's keys / raw values (None or Lk = 0: no share)
+        -> softmax(q K_all^T) V_all [B,L,64], identical on all ranks."""
+        from . import ops
+        B, L, _ = q.shape
+        part = ops.attention_dv_partial(q, k, v)
+        if self.world == 1:
+            parts = part[None]
+        else:
+            parts = torch.empty((self.world, part.numel()), dtype=part.dtype, device=part.device)
+            dist.all_gather_into_tensor(parts.view(-1), part, group=self.group)      # the exchange step
+            self.exchanges += 1
+        return ops.attention_merge(parts, B, L)
+
+
+def shard_memory_attention(predictor, group=None):
+    """Switch `predictor.memory_attention` to split-KV over the ranks of `group` (all ranks must then drive the
+    predictor with the same calls).  Returns the KVShard (None when not distributed)."""
+    on = dist.is_available() and dist.is_initialized()
+    if not on or dist.get_world_size(group) == 1:
+        predictor.memory_attention.kv_shard = None
+        return None
+    shard = KVShard(dist.get_rank(group), dist.get_world_size(group), group)
+    predictor.memory_attention.kv_shard = shard
+    return shard

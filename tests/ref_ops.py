@@ -253,6 +253,39 @@ def attention_dv(q, k, v, scale=None):
     return o.to(q.dtype)
 
 
+def attention_dv_partial(q, k, v, out=None, scale=None):
+    """plain statement of ms2_attention_dv_partial: packed (O un-normalised, row max in log2 units, row sum)."""
+    B, Lq, D = q.shape
+    DV, rows = 64, B * Lq
+    if out is None:
+        out = torch.empty(rows * (DV + 2), dtype=torch.float32, device=q.device)
+    po, pml = out[: rows * DV].view(rows, DV), out[rows * DV:].view(rows, 2)
+    if k is None or k.shape[1] == 0:
+        po.zero_()
+        pml[:, 0] = float("-inf")
+        pml[:, 1] = 0.0
+        return out
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    s = torch.einsum("bqd,bkd->bqk", q.float(), k.float()) * (scale * 1.4426950408889634)
+    m = s.amax(-1, keepdim=True)
+    p = torch.exp2(s - m)
+    po.copy_(torch.einsum("bqk,bkd->bqd", p, v.float()).reshape(rows, DV))
+    pml[:, 0] = m.reshape(rows)
+    pml[:, 1] = p.sum(-1).reshape(rows)
+    return out
+
+
+def attention_merge(parts, B, Lq, DV=64):
+    rows = B * Lq
+    o = parts[:, : rows * DV].view(-1, rows, DV)
+    ml = parts[:, rows * DV:].view(-1, rows, 2)
+    m = ml[..., 0].amax(0)
+    w = torch.where(ml[..., 1] > 0, torch.exp2(ml[..., 0] - m), torch.zeros_like(m))
+    num = (w[..., None] * o).sum(0)
+    den = (w * ml[..., 1]).sum(0)
+    return (num / den[:, None]).view(B, Lq, DV).to(torch.bfloat16)
+
+
 def patch_im2col(img, ldk=152):
     B, _, H, W = img.shape
     cols = F.unfold(img.float(), 7, stride=4, padding=3)                      # [B, 3*49, L] in (c, ky, kx) order

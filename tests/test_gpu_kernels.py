@@ -262,6 +262,29 @@ def test_attention_dv(ops, B, Lq, Lk, qs):
     assert (o.float() - r).abs().mean().item() < 2e-3
 
 
+@pytest.mark.parametrize("B,Lq,cuts,qs", [(1, 4096, (64, 4197, 24576), 1.0), (1, 4096, (8192,), 4.0), (2, 256, (100, 300, 1000), 3.0)])
+def test_attention_dv_partial_and_merge(ops, B, Lq, cuts, qs):
+    """split-KV over several GPUs, on one GPU: partials over disjoint key ranges (plus an empty share) merged by
+    ms2_attention_merge == attention over all keys."""
+    Lk = cuts[-1]
+    q = (rnd(B, Lq, 256, seed=1) * qs).to(torch.bfloat16)
+    k = rnd(B, Lk, 256, seed=2).to(torch.bfloat16)
+    v = rnd(B, Lk, 64, seed=3).to(torch.bfloat16)
+    parts, lo = [], 0
+    for hi in cuts:
+        parts.append(ops.attention_dv_partial(q, k[:, lo:hi].contiguous(), v[:, lo:hi].contiguous()))
+        lo = hi
+    parts.append(ops.attention_dv_partial(q, None, None))
+    parts = torch.stack(parts)
+    o = ops.attention_merge(parts, B, Lq)
+    ref = ref_ops.attention_dv(q, k, v).float()
+    close_rel(o, ref, 1e-2, 8e-3, "partial+merge vs full attention")
+    close_rel(o, ops.attention_dv(q, k, v), 1e-2, 8e-3, "partial+merge vs single-GPU kernel")
+    # the partial of one share alone, merged, is plain attention over that share
+    one = ops.attention_merge(ops.attention_dv_partial(q, k[:, : cuts[0]].contiguous(), v[:, : cuts[0]].contiguous())[None], B, Lq)
+    close_rel(one, ref_ops.attention_dv(q, k[:, : cuts[0]], v[:, : cuts[0]]).float(), 1e-2, 8e-3, "single share")
+
+
 def test_attention_tc_rescale_every_tile(ops, monkeypatch):
     """MS2_LAZY_TAU=0 forces the in-TMEM rescale of O whenever a row maximum grows (normally only beyond 2^8):
     exercises the softmax <-> MMA hand-shake of that rare path on every tile."""

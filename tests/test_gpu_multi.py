@@ -46,3 +46,56 @@ def test_sharded_encode_nccl_matches_local():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, 29641, out), nprocs=2, join=True)
     assert out[0] and out[1], dict(out)
+
+
+def _kv_worker(rank, world, port, out):
+    import torch.distributed as dist
+    import medsam2_b200
+    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from oracle.config import get_config
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_t", device="cuda", hydra_overrides_extra=[
+        "++model.image_size=512", "++model.feature_cache_size=16", "++model.feature_encode_batch=2"])
+    m.load_state_dict(make_state_dict(get_config("sam2_hiera_t")), strict=True)
+    T = 10
+    vol, boxes = btcv_volume(T, 512, 5, 1)
+
+    def run(sharded):
+        st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=512, video_width=512)
+        if sharded:
+            encode_volume_sharded(m, st)
+        for f in (0, 3, 6):
+            m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+        return {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}, st
+
+    ref, _ = run(False)
+    shard = shard_memory_attention(m)
+    got, st = run(True)
+    ok = shard is not None and shard.exchanges == 7 * len(m.memory_attention.layers)   # 7 tracked frames x 4 layers
+    bank = st["output_dict"]["_ms2_bank"]
+    ok &= bank.n_static == 1024 * len([i for i in range(3) if i % world == rank])       # only this rank's cond memories
+    for f in range(T):
+        a, b = got[f].float(), ref[f].float()
+        keep = ((a - 0.1).abs() > 1e-6) & ((b - 0.1).abs() > 1e-6)                        # hole filling is discrete
+        ok &= bool((a - b)[keep].abs().max().item() <= 3e-2) and ((a > 0) == (b > 0)).float().mean().item() >= 0.998
+    mine = torch.stack([got[f] for f in range(T)]).contiguous()
+    theirs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(theirs, mine)
+    ok &= all(torch.equal(t, theirs[0]) for t in theirs)                                  # ranks stay in lockstep
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_split_kv_memory_attention_nccl_matches_single_gpu():
+    """the memory bank dealt to 2 GPUs (partials all-gathered and merged per layer) tracks a
+    volume to the same masks as one GPU attending over the whole bank, and all ranks hold identical outputs."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_kv_worker, args=(2, 29651, out), nprocs=2, join=True)
+    assert out[0] and out[1], dict(out)

@@ -87,3 +87,78 @@ def test_volume_sharding_partitions():
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     assert slice_block(10, 0, 4) == (0, 3, 3) and slice_block(10, 3, 4) == (9, 10, 3)
     assert slice_block(2, 3, 4) == (2, 2, 1)
+
+
+# ---------------------------------------------------------------- split-KV memory attention over ranks (§8(f) rank 1)
+def _mem_attn_inputs(B=1, hw=64, n_cond=5, n_recent=3, n_ptr=4):
+    g = torch.Generator().manual_seed(11)
+    r = lambda *s: torch.randn(*s, generator=g)
+    pos = r(hw, 64) * 0.5
+    cond = [(("c", i), None, r(B, hw, 64), pos) for i in range(n_cond)]
+    recent = [(("r", j), None, r(B, hw, 64), pos + 0.1 * (j + 1)) for j in range(n_recent)]
+    return r(B, hw, 256), r(B, hw, 256) * 0.3, cond, recent, r(B, 4 * n_ptr, 64), torch.zeros(B, 4 * n_ptr, 64)
+
+
+def _kv_worker(rank, world, port, out):
+    import pytest
+    import medsam2_b200
+    import ref_ops
+    from medsam2_b200.modeling.memory_attention import MemoryBank
+    from medsam2_b200.parallel import KVShard, shard_memory_attention
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mp_ = pytest.MonkeyPatch()
+    ref_ops.install(mp_)
+    torch.manual_seed(0)
+    ok = True
+    with medsam2_b200.compute(torch.bfloat16), torch.no_grad():
+        m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_t", device="cpu", hydra_overrides_extra=["++model.image_size=128"])
+        ma = m.memory_attention
+        curr, curr_pos, cond, recent, ptrs, ptr_pos = _mem_attn_inputs()
+        ref1 = ma.forward_tokens_banked(curr, curr_pos, MemoryBank(), cond[:2], recent[:1], ptrs, ptr_pos)
+        ref2 = ma.forward_tokens_banked(curr, curr_pos, MemoryBank(), cond, recent, ptrs, ptr_pos)
+        ref3 = ma.forward_tokens_banked(curr, curr_pos, MemoryBank(), cond[:1], [], ptrs, ptr_pos)
+        shard = shard_memory_attention(m)
+        assert isinstance(shard, KVShard) and shard.world == world and ma.kv_shard is shard
+        bank = MemoryBank()
+        got1 = ma.forward_tokens_banked(curr, curr_pos, bank, cond[:2], recent[:1], ptrs, ptr_pos)
+        got2 = ma.forward_tokens_banked(curr, curr_pos, bank, cond, recent, ptrs, ptr_pos)     # bank grows: 2 -> 5 cond
+        got3 = ma.forward_tokens_banked(curr, curr_pos, MemoryBank(), cond[:1], [], ptrs, ptr_pos)   # rank 1: no keys at all
+        ok &= shard.exchanges == 3 * len(ma.layers)
+        # this rank holds only its share of the conditioning memories
+        ok &= bank.n_static == 64 * len([i for i in range(5) if i % world == rank])
+        for a, b in ((got1, ref1), (got2, ref2), (got3, ref3)):
+            ok &= bool(torch.isfinite(a).all()) and (a - b).abs().max().item() <= 6e-2 * max(1.0, b.abs().max().item())
+        # all ranks hold the same result (the merge consumes the same gathered partials in the same order)
+        theirs = [torch.empty_like(got2) for _ in range(world)]
+        dist.all_gather(theirs, got2.contiguous())
+        ok &= all(torch.equal(t, theirs[0]) for t in theirs)
+    mp_.undo()
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_split_kv_memory_attention_two_ranks():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_kv_worker, args=(2, 29733, out), nprocs=2, join=True)
+    assert out[0] and out[1], dict(out)
+
+
+def test_kv_shard_partition_is_exact():
+    """every conditioning / recent memory and the pointer tokens belong to exactly one rank, rank 0 owns the first
+    conditioning memory, and the pointer tokens never sit alone on a rank."""
+    from medsam2_b200.parallel import KVShard
+    for world in (1, 2, 3, 8):
+        shards = [KVShard(r, world) for r in range(world)]
+        for n_cond in range(1, 20):
+            for i in range(n_cond):
+                assert sum(s.owns_cond(i) for s in shards) == 1
+            assert shards[0].owns_cond(0)
+            for n_recent in range(0, 7):
+                for j in range(n_recent):
+                    assert sum(s.owns_recent(j, n_cond) for s in shards) == 1
+                owners = [s for s in shards if s.owns_pointers(n_recent, n_cond)]
+                assert len(owners) == 1
+                o = owners[0]
+                assert o.owns_recent(0, n_cond) if n_recent else o.owns_cond(0)
