@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ...runtime import compute_dtype, convT_w_c, p32, w_c
+from ...runtime import compute_dtype, convT_w_c, p32, par, w_c
 from ..sam2_utils import LayerNorm2d, MLP, as_nchw_view, as_nhwc, to_compute
 
 
@@ -76,28 +76,39 @@ class MaskDecoder(nn.Module):
         tokens = torch.cat((out_tok.unsqueeze(0).expand(B, -1, -1), sparse), dim=1).contiguous()
         hs, keys = self.transformer.forward_tokens(src, pos, tokens)
         Nt = hs.shape[1]
-        hs2 = to_compute(hs).view(B * Nt, C)        # token rows feed the head MLPs as row-strided GEMM operands
         mask_tokens_out = hs[:, s + 1: s + 1 + self.num_mask_tokens, :]
         dc1, ln1, _, dc2, _ = self.output_upscaling
-        g1 = ops.gemm(to_compute(keys), convT_w_c(dc1.weight), None, out_dtype=torch.float32)     # [B,HW,4*C/4]
-        u1 = ops.pixel_shuffle_add(g1, p32(dc1.bias), feat_s1, B, h, w, C // 4)
-        u1 = ln1(u1, out_dtype=cd, act=ops.ACT_GELU)                                             # [B,2h,2w,C/4]
-        g2 = ops.gemm(u1, convT_w_c(dc2.weight), None, out_dtype=torch.float32)                   # [B,4hw,4*C/8]
-        up = ops.pixel_shuffle_add(g2, p32(dc2.bias), feat_s0, B, 2 * h, 2 * w, C // 8, act=ops.ACT_GELU)
+
+        def upscale():
+            g1 = ops.gemm(to_compute(keys), convT_w_c(dc1.weight), None, out_dtype=torch.float32)     # [B,HW,4*C/4]
+            u1 = ops.pixel_shuffle_add(g1, p32(dc1.bias), feat_s1, B, h, w, C // 4)
+            u1 = ln1(u1, out_dtype=cd, act=ops.ACT_GELU)                                             # [B,2h,2w,C/4]
+            g2 = ops.gemm(u1, convT_w_c(dc2.weight), None, out_dtype=torch.float32)                   # [B,4hw,4*C/8]
+            return ops.pixel_shuffle_add(g2, p32(dc2.bias), feat_s0, B, 2 * h, 2 * w, C // 8, act=ops.ACT_GELU)
+
         hyper = torch.empty((B, self.num_mask_tokens, C // 8), dtype=torch.float32, device=src.device)
         heads = list(self.output_hypernetworks_mlps) + [self.iou_prediction_head]
-        rows = [hs2[s + 1 + i:: Nt] for i in range(self.num_mask_tokens)] + [hs2[s:: Nt]]     # row-strided [B, C] views
         obj = None
-        if self.pred_obj_scores and isinstance(self.pred_obj_score_head, MLP):
+        grouped_obj = self.pred_obj_scores and isinstance(self.pred_obj_score_head, MLP)
+        if grouped_obj:
             heads.append(self.pred_obj_score_head)
-            rows.append(hs2[0:: Nt])
-        # the hyper-network outputs land directly in their rows of `hyper`
-        dst = [hyper[:, i, :] for i in range(self.num_mask_tokens)] + [None] * (len(heads) - self.num_mask_tokens)
-        outs = self._grouped_mlps(heads, rows, dst) if B <= 64 and len(heads) <= 8 else None
-        if outs is None:
-            outs = [m(r) for m, r in zip(heads, rows)]
-            for i in range(self.num_mask_tokens):
-                hyper[:, i, :] = outs[i]
+
+        def head_mlps():
+            hs2 = to_compute(hs).view(B * Nt, C)        # token rows feed the head MLPs as row-strided GEMM operands
+            rows = [hs2[s + 1 + i:: Nt] for i in range(self.num_mask_tokens)] + [hs2[s:: Nt]]     # row-strided [B, C] views
+            if grouped_obj:
+                rows.append(hs2[0:: Nt])
+            # the hyper-network outputs land directly in their rows of `hyper`
+            dst = [hyper[:, i, :] for i in range(self.num_mask_tokens)] + [None] * (len(heads) - self.num_mask_tokens)
+            outs = self._grouped_mlps(heads, rows, dst) if B <= 64 and len(heads) <= 8 else None
+            if outs is None:
+                outs = [m(r) for m, r in zip(heads, rows)]
+                for i in range(self.num_mask_tokens):
+                    hyper[:, i, :] = outs[i]
+            return hs2, outs
+
+        # the up-scaling of the image tokens and the head MLPs on the output tokens do not depend on each other
+        up, (hs2, outs) = par(upscale, head_mlps)
         masks = ops.hyper_mask(up.view(B, 16 * HW, C // 8), hyper).view(B, self.num_mask_tokens, 4 * h, 4 * w)
         iou_pred = outs[self.num_mask_tokens]
         if self.pred_obj_scores:

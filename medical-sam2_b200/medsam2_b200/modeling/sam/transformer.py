@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ...runtime import cat_p32, cat_w_c, compute_dtype, p32, w_c
+from ...runtime import cat_p32, cat_w_c, compute_dtype, p32, par, w_c
 from ..position_encoding import rope_table
 from ..sam2_utils import LayerNorm, Linear, MLP, to_compute
 
@@ -33,26 +33,27 @@ class Attention(nn.Module):
     def forward(self, q, k, v, residual=None):
         """q [B,Lq,C], k/v [B,Lk,Ckv] (fp32 or compute dtype) -> fp32 [B,Lq,C] (+ residual)."""
         cd = compute_dtype()
-        qp = kp = vp = None
-        # token-side projections (a handful of rows: pure launch latency) share one grouped small-M launch
         B, Lk = k.shape[0], k.shape[1]
-        if B * Lk <= 64 and k.shape == v.shape:
-            kc, vc = to_compute(k).reshape(B * Lk, -1), to_compute(v).reshape(B * Lk, -1)
-            xs, ls = [kc, vc], [self.k_proj, self.v_proj]
-            if q.shape == k.shape and self.q_proj.weight.shape[1] == self.k_proj.weight.shape[1]:
+        small_kv = B * Lk <= 64 and k.shape == v.shape and k.shape[-1] % 8 == 0 and v.shape[-1] % 8 == 0
+        with_q = small_kv and q.shape == k.shape and self.q_proj.weight.shape[1] == self.k_proj.weight.shape[1]
+
+        def kv_side():
+            # token-side projections (a handful of rows: pure launch latency) share one grouped small-M launch
+            if not small_kv:
+                return None, self.k_proj(k, out_dtype=cd), self.v_proj(v, out_dtype=cd)
+            xs = [to_compute(k).reshape(B * Lk, -1), to_compute(v).reshape(B * Lk, -1)]
+            ls = [self.k_proj, self.v_proj]
+            if with_q:
                 xs.insert(0, to_compute(q).reshape(B * Lk, -1))
                 ls.insert(0, self.q_proj)
-            if all(x.shape[1] % 8 == 0 for x in xs):
-                outs = ops.gemm_grouped(xs, [w_c(l.weight) for l in ls], [p32(l.bias) for l in ls], out_dtype=cd)
-                outs = [o.view(B, Lk, -1) for o in outs]
-                kp, vp = outs[-2], outs[-1]
-                if len(outs) == 3:
-                    qp = outs[0]
-        if qp is None:
-            qp = self.q_proj(q, out_dtype=cd)
-        if kp is None:
-            kp = self.k_proj(k, out_dtype=cd)
-            vp = self.v_proj(v, out_dtype=cd)
+            outs = ops.gemm_grouped(xs, [w_c(l.weight) for l in ls], [p32(l.bias) for l in ls], out_dtype=cd)
+            outs = [o.view(B, Lk, -1) for o in outs]
+            return (outs[0] if with_q else None), outs[-2], outs[-1]
+
+        if with_q:
+            qp, kp, vp = kv_side()
+        else:       # queries and keys/values live on different sides (tokens vs image): independent branches
+            qp, (_, kp, vp) = par(lambda: self.q_proj(q, out_dtype=cd), kv_side)
         o = ops.attention(qp, kp, vp, self.num_heads)
         return self.out_proj(o, out_dtype=torch.float32, residual=residual)
 
@@ -149,9 +150,8 @@ class TwoWayAttentionBlock(nn.Module):
         else:
             q = ops.axpby(queries, 1.0, query_pe, 1.0, out_dtype=cd)
             queries = self.norm1(queries, add=self.self_attn(q, q, to_compute(queries)))
-        q = ops.axpby(queries, 1.0, query_pe, 1.0, out_dtype=cd)
-        k = ops.axpby(keys, 1.0, key_pe, 1.0, out_dtype=cd)
-        keys_c = to_compute(keys)
+        q, k, keys_c = par(lambda: ops.axpby(queries, 1.0, query_pe, 1.0, out_dtype=cd),
+                           lambda: ops.axpby(keys, 1.0, key_pe, 1.0, out_dtype=cd), lambda: to_compute(keys))
         queries = self.norm2(queries, add=self.cross_attn_token_to_image(q, k, keys_c))
         queries = self.norm3(queries, add=self.mlp(queries))
         q = ops.axpby(queries, 1.0, query_pe, 1.0, out_dtype=cd)
@@ -175,9 +175,9 @@ class TwoWayTransformer(nn.Module):
         queries = point_embedding
         for layer in self.layers:
             queries, keys = layer(queries, keys, point_embedding, key_pe)
-        q = ops.axpby(queries, 1.0, point_embedding, 1.0, out_dtype=cd)
-        k = ops.axpby(keys, 1.0, key_pe, 1.0, out_dtype=cd)
-        queries = self.norm_final_attn(queries, add=self.final_attn_token_to_image(q, k, to_compute(keys)))
+        q, k, keys_c = par(lambda: ops.axpby(queries, 1.0, point_embedding, 1.0, out_dtype=cd),
+                           lambda: ops.axpby(keys, 1.0, key_pe, 1.0, out_dtype=cd), lambda: to_compute(keys))
+        queries = self.norm_final_attn(queries, add=self.final_attn_token_to_image(q, k, keys_c))
         return queries, keys
 
     def forward(self, image_embedding, image_pe, point_embedding):

@@ -10,7 +10,7 @@ from torch import nn
 from torch.nn.init import trunc_normal_
 
 from .. import ops
-from ..runtime import CACHE, compute_dtype, conv_w_c, p32, w_c
+from ..runtime import CACHE, compute_dtype, conv_w_c, p32, par, w_c
 from .sam.mask_decoder import MaskDecoder
 from .sam.prompt_encoder import PromptEncoder
 from .sam.transformer import TwoWayTransformer
@@ -214,30 +214,32 @@ class SAM2Base(nn.Module):
             sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=multimask_output,
             repeat_image=False, high_res_features=high_res_features)
         low_res_multimasks = low_res_multimasks.float().contiguous()
-        if self.pred_obj_scores:
-            is_obj_appearing = object_score_logits > 0
-            low_res_multimasks = ops.gate_rows(low_res_multimasks, object_score_logits.float().contiguous().view(-1),
-                                               NO_OBJ_SCORE)
-        high_res_multimasks = ops.resize_bilinear(low_res_multimasks, (self.image_size, self.image_size))
-        sam_output_token = sam_output_tokens[:, 0]
-        if multimask_output:
-            best = torch.argmax(ious, dim=-1)
-            idx = best.to(torch.int32)
-            low_res_masks = ops.select_plane(low_res_multimasks, idx)
-            high_res_masks = ops.select_plane(high_res_multimasks, idx)
-            if sam_output_tokens.size(1) > 1:
-                sam_output_token = sam_output_tokens[torch.arange(B, device=device), best]
-        else:
-            low_res_masks, high_res_masks = low_res_multimasks, high_res_multimasks
-        obj_ptr = self.obj_ptr_proj(sam_output_token.contiguous())
-        if self.pred_obj_scores:
-            if self.soft_no_obj_ptr:
-                lam = object_score_logits.sigmoid()
-            else:
-                lam = is_obj_appearing.float()
-            if self.fixed_no_obj_ptr:
-                obj_ptr = lam * obj_ptr
-            obj_ptr = obj_ptr + (1 - lam) * p32(self.no_obj_ptr)
+        best = torch.argmax(ious, dim=-1) if multimask_output else None
+
+        def mask_side():
+            lr = low_res_multimasks
+            if self.pred_obj_scores:
+                lr = ops.gate_rows(lr, object_score_logits.float().contiguous().view(-1), NO_OBJ_SCORE)
+            hr = ops.resize_bilinear(lr, (self.image_size, self.image_size))
+            if multimask_output:
+                idx = best.to(torch.int32)
+                return lr, hr, ops.select_plane(lr, idx), ops.select_plane(hr, idx)
+            return lr, hr, lr, hr
+
+        def pointer_side():
+            tok = sam_output_tokens[:, 0]
+            if multimask_output and sam_output_tokens.size(1) > 1:
+                tok = sam_output_tokens[torch.arange(B, device=device), best]
+            ptr = self.obj_ptr_proj(tok.contiguous())
+            if self.pred_obj_scores:
+                lam = object_score_logits.sigmoid() if self.soft_no_obj_ptr else (object_score_logits > 0).float()
+                if self.fixed_no_obj_ptr:
+                    ptr = lam * ptr
+                ptr = ptr + (1 - lam) * p32(self.no_obj_ptr)
+            return ptr
+
+        # the mask path (gating, x4 up-sampling, plane selection) and the object pointer do not depend on each other
+        (low_res_multimasks, high_res_multimasks, low_res_masks, high_res_masks), obj_ptr = par(mask_side, pointer_side)
         return (low_res_multimasks, high_res_multimasks, ious, low_res_masks, high_res_masks, obj_ptr,
                 object_score_logits)
 

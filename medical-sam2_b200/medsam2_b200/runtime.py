@@ -105,6 +105,39 @@ def cat_p32(*ps):
     return CACHE.get(ps, "cat32", lambda *ts: torch.cat([t.detach().float().reshape(-1) for t in ts], 0).contiguous())
 
 
+# ---------------------------------------------------------------- parallel branches inside a captured graph
+_CAPTURING = False
+_IN_PAR = False
+_BRANCH_STREAMS = []
+
+
+def par(*fns):
+    """Run independent closures and return their results.  Eagerly they simply run one after the other; while a
+    GraphRunner is capturing, every closure after the first runs on its own stream that forks from / joins the
+    capturing stream, so the captured graph has parallel branches (the SAM heads are ~115 dependent 2-12 us kernels:
+    image-side and token-side projections, the up-scaling path and the head MLPs do not depend on each other)."""
+    global _IN_PAR
+    if not _CAPTURING or _IN_PAR or len(fns) < 2:
+        return [f() for f in fns]
+    main = torch.cuda.current_stream()
+    while len(_BRANCH_STREAMS) < len(fns) - 1:
+        _BRANCH_STREAMS.append(torch.cuda.Stream())
+    outs = [None] * len(fns)
+    _IN_PAR = True
+    try:
+        for i, f in enumerate(fns[1:]):
+            s = _BRANCH_STREAMS[i]
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                outs[i + 1] = f()
+        outs[0] = fns[0]()
+        for i in range(len(fns) - 1):
+            main.wait_stream(_BRANCH_STREAMS[i])
+    finally:
+        _IN_PAR = False
+    return outs
+
+
 class GraphRunner:
     """CUDA-graph replay of a fixed-shape sub-pipeline of native kernels (the mask decoder is
     ~170 tiny launches per slice and launch-bound).  `run(key, fn, tensors, clone=True)` executes
@@ -142,8 +175,15 @@ class GraphRunner:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = native.launch_count
-            with torch.cuda.graph(graph):
-                static_out = fn(*static_in)
+            global _CAPTURING
+            while len(_BRANCH_STREAMS) < 2:            # branch streams of par() exist before the capture starts
+                _BRANCH_STREAMS.append(torch.cuda.Stream())
+            _CAPTURING = True
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = fn(*static_in)
+            finally:
+                _CAPTURING = False
             entry = self._graphs[full_key] = [graph, static_in, static_out, native.launch_count - n0, None]
         graph, static_in, static_out, launches, last = entry
         cur = torch.cuda.current_stream()
