@@ -36,38 +36,91 @@ template <> struct Vec8<float> {
 constexpr int SM_MT = 16;       // rows per pass
 constexpr int SM_WARPS = 4;     // grouped kernel: 4 warps x 4 columns = 16 columns per CTA
 
-// acc[m] += sum_k A[m0+m, k] * wrow[k] over this lane's 16-byte chunks (chunk stride KL*8 elements).  Four chunks per
-// pass: their weight loads (and the activation loads behind them) are all issued before the first FMA, so a
-// K = 256 column costs one global-memory round trip instead of four dependent ones.
+// Stage rows [m0, m0+mt) of A (K elements each) in shared memory with asynchronous 16-byte copies: the row loop used
+// to fetch its activations row by row from global memory, each row behind a branch - one L2 round trip PER ROW
+// (measured 3.3 us for M = 1 vs 7.8 us for M = 9 at N = K = 256).
+template <typename T>
+__device__ __forceinline__ void smallm_stage_a(const T* __restrict__ A, long lda, int K, int m0, int mt, T* sA) {
+  constexpr int VE = 16 / sizeof(T);                         // elements per 16-byte vector
+  const int vpr = K / VE;
+  __syncthreads();                                           // previous pass has finished reading sA
+  for (int r = 0; r < mt; ++r) {
+    const T* src = A + (long)(m0 + r) * lda;
+    T* dst = sA + (long)r * K;
+    for (int c = threadIdx.x; c < vpr; c += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + c * VE)),
+                   "l"(src + c * VE) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void smallm_stage_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+// acc[m] += sum_k sA[m, k] * wrow[k] over this lane's 16-byte chunks (chunk stride KL*8 elements), four chunks per
+// pass.  Branch-free: rows beyond mt re-read the last row and chunks beyond K multiply by a zero weight, so every
+// shared-memory load of a pass is independent and the compiler batches them.
 template <typename T, int KL>
-__device__ __forceinline__ void smallm_accumulate(const T* __restrict__ A, long lda, const T* __restrict__ wrow, int K,
-                                                  int kl, int m0, int mt, float (&acc)[SM_MT]) {
+__device__ __forceinline__ void smallm_load_w(const T* __restrict__ wrow, int K, int k0, float (&w)[4][8], int (&kc)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = k0 + u * KL * 8;
+    kc[u] = k < K ? k : K - 8;
+    Vec8<T>::load(wrow + kc[u], w[u]);
+    if (k >= K) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[u][i] = 0.f;
+    }
+  }
+}
+
+// (w, kc): the weights of the first pass, loaded by the caller BEFORE it waits for the staged activations, so that the
+// weight round trip (HBM once per slice) overlaps the activation round trip
+template <typename T, int KL>
+__device__ __forceinline__ void smallm_accumulate(const T* sA, const T* __restrict__ wrow, int K, int kl, int mt,
+                                                  float (&acc)[SM_MT], float (&w)[4][8], int (&kc)[4]) {
   constexpr int U = 4;
   for (int k0 = kl * 8; k0 < K; k0 += KL * 8 * U) {
-    float w[U][8];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * KL * 8;
-      if (k < K) Vec8<T>::load(wrow + k, w[u]);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[u][i] = 0.f;
-      }
-    }
+    if (k0 != kl * 8) smallm_load_w<T, KL>(wrow, K, k0, w, kc);
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) {
-      if (m < mt) {
+      const T* arow = sA + (long)(m < mt ? m : mt - 1) * K;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int k = k0 + u * KL * 8;
-          if (k < K) {
-            float a[8];
-            Vec8<T>::load(A + (long)(m0 + m) * lda + k, a);
+      for (int u = 0; u < U; ++u) {
+        float a[8];
+        Vec8<T>::load(arow + kc[u], a);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[u][i], acc[m]);
-          }
-        }
+        for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[u][i], acc[m]);
       }
+    }
+  }
+}
+
+// epilogue of one pass: after the reduction over the KL lanes of a column every lane holds all row sums; lane kl
+// finishes rows kl, kl+KL, ... (bias / colscale are loaded once, the row stores of a column go out in parallel)
+template <typename TO, int KL>
+__device__ __forceinline__ void smallm_epilogue(float (&acc)[SM_MT], int kl, bool n_ok, int n, int m0, int mt,
+                                                float bv, float cs, const float* __restrict__ residual, long ldr,
+                                                TO* __restrict__ out, long ldo, int act) {
+#pragma unroll
+  for (int m = 0; m < SM_MT; ++m) {
+    float v = acc[m];
+#pragma unroll
+    for (int o = KL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[m] = v;
+  }
+  if (!n_ok) return;
+#pragma unroll
+  for (int m = 0; m < SM_MT; ++m) {
+    if (m % KL == kl && m < mt) {
+      float v = acc[m] + bv;
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = 1.f / (1.f + __expf(-v));
+      v *= cs;
+      if (residual) v += residual[(long)(m0 + m) * ldr + n];
+      out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
     }
   }
 }
@@ -80,41 +133,28 @@ template <typename T, typename TO, int KL>
 __global__ void __launch_bounds__(SMK_WARPS * 32)
 gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, const float* __restrict__ bias,
                    const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
-                   TO* __restrict__ out, long ldo, int M, int N, int K, int act) {
+                   TO* __restrict__ out, long ldo, int M, int N, int K, int act, int rows_per_pass) {
   constexpr int CPW = 32 / KL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = lane / KL, kl = lane % KL;
   const int n = (blockIdx.x * SMK_WARPS + warp) * CPW + cg;
   const bool n_ok = n < N;
   const T* wrow = W + (long)(n_ok ? n : 0) * K;
-  for (int m0 = 0; m0 < M; m0 += SM_MT) {
-    const int mt = min(SM_MT, M - m0);
+  extern __shared__ uint4 smallm_smem[];
+  T* sA = (T*)smallm_smem;
+  for (int m0 = 0; m0 < M; m0 += rows_per_pass) {
+    const int mt = min(rows_per_pass, M - m0);
     float acc[SM_MT];
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
-    smallm_accumulate<T, KL>(A, lda, wrow, K, kl, m0, mt, acc);
-#pragma unroll
-    for (int m = 0; m < SM_MT; ++m) {
-      float v = acc[m];
-#pragma unroll
-      for (int o = KL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[m] = v;
-    }
-    if (kl == 0 && n_ok) {
-#pragma unroll
-      for (int m = 0; m < SM_MT; ++m) {
-        if (m < mt) {
-          float v = acc[m];
-          if (bias) v += bias[n];
-          if (act == 1) v = gelu_erf(v);
-          else if (act == 2) v = fmaxf(v, 0.f);
-          else if (act == 3) v = 1.f / (1.f + __expf(-v));
-          if (colscale) v *= colscale[n];
-          if (residual) v += residual[(long)(m0 + m) * ldr + n];
-          out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
-        }
-      }
-    }
+    smallm_stage_a<T>(A, lda, K, m0, mt, sA);
+    float w[4][8];
+    int kc[4];
+    smallm_load_w<T, KL>(wrow, K, kl * 8, w, kc);
+    const float bv = (bias && n_ok) ? bias[n] : 0.f, cs = (colscale && n_ok) ? colscale[n] : 1.f;
+    smallm_stage_wait();
+    smallm_accumulate<T, KL>(sA, wrow, K, kl, mt, acc, w, kc);
+    smallm_epilogue<TO, KL>(acc, kl, n_ok, n, m0, mt, bv, cs, residual, ldr, out, ldo, act);
   }
 }
 
@@ -134,7 +174,7 @@ struct GroupedP {
 
 template <typename T, typename TO>
 __global__ void __launch_bounds__(SM_WARPS * 32)
-gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K) {
+gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K, int rows_per_pass) {
   const int g = blockIdx.y;
   const int N = p.N[g];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,33 +189,21 @@ gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K) {
   TO* out = (TO*)p.out[g];
   const long ldo = p.ldo[g];
   const int act = p.act[g];
-  for (int m0 = 0; m0 < M; m0 += SM_MT) {
-    const int mt = min(SM_MT, M - m0);
+  extern __shared__ uint4 smallm_smem[];
+  T* sA = (T*)smallm_smem;
+  for (int m0 = 0; m0 < M; m0 += rows_per_pass) {
+    const int mt = min(rows_per_pass, M - m0);
     float acc[SM_MT];
 #pragma unroll
     for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
-    smallm_accumulate<T, 8>(A, lda, wrow, K, kl, m0, mt, acc);
-#pragma unroll
-    for (int m = 0; m < SM_MT; ++m) {
-      float v = acc[m];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      acc[m] = v;
-    }
-    if (kl == 0 && n_ok) {
-#pragma unroll
-      for (int m = 0; m < SM_MT; ++m) {
-        if (m < mt) {
-          float v = acc[m];
-          if (bias) v += bias[n];
-          if (act == 1) v = gelu_erf(v);
-          else if (act == 2) v = fmaxf(v, 0.f);
-          else if (act == 3) v = 1.f / (1.f + __expf(-v));
-          out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
-        }
-      }
-    }
+    smallm_stage_a<T>(A, lda, K, m0, mt, sA);
+    float w[4][8];
+    int kc[4];
+    smallm_load_w<T, 8>(wrow, K, kl * 8, w, kc);
+    const float bv = (bias && n_ok) ? bias[n] : 0.f;
+    smallm_stage_wait();
+    smallm_accumulate<T, 8>(sA, wrow, K, kl, mt, acc, w, kc);
+    smallm_epilogue<TO, 8>(acc, kl, n_ok, n, m0, mt, bv, 1.f, nullptr, 0, out, ldo, act);
   }
 }
 
@@ -186,13 +214,36 @@ attn_fewk_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
                  long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
                  long o_bs, long o_hs, long o_ts, int Hh, int Lq, int Lk, float scale) {
   extern __shared__ float smf[];
-  float* Ks = smf;                       // [Hh][Lk][D]
-  float* Vs = smf + Hh * Lk * D;
+  const int HS = Lk * D + 4;             // head stride, padded: heads land in different banks
+  float* Ks = smf;                       // [Hh][Lk][D] (+4 per head)
+  float* Vs = smf + Hh * HS;
   const int b = blockIdx.y;
-  for (int idx = threadIdx.x; idx < Hh * Lk * D; idx += blockDim.x) {
-    const int d = idx % D, j = (idx / D) % Lk, h = idx / (D * Lk);
-    Ks[idx] = to_f(k[b * k_bs + h * k_hs + (long)j * k_ts + d]);
-    Vs[idx] = to_f(v[b * v_bs + h * v_hs + (long)j * v_ts + d]);
+  // 16-byte vectors, two per thread in flight (the scalar loop paid one global round trip per element and pass)
+  constexpr int VPR = D / 8;
+  const int nvec = Hh * Lk * VPR;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 2 * blockDim.x) {
+    float kk[2][8], vv[2][8];
+    int dst[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * blockDim.x;
+      dst[u] = -1;
+      if (i < nvec) {
+        const int d8 = i % VPR, j = (i / VPR) % Lk, h = i / (VPR * Lk);
+        Vec8<T>::load(k + b * k_bs + h * k_hs + (long)j * k_ts + d8 * 8, kk[u]);
+        Vec8<T>::load(v + b * v_bs + h * v_hs + (long)j * v_ts + d8 * 8, vv[u]);
+        dst[u] = h * HS + j * D + d8 * 8;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (dst[u] >= 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          Ks[dst[u] + e] = kk[u][e];
+          Vs[dst[u] + e] = vv[u][e];
+        }
+      }
   }
   __syncthreads();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,8 +258,8 @@ attn_fewk_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) qv[d + i] = t[i] * scale;
   }
-  const float* kh = Ks + h * Lk * D;
-  const float* vh = Vs + h * Lk * D;
+  const float* kh = Ks + h * HS;
+  const float* vh = Vs + h * HS;
   float mx = -INFINITY, l = 0.f, acc[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) acc[d] = 0.f;
@@ -416,14 +467,19 @@ int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, con
                            cudaStream_t st) {
   const bool wide = K >= 1024;                       // one column per warp, 32 lanes split K
   const int grid = ceil_div(N, SMK_WARPS * (wide ? 1 : 4));
+  const int esz = a_dt == MS2_BF16 ? 2 : 4;
+  int rpp = (int)((48 * 1024) / ((long)K * esz));    // rows of A staged per pass (<= 48 KB of shared memory)
+  if (rpp > SM_MT) rpp = SM_MT;
+  MS2_CHECK_ARG(rpp >= 1, "gemm_smallm: K = %d is too wide for the small-M kernel", K);
+  const size_t smem = (size_t)(rpp < M ? rpp : M) * K * esz;
 #define MS2_SMALLM(TA, TO)                                                                                          \
   do {                                                                                                              \
     if (wide)                                                                                                       \
-      gemm_smallm_kernel<TA, TO, 32><<<grid, SMK_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
-                                                                      residual, ldr, (TO*)out, ldo, M, N, K, act);  \
+      gemm_smallm_kernel<TA, TO, 32><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                      residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);  \
     else                                                                                                            \
-      gemm_smallm_kernel<TA, TO, 8><<<grid, SMK_WARPS * 32, 0, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
-                                                                     residual, ldr, (TO*)out, ldo, M, N, K, act);   \
+      gemm_smallm_kernel<TA, TO, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                     residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_SMALLM(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_SMALLM(bf16, float);
@@ -454,6 +510,11 @@ extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const
   }
   dim3 grid(ceil_div(nmax, SM_WARPS * 4), groups);
   cudaStream_t st = (cudaStream_t)stream;
+  const int esz = a_dt == MS2_BF16 ? 2 : 4;
+  int rpp = (int)((48 * 1024) / ((long)K * esz));
+  if (rpp > SM_MT) rpp = SM_MT;
+  MS2_CHECK_ARG(rpp >= 1, "gemm_smallm_grouped: K = %d is too wide", K);
+  const size_t smem = (size_t)(rpp < M ? rpp : M) * K * esz;
 #define MS2_GROUPED(TA, TO)                                                                        \
   do {                                                                                             \
     GroupedP<TA> p;                                                                                \
@@ -463,7 +524,7 @@ extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const
       p.out[g] = h_out[g]; p.lda[g] = h_lda[g]; p.ldo[g] = h_ldo[g]; p.N[g] = h_N[g];              \
       p.act[g] = h_act ? h_act[g] : 0;                                                             \
     }                                                                                              \
-    gemm_smallm_grouped_kernel<TA, TO><<<grid, SM_WARPS * 32, 0, st>>>(p, M, K);                   \
+    gemm_smallm_grouped_kernel<TA, TO><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);                   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_GROUPED(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_GROUPED(bf16, float);
@@ -485,12 +546,12 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
                         cudaStream_t st) {
   if (!(D == 16 || D == 32)) return 0;
   const int vb = dt == MS2_BF16 ? 8 : 4;
-  const bool vec_ok = ((q_ts | k_ts | q_hs | k_hs | q_bs | k_bs) % vb == 0) && ((uintptr_t)q % 16 == 0) &&
-                      ((uintptr_t)k % 16 == 0);
+  const bool vec_ok = ((q_ts | k_ts | q_hs | k_hs | q_bs | k_bs | v_ts | v_hs | v_bs) % vb == 0) && ((uintptr_t)q % 16 == 0) &&
+                      ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0);
   if (!vec_ok) return 0;
 #define MS2_ARGS_T(T) (const T*)q, (const T*)k, (const T*)v, (T*)o, q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts
-  if (Lk <= 32 && (size_t)2 * Hh * Lk * D * 4 <= 48 * 1024) {
-    const size_t smem = (size_t)2 * Hh * Lk * D * 4;
+  if (Lk <= 32 && (size_t)2 * Hh * (Lk * D + 4) * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)2 * Hh * (Lk * D + 4) * 4;
     dim3 grid(ceil_div((long)Lq * Hh, 256), B);
     if (dt == MS2_BF16 && D == 16) attn_fewk_kernel<bf16, 16><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
     else if (dt == MS2_BF16 && D == 32) attn_fewk_kernel<bf16, 32><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
