@@ -61,66 +61,66 @@ __device__ __forceinline__ void smallm_stage_wait() {
 // acc[m] += sum_k sA[m, k] * wrow[k] over this lane's 16-byte chunks (chunk stride KL*8 elements), four chunks per
 // pass.  Branch-free: rows beyond mt re-read the last row and chunks beyond K multiply by a zero weight, so every
 // shared-memory load of a pass is independent and the compiler batches them.
-template <typename T, int KL>
-__device__ __forceinline__ void smallm_load_w(const T* __restrict__ wrow, int K, int k0, float (&w)[4][8], int (&kc)[4]) {
+// All weight chunks of this lane (chunk c covers k = (kl + c*KL)*8 .. +8; NCH <= 8 chunks, zero beyond K) are loaded
+// ONCE, before the wait for the staged activations, so the weight round trip (HBM, once per slice) overlaps the
+// activation round trip.
+template <typename T, int KL, int NCH>
+__device__ __forceinline__ void smallm_load_w(const T* __restrict__ wrow, int K, int kl, float (&w)[NCH][8], int (&kc)[NCH]) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = k0 + u * KL * 8;
-    kc[u] = k < K ? k : K - 8;
-    Vec8<T>::load(wrow + kc[u], w[u]);
+  for (int c = 0; c < NCH; ++c) {
+    const int k = (kl + c * KL) * 8;
+    kc[c] = k < K ? k : K - 8;
+    Vec8<T>::load(wrow + kc[c], w[c]);
     if (k >= K) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[u][i] = 0.f;
+      for (int i = 0; i < 8; ++i) w[c][i] = 0.f;
     }
   }
 }
 
-// (w, kc): the weights of the first pass, loaded by the caller BEFORE it waits for the staged activations, so that the
-// weight round trip (HBM once per slice) overlaps the activation round trip
-template <typename T, int KL>
-__device__ __forceinline__ void smallm_accumulate(const T* sA, const T* __restrict__ wrow, int K, int kl, int mt,
-                                                  float (&acc)[SM_MT], float (&w)[4][8], int (&kc)[4]) {
-  constexpr int U = 4;
-  for (int k0 = kl * 8; k0 < K; k0 += KL * 8 * U) {
-    if (k0 != kl * 8) smallm_load_w<T, KL>(wrow, K, k0, w, kc);
+// One output row per iteration of a ROLLED loop: the fully unrolled 16-row version was ~2400 instructions (38 KB) that
+// every warp fetched exactly once - ncu showed the kernel waiting for instructions (stall_no_inst), not for data.
+template <typename T, typename TO, int KL, int NCH>
+__device__ __forceinline__ void smallm_rows(const T* sA, int K, int kl, bool n_ok, int n, int m0, int mt,
+                                            const float (&w)[NCH][8], const int (&kc)[NCH], float bv, float cs,
+                                            const float* __restrict__ residual, long ldr, TO* __restrict__ out, long ldo,
+                                            int act) {
+  constexpr int R = 3;                                   // rows in flight per iteration (independent chains)
+#pragma unroll 1
+  for (int m = 0; m < mt; m += R) {
+    float v[R];
 #pragma unroll
-    for (int m = 0; m < SM_MT; ++m) {
-      const T* arow = sA + (long)(m < mt ? m : mt - 1) * K;
+    for (int r = 0; r < R; ++r) {
+      const T* arow = sA + (long)(m + r < mt ? m + r : mt - 1) * K;
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int c = 0; c < NCH; ++c) {
         float a[8];
-        Vec8<T>::load(arow + kc[u], a);
+        Vec8<T>::load(arow + kc[c], a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[m] = fmaf(a[i], w[u][i], acc[m]);
+        for (int i = 0; i < 8; i += 2) {
+          acc0 = fmaf(a[i], w[c][i], acc0);
+          acc1 = fmaf(a[i + 1], w[c][i + 1], acc1);
+        }
       }
+      v[r] = acc0 + acc1;
     }
-  }
-}
-
-// epilogue of one pass: after the reduction over the KL lanes of a column every lane holds all row sums; lane kl
-// finishes rows kl, kl+KL, ... (bias / colscale are loaded once, the row stores of a column go out in parallel)
-template <typename TO, int KL>
-__device__ __forceinline__ void smallm_epilogue(float (&acc)[SM_MT], int kl, bool n_ok, int n, int m0, int mt,
-                                                float bv, float cs, const float* __restrict__ residual, long ldr,
-                                                TO* __restrict__ out, long ldo, int act) {
 #pragma unroll
-  for (int m = 0; m < SM_MT; ++m) {
-    float v = acc[m];
+    for (int o = KL / 2; o > 0; o >>= 1)
 #pragma unroll
-    for (int o = KL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    acc[m] = v;
-  }
-  if (!n_ok) return;
+      for (int r = 0; r < R; ++r) v[r] += __shfl_xor_sync(0xffffffffu, v[r], o);
+    // lane kl finishes row m + kl (kl < R): the row stores of a column go out in parallel
+    float mine = v[0];
 #pragma unroll
-  for (int m = 0; m < SM_MT; ++m) {
-    if (m % KL == kl && m < mt) {
-      float v = acc[m] + bv;
-      if (act == 1) v = gelu_erf(v);
-      else if (act == 2) v = fmaxf(v, 0.f);
-      else if (act == 3) v = 1.f / (1.f + __expf(-v));
-      v *= cs;
-      if (residual) v += residual[(long)(m0 + m) * ldr + n];
-      out[(long)(m0 + m) * ldo + n] = from_f<TO>(v);
+    for (int r = 1; r < R; ++r) mine = kl == r ? v[r] : mine;
+    if (kl < R && m + kl < mt && n_ok) {
+      float x = mine + bv;
+      if (act == 1) x = gelu_erf(x);
+      else if (act == 2) x = fmaxf(x, 0.f);
+      else if (act == 3) x = 1.f / (1.f + __expf(-x));
+      x *= cs;
+      if (residual) x += residual[(long)(m0 + m + kl) * ldr + n];
+      out[(long)(m0 + m + kl) * ldo + n] = from_f<TO>(x);
     }
   }
 }
@@ -129,7 +129,7 @@ __device__ __forceinline__ void smallm_epilogue(float (&acc)[SM_MT], int kl, boo
 // per warp, for K >= 1024 where 8 lanes would each walk 128+ elements serially).  Two warps per CTA so that even
 // N = 256 gives 32..128 CTAs: these GEMMs are pure latency (W is 0.1-1 MB, A a few KB).
 constexpr int SMK_WARPS = 2;
-template <typename T, typename TO, int KL>
+template <typename T, typename TO, int KL, int NCH>
 __global__ void __launch_bounds__(SMK_WARPS * 32)
 gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, const float* __restrict__ bias,
                    const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
@@ -144,17 +144,13 @@ gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, c
   T* sA = (T*)smallm_smem;
   for (int m0 = 0; m0 < M; m0 += rows_per_pass) {
     const int mt = min(rows_per_pass, M - m0);
-    float acc[SM_MT];
-#pragma unroll
-    for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
     smallm_stage_a<T>(A, lda, K, m0, mt, sA);
-    float w[4][8];
-    int kc[4];
-    smallm_load_w<T, KL>(wrow, K, kl * 8, w, kc);
+    float w[NCH][8];
+    int kc[NCH];
+    smallm_load_w<T, KL, NCH>(wrow, K, kl, w, kc);
     const float bv = (bias && n_ok) ? bias[n] : 0.f, cs = (colscale && n_ok) ? colscale[n] : 1.f;
     smallm_stage_wait();
-    smallm_accumulate<T, KL>(sA, wrow, K, kl, mt, acc, w, kc);
-    smallm_epilogue<TO, KL>(acc, kl, n_ok, n, m0, mt, bv, cs, residual, ldr, out, ldo, act);
+    smallm_rows<T, TO, KL, NCH>(sA, K, kl, n_ok, n, m0, mt, w, kc, bv, cs, residual, ldr, out, ldo, act);
   }
 }
 
@@ -172,7 +168,7 @@ struct GroupedP {
   int N[SM_MAXG], act[SM_MAXG];
 };
 
-template <typename T, typename TO>
+template <typename T, typename TO, int NCH>
 __global__ void __launch_bounds__(SM_WARPS * 32)
 gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K, int rows_per_pass) {
   const int g = blockIdx.y;
@@ -193,17 +189,13 @@ gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K, int rows_per_pass)
   T* sA = (T*)smallm_smem;
   for (int m0 = 0; m0 < M; m0 += rows_per_pass) {
     const int mt = min(rows_per_pass, M - m0);
-    float acc[SM_MT];
-#pragma unroll
-    for (int m = 0; m < SM_MT; ++m) acc[m] = 0.f;
     smallm_stage_a<T>(A, lda, K, m0, mt, sA);
-    float w[4][8];
-    int kc[4];
-    smallm_load_w<T, 8>(wrow, K, kl * 8, w, kc);
+    float w[NCH][8];
+    int kc[NCH];
+    smallm_load_w<T, 8, NCH>(wrow, K, kl, w, kc);
     const float bv = (bias && n_ok) ? bias[n] : 0.f;
     smallm_stage_wait();
-    smallm_accumulate<T, 8>(sA, wrow, K, kl, mt, acc, w, kc);
-    smallm_epilogue<TO, 8>(acc, kl, n_ok, n, m0, mt, bv, 1.f, nullptr, 0, out, ldo, act);
+    smallm_rows<T, TO, 8, NCH>(sA, K, kl, n_ok, n, m0, mt, w, kc, bv, 1.f, nullptr, 0, out, ldo, act);
   }
 }
 
@@ -385,13 +377,14 @@ attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
   const T* kb = k + b * k_bs + h * k_hs;
   const T* vb = v + b * v_bs + h * v_hs;
   for (int j = tid; j < nk; j += FS_THREADS) {
-    float kv[D];
+    float kv[D], vv[D];                                      // K and V rows of this key: all loads issued up front
 #pragma unroll
     for (int d = 0; d < D; d += 8) {
-      float t[8];
+      float t[8], u[8];
       Vec8<T>::load(kb + (long)(j0 + j) * k_ts + d, t);
+      Vec8<T>::load(vb + (long)(j0 + j) * v_ts + d, u);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) kv[d + i] = t[i];
+      for (int i = 0; i < 8; ++i) { kv[d + i] = t[i]; vv[d + i] = u[i]; }
     }
     for (int qi = 0; qi < Lq; ++qi) {
       float a = 0.f;
@@ -400,7 +393,7 @@ attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
       S[qi][j] = a;
     }
 #pragma unroll
-    for (int d = 0; d < D; ++d) Vs[j][d] = to_f(vb[(long)(j0 + j) * v_ts + d]);
+    for (int d = 0; d < D; ++d) Vs[j][d] = vv[d];
   }
   __syncthreads();
   float* pbase = part + ((((long)b * gridDim.x + h) * ns + sp) * Lq) * (D + 2);
@@ -429,23 +422,44 @@ attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
   }
 }
 
+// one warp per (batch*head, query): lane = key split (two rounds when ns > 32), so the D+2 loads of a lane are all
+// independent and the merge is a handful of warp reductions (the per-thread loop over the splits walked the
+// partials with one L2 round trip per unrolled batch: 8 us for 9 queries)
 template <typename T, int D>
-__global__ void attn_fewq_combine_kernel(const float* __restrict__ part, T* __restrict__ o, long o_bs, long o_hs, long o_ts,
-                                         int Hh, int Lq, int ns) {
-  const int bh = blockIdx.x, b = bh / Hh, h = bh - b * Hh;
-  for (int idx = threadIdx.x; idx < Lq * D; idx += blockDim.x) {
-    const int qi = idx / D, d = idx % D;
-    const float* pb = part + ((long)bh * ns * Lq + qi) * (D + 2);
-    const long sstride = (long)Lq * (D + 2);
-    float mstar = -INFINITY;
-    for (int s = 0; s < ns; ++s) mstar = fmaxf(mstar, pb[s * sstride + D]);
-    float acc = 0.f, l = 0.f;
-    for (int s = 0; s < ns; ++s) {
-      const float w = __expf(pb[s * sstride + D] - mstar);
-      acc = fmaf(w, pb[s * sstride + d], acc);
-      l = fmaf(w, pb[s * sstride + D + 1], l);
+__global__ void __launch_bounds__(256)
+attn_fewq_combine_kernel(const float* __restrict__ part, T* __restrict__ o, long o_bs, long o_hs, long o_ts,
+                         int Hh, int Lq, int ns, int nrows) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const int bh = row / Lq, qi = row - bh * Lq;
+  const int b = bh / Hh, h = bh - b * Hh;
+  const long sstride = (long)Lq * (D + 2);
+  const float* pb = part + ((long)bh * ns * Lq + qi) * (D + 2);
+  float m[2], l[2], v[2][D];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int s = lane + 32 * r;
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[r][d] = 0.f;
+    if (s < ns) {
+      const float* ps = pb + s * sstride;
+      m[r] = ps[D];
+      l[r] = ps[D + 1];
+#pragma unroll
+      for (int d = 0; d < D; ++d) v[r][d] = ps[d];
     }
-    o[b * o_bs + h * o_hs + (long)qi * o_ts + d] = from_f<T>(acc / l);
+  }
+  const float mstar = warp_max(fmaxf(m[0], m[1]));
+  const float w0 = __expf(m[0] - mstar), w1 = __expf(m[1] - mstar);       // exp(-inf) = 0 for absent splits
+  const float lsum = warp_sum(w0 * l[0] + w1 * l[1]);
+  const float inv = 1.f / lsum;
+  T* op = o + b * o_bs + h * o_hs + (long)qi * o_ts;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float a = warp_sum(w0 * v[0][d] + w1 * v[1][d]);
+    if (lane == (d & 31)) op[d] = from_f<T>(a * inv);
   }
 }
 
@@ -457,7 +471,7 @@ size_t fewq_smem(int Lq, int Lk, int D) {
 
 // -------- dispatch helpers used by ms2_gemm / ms2_attention_ws
 bool ms2_gemm_smallm_supported(int a_dt, int w_dt, const void* A, const void* W, long lda, int M, int N, int K) {
-  if (a_dt != w_dt || M > 64) return false;
+  if (a_dt != w_dt || M > 64 || K > 2048) return false;     // <= 8 register-resident weight chunks per lane
   const int vb = a_dt == MS2_BF16 ? 8 : 4;          // 16-byte vectors
   return K % 8 == 0 && lda % vb == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0);
 }
@@ -465,7 +479,7 @@ bool ms2_gemm_smallm_supported(int a_dt, int w_dt, const void* A, const void* W,
 int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, const float* bias, const float* colscale,
                            const float* residual, long ldr, void* out, int o_dt, long ldo, int M, int N, int K, int act,
                            cudaStream_t st) {
-  const bool wide = K >= 1024;                       // one column per warp, 32 lanes split K
+  const bool wide = K > 512;                         // one column per warp, 32 lanes split K (<= 8 chunks per lane)
   const int grid = ceil_div(N, SMK_WARPS * (wide ? 1 : 4));
   const int esz = a_dt == MS2_BF16 ? 2 : 4;
   int rpp = (int)((48 * 1024) / ((long)K * esz));    // rows of A staged per pass (<= 48 KB of shared memory)
@@ -475,11 +489,14 @@ int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, con
 #define MS2_SMALLM(TA, TO)                                                                                          \
   do {                                                                                                              \
     if (wide)                                                                                                       \
-      gemm_smallm_kernel<TA, TO, 32><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
-                                                                      residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);  \
+      gemm_smallm_kernel<TA, TO, 32, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                         residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);  \
+    else if (K <= 256)                                                                                              \
+      gemm_smallm_kernel<TA, TO, 8, 4><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                        residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
     else                                                                                                            \
-      gemm_smallm_kernel<TA, TO, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
-                                                                     residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
+      gemm_smallm_kernel<TA, TO, 8, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+                                                                        residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_SMALLM(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_SMALLM(bf16, float);
@@ -499,7 +516,7 @@ extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const
                                        const int* h_N, const int* h_act, int a_dt, int o_dt, int M, int K,
                                        void* stream) {
   MS2_CHECK_ARG(groups >= 1 && groups <= SM_MAXG, "gemm_smallm_grouped: 1..%d groups", SM_MAXG);
-  MS2_CHECK_ARG(M >= 1 && M <= 64 && K > 0 && K % 8 == 0, "gemm_smallm_grouped: M in 1..64, K %% 8 == 0");
+  MS2_CHECK_ARG(M >= 1 && M <= 64 && K > 0 && K % 8 == 0 && K <= 512, "gemm_smallm_grouped: M in 1..64, K %% 8 == 0, K <= 512");
   int nmax = 0;
   const int vb = a_dt == MS2_BF16 ? 8 : 4;
   for (int g = 0; g < groups; ++g) {
@@ -524,7 +541,8 @@ extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const
       p.out[g] = h_out[g]; p.lda[g] = h_lda[g]; p.ldo[g] = h_ldo[g]; p.N[g] = h_N[g];              \
       p.act[g] = h_act ? h_act[g] : 0;                                                             \
     }                                                                                              \
-    gemm_smallm_grouped_kernel<TA, TO><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);                   \
+    if (K <= 256) gemm_smallm_grouped_kernel<TA, TO, 4><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);         \
+    else gemm_smallm_grouped_kernel<TA, TO, 8><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);                   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_GROUPED(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_GROUPED(bf16, float);
@@ -571,7 +589,7 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
   do {                                                                                                                \
     attn_fewq_split_kernel<T, DD><<<grid, FS_THREADS, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (float*)ws, q_bs, \
                                                                q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, Lq, Lk, chunk, scale); \
-    attn_fewq_combine_kernel<T, DD><<<B * Hh, 256, 0, st>>>((const float*)ws, (T*)o, o_bs, o_hs, o_ts, Hh, Lq, ns);    \
+    attn_fewq_combine_kernel<T, DD><<<ceil_div((long)B * Hh * Lq, 8), 256, 0, st>>>((const float*)ws, (T*)o, o_bs, o_hs, o_ts, Hh, Lq, ns, B * Hh * Lq); \
   } while (0)
       if (dt == MS2_BF16 && D == 16) MS2_FEWQS(bf16, 16);
       else if (dt == MS2_BF16 && D == 32) MS2_FEWQS(bf16, 32);
