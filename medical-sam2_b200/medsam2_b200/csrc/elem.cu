@@ -17,6 +17,33 @@ __global__ void axpby_kernel(const float* __restrict__ x, float a, const float* 
     y[i] = from_f<TO>(a * x[i] + (z ? b * z[i % zn] : 0.f) + c);
 }
 
+// 4 elements per thread (16-byte loads, 8/16-byte stores), the broadcast index of z computed once per vector with
+// 32-bit arithmetic; used when n, zn are multiples of 4, n < 2^31 and the pointers are 16-byte aligned
+__device__ __forceinline__ void store4(float* y, long i, float4 v) { *(float4*)(y + i) = v; }
+__device__ __forceinline__ void store4(bf16* y, long i, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *(uint32_t*)&lo;
+  u.y = *(uint32_t*)&hi;
+  *(uint2*)(y + i) = u;
+}
+template <typename TO>
+__global__ void axpby_vec4_kernel(const float* __restrict__ x, float a, const float* __restrict__ z, float b, float c,
+                                  TO* __restrict__ y, unsigned n4, unsigned zn4) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 xv = *(const float4*)(x + 4L * i);
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (z) zv = *(const float4*)(z + 4L * (i % zn4));
+    store4(y, 4L * i, make_float4(a * xv.x + b * zv.x + c, a * xv.y + b * zv.y + c, a * xv.z + b * zv.z + c,
+                                  a * xv.w + b * zv.w + c));
+  }
+}
+template <typename TO>
+__global__ void cast_vec4_kernel(const float* __restrict__ x, TO* __restrict__ y, unsigned n4) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    store4(y, 4L * i, *(const float4*)(x + 4L * i));
+}
+
 __global__ void gate_rows_kernel(const float* __restrict__ x, const float* __restrict__ gate, float fill,
                                  float* __restrict__ y, long n, long P) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -202,7 +229,14 @@ extern "C" int ms2_axpby(const float* x, float a, const float* z, float b, float
   MS2_CHECK_ARG(x && y && n >= 0, "axpby: bad args");
   MS2_CHECK_ARG(!z || (zn > 0 && n % zn == 0), "axpby: z length must divide n");
   if (!n) return MS2_OK;
-  MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_kernel<TO><<<grid_for(n), 256, 0, ST>>>(x, a, z, b, c, (TO*)y, n, z ? zn : 1)));
+  const bool vec = n % 4 == 0 && n < (1L << 31) && (!z || zn % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
+                   ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0);
+  if (vec) {
+    MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_vec4_kernel<TO><<<grid_for(n / 4), 256, 0, ST>>>(
+                                     x, a, z, b, c, (TO*)y, (unsigned)(n / 4), (unsigned)(z ? zn / 4 : 1))));
+  } else {
+    MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_kernel<TO><<<grid_for(n), 256, 0, ST>>>(x, a, z, b, c, (TO*)y, n, z ? zn : 1)));
+  }
   MS2_CHECK_LAUNCH("axpby");
   return MS2_OK;
 }
@@ -225,7 +259,10 @@ extern "C" int ms2_select_plane(const float* x, const int32_t* idx, float* y, in
 extern "C" int ms2_add_rowvec(const float* x, const float* v, float s, float* y, long M, int C, void* stream) {
   MS2_CHECK_ARG(x && v && y && M >= 0 && C > 0, "add_rowvec: bad args");
   if (!M) return MS2_OK;
-  add_rowvec_kernel<<<grid_for(M * C), 256, 0, ST>>>(x, v, s, y, M * C, C);
+  if (C % 4 == 0 && M * C < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)v % 16 == 0))
+    axpby_vec4_kernel<float><<<grid_for(M * C / 4), 256, 0, ST>>>(x, 1.f, v, s, 0.f, y, (unsigned)(M * C / 4), (unsigned)(C / 4));
+  else
+    add_rowvec_kernel<<<grid_for(M * C), 256, 0, ST>>>(x, v, s, y, M * C, C);
   MS2_CHECK_LAUNCH("add_rowvec");
   return MS2_OK;
 }
@@ -233,7 +270,10 @@ extern "C" int ms2_cast(const void* x, int x_dt, void* y, int y_dt, long n, void
   MS2_CHECK_ARG(x && y && n >= 0, "cast: bad args");
   if (!n) return MS2_OK;
   int g = grid_for(n);
-  if (x_dt == MS2_F32 && y_dt == MS2_BF16) cast_kernel<float, bf16><<<g, 256, 0, ST>>>((const float*)x, (bf16*)y, n);
+  const bool vec = n % 4 == 0 && n < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  if (x_dt == MS2_F32 && y_dt == MS2_BF16 && vec)
+    cast_vec4_kernel<bf16><<<grid_for(n / 4), 256, 0, ST>>>((const float*)x, (bf16*)y, (unsigned)(n / 4));
+  else if (x_dt == MS2_F32 && y_dt == MS2_BF16) cast_kernel<float, bf16><<<g, 256, 0, ST>>>((const float*)x, (bf16*)y, n);
   else if (x_dt == MS2_BF16 && y_dt == MS2_F32) cast_kernel<bf16, float><<<g, 256, 0, ST>>>((const bf16*)x, (float*)y, n);
   else if (x_dt == MS2_F32 && y_dt == MS2_F32) cast_kernel<float, float><<<g, 256, 0, ST>>>((const float*)x, (float*)y, n);
   else if (x_dt == MS2_BF16 && y_dt == MS2_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, ST>>>((const bf16*)x, (bf16*)y, n);

@@ -408,6 +408,11 @@ def test_elementwise_family(ops):
     close(ops.axpby(x, 20.0, None, 0.0, -10.0), ref_ops.axpby(x, 20.0, None, 0.0, -10.0), 1e-5, "axpby const")
     close(ops.axpby(x, 1.0, z[0], 1.0), ref_ops.axpby(x, 1.0, z[0], 1.0), 1e-6, "axpby bcast")
     close(ops.axpby(x, 1.0, z, 1.0, out_dtype=torch.bfloat16), ref_ops.axpby(x, 1.0, z, 1.0), 3e-2, "axpby bf16")
+    xo, zo = rnd(3, 7, 5, seed=6), rnd(3, 7, 5, seed=7)          # odd sizes: the scalar kernels
+    close(ops.axpby(xo, 2.0, zo, 0.5, 1.0), ref_ops.axpby(xo, 2.0, zo, 0.5, 1.0), 1e-6, "axpby odd")
+    close(ops.axpby(xo, 1.0, zo[0], 1.0, out_dtype=torch.bfloat16), ref_ops.axpby(xo, 1.0, zo[0], 1.0), 3e-2, "axpby odd bcast")
+    close(ops.cast(ops.cast(xo, torch.bfloat16), torch.float32), xo.bfloat16().float(), 0.0, "cast odd")
+    close(ops.add_rowvec(xo, rnd(5, seed=8)), ref_ops.add_rowvec(xo, rnd(5, seed=8)), 1e-6, "add_rowvec odd")
     v = rnd(64, seed=3)
     close(ops.add_rowvec(x, v), ref_ops.add_rowvec(x, v), 1e-6, "add_rowvec")
     close(ops.cast(ops.cast(x, torch.bfloat16), torch.float32), x.bfloat16().float(), 0.0, "cast")
