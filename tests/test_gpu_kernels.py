@@ -438,8 +438,15 @@ def test_layout_kernels(ops):
     g, bias, skip = rnd(2, 16, 16, 4 * 64, seed=5), rnd(64, seed=6), rnd(2, 32, 32, 64, seed=7)
     close(ops.pixel_shuffle_add(g, bias, skip, 2, 16, 16, 64, act=1), ref_ops.pixel_shuffle_add(g, bias, skip, 2, 16, 16, 64, act=1),
           1e-6, "pixel_shuffle_add")
+    g2, skip2 = rnd(1, 9, 7, 4 * 6, seed=10), rnd(1, 18, 14, 6, seed=11)         # C % 4 != 0: the scalar kernel, no bias
+    close(ops.pixel_shuffle_add(g2, None, skip2, 1, 9, 7, 6), ref_ops.pixel_shuffle_add(g2, None, skip2, 1, 9, 7, 6), 1e-6,
+          "pixel_shuffle_add scalar")
     up, hyper = rnd(2, 4096, 32, seed=8), rnd(2, 4, 32, seed=9)
     close(ops.hyper_mask(up, hyper), ref_ops.hyper_mask(up, hyper), 1e-4, "hyper_mask")
+    up, hyper = rnd(2, 1000, 32, seed=12), rnd(2, 4, 32, seed=13)                  # ragged pixel count
+    close(ops.hyper_mask(up, hyper), ref_ops.hyper_mask(up, hyper), 1e-4, "hyper_mask ragged")
+    up, hyper = rnd(1, 333, 16, seed=14), rnd(1, 3, 16, seed=15)                   # generic (warp-per-pixel) kernel
+    close(ops.hyper_mask(up, hyper), ref_ops.hyper_mask(up, hyper), 1e-4, "hyper_mask generic")
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
