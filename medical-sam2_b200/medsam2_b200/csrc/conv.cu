@@ -147,9 +147,31 @@ conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ 
                          int H, int W, int Ho, int Wo, float eps, int pre, float pre_scale, float pre_bias) {
   __shared__ float ws[9 * CIN * COUT];                 // [tap][ci][co]
   __shared__ float sb[3 * COUT];
-  for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) {
-    const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
-    ws[i] = w[((long)co * CIN + ci) * 9 + tap];       // conv weight [Cout, Cin, 3, 3]
+  // conv weight [Cout, Cin, 3, 3] -> [tap][ci][co]: read in SOURCE order with 16-byte loads that are all issued before
+  // the first store (the element-wise gather paid one global round trip per pass: 72 passes for 16 -> 64 channels,
+  // most of the kernel's 65 us), scatter into shared memory
+  {
+    constexpr int NW = 9 * CIN * COUT, NV = NW / 4, PASSES = (NV + 127) / 128;
+    static_assert(NW % 4 == 0, "weight count must be a multiple of 4");
+    float4 v[PASSES];
+#pragma unroll
+    for (int u = 0; u < PASSES; ++u) {
+      const int i4 = threadIdx.x + u * 128;
+      if (i4 < NV) v[u] = __ldg((const float4*)w + i4);
+    }
+#pragma unroll
+    for (int u = 0; u < PASSES; ++u) {
+      const int i4 = threadIdx.x + u * 128;
+      if (i4 < NV) {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i4 * 4 + k;
+          const int tap = i % 9, ci = (i / 9) % CIN, co = i / (9 * CIN);
+          ws[(tap * CIN + ci) * COUT + co] = e[k];
+        }
+      }
+    }
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
     sb[i] = bias[i];
@@ -205,7 +227,7 @@ constexpr int DW_T = 8, DW_C = 32, DW_IN = DW_T + 6;
 __global__ void __launch_bounds__(DW_T * DW_C)
 dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y, int B, int H, int W, int C) {
-  __shared__ float tile[DW_IN][DW_IN][DW_C];
+  __shared__ __align__(16) float tile[DW_IN][DW_IN][DW_C];
   __shared__ float ws[49][DW_C];
   const int tilesx = (W + DW_T - 1) / DW_T;
   const int tx0 = (blockIdx.x % tilesx) * DW_T, ty0 = (blockIdx.x / tilesx) * DW_T;
@@ -215,12 +237,29 @@ dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const int c = i % DW_C, tap = i / DW_C;
     ws[tap][c] = (c0 + c < C) ? w[(long)(c0 + c) * 49 + tap] : 0.f;
   }
-  for (int i = threadIdx.x; i < DW_IN * DW_IN * DW_C; i += blockDim.x) {
-    const int c = i % DW_C, col = (i / DW_C) % DW_IN, row = i / (DW_C * DW_IN);
-    const int sy = ty0 + row - 3, sx = tx0 + col - 3;
-    float v = 0.f;
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W && c0 + c < C) v = x[(((long)b * H + sy) * W + sx) * C + c0 + c];
-    tile[row][col][c] = v;
+  if (c0 + DW_C <= C && C % 4 == 0 && ((uintptr_t)x % 16 == 0)) {
+    // halo tile as asynchronous 16-byte copies (a pixel's 32 channels are one 128-byte line): every piece of a
+    // thread is in flight at once; out-of-image pixels are zero-filled with ordinary stores
+    for (int i = threadIdx.x; i < DW_IN * DW_IN * (DW_C / 4); i += blockDim.x) {
+      const int c4 = i % (DW_C / 4), col = (i / (DW_C / 4)) % DW_IN, row = i / ((DW_C / 4) * DW_IN);
+      const int sy = ty0 + row - 3, sx = tx0 + col - 3;
+      float* dst = &tile[row][col][c4 * 4];
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                     "l"(x + (((long)b * H + sy) * W + sx) * C + c0 + c4 * 4) : "memory");
+      else
+        *(float4*)dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int i = threadIdx.x; i < DW_IN * DW_IN * DW_C; i += blockDim.x) {
+      const int c = i % DW_C, col = (i / DW_C) % DW_IN, row = i / (DW_C * DW_IN);
+      const int sy = ty0 + row - 3, sx = tx0 + col - 3;
+      float v = 0.f;
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W && c0 + c < C) v = x[(((long)b * H + sy) * W + sx) * C + c0 + c];
+      tile[row][col][c] = v;
+    }
   }
   __syncthreads();
   const int c = c0 + cl;
@@ -288,6 +327,7 @@ extern "C" int ms2_conv3x3s2_ln_gelu(const float* x, const float* w, const float
                                      const float* beta, void* y, int y_dt, int B, int H, int W, int Cin, int Cout,
                                      float eps, int pre, float pre_scale, float pre_bias, void* stream) {
   MS2_CHECK_ARG(x && w && bias && gamma && beta && y, "conv3x3s2_ln_gelu: null pointer");
+  MS2_CHECK_ARG((uintptr_t)w % 16 == 0, "conv3x3s2_ln_gelu: w must be 16-byte aligned");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long np = (long)B * Ho * Wo;
   if (!np) return MS2_OK;
