@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128)
 conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ gamma, const float* __restrict__ beta, TO* __restrict__ y, int B,
                          int H, int W, int Ho, int Wo, float eps, int pre, float pre_scale, float pre_bias) {
-  __shared__ float ws[9 * CIN * COUT];                 // [tap][ci][co]
+  __shared__ __align__(16) float ws[9 * CIN * COUT];   // [tap][ci][co]
   __shared__ float sb[3 * COUT];
   // conv weight [Cout, Cin, 3, 3] -> [tap][ci][co]: read in SOURCE order with 16-byte loads that are all issued before
   // the first store (the element-wise gather paid one global round trip per pass: 72 passes for 16 -> 64 channels,
@@ -192,15 +192,32 @@ conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ 
     const int yy = yo * 2 - 1 + tap / 3, xx = xo * 2 - 1 + tap % 3;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
     const float* src = x + (((long)b * H + yy) * W + xx) * CIN;
+    float in[CIN];
+    if (CIN % 4 == 0) {                                  // a pixel's channels as 16-byte loads
+#pragma unroll
+      for (int c4 = 0; c4 < CIN / 4; ++c4) {
+        const float4 t = *(const float4*)(src + c4 * 4);
+        in[c4 * 4] = t.x; in[c4 * 4 + 1] = t.y; in[c4 * 4 + 2] = t.z; in[c4 * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) in[ci] = src[ci];
+    }
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      float v = src[ci];
+      float v = in[ci];
       if (pre == 1) v = 1.f / (1.f + expf(-v));
       else if (pre == 2) v = v > 0.f ? 1.f : 0.f;
       if (pre) v = v * pre_scale + pre_bias;
-      const float* wr = ws + (tap * CIN + ci) * COUT;
+      const float4* wr = (const float4*)(ws + (tap * CIN + ci) * COUT);      // broadcast 16-byte reads
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 wv = wr[c4];
+        acc[c4 * 4] = fmaf(v, wv.x, acc[c4 * 4]);
+        acc[c4 * 4 + 1] = fmaf(v, wv.y, acc[c4 * 4 + 1]);
+        acc[c4 * 4 + 2] = fmaf(v, wv.z, acc[c4 * 4 + 2]);
+        acc[c4 * 4 + 3] = fmaf(v, wv.w, acc[c4 * 4 + 3]);
+      }
     }
   }
   float mean = 0.f;
@@ -215,8 +232,21 @@ conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
   const float rstd = rsqrtf(var * (1.f / COUT) + eps);
   TO* dst = y + p * COUT;
+  if (sizeof(TO) == 4) {
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) dst[c] = from_f<TO>(gelu_erf((acc[c] - mean) * rstd * sb[COUT + c] + sb[2 * COUT + c]));
+    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c4 * 4 + k;
+        o[k] = gelu_erf((acc[c] - mean) * rstd * sb[COUT + c] + sb[2 * COUT + c]);
+      }
+      *(float4*)((float*)dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) dst[c] = from_f<TO>(gelu_erf((acc[c] - mean) * rstd * sb[COUT + c] + sb[2 * COUT + c]));
+  }
 }
 
 // ------------------------------------------------------------------ depth-wise 7x7

@@ -131,6 +131,23 @@ __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// 4 channels per thread (16-byte loads / stores), 32-bit indices: C % 4 == 0 and < 2^31 input elements
+__global__ void maxpool2x2_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned n4, unsigned H,
+                                       unsigned W, unsigned C4) {
+  const unsigned Ho = H / 2, Wo = W / 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4;
+    unsigned t = i / C4;
+    const unsigned xo = t % Wo; t /= Wo;
+    const unsigned yo = t % Ho;
+    const unsigned b = t / Ho;
+    const float4* p = (const float4*)x + ((b * H + 2 * yo) * W + 2 * xo) * C4 + c4;
+    const float4 a = p[0], bq = p[C4], c = p[W * C4], d = p[W * C4 + C4];
+    *((float4*)y + i) = make_float4(fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y)),
+                                    fmaxf(fmaxf(a.z, bq.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, bq.w), fmaxf(c.w, d.w)));
+  }
+}
+
 __global__ void pixel_shuffle_add_kernel(const float* __restrict__ g, const float* __restrict__ bias,
                                          const float* __restrict__ skip, float* __restrict__ out, int B, int H,
                                          int W, int C, int act) {
@@ -373,7 +390,10 @@ extern "C" int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int
   MS2_CHECK_ARG(x && y && (H % 2 == 0) && (W % 2 == 0), "maxpool2x2: bad args");
   long n = (long)B * (H / 2) * (W / 2) * C;
   if (!n) return MS2_OK;
-  maxpool2x2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, B, H, W, C);
+  if (C % 4 == 0 && (long)B * H * W * C < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0))
+    maxpool2x2_vec4_kernel<<<grid_for(n / 4), 256, 0, ST>>>(x, y, (unsigned)(n / 4), (unsigned)H, (unsigned)W, (unsigned)(C / 4));
+  else
+    maxpool2x2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, B, H, W, C);
   MS2_CHECK_LAUNCH("maxpool2x2");
   return MS2_OK;
 }

@@ -430,6 +430,8 @@ def test_elementwise_family(ops):
 def test_layout_kernels(ops):
     x = rnd(2, 32, 48, 96, seed=1)
     close(ops.maxpool2x2(x), ref_ops.maxpool2x2(x), 0.0, "maxpool")
+    xs_ = rnd(1, 6, 10, 6, seed=21)                                   # C % 4 != 0: the scalar kernel
+    close(ops.maxpool2x2(xs_), ref_ops.maxpool2x2(xs_), 0.0, "maxpool scalar")
     close(ops.nhwc_to_nchw(x), ref_ops.nhwc_to_nchw(x), 0.0, "nhwc->nchw")
     y = rnd(2, 96, 32, 48, seed=2)
     close(ops.nchw_to_nhwc(y), ref_ops.nchw_to_nhwc(y), 0.0, "nchw->nhwc")
