@@ -124,7 +124,8 @@ def test_fill_holes_local_vs_labels(ops, density, area):
 
 
 # ------------------------------------------------------------------ norm / gemm
-@pytest.mark.parametrize("M,C", [(1000, 96), (333, 768), (4096, 256), (5000, 4), (777, 16), (129, 64), (9, 256)])
+@pytest.mark.parametrize("M,C", [(1000, 96), (333, 768), (4096, 256), (5000, 4), (777, 16), (129, 64), (9, 256), (5001, 96),
+                                 (4097, 192), (4099, 128)])
 def test_layernorm(ops, M, C):
     x, a = rnd(M, C, seed=1, scale=2.0), rnd(M, C, seed=2)
     g, b = rnd(C, seed=3), rnd(C, seed=4)
