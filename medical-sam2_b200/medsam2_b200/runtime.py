@@ -203,11 +203,18 @@ class GraphRunner:
         return out
 
 
-def _clone_tree(x):
+def _clone_tree(x, memo=None):
+    """clone every tensor of a nested result ONCE (the SAM heads return the same mask tensor under two names when a
+    single mask is requested: two 4 MB copies per slice otherwise)."""
+    if memo is None:
+        memo = {}
     if isinstance(x, torch.Tensor):
-        return x.clone()
+        k = id(x)
+        if k not in memo:
+            memo[k] = x.clone()
+        return memo[k]
     if isinstance(x, (list, tuple)):
-        return type(x)(_clone_tree(v) for v in x)
+        return type(x)(_clone_tree(v, memo) for v in x)
     if isinstance(x, dict):
-        return {k: _clone_tree(v) for k, v in x.items()}
+        return {k: _clone_tree(v, memo) for k, v in x.items()}
     return x
