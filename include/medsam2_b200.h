@@ -209,6 +209,12 @@ int ms2_resize_bilinear(const float* x, float* y, int N, int H, int W, int Ho, i
  *      coords fp32 [n,2] already normalised to [0,1]; gauss fp32 [2,F]; out fp32 [n,2F] = [sin|cos]. */
 int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, int F, ms2_stream_t stream);
 
+/* ---- sparse prompt embedding in one launch (prompt_encoder.py:79-101 `_embed_points`): coords fp32 [B,N,2] in input
+ *      pixels, labels int32 [B,N], gauss fp32 [2,F], table fp32 [5,2F] = [not_a_point, point_embeddings 0..3];
+ *      out fp32 [B,N+pad,2F]; pad != 0 appends the padding point (label -1) used when no box is given. */
+int ms2_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float* out,
+                    int B, int N, int pad, int F, int image_w, int image_h, ms2_stream_t stream);
+
 /* ---- frame ingest (utils/misc.py:215-244, transforms.py:28-42): out fp32 NCHW = (x/255 - mean)/std.
  *      x is fp32 NCHW (video tensor, in_layout 0) or uint8 NHWC (image predictor, in_layout 1). */
 int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, ms2_stream_t stream);

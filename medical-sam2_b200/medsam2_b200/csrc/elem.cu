@@ -255,6 +255,38 @@ __global__ void fourier_pe_kernel(const float* __restrict__ coords, const float*
   }
 }
 
+// Sparse prompt embedding in ONE launch (prompt_encoder.py:79-101: +0.5 shift, optional padding point with label -1,
+// normalisation by the image size, random-Fourier features, zeroing of "not a point" rows, label embedding row):
+// out[b, j, :] = keep(label) * [sin | cos](2*pi * ((2*xy/size - 1) @ gauss)) + table[clamp(label + 1, 0, 4)]
+// with label = -1 and xy = 0 for the padding point j == N.  Replaces ~14 element-wise torch kernels per slice.
+__global__ void point_embed_kernel(const float* __restrict__ coords, const int* __restrict__ labels,
+                                   const float* __restrict__ gauss, const float* __restrict__ table,
+                                   float* __restrict__ out, int B, int N, int pad, int F, float inv_w, float inv_h) {
+  const int Np = N + (pad ? 1 : 0);
+  const long total = (long)B * Np * F;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long r = i / F;
+    const int j = (int)(r % Np), b = (int)(r / Np);
+    float x = 0.f, y = 0.f;
+    int lab = -1;
+    if (j < N) {
+      x = coords[((long)b * N + j) * 2] + 0.5f;
+      y = coords[((long)b * N + j) * 2 + 1] + 0.5f;
+      lab = labels[(long)b * N + j];
+    }
+    const float cx = 2.f * (x * inv_w) - 1.f, cy = 2.f * (y * inv_h) - 1.f;
+    const float v = 6.283185307179586f * (cx * gauss[f] + cy * gauss[F + f]);
+    const float keep = lab != -1 ? 1.f : 0.f;
+    int row = lab + 1;
+    row = row < 0 ? 0 : (row > 4 ? 4 : row);
+    const float* t = table + (long)row * 2 * F;
+    float* o = out + r * 2 * F;
+    o[f] = sinf(v) * keep + t[f];
+    o[F + f] = cosf(v) * keep + t[F + f];
+  }
+}
+
 __global__ void normalize_image_kernel(const void* __restrict__ x, int in_layout, float* __restrict__ out, int B,
                                        int H, int W) {
   const float mean[3] = {0.485f, 0.456f, 0.406f};
@@ -430,6 +462,17 @@ extern "C" int ms2_fourier_pe(const float* coords, const float* gauss, float* ou
   if (!n) return MS2_OK;
   fourier_pe_kernel<<<grid_for((long)n * F), 256, 0, ST>>>(coords, gauss, out, n, F);
   MS2_CHECK_LAUNCH("fourier_pe");
+  return MS2_OK;
+}
+extern "C" int ms2_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float* out,
+                               int B, int N, int pad, int F, int image_w, int image_h, void* stream) {
+  MS2_CHECK_ARG(coords && labels && gauss && table && out && N >= 0 && F > 0 && image_w > 0 && image_h > 0,
+                "point_embed: bad args");
+  const long total = (long)B * (N + (pad ? 1 : 0)) * F;
+  if (!total) return MS2_OK;
+  point_embed_kernel<<<grid_for(total), 256, 0, ST>>>(coords, labels, gauss, table, out, B, N, pad, F, 1.f / image_w,
+                                                      1.f / image_h);
+  MS2_CHECK_LAUNCH("point_embed");
   return MS2_OK;
 }
 extern "C" int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, void* stream) {

@@ -81,6 +81,9 @@ class PromptEncoder(nn.Module):
         return CACHE.get(ps, "label_table", lambda *ts: torch.cat([t.float() for t in ts], 0).contiguous())
 
     def _embed_points(self, points, labels, pad):
+        if points.dim() == 3 and labels.dim() == 2 and not labels.dtype.is_floating_point:
+            return ops.point_embed(points, labels, p32(self.pe_layer.positional_encoding_gaussian_matrix),
+                                   self._label_table(), pad, self.input_image_size)
         points = points.float() + 0.5
         if pad:
             points = torch.cat([points, torch.zeros((points.shape[0], 1, 2), device=points.device)], dim=1)

@@ -487,6 +487,19 @@ def fourier_pe(coords01, gauss):
     return out
 
 
+def point_embed(coords, labels, gauss, table, pad, image_size):
+    """coords fp32 [B,N,2] (input pixels), labels int [B,N] -> sparse prompt embeddings fp32 [B,N+pad,2F]."""
+    B, N, _ = coords.shape
+    Fh = gauss.shape[1]
+    out = torch.empty((B, N + (1 if pad else 0), 2 * Fh), dtype=torch.float32, device=coords.device)
+    lab = labels if labels.dtype == torch.int32 else labels.to(torch.int32)
+    native.call("ms2_point_embed", _chk(coords.float().contiguous(), "coords", torch.float32),
+                _chk(lab.contiguous(), "labels", torch.int32), _chk(gauss, "gauss", torch.float32),
+                _chk(table, "table", torch.float32), out.data_ptr(), B, N, 1 if pad else 0, Fh, int(image_size[1]),
+                int(image_size[0]), _st())
+    return out
+
+
 def normalize_image(x, out=None):
     """fp32 [B,3,H,W] in 0..255 or uint8 [B,H,W,3] -> fp32 NCHW (x/255-mean)/std (optionally into `out`)."""
     if x.dtype == torch.uint8:

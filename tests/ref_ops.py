@@ -286,6 +286,20 @@ def attention_merge(parts, B, Lq, DV=64):
     return (num / den[:, None]).view(B, Lq, DV).to(torch.bfloat16)
 
 
+def point_embed(coords, labels, gauss, table, pad, image_size):
+    pts = coords.float() + 0.5
+    lab = labels.long()
+    if pad:
+        pts = torch.cat([pts, torch.zeros((pts.shape[0], 1, 2), device=pts.device)], dim=1)
+        lab = torch.cat([lab, -torch.ones((lab.shape[0], 1), device=lab.device, dtype=lab.dtype)], dim=1)
+    c = pts.clone()
+    c[:, :, 0] = c[:, :, 0] / image_size[1]
+    c[:, :, 1] = c[:, :, 1] / image_size[0]
+    pe = fourier_pe(c.contiguous(), gauss)
+    keep = (lab != -1).to(pe.dtype).unsqueeze(-1)
+    return pe * keep + table[(lab + 1).clamp(0, 4)]
+
+
 def patch_im2col(img, ldk=152):
     B, _, H, W = img.shape
     cols = F.unfold(img.float(), 7, stride=4, padding=3)                      # [B, 3*49, L] in (c, ky, kx) order

@@ -477,6 +477,18 @@ def test_resize(ops, size, out, aa):
     close(ops.resize_bilinear(x, out, aa), ref_ops.resize_bilinear(x, out, aa), 2e-5, "resize")
 
 
+def test_point_embed(ops):
+    g = rnd(2, 64, seed=1)
+    table = rnd(5, 128, seed=2)
+    coords = (rnd(3, 4, 2, seed=3).abs() * 300).contiguous()
+    labels = torch.tensor([[1, 0, 2, 3], [-1, 1, 1, 0], [2, 3, -1, -1]], dtype=torch.int32).cuda()
+    for pad in (True, False):
+        close(ops.point_embed(coords, labels, g, table, pad, (1024, 768)), ref_ops.point_embed(coords, labels, g, table, pad, (1024, 768)),
+              2e-4, f"point_embed pad={pad}")
+    close(ops.point_embed(coords, labels.long(), g, table, True, (512, 512)), ref_ops.point_embed(coords, labels, g, table, True, (512, 512)),
+          2e-4, "point_embed int64 labels")
+
+
 def test_fourier_and_normalize(ops):
     c, gm = torch.rand(5, 3, 2, generator=gen(1)).cuda(), rnd(2, 128, seed=2)
     close(ops.fourier_pe(c, gm), ref_ops.fourier_pe(c, gm), 2e-5, "fourier_pe")
