@@ -223,6 +223,12 @@ int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, 
  *      logits [N,P]: counts[n,0] = #(x>delta), counts[n,1] = #(x>-delta). */
 int ms2_mask_stability_counts(const float* x, int32_t* counts, int N, long P, float delta, ms2_stream_t stream);
 
+/* ---- segmentation metric counts in one pass (reference repo root: func_3d/utils.py:139-202 `eval_seg`, :204-214 `iou`,
+ *      :215-240 `dice_coeff`; call site func_3d/function.py:300): pred, gt fp32 [N,P] device planes, thr_host = T <= 8
+ *      thresholds in HOST memory; counts int32 [N,T,3] = (#(pred>th & gt>th), #(pred>th), #(gt>th)), exact. */
+int ms2_seg_counts(const float* pred, const float* gt, const float* thr_host, int T, int32_t* counts, int N, long P,
+                   ms2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,6 +305,82 @@ __global__ void normalize_image_kernel(const void* __restrict__ x, int in_layout
   }
 }
 
+// Segmentation-metric counts (func_3d/utils.py:139-202 `eval_seg`, :204-214 `iou`, :215-240 `dice_coeff`): the reference
+// binarises prediction and ground truth once per threshold, copies both to the host and reduces them there (for the
+// default 5 thresholds: 10 full-resolution passes + 10 D2H copies per object and slice).  Here ONE pass over the two
+// planes yields, for every threshold, |pred>th & gt>th|, |pred>th| and |gt>th| as exact integers; IoU and Dice
+// follow on the host from 3*T integers per plane.  HBM roofline: 8 bytes per pixel, read once.
+struct SegThr { float v[8]; };
+template <int T, bool VEC>
+__global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                         SegThr thr, int32_t* __restrict__ counts, long P) {
+  __shared__ int sh[3 * T];
+  const int n = blockIdx.y;
+  const float* pp = pred + (long)n * P;
+  const float* gp = gt + (long)n * P;
+  int c[3 * T];
+#pragma unroll
+  for (int k = 0; k < 3 * T; ++k) c[k] = 0;
+  if (threadIdx.x < 3 * T) sh[threadIdx.x] = 0;
+  auto acc = [&](float a, float b) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const bool pa = a > thr.v[t], pb = b > thr.v[t];
+      c[3 * t] += pa && pb;
+      c[3 * t + 1] += pa;
+      c[3 * t + 2] += pb;
+    }
+  };
+  auto acc4 = [&](const float4& a, const float4& b) { acc(a.x, b.x); acc(a.y, b.y); acc(a.z, b.z); acc(a.w, b.w); };
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const long P4 = P >> 2;
+    const float4* p4 = (const float4*)pp;
+    const float4* g4 = (const float4*)gp;
+    for (; i + stride < P4; i += 2 * stride) {            // four 16-byte loads in flight per thread
+      const float4 a0 = __ldcs(p4 + i), b0 = __ldcs(g4 + i), a1 = __ldcs(p4 + i + stride), b1 = __ldcs(g4 + i + stride);
+      acc4(a0, b0);
+      acc4(a1, b1);
+    }
+    if (i < P4) acc4(__ldcs(p4 + i), __ldcs(g4 + i));
+  } else {
+    for (; i < P; i += stride) acc(pp[i], gp[i]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 3 * T; ++k) {
+    const int v = __reduce_add_sync(0xffffffffu, c[k]);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * T && sh[threadIdx.x]) atomicAdd(counts + (long)n * 3 * T + threadIdx.x, sh[threadIdx.x]);
+}
+// One wave: the grid never exceeds the resident CTA slots (a grid-stride row split over a partial second wave would
+// double the time), at most one CTA per 8192 pixels of a plane.
+template <int T, bool VEC>
+void seg_counts_launch2(cudaStream_t st, const float* pred, const float* gt, const SegThr& thr, int32_t* counts, int N,
+                        long P) {
+  static int slots = 0;
+  if (!slots) {
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_counts_kernel<T, VEC>, 256, 0);
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  long per_plane = slots / N, by_size = (P + 8191) / 8192;
+  if (per_plane > by_size) per_plane = by_size;
+  dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
+  seg_counts_kernel<T, VEC><<<grid, 256, 0, st>>>(pred, gt, thr, counts, P);
+}
+template <int T>
+void seg_counts_launch(bool vec, cudaStream_t st, const float* pred, const float* gt, const SegThr& thr, int32_t* counts,
+                       int N, long P) {
+  if (vec) seg_counts_launch2<T, true>(st, pred, gt, thr, counts, N, P);
+  else seg_counts_launch2<T, false>(st, pred, gt, thr, counts, N, P);
+}
+
 __global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
   const int nidx = blockIdx.y;
   const float* xp = x + (long)nidx * P;
@@ -490,5 +566,30 @@ extern "C" int ms2_mask_stability_counts(const float* x, int32_t* counts, int N,
   dim3 grid(64, N);
   stability_counts_kernel<<<grid, 256, 0, ST>>>(x, counts, P, delta);
   MS2_CHECK_LAUNCH("stability_counts");
+  return MS2_OK;
+}
+extern "C" int ms2_seg_counts(const float* pred, const float* gt, const float* thr_host, int T, int32_t* counts, int N,
+                              long P, void* stream) {
+  MS2_CHECK_ARG(thr_host && T >= 1 && T <= 8 && N >= 0 && P >= 0, "seg_counts: bad args (1..8 thresholds)");
+  if (!N) return MS2_OK;
+  MS2_CHECK_ARG(counts, "seg_counts: counts is null");
+  MS2_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * T * N, ST), "seg_counts memset");
+  if (!P) return MS2_OK;
+  MS2_CHECK_ARG(pred && gt, "seg_counts: null planes");
+  MS2_CHECK_ARG(N <= 65535, "seg_counts: at most 65535 planes per call");
+  SegThr thr;
+  for (int t = 0; t < 8; ++t) thr.v[t] = t < T ? thr_host[t] : INFINITY;
+  const bool vec = (P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)gt) % 16 == 0);
+  switch (T) {
+    case 1: seg_counts_launch<1>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 2: seg_counts_launch<2>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 3: seg_counts_launch<3>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 4: seg_counts_launch<4>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 5: seg_counts_launch<5>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 6: seg_counts_launch<6>(vec, ST, pred, gt, thr, counts, N, P); break;
+    case 7: seg_counts_launch<7>(vec, ST, pred, gt, thr, counts, N, P); break;
+    default: seg_counts_launch<8>(vec, ST, pred, gt, thr, counts, N, P); break;
+  }
+  MS2_CHECK_LAUNCH("seg_counts");
   return MS2_OK;
 }

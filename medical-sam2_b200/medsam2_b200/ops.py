@@ -524,3 +524,20 @@ def mask_stability_counts(x, delta):
     counts = torch.empty((N, 2), dtype=torch.int32, device=x.device)
     native.call("ms2_mask_stability_counts", _chk(x, "x", torch.float32), counts.data_ptr(), N, P, float(delta), _st())
     return counts
+
+
+def seg_counts(pred, gt, thresholds):
+    """pred, gt fp32 [N, ...] (same shape) -> int32 [N,T,3] = (#(pred>th & gt>th), #(pred>th), #(gt>th)) per threshold."""
+    import ctypes
+    T = len(thresholds)
+    if not 1 <= T <= 8:
+        raise ValueError("seg_counts: 1..8 thresholds per call")
+    if pred.shape != gt.shape:
+        raise ValueError(f"seg_counts: pred {tuple(pred.shape)} vs gt {tuple(gt.shape)}")
+    N = pred.shape[0]
+    P = pred.numel() // max(N, 1)
+    counts = torch.empty((N, T, 3), dtype=torch.int32, device=pred.device)
+    thr = (ctypes.c_float * T)(*[float(t) for t in thresholds])
+    native.call("ms2_seg_counts", _chk(pred, "pred", torch.float32), _chk(gt, "gt", torch.float32),
+                ctypes.cast(thr, ctypes.c_void_p), T, counts.data_ptr(), N, P, _st())
+    return counts
