@@ -229,6 +229,12 @@ int ms2_mask_stability_counts(const float* x, int32_t* counts, int N, long P, fl
 int ms2_seg_counts(const float* pred, const float* gt, const float* thr_host, int T, int32_t* counts, int N, long P,
                    ms2_stream_t stream);
 
+/* ---- validation loss in one pass (reference repo root: func_3d/function.py:35-36,299 `BCEWithLogitsLoss(pos_weight)`):
+ *      pred (logits), gt fp32 [N,P] device planes; sums fp64 [N] (device) = per-plane SUM of the element losses
+ *      (1-y)*x + (1+(pos_weight-1)*y)*(log1p(exp(-|x|)) + max(-x,0)); the caller divides by the element count. */
+int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_weight, double* sums, int N, long P,
+                       ms2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -383,6 +383,43 @@ void seg_counts_launch(bool vec, cudaStream_t st, const float* pred, const float
   else seg_counts_launch2<T, false>(st, pred, gt, thr, counts, N, P);
 }
 
+// Validation loss of func_3d/function.py:35-36,299 (`BCEWithLogitsLoss(pos_weight)`): per plane the SUM of
+// (1-y)*x + (1 + (pw-1)*y) * (log1p(exp(-|x|)) + max(-x, 0)) in one pass (8 B/pixel); 4 pixels are added in fp32, the
+// running sums are fp64 (per thread, per CTA and in the per-plane atomics), so the mean on the host is good to fp32 ulps.
+template <bool VEC>
+__global__ void __launch_bounds__(256) bce_logits_sum_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                             float pwm1, double* __restrict__ sums, long P) {
+  __shared__ double sh[8];
+  const int n = blockIdx.y;
+  const float* pp = pred + (long)n * P;
+  const float* gp = gt + (long)n * P;
+  auto term = [&](float x, float y) {
+    return (1.f - y) * x + (1.f + pwm1 * y) * (log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f));
+  };
+  double acc = 0.0;
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const long P4 = P >> 2;
+    for (; i < P4; i += stride) {
+      const float4 a = __ldcs((const float4*)pp + i), b = __ldcs((const float4*)gp + i);
+      acc += (double)((term(a.x, b.x) + term(a.y, b.y)) + (term(a.z, b.z) + term(a.w, b.w)));
+    }
+  } else {
+    for (; i < P; i += stride) acc += (double)term(pp[i], gp[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(sums + n, t);
+  }
+}
+
 __global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
   const int nidx = blockIdx.y;
   const float* xp = x + (long)nidx * P;
@@ -593,5 +630,22 @@ extern "C" int ms2_seg_counts(const float* pred, const float* gt, const float* t
     default: seg_counts_launch<8>(vec, ST, pred, gt, thr, counts, N, P); break;
   }
   MS2_CHECK_LAUNCH("seg_counts");
+  return MS2_OK;
+}
+extern "C" int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_weight, double* sums, int N, long P,
+                                  void* stream) {
+  MS2_CHECK_ARG(N >= 0 && P >= 0, "bce_logits_sum: bad sizes");
+  if (!N) return MS2_OK;
+  MS2_CHECK_ARG(sums, "bce_logits_sum: sums is null");
+  MS2_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * N, ST), "bce_logits_sum memset");
+  if (!P) return MS2_OK;
+  MS2_CHECK_ARG(pred && gt && N <= 65535, "bce_logits_sum: null planes or more than 65535 planes");
+  const bool vec = (P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)gt) % 16 == 0);
+  long per_plane = (148L * 6) / N, by_size = (P + 8191) / 8192;      // one resident wave (6 CTAs of 256 threads per SM)
+  if (per_plane > by_size) per_plane = by_size;
+  dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
+  if (vec) bce_logits_sum_kernel<true><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
+  else bce_logits_sum_kernel<false><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
+  MS2_CHECK_LAUNCH("bce_logits_sum");
   return MS2_OK;
 }

@@ -541,3 +541,15 @@ def seg_counts(pred, gt, thresholds):
     native.call("ms2_seg_counts", _chk(pred, "pred", torch.float32), _chk(gt, "gt", torch.float32),
                 ctypes.cast(thr, ctypes.c_void_p), T, counts.data_ptr(), N, P, _st())
     return counts
+
+
+def bce_logits_sum(pred, gt, pos_weight):
+    """pred (logits), gt fp32 [N, ...] -> fp64 [N]: per-plane sum of the BCE-with-logits element losses."""
+    if pred.shape != gt.shape:
+        raise ValueError(f"bce_logits_sum: pred {tuple(pred.shape)} vs gt {tuple(gt.shape)}")
+    N = pred.shape[0]
+    P = pred.numel() // max(N, 1)
+    sums = torch.empty((N,), dtype=torch.float64, device=pred.device)
+    native.call("ms2_bce_logits_sum", _chk(pred, "pred", torch.float32), _chk(gt, "gt", torch.float32), float(pos_weight),
+                sums.data_ptr(), N, P, _st())
+    return sums

@@ -102,3 +102,20 @@ def dice_coeff(input, target):
     b = input.shape[0]
     k = seg_counts(input.reshape(b, 1, 1, -1), target.reshape(b, 1, 1, -1), (0.5,))
     return torch.tensor([_dice_from_counts(k[:, 0, 0])], dtype=torch.float32, device=input.device)
+
+
+def bce_with_logits_frames(preds, targets, pos_weight=2.0):
+    """Validation loss of func_3d/function.py:35-36,299 (`BCEWithLogitsLoss(pos_weight=2)(pred, mask)`, mean reduction) for
+    every row of preds / targets [n, ...] at once: fp32 tensor [n] on the device, one launch, no synchronisation."""
+    if preds.shape != targets.shape:
+        raise ValueError("bce_with_logits_frames: expected tensors of the same shape")
+    n = preds.shape[0]
+    p, g = _planes(preds).reshape(n, -1), _planes(targets).reshape(n, -1)
+    return (ops.bce_logits_sum(p, g, pos_weight) / max(p.shape[1], 1)).float()
+
+
+def bce_with_logits(pred, target, pos_weight=2.0):
+    """`torch.nn.BCEWithLogitsLoss(pos_weight=pos_weight)(pred, target)`: scalar fp32 tensor on the device."""
+    if pred.shape != target.shape:
+        raise ValueError("bce_with_logits: expected tensors of the same shape")
+    return bce_with_logits_frames(pred.reshape(1, -1), target.reshape(1, -1), pos_weight)[0]

@@ -57,3 +57,12 @@ def eval_seg_np(pred, true_mask_p, threshold):
     if c == 2:
         return ious[0] / n, ious[1] / n, dices[0] / n, dices[1] / n
     return tuple(np.array(ious + dices) / n)
+
+
+def bce_with_logits_np(pred, target, pos_weight=2.0):
+    """func_3d/function.py:35-36,299: `torch.nn.BCEWithLogitsLoss(pos_weight=2)(pred, mask)`, mean over all elements;
+    torch's element formula (1-y)*x + (1+(pw-1)*y)*(log1p(exp(-|x|)) + max(-x,0)), evaluated here in float64."""
+    x = np.asarray(pred, dtype=np.float64)
+    y = np.asarray(target, dtype=np.float64)
+    el = (1 - y) * x + (1 + (pos_weight - 1) * y) * (np.log1p(np.exp(-np.abs(x))) + np.maximum(-x, 0))
+    return float(el.mean())

@@ -1,6 +1,7 @@
 """Generate tests/golden/eval_seg_cases.npz by running the REAL reference metric
 (/root/reference/func_3d/utils.py `eval_seg`) on seeded inputs.  Build container only
-(`python tests/golden/make_golden_eval.py`); tests read the committed .npz, never /root/reference."""
+(`python tests/golden/make_golden_eval.py`); also the validation loss `BCEWithLogitsLoss(pos_weight=2)` of
+func_3d/function.py:35-36 per example and over the batch.  Tests read the committed .npz, never /root/reference."""
 import os
 import sys
 
@@ -50,6 +51,10 @@ def main():
         cases[name + "/gt"] = gt.numpy()
         cases[name + "/thr"] = np.array(thr, dtype=np.float64)
         cases[name + "/res"] = np.array([float(r) for r in res], dtype=np.float64)
+        # the validation loss exactly as func_3d/function.py:35-36,299 builds and calls it (pos_weight = 2), CPU fp32
+        crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.ones([1]) * 2)
+        cases[name + "/bce"] = np.array([float(crit(pred[i:i + 1], gt[i:i + 1])) for i in range(b)] + [float(crit(pred, gt))],
+                                        dtype=np.float64)
         print(name, [float(r) for r in res])
     np.savez_compressed(os.path.join(OUT, "eval_seg_cases.npz"), **cases)
 

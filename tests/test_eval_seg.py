@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.eval_seg import eval_seg_np
+from oracle.eval_seg import bce_with_logits_np, eval_seg_np
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["c1_b1", "c1_b3", "c2_b2", "c1_odd", "c1_empty", "c1_full", "c3_b2_one_thr", "c1_hard01"]
@@ -47,6 +47,15 @@ def test_host_reduction_matches_reference_answers(name):
     pred, gt, thr, res = _case(name)
     got = np.array([float(r) for r in _reduce(_counts_np(pred, gt, thr))])
     assert np.array_equal(got, res), (name, got, res)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_bce_matches_reference_loss(name):
+    """float64 restatement vs `BCEWithLogitsLoss(pos_weight=2)` of the reference (CPU fp32): relative 2e-6"""
+    z = np.load(f"{G}/eval_seg_cases.npz")
+    pred, gt, want = z[name + "/pred"], z[name + "/gt"], z[name + "/bce"]
+    got = [bce_with_logits_np(pred[i:i + 1], gt[i:i + 1]) for i in range(len(pred))] + [bce_with_logits_np(pred, gt)]
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-9)
 
 
 def test_product_refuses_cpu_tensors():
@@ -123,3 +132,48 @@ def test_gpu_eval_seg_frames_and_helpers():
     assert iou(a.cuda(), b.cuda()) == iou_np(a.numpy().astype("int32"), b.numpy().astype("int32"))
     d = dice_coeff(a.cuda(), b.cuda())
     assert d.is_cuda and d.shape == (1,) and float(d) == dice_coeff_np(a.numpy(), b.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_bce_matches_reference_loss(name):
+    """validation loss kernel vs the golden `BCEWithLogitsLoss(pos_weight=2)` values and the float64 oracle.
+    Tolerance: relative 2e-6 against the fp32 reference values (its own summation error), 5e-7 against the oracle."""
+    from medsam2_b200.utils.eval import bce_with_logits, bce_with_logits_frames
+    z = np.load(f"{G}/eval_seg_cases.npz")
+    pred, gt, want = z[name + "/pred"], z[name + "/gt"], z[name + "/bce"]
+    p, g = torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda()
+    per = bce_with_logits_frames(p, g, 2.0)
+    assert per.is_cuda and per.dtype == torch.float32 and per.shape == (len(pred),)
+    whole = bce_with_logits(p, g, 2.0)
+    got = np.concatenate([per.cpu().numpy().astype(np.float64), [float(whole)]])
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-9)
+    oracle = [bce_with_logits_np(pred[i:i + 1], gt[i:i + 1]) for i in range(len(pred))] + [bce_with_logits_np(pred, gt)]
+    np.testing.assert_allclose(got, oracle, rtol=5e-7, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_bce_edges():
+    """saturated logits stay finite, pos_weight other than 2, ragged / unaligned rows, empty inputs, full-size planes"""
+    from medsam2_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.tensor([[-100.0, 100.0, 0.0, 88.0, -88.0, 1e4, -1e4]]).cuda()
+    y = torch.tensor([[1.0, 0.0, 0.5, 1.0, 0.0, 1.0, 0.0]]).cuda()
+    for pw in (1.0, 2.0, 0.25):
+        got = float(ops.bce_logits_sum(x, y, pw)[0])
+        want = bce_with_logits_np(x.cpu().numpy(), y.cpu().numpy(), pw) * 7
+        assert np.isfinite(got) and abs(got - want) <= 1e-6 * abs(want), (pw, got, want)
+        ref = torch.nn.functional.binary_cross_entropy_with_logits(x.cpu(), y.cpu(), pos_weight=torch.tensor([pw]), reduction="sum")
+        assert abs(got - float(ref)) <= 2e-6 * abs(float(ref))
+    base_x, base_y = torch.randn(3 * 1001 + 1, generator=g).cuda(), torch.rand(3 * 1001 + 1, generator=g).cuda()
+    xs, ys = base_x[1:].view(3, 1001), base_y[1:].view(3, 1001)
+    got = ops.bce_logits_sum(xs, ys, 2.0).cpu().numpy()
+    want = [bce_with_logits_np(xs[i].cpu().numpy(), ys[i].cpu().numpy()) * 1001 for i in range(3)]
+    np.testing.assert_allclose(got, want, rtol=5e-7)
+    assert ops.bce_logits_sum(xs[:0], ys[:0], 2.0).shape == (0,)
+    assert float(ops.bce_logits_sum(xs[:, :0], ys[:, :0], 2.0).abs().sum()) == 0.0
+    big_y = (torch.rand(4, 1024 * 1024, generator=g) > 0.7).float()
+    big_x = (big_y * 4 - 1.5 + torch.randn(4, 1024 * 1024, generator=g))
+    got = ops.bce_logits_sum(big_x.cuda(), big_y.cuda(), 2.0).cpu().numpy() / (1024 * 1024)
+    want = [bce_with_logits_np(big_x[i].numpy(), big_y[i].numpy()) for i in range(4)]
+    np.testing.assert_allclose(got, want, rtol=5e-7)

@@ -31,6 +31,16 @@ peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.ex
 print(f"ms2_seg_counts 96 x 1024^2, 5 thresholds: {ms:.3f} ms per launch (memset included), {nbytes / ms / 1e6:.0f} GB/s algorithmic "
       f"(8 B/pixel); MEASURED_PEAKS: {peaks}")
 
+for _ in range(3):
+    ops.bce_logits_sum(p2, g2, 2.0)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps):
+    ops.bce_logits_sum(p2, g2, 2.0)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"ms2_bce_logits_sum 96 x 1024^2 (validation loss, pos_weight 2): {ms:.3f} ms per launch, {nbytes / ms / 1e6:.0f} GB/s algorithmic (8 B/pixel)")
 if "--kernel-only" in sys.argv:
     sys.exit(0)
 t0 = time.perf_counter(); ours = eval_seg_frames(pred, gt, thr); t_ours = time.perf_counter() - t0
