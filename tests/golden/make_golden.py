@@ -11,6 +11,7 @@ What is dumped (all fp32, sub-sampled where large so the directory stays < 10 MB
   video_hiera_s_512.npz      config 3 shape, shrunk: 7 slices @512², bbox on 0,2,4, 1 object
   video_hiera_t_512_2obj.npz 2 objects, object 2 absent on slice 2 (mask prompt of zeros)
   modules_hiera_t.npz        per-module known answers (memory attention / encoder, decoder)
+  func2d_hiera_t_512.npz     the 2D memory-bank validation step of func_2d/function.py:423-534 (tests/func2d_replay.py)
   cc_*.npz                   connected-component labels from a transliteration of the .cu kernels
 """
 
@@ -274,6 +275,30 @@ def golden_modules():
     print("modules", {k: v.shape for k, v in out.items()})
 
 
+@torch.no_grad()
+def golden_func2d():
+    """The 2D memory-bank validation step (func_2d/function.py:423-534) replayed on the real reference by
+    tests/func2d_replay.py: hiera_t, 512^2, a 3-element memory bank; one image with 3 point prompts (cell_nums = [3])
+    and two images with one prompt each (bank sampling [2,2])."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from func2d_replay import make_inputs, replay
+    m = load_reference("sam2_hiera_t", video=True, image_size=512)
+    load_seeded(m)
+    out = {}
+    for tag, (bi, nb, npr) in {"b1_p3": (1, 3, 3), "b2_p2": (2, 3, 2)}.items():
+        r = replay(m, *make_inputs(bi, nb, npr))
+        out[f"{tag}/similarity"] = npy(r["similarity"])
+        out[f"{tag}/sampled_indices"] = r["sampled_indices"].numpy()
+        out[f"{tag}/memattn_sub"] = npy(r["memattn"][::4])
+        out[f"{tag}/low_res"] = npy(r["low_res"])
+        out[f"{tag}/iou"] = npy(r["iou"])
+        out[f"{tag}/obj"] = npy(r["obj"])
+        out[f"{tag}/maskmem_feat_sub"] = npy(r["maskmem_feat"][..., ::2, ::2])
+        out[f"{tag}/maskmem_pos_sub"] = npy(r["maskmem_pos"][..., ::2, ::2])
+    np.savez_compressed(f"{OUT}/func2d_hiera_t_512.npz", **out)
+    print("func2d", {k: v.shape for k, v in out.items()})
+
+
 # ----------------------------------------------------------------------------- CC transliteration
 def cc_transliterated(img):
     """Sequential transliteration of csrc/connected_components.cu:30-209 for ONE image [H,W]
@@ -384,13 +409,15 @@ def golden_cc():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["layout", "cc", "modules", "image_t", "image_s", "video_s", "video_t2"]
+    which = sys.argv[1:] or ["layout", "cc", "modules", "func2d", "image_t", "image_s", "video_s", "video_t2"]
     if "layout" in which:
         golden_layout()
     if "cc" in which:
         golden_cc()
     if "modules" in which:
         golden_modules()
+    if "func2d" in which:
+        golden_func2d()
     if "image_t" in which:
         golden_image_t()
     if "image_s" in which:

@@ -214,3 +214,26 @@ def test_full_size_properties_bf16():
         if low is not None:
             pm = low["pred_masks"]
             assert torch.equal(fill_holes_in_mask_scores(pm, 8), pm)
+
+
+@pytest.mark.parametrize("tag,shape", [("b1_p3", (1, 3, 3)), ("b2_p2", (2, 3, 2))])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_func2d_memory_bank_step(tag, shape, dt):
+    """2D memory-bank validation step (func_2d/function.py:423-534) through the CUDA path against
+    the answers of the real reference (tests/golden/func2d_hiera_t_512.npz, made by make_golden.py func2d):
+    memory attention with num_obj_ptr_tokens=0 on a sampled bank, many prompts per image via `cell_nums`, memory
+    encoding.  Tolerances: fp32 mode 1e-3 on features / logits; bf16 mode 8e-2 on features, 3e-2 on logits."""
+    import medsam2_b200
+    from func2d_replay import make_inputs, replay
+    z = np.load(f"{G}/func2d_hiera_t_512.npz")
+    f32 = dt == torch.float32
+    with medsam2_b200.compute(dt), torch.no_grad():
+        m = _build("sam2_hiera_t", video=True, image_size=512)
+        r = replay(m, *make_inputs(*shape), sampled_indices=torch.from_numpy(z[f"{tag}/sampled_indices"]), device="cuda")
+    _close(r["similarity"], z[f"{tag}/similarity"], 1e-5 if f32 else 1e-3, "similarity")
+    _close(r["memattn"][::4], z[f"{tag}/memattn_sub"], 1e-3 if f32 else 8e-2, "memory attention")
+    _close(r["low_res"], z[f"{tag}/low_res"], 1e-3 if f32 else 3e-2, "low-res masks")
+    _close(r["iou"], z[f"{tag}/iou"], 1e-4 if f32 else 5e-3, "iou")
+    _close(r["obj"], z[f"{tag}/obj"], 1e-3 if f32 else 5e-2, "object score")
+    _close(r["maskmem_feat"][..., ::2, ::2], z[f"{tag}/maskmem_feat_sub"], 1e-3 if f32 else 8e-2, "maskmem features")
+    _close(r["maskmem_pos"][..., ::2, ::2], z[f"{tag}/maskmem_pos_sub"], 1e-5, "maskmem pos")

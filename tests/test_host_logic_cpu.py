@@ -137,6 +137,25 @@ def test_submodule_surface(fake_backend):
     _close(m.sam_prompt_encoder.get_dense_pe(), z["dense_pe"], 1e-5, "dense pe")
 
 
+@pytest.mark.parametrize("tag,shape", [("b1_p3", (1, 3, 3)), ("b2_p2", (2, 3, 2))])
+def test_func2d_memory_bank_step(fake_backend, tag, shape):
+    """The 2D memory-bank validation step (func_2d/function.py:423-534) replayed on the product
+    by tests/func2d_replay.py against the answers of the real reference: memory attention without object pointers,
+    bank sampling of shape [B,B], many prompts per image through `cell_nums`, memory encoding of the merged mask."""
+    from func2d_replay import make_inputs, replay
+    z = np.load(f"{G}/func2d_hiera_t_512.npz")
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    with torch.no_grad():
+        r = replay(m, *make_inputs(*shape), sampled_indices=torch.from_numpy(z[f"{tag}/sampled_indices"]))
+    _close(r["similarity"], z[f"{tag}/similarity"], 1e-5, "similarity")
+    _close(r["memattn"][::4], z[f"{tag}/memattn_sub"], 5e-4, "memory attention")
+    _close(r["low_res"], z[f"{tag}/low_res"], 1e-3, "low-res masks")
+    _close(r["iou"], z[f"{tag}/iou"], 1e-4, "iou")
+    _close(r["obj"], z[f"{tag}/obj"], 1e-4, "object score")
+    _close(r["maskmem_feat"][..., ::2, ::2], z[f"{tag}/maskmem_feat_sub"], 5e-4, "maskmem features")
+    _close(r["maskmem_pos"][..., ::2, ::2], z[f"{tag}/maskmem_pos_sub"], 1e-6, "maskmem pos")
+
+
 def test_product_refuses_cpu_without_backend():
     """No fake backend installed -> the hot path must fail loudly on CPU tensors (no fallback)."""
     from medsam2_b200 import ops
