@@ -237,3 +237,47 @@ def test_func2d_memory_bank_step(tag, shape, dt):
     _close(r["obj"], z[f"{tag}/obj"], 1e-3 if f32 else 5e-2, "object score")
     _close(r["maskmem_feat"][..., ::2, ::2], z[f"{tag}/maskmem_feat_sub"], 1e-3 if f32 else 8e-2, "maskmem features")
     _close(r["maskmem_pos"][..., ::2, ::2], z[f"{tag}/maskmem_pos_sub"], 1e-5, "maskmem pos")
+
+
+def test_validation_loop_metrics_fp32():
+    """The reference's validation step on one volume, end to end (func_3d/function.py:229-305): prompts on slices
+    0/2/4 -> propagate_in_video -> per-slice `eval_seg` at thresholds (0.1 ... 0.9) + `BCEWithLogitsLoss(pos_weight=2)`
+    against ground-truth masks.  Product: CUDA path in fp32 mode + eval_seg_frames / bce_with_logits_frames (one launch
+    each for the volume); checker: the oracle predictor on the same device + the numpy metric oracle per slice.
+    Logits agree to 3e-3, so a handful of pixels may sit on the other side of a threshold: IoU / Dice within 5e-3,
+    loss within max(5e-3, 1e-3 relative)."""
+    import medsam2_b200
+    from medsam2_b200.utils.eval import bce_with_logits_frames, eval_seg_frames
+    from oracle.eval_seg import bce_with_logits_np, eval_seg_np
+    from oracle.sam2_oracle import OracleSAM2, OracleVideoPredictor
+    size, T, thr = 512, 7, (0.1, 0.3, 0.5, 0.7, 0.9)
+    vol, boxes = btcv_volume(T, size, 1234, 1)
+    cfg = get_config("sam2_hiera_s", image_size=size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg), device="cuda"), fill_hole_area=8)
+    with torch.no_grad():
+        st = vp.init_state(vol.cuda(), size, size)
+        for f in (0, 2, 4):
+            vp.add_new_bbox(st, f, 1, boxes[f][0], clear_old_points=False)
+        ref = {f: mk.float().cpu() for f, _, mk in vp.propagate_in_video(st, start_frame_idx=0)}
+    # ground truth with a non-trivial overlap (random weights do not segment the phantom): the NEXT slice's mask
+    gt = torch.stack([(ref[(f + 1) % T][0] > 0).float() for f in range(T)])          # [T,1,H,W]
+    with medsam2_b200.compute(torch.float32):
+        m = _build("sam2_hiera_s", video=True, image_size=size)
+        _, outs = _run_video(m, size, T, 1, (0, 2, 4), (), 1234)
+    preds = torch.stack([outs[f][0] for f in range(T)]).float()                      # [T,1,H,W] video-res logits
+    ours = eval_seg_frames(preds, gt.cuda(), thr)
+    ours_loss = bce_with_logits_frames(preds, gt.cuda(), 2.0).cpu().numpy()
+    ious = []
+    for f in range(T):
+        rp = ref[f][0][None].numpy()
+        want = eval_seg_np(rp, gt[f:f + 1].numpy(), thr)
+        ious.append(want[0])
+        assert abs(ours[f][0] - want[0]) <= 5e-3 and abs(ours[f][1] - want[1]) <= 5e-3, (f, ours[f], want)
+        wl = bce_with_logits_np(rp, gt[f:f + 1].numpy(), 2.0)
+        assert abs(ours_loss[f] - wl) <= max(5e-3, 1e-3 * abs(wl)), (f, ours_loss[f], wl)
+        # and the metric code itself is exact on identical inputs: product metrics of the ORACLE's logits == numpy oracle
+        assert eval_seg_frames(ref[f][0][None].cuda(), gt[f:f + 1].cuda(), thr)[0] == want
+        # ... also at thresholds inside the logit range of the random-weight model (|logit| < 0.2), where the masks overlap
+        thr_in = (-0.1, -0.05, 0.0, 0.05, 0.1)
+        assert eval_seg_frames(ref[f][0][None].cuda(), gt[f:f + 1].cuda(), thr_in)[0] == eval_seg_np(rp, gt[f:f + 1].numpy(), thr_in)
+    print("validation loop: per-slice IoU of the checker", [round(float(i), 3) for i in ious])
