@@ -235,6 +235,17 @@ int ms2_seg_counts(const float* pred, const float* gt, const float* thr_host, in
 int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_weight, double* sums, int N, long P,
                        ms2_stream_t stream);
 
+/* ---- automatic mask generator, per-plane statistics in one pass (automatic_mask_generator.py:300-340; utils/amg.py:158-180
+ *      `calculate_stability_score`, :296-348 `batched_mask_to_box`): x fp32 logits [N,H,W]; stats int32 [N,7] =
+ *      (#(x>thr+off), #(x>thr-off), #(x>thr), min col, min row, max col, max row of x>thr); an empty plane gives
+ *      (.., 0, W, H, -1, -1). */
+int ms2_mask_stats(const float* x, int32_t* stats, int N, int H, int W, float thr, float off, ms2_stream_t stream);
+
+/* ---- binarise + un-crop + transpose selected planes for run-length encoding (utils/amg.py:279-293 `uncrop_masks`,
+ *      :107-134 `mask_to_rle_pytorch`): out uint8 [K,OW,OH], out[k, x0+c, y0+r] = x[sel[k], r, c] > thr, 0 elsewhere. */
+int ms2_mask_binarize_t(const float* x, const int32_t* sel, uint8_t* out, int K, int H, int W, float thr, int OH, int OW,
+                        int x0, int y0, ms2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

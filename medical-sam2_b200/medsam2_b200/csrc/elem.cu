@@ -420,6 +420,82 @@ __global__ void __launch_bounds__(256) bce_logits_sum_kernel(const float* __rest
   }
 }
 
+// Automatic-mask-generator statistics (automatic_mask_generator.py:300-340 + utils/amg.py:158-180 `calculate_stability_score`,
+// :296-348 `batched_mask_to_box`): the reference makes two thresholded int16/int32 reductions, one binarisation and six
+// max/min reductions over every [H,W] logit plane; here ONE pass (4 B/pixel) yields per plane
+// (#(x > thr+off), #(x > thr-off), #(x > thr), min col, min row, max col, max row of x > thr).
+__global__ void mask_stats_init_kernel(int32_t* __restrict__ out, int N, int H, int W) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int32_t* o = out + (long)n * 7;
+  o[0] = o[1] = o[2] = 0;
+  o[3] = W; o[4] = H; o[5] = -1; o[6] = -1;
+}
+__global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int H, int W,
+                                                         float thr, float off) {
+  const int n = blockIdx.y;
+  const float* xp = x + (long)n * H * W;
+  const float hi = thr + off, lo = thr - off;
+  int chi = 0, clo = 0, cmid = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
+  // a CTA walks whole rows (coalesced along the row); rows are dealt round-robin over the CTAs of the plane
+  for (int r = blockIdx.x; r < H; r += gridDim.x) {
+    const float* row = xp + (long)r * W;
+    bool any = false;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+      const float v = row[c];
+      chi += v > hi;
+      clo += v > lo;
+      if (v > thr) {
+        ++cmid;
+        any = true;
+        x0 = min(x0, c);
+        x1 = max(x1, c);
+      }
+    }
+    if (any) { y0 = min(y0, r); y1 = max(y1, r); }
+  }
+  chi = __reduce_add_sync(0xffffffffu, chi);
+  clo = __reduce_add_sync(0xffffffffu, clo);
+  cmid = __reduce_add_sync(0xffffffffu, cmid);
+  x0 = __reduce_min_sync(0xffffffffu, x0);
+  y0 = __reduce_min_sync(0xffffffffu, y0);
+  x1 = __reduce_max_sync(0xffffffffu, x1);
+  y1 = __reduce_max_sync(0xffffffffu, y1);
+  if ((threadIdx.x & 31) == 0) {
+    int32_t* o = out + (long)n * 7;
+    if (chi) atomicAdd(o, chi);
+    if (clo) atomicAdd(o + 1, clo);
+    if (cmid) {
+      atomicAdd(o + 2, cmid);
+      atomicMin(o + 3, x0); atomicMin(o + 4, y0); atomicMax(o + 5, x1); atomicMax(o + 6, y1);
+    }
+  }
+}
+
+// Binarised, un-cropped, TRANSPOSED copies of selected planes for run-length encoding (utils/amg.py:279-293 `uncrop_masks`,
+// :107-134 `mask_to_rle_pytorch`, which encodes in column-major order): out[k, x0 + c, y0 + r] = x[sel[k], r, c] > thr as
+// uint8, out is [K, OW, OH] and zero outside the crop.  32x32 shared-memory tiles: coalesced reads and writes.
+__global__ void mask_binarize_t_kernel(const float* __restrict__ x, const int32_t* __restrict__ sel, uint8_t* __restrict__ out,
+                                       int H, int W, float thr, int OH, int OW, int x0, int y0) {
+  __shared__ uint8_t tile[32][33];
+  const int k = blockIdx.z;
+  const float* xp = x + (long)sel[k] * H * W;
+  uint8_t* op = out + (long)k * OH * OW;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = blockIdx.y * 32 + threadIdx.y + j;
+    tile[threadIdx.y + j][threadIdx.x] = (r < H && c < W) ? (uint8_t)(xp[(long)r * W + c] > thr) : (uint8_t)0;
+  }
+  __syncthreads();
+  const int r = blockIdx.y * 32 + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int cc = blockIdx.x * 32 + threadIdx.y + j;
+    if (r < H && cc < W) op[(long)(x0 + cc) * OH + (y0 + r)] = tile[threadIdx.x][threadIdx.y + j];
+  }
+}
+
 __global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
   const int nidx = blockIdx.y;
   const float* xp = x + (long)nidx * P;
@@ -647,5 +723,34 @@ extern "C" int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_
   if (vec) bce_logits_sum_kernel<true><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
   else bce_logits_sum_kernel<false><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
   MS2_CHECK_LAUNCH("bce_logits_sum");
+  return MS2_OK;
+}
+extern "C" int ms2_mask_stats(const float* x, int32_t* stats, int N, int H, int W, float thr, float off, void* stream) {
+  MS2_CHECK_ARG(N >= 0 && H >= 0 && W >= 0, "mask_stats: bad sizes");
+  if (!N) return MS2_OK;
+  MS2_CHECK_ARG(stats && N <= 65535, "mask_stats: stats is null or more than 65535 planes");
+  mask_stats_init_kernel<<<(N + 255) / 256, 256, 0, ST>>>(stats, N, H, W);
+  MS2_CHECK_LAUNCH("mask_stats_init");
+  if (!H || !W) return MS2_OK;
+  MS2_CHECK_ARG(x, "mask_stats: x is null");
+  long per_plane = (148L * 8) / N;                        // one resident wave of 256-thread CTAs, at most one per row
+  if (per_plane > H) per_plane = H;
+  dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
+  mask_stats_kernel<<<grid, 256, 0, ST>>>(x, stats, H, W, thr, off);
+  MS2_CHECK_LAUNCH("mask_stats");
+  return MS2_OK;
+}
+extern "C" int ms2_mask_binarize_t(const float* x, const int32_t* sel, uint8_t* out, int K, int H, int W, float thr, int OH,
+                                   int OW, int x0, int y0, void* stream) {
+  MS2_CHECK_ARG(K >= 0 && H >= 0 && W >= 0 && x0 >= 0 && y0 >= 0 && x0 + W <= OW && y0 + H <= OH,
+                "mask_binarize_t: the crop does not fit the output");
+  if (!K || !OH || !OW) return MS2_OK;
+  MS2_CHECK_ARG(out && K <= 65535, "mask_binarize_t: out is null or more than 65535 planes");
+  if (H != OH || W != OW) MS2_CUDA(cudaMemsetAsync(out, 0, (size_t)K * OH * OW, ST), "mask_binarize_t memset");
+  if (!H || !W) return MS2_OK;
+  MS2_CHECK_ARG(x && sel, "mask_binarize_t: null input");
+  dim3 grid((W + 31) / 32, (H + 31) / 32, K), block(32, 8);
+  mask_binarize_t_kernel<<<grid, block, 0, ST>>>(x, sel, out, H, W, thr, OH, OW, x0, y0);
+  MS2_CHECK_LAUNCH("mask_binarize_t");
   return MS2_OK;
 }

@@ -553,3 +553,24 @@ def bce_logits_sum(pred, gt, pos_weight):
     native.call("ms2_bce_logits_sum", _chk(pred, "pred", torch.float32), _chk(gt, "gt", torch.float32), float(pos_weight),
                 sums.data_ptr(), N, P, _st())
     return sums
+
+
+def mask_stats(x, thr, off):
+    """x fp32 logits [N,H,W] -> int32 [N,7] = (#(x>thr+off), #(x>thr-off), #(x>thr), min col, min row, max col, max row
+    of x>thr); an empty plane gives (.., 0, W, H, -1, -1)."""
+    N, H, W = x.shape
+    stats = torch.empty((N, 7), dtype=torch.int32, device=x.device)
+    native.call("ms2_mask_stats", _chk(x, "x", torch.float32), stats.data_ptr(), N, H, W, float(thr), float(off), _st())
+    return stats
+
+
+def mask_binarize_t(x, sel, thr, out_hw, origin):
+    """x fp32 logits [N,H,W], sel int32 [K] plane indices -> uint8 [K,OW,OH]: (x[sel] > thr) placed at origin = (x0, y0)
+    of a zero [OH,OW] canvas and transposed (column-major order of the canvas, the order RLE encodes in)."""
+    N, H, W = x.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    K = sel.numel()
+    out = torch.empty((K, OW, OH), dtype=torch.uint8, device=x.device)
+    native.call("ms2_mask_binarize_t", _chk(x, "x", torch.float32), _chk(sel, "sel", torch.int32), out.data_ptr(), K, H, W,
+                float(thr), OH, OW, int(origin[0]), int(origin[1]), _st())
+    return out

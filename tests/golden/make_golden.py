@@ -11,6 +11,7 @@ What is dumped (all fp32, sub-sampled where large so the directory stays < 10 MB
   video_hiera_s_512.npz      config 3 shape, shrunk: 7 slices @512², bbox on 0,2,4, 1 object
   video_hiera_t_512_2obj.npz 2 objects, object 2 absent on slice 2 (mask prompt of zeros)
   modules_hiera_t.npz        per-module known answers (memory attention / encoder, decoder)
+  amg_hiera_t_1024.npz        SAM2AutomaticMaskGenerator.generate records + utils/amg.py helper answers
   func2d_hiera_t_512.npz     the 2D memory-bank validation step of func_2d/function.py:423-534 (tests/func2d_replay.py)
   cc_*.npz                   connected-component labels from a transliteration of the .cu kernels
 """
@@ -299,6 +300,75 @@ def golden_func2d():
     print("func2d", {k: v.shape for k, v in out.items()})
 
 
+# thresholds sit in gaps of the candidate statistics of the seeded random-weight model (predicted IoU: 16 values >= 0.5238, the
+# rest <= 0.5195; stability of those 16: 8 values <= 0.634, 8 values >= 0.667; pairwise box IoU 0.86 / 0.92 / 0.994+), so that fp32 rounding differences cannot flip a decision
+AMG_KW = dict(points_per_side=4, points_per_batch=8, pred_iou_thresh=0.5216, stability_score_thresh=0.65,
+              stability_score_offset=0.02, mask_threshold=0.0, box_nms_thresh=0.95, crop_n_layers=1, crop_nms_thresh=0.95,
+              crop_n_points_downscale_factor=2, output_mode="uncompressed_rle")
+
+
+def amg_image(h=300, w=400, seed=3):
+    """smooth blobs: with random weights the logits follow the image structure only loosely, but smooth inputs give
+    connected masks rather than speckle"""
+    g = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 3), np.float32)
+    for _ in range(6):
+        cy, cx, r = g.uniform(0, h), g.uniform(0, w), g.uniform(30, 90)
+        col = g.uniform(40, 255, size=3)
+        img += np.exp(-(((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r)))[..., None] * col
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@torch.no_grad()
+def golden_amg():
+    """`SAM2AutomaticMaskGenerator.generate` of the real reference (hiera_t at 1024^2, a 300x400 image, one crop layer)
+    plus known answers of the helper functions of utils/amg.py on seeded tensors."""
+    m = load_reference("sam2_hiera_t", video=False)       # the reference's image predictor hard-codes the 1024^2 feature sizes
+    load_seeded(m)
+    from sam2_train.automatic_mask_generator import SAM2AutomaticMaskGenerator
+    from sam2_train.utils import amg as ramg
+    out = {}
+    for tag, kw in {"plain": {}, "nonms": dict(box_nms_thresh=1.0, crop_nms_thresh=1.0),
+                    "m2m": dict(use_m2m=True, crop_n_layers=0, box_nms_thresh=1.0, pred_iou_thresh=0.0, stability_score_thresh=0.0)}.items():
+        gen = SAM2AutomaticMaskGenerator(m, **{**AMG_KW, **kw})
+        anns = gen.generate(amg_image())
+        print("amg", tag, len(anns), [(a["area"], a["bbox"], round(a["predicted_iou"], 3), round(a["stability_score"], 3),
+                                       a["crop_box"]) for a in anns][:8])
+        out[f"{tag}/n"] = np.array(len(anns))
+        out[f"{tag}/area"] = np.array([a["area"] for a in anns], np.int64)
+        out[f"{tag}/bbox"] = np.array([a["bbox"] for a in anns], np.int64).reshape(-1, 4)
+        out[f"{tag}/predicted_iou"] = np.array([a["predicted_iou"] for a in anns], np.float64)
+        out[f"{tag}/stability_score"] = np.array([a["stability_score"] for a in anns], np.float64)
+        out[f"{tag}/point_coords"] = np.array([a["point_coords"][0] for a in anns], np.float64).reshape(-1, 2)
+        out[f"{tag}/crop_box"] = np.array([a["crop_box"] for a in anns], np.int64).reshape(-1, 4)
+        out[f"{tag}/n_runs"] = np.array([len(a["segmentation"]["counts"]) for a in anns], np.int64)
+    # helper known answers on seeded logits
+    g = torch.Generator().manual_seed(21)
+    logits = torch.randn(5, 37, 53, generator=g)
+    logits[3] = -1.0                                                   # an empty mask
+    logits[4] = 1.0                                                    # a full mask
+    out["h/logits"] = npy(logits)
+    out["h/stability"] = npy(ramg.calculate_stability_score(logits, 0.1, 0.5))
+    out["h/boxes"] = ramg.batched_mask_to_box(logits > 0.1).numpy()
+    rles = ramg.mask_to_rle_pytorch(logits > 0.1)
+    out["h/rle_lens"] = np.array([len(r["counts"]) for r in rles])
+    out["h/rle_counts"] = np.concatenate([np.asarray(r["counts"], np.int64) for r in rles])
+    out["h/areas"] = np.array([ramg.area_from_rle(r) for r in rles])
+    boxes = torch.tensor([[0, 0, 10, 10], [1, 1, 11, 11], [20, 20, 30, 30], [0, 0, 10, 9], [21, 19, 30, 31], [5, 5, 6, 6]])
+    scores = torch.tensor([0.9, 0.8, 0.7, 0.95, 0.71, 0.1])
+    from torchvision.ops.boxes import batched_nms
+    out["h/nms_boxes"], out["h/nms_scores"] = boxes.numpy(), scores.numpy()
+    for thr in (0.3, 0.7):
+        out[f"h/nms_keep_{thr}"] = batched_nms(boxes.float(), scores, torch.zeros(6), thr).numpy()
+    out["h/near_edge"] = ramg.is_box_near_crop_edge(torch.tensor([[0, 0, 50, 50], [30, 5, 99, 60], [25, 25, 60, 60], [0, 40, 60, 99]]),
+                                                    [100, 0, 200, 100], [0, 0, 400, 100]).numpy()
+    cb, li = ramg.generate_crop_boxes((300, 400), 2, 512 / 1500)
+    out["h/crop_boxes"], out["h/crop_layers"] = np.array(cb), np.array(li)
+    out["h/grid3"] = ramg.build_point_grid(3)
+    np.savez_compressed(f"{OUT}/amg_hiera_t_1024.npz", **out)
+
+
 # ----------------------------------------------------------------------------- CC transliteration
 def cc_transliterated(img):
     """Sequential transliteration of csrc/connected_components.cu:30-209 for ONE image [H,W]
@@ -409,7 +479,7 @@ def golden_cc():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["layout", "cc", "modules", "func2d", "image_t", "image_s", "video_s", "video_t2"]
+    which = sys.argv[1:] or ["layout", "cc", "modules", "func2d", "amg", "image_t", "image_s", "video_s", "video_t2"]
     if "layout" in which:
         golden_layout()
     if "cc" in which:
@@ -418,6 +488,8 @@ if __name__ == "__main__":
         golden_modules()
     if "func2d" in which:
         golden_func2d()
+    if "amg" in which:
+        golden_amg()
     if "image_t" in which:
         golden_image_t()
     if "image_s" in which:

@@ -224,6 +224,25 @@ def mask_stability_counts(x, delta):
     return torch.stack([(f > delta).sum(-1), (f > -delta).sum(-1)], dim=1).to(torch.int32)
 
 
+def mask_stats(x, thr, off):
+    N, H, W = x.shape
+    out = torch.zeros((N, 7), dtype=torch.int32)
+    for n in range(N):
+        m = x[n] > thr
+        out[n, 0], out[n, 1], out[n, 2] = int((x[n] > thr + off).sum()), int((x[n] > thr - off).sum()), int(m.sum())
+        ys, xs = torch.nonzero(m, as_tuple=True)
+        out[n, 3:] = torch.tensor([xs.min(), ys.min(), xs.max(), ys.max()] if len(xs) else [W, H, -1, -1])
+    return out.to(x.device)
+
+
+def mask_binarize_t(x, sel, thr, out_hw, origin):
+    N, H, W = x.shape
+    OH, OW = out_hw
+    out = torch.zeros((sel.numel(), OH, OW), dtype=torch.uint8, device=x.device)
+    out[:, origin[1]:origin[1] + H, origin[0]:origin[0] + W] = (x[sel.long()] > thr).to(torch.uint8)
+    return out.transpose(1, 2).contiguous()
+
+
 def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
     xi = x.float()
     if pre == 1:
