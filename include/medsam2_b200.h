@@ -246,6 +246,11 @@ int ms2_mask_stats(const float* x, int32_t* stats, int N, int H, int W, float th
 int ms2_mask_binarize_t(const float* x, const int32_t* sel, uint8_t* out, int K, int H, int W, float thr, int OH, int OW,
                         int x0, int y0, ms2_stream_t stream);
 
+/* ---- run-length encoding on the device (utils/amg.py:107-134 `mask_to_rle_pytorch`): m uint8 [K,L] (0/1 masks already in
+ *      encoding order); pos int32 [K,cap] receives, in increasing order, the positions p >= 1 with m[k,p] != m[k,p-1];
+ *      cnt int32 [K] = the TOTAL number of such positions (if cnt[k] > cap the tail was dropped: call again with a larger cap). */
+int ms2_rle_transitions(const uint8_t* m, int32_t* pos, int32_t* cnt, int K, long L, int cap, ms2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,8 @@ candidates live: the reference carries every candidate of a point batch as full-
 `calculate_stability_score`, a binarisation, `batched_mask_to_box`, `uncrop_masks` and a per-mask `nonzero`; here one
 kernel pass over the logits (`ops.mask_stats`) returns the three threshold counts and the box of every candidate, the
 filters run on those few integers on the host, and only the survivors are binarised, un-cropped and transposed on the
-GPU (`ops.mask_binarize_t`) for run-length encoding.  Box NMS runs on the host over the surviving boxes.
+GPU (`ops.mask_binarize_t`) and their run boundaries compacted there (`ops.rle_transitions`), so a survivor costs a few
+KB of D2H traffic instead of its H*W mask.  Box NMS runs on the host over the surviving boxes.
 """
 import numpy as np
 import torch
@@ -164,19 +165,18 @@ class SAM2AutomaticMaskGenerator:
         out = _Candidates()
         if len(keep):
             sel = torch.as_tensor(keep, dtype=torch.int32, device=masks.device)
-            mt = self._binarize_survivors(masks, sel, crop_box, orig_h, orig_w)
-            out.rles = [amg.rle_from_transposed(mt[i]) for i in range(len(keep))]
+            out.rles = amg.rles_from_device(self._binarize_survivors(masks, sel, crop_box, orig_h, orig_w))
         out.boxes, out.iou_preds, out.points = boxes[keep], ious[keep], pts[keep]
         out.stability_score = stability[keep]
         out.crop_boxes = np.zeros((len(keep), 4), np.int64)
         return out
 
     def _binarize_survivors(self, masks, sel, crop_box, orig_h, orig_w):
-        """(masks[sel] > mask_threshold) un-cropped to the original image and transposed, as uint8 on the host."""
+        """(masks[sel] > mask_threshold) un-cropped to the original image and transposed, uint8 [K,W,H] on the GPU."""
         from . import ops
         m = masks if masks.dtype == torch.float32 else masks.float()
         return ops.mask_binarize_t(m.contiguous(), sel, self.mask_threshold, (orig_h, orig_w),
-                                   (crop_box[0], crop_box[1])).cpu().numpy()
+                                   (crop_box[0], crop_box[1]))
 
     # ------------------------------------------------------------------------------------------ optional clean-up
     @staticmethod

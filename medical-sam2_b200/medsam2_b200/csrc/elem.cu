@@ -503,6 +503,71 @@ __global__ void mask_binarize_t_kernel(const float* __restrict__ x, const int32_
   }
 }
 
+// Run-length encoding on the device (utils/amg.py:107-134 `mask_to_rle_pytorch` finds the change positions with a
+// whole-tensor XOR + `nonzero` and slices them per mask on the host): one CTA per mask walks its bytes in order, 16 per thread
+// and step, and appends the positions p with m[p] != m[p-1] through a block-wide exclusive scan, so pos[k, 0..cnt[k]) is
+// sorted.  cnt[k] is the TOTAL number of transitions; positions beyond `cap` are dropped (the caller re-runs with a larger cap).
+__global__ void __launch_bounds__(1024) rle_transitions_kernel(const uint8_t* __restrict__ m, long L, int32_t* __restrict__ pos,
+                                                               int32_t* __restrict__ cnt, int cap, bool vec) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_sh;
+  const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint8_t* mp = m + (long)k * L;
+  int32_t* out = pos + (long)k * cap;
+  if (tid == 0) base_sh = 0;
+  __syncthreads();
+  for (long start = 0; start < L; start += 1024L * 16) {
+    const long p0 = start + (long)tid * 16;
+    __align__(16) uint8_t b[16];
+    unsigned bits = 0;
+    if (p0 < L) {
+      const int nv = (int)min(16L, L - p0);
+      if (vec && nv == 16) {
+        *(uint4*)b = *(const uint4*)(mp + p0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = j < nv ? mp[p0 + j] : (uint8_t)0;
+      }
+      uint8_t prev = p0 > 0 ? mp[p0 - 1] : b[0];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < nv && b[j] != prev) bits |= 1u << j;
+        prev = b[j];
+      }
+    }
+    const int n = __popc(bits);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;                             // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    int off = base_sh + warp_tot[wid] + (incl - n);
+    while (bits) {
+      const int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (off < cap) out[off] = (int32_t)(p0 + j);
+      ++off;
+    }
+    __syncthreads();
+    if (tid == 1023) base_sh = off;                        // the last thread's end offset = running total
+    __syncthreads();
+  }
+  if (tid == 0) cnt[k] = base_sh;
+}
+
 __global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
   const int nidx = blockIdx.y;
   const float* xp = x + (long)nidx * P;
@@ -759,5 +824,14 @@ extern "C" int ms2_mask_binarize_t(const float* x, const int32_t* sel, uint8_t* 
   dim3 grid((W + 31) / 32, (H + 31) / 32, K), block(32, 8);
   mask_binarize_t_kernel<<<grid, block, 0, ST>>>(x, sel, out, H, W, thr, OH, OW, x0, y0);
   MS2_CHECK_LAUNCH("mask_binarize_t");
+  return MS2_OK;
+}
+extern "C" int ms2_rle_transitions(const uint8_t* m, int32_t* pos, int32_t* cnt, int K, long L, int cap, void* stream) {
+  MS2_CHECK_ARG(K >= 0 && L >= 0 && L < (1L << 31) && cap >= 0, "rle_transitions: bad sizes");
+  if (!K) return MS2_OK;
+  MS2_CHECK_ARG(cnt && (pos || !cap) && (m || !L), "rle_transitions: null pointer");
+  const bool vec = (L % 16 == 0) && ((uintptr_t)m % 16 == 0);
+  rle_transitions_kernel<<<K, 1024, 0, ST>>>(m, L, pos, cnt, cap, vec);
+  MS2_CHECK_LAUNCH("rle_transitions");
   return MS2_OK;
 }

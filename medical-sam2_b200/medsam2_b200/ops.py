@@ -574,3 +574,13 @@ def mask_binarize_t(x, sel, thr, out_hw, origin):
     native.call("ms2_mask_binarize_t", _chk(x, "x", torch.float32), _chk(sel, "sel", torch.int32), out.data_ptr(), K, H, W,
                 float(thr), OH, OW, int(origin[0]), int(origin[1]), _st())
     return out
+
+
+def rle_transitions(m, cap):
+    """m uint8 [K,L] (0/1, already in encoding order) -> (pos int32 [K,cap], cnt int32 [K]): sorted positions p >= 1 with
+    m[k,p] != m[k,p-1]; cnt is the total per mask (cnt[k] > cap: the tail was dropped, call again with a larger cap)."""
+    K, L = m.shape
+    pos = torch.empty((K, cap), dtype=torch.int32, device=m.device)
+    cnt = torch.empty((K,), dtype=torch.int32, device=m.device)
+    native.call("ms2_rle_transitions", _chk(m, "m", torch.uint8), pos.data_ptr(), cnt.data_ptr(), K, L, int(cap), _st())
+    return pos, cnt

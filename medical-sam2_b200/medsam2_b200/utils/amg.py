@@ -111,12 +111,32 @@ def rle_from_transposed(mt):
     return {"size": [h, w], "counts": counts}
 
 
+def rles_from_device(mt, cap=4096):
+    """mt uint8 [K,W,H] on the GPU (column-major masks from `ops.mask_binarize_t`) -> list of uncompressed RLE dicts.
+    The change positions are found and compacted on the device (`ops.rle_transitions`); the host receives cap positions
+    per mask (16 KB instead of the W*H-byte mask) and turns them into run lengths; a mask with more transitions than
+    `cap` triggers one re-run with the exact capacity."""
+    K, w, h = mt.shape
+    if K == 0:
+        return []
+    flat = mt.reshape(K, -1)
+    pos, cnt = ops.rle_transitions(flat, cap)
+    cnt_h = cnt.cpu().numpy()
+    if int(cnt_h.max()) > cap:
+        pos, _ = ops.rle_transitions(flat, int(cnt_h.max()))
+    pos_h, first = pos.cpu().numpy(), flat[:, 0].cpu().numpy()
+    out = []
+    for k in range(K):
+        edges = np.concatenate([[0], pos_h[k, :cnt_h[k]], [h * w]])
+        out.append({"size": [h, w], "counts": ([] if first[k] == 0 else [0]) + np.diff(edges).tolist()})
+    return out
+
+
 def mask_to_rle_pytorch(tensor):
     """Drop-in for utils/amg.py:107-134: boolean masks [b,h,w] on the GPU -> list of uncompressed RLE dicts."""
     b, h, w = tensor.shape
     sel = torch.arange(b, dtype=torch.int32, device=tensor.device)
-    mt = ops.mask_binarize_t(tensor.float().contiguous(), sel, 0.5, (h, w), (0, 0)).cpu().numpy()
-    return [rle_from_transposed(mt[i]) for i in range(b)]
+    return rles_from_device(ops.mask_binarize_t(tensor.float().contiguous(), sel, 0.5, (h, w), (0, 0)))
 
 
 def rle_to_mask(rle):

@@ -243,6 +243,17 @@ def mask_binarize_t(x, sel, thr, out_hw, origin):
     return out.transpose(1, 2).contiguous()
 
 
+def rle_transitions(m, cap):
+    K, L = m.shape
+    pos = torch.zeros((K, cap), dtype=torch.int32, device=m.device)
+    cnt = torch.zeros((K,), dtype=torch.int32, device=m.device)
+    for k in range(K):
+        p = torch.nonzero(m[k, 1:] != m[k, :-1]).flatten() + 1
+        cnt[k] = len(p)
+        pos[k, :min(cap, len(p))] = p[:cap].to(torch.int32)
+    return pos, cnt
+
+
 def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
     xi = x.float()
     if pre == 1:

@@ -94,6 +94,21 @@ def test_host_helpers_match_reference():
     assert amg.box_xyxy_to_xywh(np.array([3, 4, 10, 20])).tolist() == [3, 4, 7, 16]
 
 
+def test_device_rle_host_side(monkeypatch):
+    """`rles_from_device` (positions compacted by `ops.rle_transitions`, here its torch statement) == the plain host
+    encoder, including the re-run when a mask has more transitions than the first capacity"""
+    from medsam2_b200.utils import amg
+    ref_ops.install(monkeypatch)
+    z = Z()
+    logits = torch.from_numpy(z["h/logits"])
+    mt = ref_ops.mask_binarize_t(logits, torch.arange(5, dtype=torch.int32), 0.1, (37, 53), (0, 0))
+    for cap in (4096, 7):
+        rles = amg.rles_from_device(mt, cap=cap)
+        assert rles == [amg.rle_from_transposed(mt[i].numpy()) for i in range(5)]
+        assert np.array_equal(np.concatenate([r["counts"] for r in rles]), z["h/rle_counts"])
+    assert amg.rles_from_device(mt[:0]) == []
+
+
 @pytest.mark.parametrize("tag", ["plain", "m2m"])
 def test_generate_host_logic(monkeypatch, tag):
     """`generate()` with the native ops replaced by their torch statements vs the records of the real reference."""
@@ -147,6 +162,32 @@ def test_gpu_mask_binarize_t_bit_exact(shape, canvas, origin):
     assert ops.mask_binarize_t(x.cuda(), sel.cuda()[:0], 0.1, canvas, origin).shape == (0, canvas[1], canvas[0])
     with pytest.raises(native.NativeError):
         ops.mask_binarize_t(x.cuda(), sel.cuda(), 0.1, (shape[1] - 1, shape[2]), (0, 0))      # crop larger than canvas
+
+
+@pytest.mark.gpu
+def test_gpu_rle_transitions_bit_exact():
+    """device run-length boundaries vs the host encoder: noise (capacity overflow -> re-run), blobs, constant masks,
+    lengths that are not a multiple of 16, a base pointer that is not 16-byte aligned, more than one chunk per CTA"""
+    from medsam2_b200 import ops
+    from medsam2_b200.utils import amg
+    g = torch.Generator().manual_seed(9)
+    cases = [(torch.rand(3, 53, 37, generator=g) > 0.5), (torch.rand(2, 400, 300, generator=g) > 0.98),
+             torch.zeros(2, 64, 64, dtype=torch.bool), torch.ones(1, 33, 31, dtype=torch.bool)]
+    yy, xx = torch.meshgrid(torch.arange(1024), torch.arange(1024), indexing="ij")
+    cases.append(torch.stack([((yy - 300) ** 2 + (xx - 500) ** 2 < 200 ** 2), ((yy > 100) & (xx % 97 < 40))]))
+    for m in cases:
+        mt = m.to(torch.uint8).contiguous()
+        want = [amg.rle_from_transposed(mt[i].numpy()) for i in range(len(mt))]
+        assert amg.rles_from_device(mt.cuda(), cap=64) == want
+        assert amg.rles_from_device(mt.cuda()) == want
+    base = (torch.rand(2 * 1000 + 1, generator=g) > 0.7).to(torch.uint8).cuda()
+    un = base[1:].view(2, 1000)                                           # rows start 1 byte off a 16-byte boundary
+    pos, cnt = ops.rle_transitions(un, 1000)
+    for k in range(2):
+        want = np.flatnonzero(np.diff(un[k].cpu().numpy().astype(np.int8)) != 0) + 1
+        assert int(cnt[k]) == len(want) and np.array_equal(pos[k, :len(want)].cpu().numpy(), want)
+    pos, cnt = ops.rle_transitions(un, 0)                                  # counting only
+    assert pos.shape == (2, 0) and int(cnt.sum()) > 0
 
 
 @pytest.mark.gpu
