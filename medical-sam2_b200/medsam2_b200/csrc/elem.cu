@@ -437,30 +437,66 @@ __global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict
   const float* xp = x + (long)n * H * W;
   const float hi = thr + off, lo = thr - off;
   int chi = 0, clo = 0, cmid = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
+  float fhi = 0.f, flo = 0.f, fmid = 0.f, colf[4] = {0.f, 0.f, 0.f, 0.f};
   // a CTA walks whole rows (coalesced along the row); rows are dealt round-robin over the CTAs of the plane
-  for (int r = blockIdx.x; r < H; r += gridDim.x) {
-    const float* row = xp + (long)r * W;
-    bool any = false;
-    auto visit = [&](float v, int c) {
-      chi += v > hi;
-      clo += v > lo;
-      if (v > thr) {
-        ++cmid;
-        any = true;
-        x0 = min(x0, c);
-        x1 = max(x1, c);
+  if (vec && W <= 4 * (int)blockDim.x) {
+    // fast path (16-byte loads; every thread owns the SAME four columns in every row, four rows in flight): counts as 0/1
+    // floats (FSET + FADD, exact: a thread sees < 2^24 pixels), "column ever set" as four float sums, rows per float4
+    const int c = 4 * threadIdx.x, g = gridDim.x;
+    auto process = [&](const float4& v, int r) {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      float rowsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        fhi += e[j] > hi ? 1.f : 0.f;
+        flo += e[j] > lo ? 1.f : 0.f;
+        const float m = e[j] > thr ? 1.f : 0.f;
+        rowsum += m;
+        colf[j] += m;
       }
+      fmid += rowsum;
+      if (rowsum > 0.f) { y0 = min(y0, r); y1 = max(y1, r); }
     };
-    if (vec) {                                           // 16-byte loads: W % 4 == 0 and a 16-byte aligned base
-      for (int c = 4 * threadIdx.x; c < W; c += 4 * blockDim.x) {
-        const float4 v = __ldcs((const float4*)(row + c));
-        visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
+    if (c < W) {
+      int r = blockIdx.x;
+      for (; r + 3 * g < H; r += 4 * g) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs((const float4*)(xp + (long)(r + u * g) * W + c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) process(v[u], r + u * g);
       }
-    } else {
-      for (int c = threadIdx.x; c < W; c += blockDim.x) visit(row[c], c);
+      for (; r < H; r += g) process(__ldcs((const float4*)(xp + (long)r * W + c)), r);
     }
-    if (any) { y0 = min(y0, r); y1 = max(y1, r); }
+  } else {
+    for (int r = blockIdx.x; r < H; r += gridDim.x) {
+      const float* row = xp + (long)r * W;
+      bool any = false;
+      auto visit = [&](float v, int c) {
+        chi += v > hi;
+        clo += v > lo;
+        if (v > thr) {
+          ++cmid;
+          any = true;
+          x0 = min(x0, c);
+          x1 = max(x1, c);
+        }
+      };
+      if (vec) {                                         // 16-byte loads: W % 4 == 0 and a 16-byte aligned base
+        for (int c = 4 * threadIdx.x; c < W; c += 4 * blockDim.x) {
+          const float4 v = __ldcs((const float4*)(row + c));
+          visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
+        }
+      } else {
+        for (int c = threadIdx.x; c < W; c += blockDim.x) visit(row[c], c);
+      }
+      if (any) { y0 = min(y0, r); y1 = max(y1, r); }
+    }
   }
+  chi += (int)fhi; clo += (int)flo; cmid += (int)fmid;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (colf[j] > 0.f) { x0 = min(x0, 4 * (int)threadIdx.x + j); x1 = max(x1, 4 * (int)threadIdx.x + j); }
   chi = __reduce_add_sync(0xffffffffu, chi);
   clo = __reduce_add_sync(0xffffffffu, clo);
   cmid = __reduce_add_sync(0xffffffffu, cmid);
