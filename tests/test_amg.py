@@ -94,6 +94,39 @@ def test_host_helpers_match_reference():
     assert amg.box_xyxy_to_xywh(np.array([3, 4, 10, 20])).tolist() == [3, 4, 7, 16]
 
 
+def test_remove_small_regions_matches_reference():
+    """scipy 8-connected labelling in place of OpenCV's: identical masks and `changed` flags (amg_regions.npz holds the
+    answers of the reference's `remove_small_regions` on seeded disc + salt-and-pepper masks, empty, full, tiny islands)"""
+    from medsam2_b200.utils import amg
+    z = np.load(f"{G}/amg_regions.npz")
+    for i in range(int(z["n"])):
+        for mode in ("holes", "islands"):
+            for thr in (5, 40):
+                out, changed = amg.remove_small_regions(z[f"mask_{i}"], thr, mode)
+                assert bool(changed) == bool(z[f"changed_{i}_{mode}_{thr}"]), (i, mode, thr)
+                assert np.array_equal(np.asarray(out, bool), z[f"out_{i}_{mode}_{thr}"]), (i, mode, thr)
+
+
+def test_postprocess_small_regions_host():
+    """the optional clean-up pass: islands below the area threshold disappear, the box is recomputed, a duplicate that
+    needed no change is preferred by the NMS"""
+    from medsam2_b200.automatic_mask_generator import SAM2AutomaticMaskGenerator, _Candidates
+    from medsam2_b200.utils import amg
+    big = np.zeros((64, 80), bool); big[10:40, 20:60] = True
+    noisy = big.copy(); noisy[50, 70] = True; noisy[20, 30] = False          # one island pixel, one hole pixel
+    other = np.zeros((64, 80), bool); other[45:60, 5:15] = True
+    data = _Candidates()
+    data.rles = [amg.rle_from_transposed(np.ascontiguousarray(m.T).astype(np.uint8)) for m in (noisy, big, other)]
+    data.boxes = np.array([[20, 10, 70, 50], [20, 10, 59, 39], [5, 45, 14, 59]], np.int64)
+    data.iou_preds = np.array([0.9, 0.8, 0.7], np.float32)
+    data.points = np.zeros((3, 2)); data.stability_score = np.ones(3, np.float32); data.crop_boxes = np.zeros((3, 4), np.int64)
+    out = SAM2AutomaticMaskGenerator.postprocess_small_regions(data, min_area=4, nms_thresh=0.7)
+    assert len(out) == 2                                                     # the cleaned noisy mask duplicates `big`
+    kept = [amg.rle_to_mask(r) for r in out.rles]
+    assert any(np.array_equal(k, big) for k in kept) and any(np.array_equal(k, other) for k in kept)
+    assert sorted(out.iou_preds.tolist()) == [np.float32(0.7), np.float32(0.8)]        # the unchanged duplicate won
+
+
 def test_device_rle_host_side(monkeypatch):
     """`rles_from_device` (positions compacted by `ops.rle_transitions`, here its torch statement) == the plain host
     encoder, including the re-run when a mask has more transitions than the first capacity"""
