@@ -152,6 +152,17 @@ def test_generate_host_logic(monkeypatch, tag):
     _check_records(gen.generate(amg_image()), Z(), tag, area_rtol=1.5e-2, box_atol=1, iou_atol=5e-4, stab_atol=5e-3)
 
 
+def test_generate_without_survivors(monkeypatch):
+    """nothing passes the predicted-IoU filter -> an empty list, in every output mode that needs no extra package"""
+    import medsam2_b200  # noqa: F401
+    from medsam2_b200.automatic_mask_generator import SAM2AutomaticMaskGenerator
+    ref_ops.install(monkeypatch)
+    m = _build("cpu")
+    for mode in ("binary_mask", "uncompressed_rle"):
+        gen = SAM2AutomaticMaskGenerator(m, points_per_side=2, points_per_batch=4, pred_iou_thresh=0.99, output_mode=mode)
+        assert gen.generate(amg_image(64, 96)) == []
+
+
 def test_constructor_contract():
     from medsam2_b200.automatic_mask_generator import SAM2AutomaticMaskGenerator
     m = _build("cpu")
