@@ -1,7 +1,8 @@
 """Multi-GPU plumbing of the hot path; one process per GPU, `torch.distributed` (NCCL on GPUs,
 gloo in the CPU tests).
 
-* Volumes are independent: `shard_volumes` deals them round-robin to ranks - no data-path collective (configs 3/4).
+* Volumes are independent: `shard_volumes` deals them round-robin to ranks - no data-path collective (configs 3/4);
+  `reduce_validation` turns the per-rank sums of the validation loop into the global averages with one small all-reduce.
 * Within ONE volume only the slice encoder shards (config 5): `encode_volume_sharded` lets every rank encode a
   contiguous block of slices and all-gathers the feature pyramid (fpn levels `[32,256,256] + [64,128,128] +
   [256,64,64]` per slice; the position encodings are constant tables and are never sent), filling the predictor's
@@ -24,6 +25,24 @@ def shard_volumes(n_volumes, rank=None, world=None):
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     return list(range(rank, n_volumes, world))
+
+
+def reduce_validation(loss_sum, metric_sums, n_volumes, group=None):
+    """Validation over volumes dealt to ranks by `shard_volumes` (reference: func_3d/function.py:198-314 on one GPU,
+    `return tot / n_val, tuple(a / n_val for a in mix_res)`): every rank passes the SUMS over its own volumes of the
+    per-volume loss and of the per-volume metric tuple (IoU, Dice, ...) plus its volume count; ONE all-reduce of
+    len(metric_sums) + 2 doubles gives every rank the same global averages.  Without an initialised process group
+    this is the single-process statement.  Returns (mean loss, tuple of mean metrics)."""
+    vec = torch.tensor([float(loss_sum), float(n_volumes), *[float(m) for m in metric_sums]], dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl":
+            vec = vec.cuda()
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        vec = vec.cpu()
+    n = float(vec[1])
+    if n == 0:
+        raise ZeroDivisionError("reduce_validation: no volume was evaluated on any rank")
+    return float(vec[0]) / n, tuple(float(v) / n for v in vec[2:])
 
 
 def slice_block(num_frames, rank, world):

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from medsam2_b200.parallel import encode_volume_sharded, shard_volumes, slice_block
+from medsam2_b200.parallel import encode_volume_sharded, reduce_validation, shard_volumes, slice_block
 
 
 class FakePredictor:
@@ -162,3 +162,33 @@ def test_kv_shard_partition_is_exact():
                 assert len(owners) == 1
                 o = owners[0]
                 assert o.owns_recent(0, n_cond) if n_recent else o.owns_cond(0)
+
+
+def _val_worker(rank, world, port, n_volumes, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    per_volume = torch.rand(n_volumes, 3, generator=g, dtype=torch.float64)        # (loss, iou, dice) of every volume
+    mine = shard_volumes(n_volumes)
+    loss, metrics = reduce_validation(per_volume[mine, 0].sum(), per_volume[mine, 1:].sum(0).tolist(), len(mine))
+    want = per_volume.mean(0)
+    out[rank] = bool(abs(loss - want[0]) < 1e-12 and all(abs(a - b) < 1e-12 for a, b in zip(metrics, want[1:].tolist())))
+    dist.destroy_process_group()
+
+
+def test_validation_reduce_two_ranks():
+    """volumes dealt round-robin to 2 ranks (5 volumes: 3 + 2), per-rank sums -> identical global averages on both ranks,
+    equal to the single-process means (func_3d/function.py:308-314)"""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_val_worker, args=(2, port, 5, out), nprocs=2, join=True)
+    assert out[0] and out[1]
+
+
+def test_validation_reduce_single_process():
+    loss, metrics = reduce_validation(3.0, [1.5, 0.6], 3)
+    import pytest
+    assert loss == 1.0 and metrics == pytest.approx((0.5, 0.2), abs=1e-15)
+    with pytest.raises(ZeroDivisionError):
+        reduce_validation(0.0, [0.0], 0)
