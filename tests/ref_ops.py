@@ -254,6 +254,23 @@ def rle_transitions(m, cap):
     return pos, cnt
 
 
+def seg_counts(pred, gt, thresholds):
+    N = pred.shape[0]
+    p, g = pred.reshape(N, -1).float(), gt.reshape(N, -1).float()
+    out = torch.zeros((N, len(thresholds), 3), dtype=torch.int32, device=pred.device)
+    for t, th in enumerate(thresholds):
+        a, b = p > float(th), g > float(th)
+        out[:, t, 0], out[:, t, 1], out[:, t, 2] = (a & b).sum(1), a.sum(1), b.sum(1)
+    return out
+
+
+def bce_logits_sum(pred, gt, pos_weight):
+    N = pred.shape[0]
+    x, y = pred.reshape(N, -1).double(), gt.reshape(N, -1).double()
+    el = (1 - y) * x + (1 + (pos_weight - 1) * y) * (torch.log1p(torch.exp(-x.abs())) + torch.clamp_min(-x, 0))
+    return el.sum(1)
+
+
 def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
     xi = x.float()
     if pre == 1:

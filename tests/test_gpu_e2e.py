@@ -281,3 +281,40 @@ def test_validation_loop_metrics_fp32():
         thr_in = (-0.1, -0.05, 0.0, 0.05, 0.1)
         assert eval_seg_frames(ref[f][0][None].cuda(), gt[f:f + 1].cuda(), thr_in)[0] == eval_seg_np(rp, gt[f:f + 1].numpy(), thr_in)
     print("validation loop: per-slice IoU of the checker", [round(float(i), 3) for i in ious])
+
+
+def test_validation_driver_gpu():
+    """`validation_sam` (reference func_3d/function.py:198-314) through the CUDA path: the whole-volume scoring equals
+    the per-(slice, object) accumulation of the reference, restated with the numpy metric oracle on the driver's own
+    predictions (metrics exact, loss to 1e-6 relative); a volume without annotations is skipped but counted."""
+    from medsam2_b200.validation import THRESHOLD, validation_sam
+    from oracle.eval_seg import bce_with_logits_np, eval_seg_np
+    size, T = 512, 3
+    m = _build("sam2_hiera_t", video=True, image_size=size)
+    packs = []
+    for seed in (1234, 99):
+        vol, boxes = btcv_volume(T, size, seed, 1)
+        g = torch.Generator().manual_seed(seed)
+        label = {f: {1: (torch.rand(1, size, size, generator=g) > 0.5).float()} for f in range(T)}
+        del label[1][1]
+        packs.append({"image": vol[None], "label": label, "bbox": {f: {1: torch.tensor(boxes[f][0])} for f in range(T)}})
+    packs.append({"image": btcv_volume(T, size, 5, 1)[0], "label": {f: {} for f in range(T)}, "bbox": {}})
+    seen, orig = [], m.propagate_in_video
+
+    def spy(state, start_frame_idx=0):
+        seen.append({})
+        for f, ids, logits in orig(state, start_frame_idx=start_frame_idx):
+            seen[-1][f] = logits.float().cpu().clone()
+            yield f, ids, logits
+    m.propagate_in_video = spy
+    loss, (iou, dice) = validation_sam(m, packs, prompt="bbox", prompt_freq=2)
+    want = np.zeros(3)
+    for v in range(2):
+        for f in range(T):
+            pred = seen[v][f][0][None].numpy()
+            gt = packs[v]["label"][f].get(1, torch.zeros(1, size, size))[None].numpy()
+            i_, d_ = eval_seg_np(pred, gt, THRESHOLD)
+            want += np.array([bce_with_logits_np(pred, gt, 2.0), i_, d_]) / T
+    want /= 3
+    assert abs(iou - want[1]) < 1e-12 and abs(dice - want[2]) < 1e-9, (iou, dice, want)
+    assert abs(loss - want[0]) < 1e-6 * abs(want[0]), (loss, want[0])

@@ -156,6 +156,48 @@ def test_func2d_memory_bank_step(fake_backend, tag, shape):
     _close(r["maskmem_pos"][..., ::2, ::2], z[f"{tag}/maskmem_pos_sub"], 1e-6, "maskmem pos")
 
 
+def test_validation_driver(fake_backend):
+    """`validation_sam` (reference func_3d/function.py:198-314): two prompted volumes + one without annotations.  The
+    driver's whole-volume scoring (one count launch + one loss launch) must equal the reference's per-(slice, object)
+    accumulation, restated here with the numpy metric oracle on the driver's own predictions."""
+    from medsam2_b200.validation import THRESHOLD, validation_sam
+    from oracle.eval_seg import bce_with_logits_np, eval_seg_np
+    size, T = 512, 3
+    m = _build("sam2_hiera_t", video=True, image_size=size)
+    packs = []
+    for seed in (1234, 99):
+        vol, boxes = btcv_volume(T, size, seed, 1)
+        g = torch.Generator().manual_seed(seed)
+        label = {f: {1: (torch.rand(1, size, size, generator=g) > 0.5).float()} for f in range(T)}
+        del label[1][1]                                                     # no annotation on slice 1 -> all background
+        packs.append({"image": vol[None], "label": label, "bbox": {f: {1: torch.tensor(boxes[f][0])} for f in range(T)}})
+    packs.append({"image": btcv_volume(T, size, 5, 1)[0], "label": {f: {} for f in range(T)}, "bbox": {}})
+    seen = []
+    orig = m.propagate_in_video
+
+    def spy(state, start_frame_idx=0):
+        seen.append({})
+        for f, ids, logits in orig(state, start_frame_idx=start_frame_idx):
+            seen[-1][f] = logits.clone()
+            yield f, ids, logits
+    m.propagate_in_video = spy
+    loss, (iou, dice) = validation_sam(m, packs, prompt="bbox", prompt_freq=2, device="cpu")
+    want = np.zeros(3)
+    for v in range(2):
+        acc = np.zeros(3)
+        for f in range(T):
+            pred = seen[v][f][0][None].numpy()
+            gt = packs[v]["label"][f].get(1, torch.zeros(1, size, size))[None].numpy()
+            i_, d_ = eval_seg_np(pred, gt, THRESHOLD)
+            acc += [bce_with_logits_np(pred, gt, 2.0), i_, d_]
+        want += acc / T
+    want /= 3                                                               # n_val counts the skipped volume
+    assert abs(iou - want[1]) < 1e-12 and abs(dice - want[2]) < 1e-9, (iou, dice, want)
+    assert abs(loss - want[0]) < 1e-6 * abs(want[0]), (loss, want[0])
+    with pytest.raises(ValueError):
+        validation_sam(m, packs[:1], prompt="scribble", device="cpu")
+
+
 def test_product_refuses_cpu_without_backend():
     """No fake backend installed -> the hot path must fail loudly on CPU tensors (no fallback)."""
     from medsam2_b200 import ops
