@@ -192,3 +192,48 @@ def test_validation_reduce_single_process():
     assert loss == 1.0 and metrics == pytest.approx((0.5, 0.2), abs=1e-15)
     with pytest.raises(ZeroDivisionError):
         reduce_validation(0.0, [0.0], 0)
+
+
+def _val_driver_worker(rank, world, port, out):
+    """validation_sam(shard=True) on 2 ranks == the single-process call (host logic; native ops -> torch statements)"""
+    import pytest
+    import ref_ops
+    from oracle.config import get_config
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    import medsam2_b200
+    from medsam2_b200.validation import validation_sam
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(4)
+    mpatch = pytest.MonkeyPatch()
+    ref_ops.install(mpatch)
+    size, T = 512, 2
+    m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_t", device="cpu", hydra_overrides_extra=[f"++model.image_size={size}"])
+    m.load_state_dict(make_state_dict(get_config("sam2_hiera_t")), strict=True)
+    packs = []
+    for seed in (1234, 99):
+        vol, boxes = btcv_volume(T, size, seed, 1)
+        g = torch.Generator().manual_seed(seed)
+        packs.append({"image": vol, "label": {f: {1: (torch.rand(1, size, size, generator=g) > 0.5).float()} for f in range(T)},
+                      "bbox": {f: {1: torch.tensor(boxes[f][0])} for f in range(T)}})
+    packs.append({"image": btcv_volume(T, size, 5, 1)[0], "label": {f: {} for f in range(T)}, "bbox": {}})
+    sharded = validation_sam(m, packs, prompt="bbox", prompt_freq=1, shard=True, device="cpu")
+    ok = True
+    if rank == 0:
+        whole = validation_sam(m, packs, prompt="bbox", prompt_freq=1, device="cpu")
+        ok = abs(sharded[0] - whole[0]) < 1e-9 and all(abs(a - b) < 1e-12 for a, b in zip(sharded[1], whole[1]))
+    both = [None, None]
+    dist.all_gather_object(both, sharded)
+    ok = ok and both[0] == both[1]                                      # every rank holds the same averages
+    out[rank] = bool(ok)
+    mpatch.undo()
+    dist.destroy_process_group()
+
+
+def test_validation_driver_sharded_two_ranks():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_val_driver_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
