@@ -178,7 +178,8 @@ def test_constructor_contract():
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 37, 53), (3, 300, 400), (48, 256, 256), (2, 1024, 1024), (200, 8, 8)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 37, 53), (3, 300, 400), (48, 256, 256), (2, 1024, 1024), (200, 8, 8),
+                                   (3, 8, 2048)])
 def test_gpu_mask_stats_bit_exact(shape):
     from medsam2_b200 import ops
     g = torch.Generator().manual_seed(sum(shape))
