@@ -132,6 +132,57 @@ def fill_holes_in_mask_scores(mask, max_area):
     return torch.where(is_hole, torch.full_like(mask, 0.1), mask)
 
 
+def apply_non_overlapping_constraints(pred_masks):
+    """modeling/sam2_base.py:812-830: per pixel only the object with the highest score keeps it, the others are
+    clamped to <= -10 (ties: the FIRST object, torch.argmax)."""
+    n = pred_masks.size(0)
+    if n == 1:
+        return pred_masks
+    top = torch.argmax(pred_masks, dim=0, keepdim=True)
+    keep = top == torch.arange(n, device=pred_masks.device)[:, None, None, None]
+    return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
+
+
+def postprocess_masks(masks, orig_hw, mask_threshold=0.0, max_hole_area=0.0, max_sprinkle_area=0.0):
+    """utils/transforms.py:74-99.  Note the reference's order: the sprinkle test runs on the components of the
+    ORIGINAL scores (`mask_flat` is taken before the holes are filled), its result is applied on top."""
+    masks = masks.float()
+    flat = masks.flatten(0, 1).unsqueeze(1)
+
+    def cc(x):
+        lab, area = connected_components_np(x.cpu().numpy().astype(np.uint8))
+        return torch.from_numpy(lab).to(masks.device), torch.from_numpy(area).to(masks.device)
+    if max_hole_area > 0:
+        lab, area = cc(flat <= mask_threshold)
+        hole = ((lab > 0) & (area <= max_hole_area)).reshape_as(masks)
+        masks = torch.where(hole, torch.full_like(masks, mask_threshold + 10.0), masks)
+    if max_sprinkle_area > 0:
+        lab, area = cc(flat > mask_threshold)
+        spr = ((lab > 0) & (area <= max_sprinkle_area)).reshape_as(masks)
+        masks = torch.where(spr, torch.full_like(masks, mask_threshold - 10.0), masks)
+    return F.interpolate(masks, tuple(orig_hw), mode="bilinear", align_corners=False)
+
+
+def load_video_frames(video_path, image_size, img_mean=(0.485, 0.456, 0.406), img_std=(0.229, 0.224, 0.225)):
+    """utils/misc.py:92-101,163-212: "<index>.jpg" files sorted by index; PIL decode -> RGB -> PIL resize (default
+    resampling) -> /255 (float64, stored as fp32) -> (x - mean) / std.  -> (frames fp32 [T,3,S,S], video H, video W)."""
+    import os
+    from PIL import Image
+    names = [p for p in os.listdir(video_path) if os.path.splitext(p)[-1] in (".jpg", ".jpeg", ".JPG", ".JPEG")]
+    names.sort(key=lambda p: int(os.path.splitext(p)[0]))
+    if not names:
+        raise RuntimeError(f"no images found in {video_path}")
+    frames = torch.zeros(len(names), 3, image_size, image_size, dtype=torch.float32)
+    for n, name in enumerate(names):
+        pil = Image.open(os.path.join(video_path, name))
+        arr = np.array(pil.convert("RGB").resize((image_size, image_size))) / 255.0
+        frames[n] = torch.from_numpy(arr).permute(2, 0, 1)
+        w, h = pil.size
+    frames -= torch.tensor(img_mean, dtype=torch.float32)[:, None, None]
+    frames /= torch.tensor(img_std, dtype=torch.float32)[:, None, None]
+    return frames, h, w
+
+
 # --------------------------------------------------------------------------------------
 # the model
 # --------------------------------------------------------------------------------------
@@ -722,6 +773,18 @@ class OracleVideoPredictor:
         st["output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
         st["temp_output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
         return idx
+
+    def reset_state(self, st):
+        """sam2_video_predictor.py:1239-1268."""
+        for k in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj",
+                  "obj_id_to_idx", "obj_idx_to_id"):
+            st[k].clear()
+        st["obj_ids"] = []
+        for d in (st["output_dict"], st["consolidated_frame_inds"]):
+            d["cond_frame_outputs"].clear()
+            d["non_cond_frame_outputs"].clear()
+        st["tracking_has_started"] = False
+        st["frames_already_tracked"].clear()
 
     def _image_feature(self, st, frame_idx, batch_size):
         """sam2_video_predictor.py:1270-1300 (1-frame cache)."""

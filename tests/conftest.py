@@ -37,3 +37,23 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+# ------------------------------------------------------------------ measured parity errors (profiles/r2_parity_table.txt)
+_PARITY = {}
+
+
+def record_parity(tag, values):
+    """tests call this with their measured max-abs errors; with MS2_PARITY_TABLE=<path> the session writes them there."""
+    _PARITY[tag] = values
+
+
+def pytest_sessionfinish(session, exitstatus):
+    path = os.environ.get("MS2_PARITY_TABLE")
+    if not path or not _PARITY:
+        return
+    import json
+    with open(path, "w") as fh:
+        for tag in sorted(_PARITY):
+            fh.write(json.dumps({"case": tag, **{k: (round(v, 7) if isinstance(v, float) else v)
+                                                 for k, v in _PARITY[tag].items()}}) + "\n")

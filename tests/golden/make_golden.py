@@ -7,12 +7,15 @@ Run in the build container only (`python tests/golden/make_golden.py`); the GPU 
 What is dumped (all fp32, sub-sampled where large so the directory stays < 10 MB):
   state_dict_<cfg>.json      names + shapes of the reference state_dict (checkpoint layout)
   image_hiera_t_1024.npz     config 1: set_image + predict(point) on a 1024² random image
-  image_hiera_s_1024.npz     config 2 (B=2): set_image_batch + predict_batch on fundus images
+  image_hiera_s_1024.npz     config 2 (B=4): set_image_batch + predict_batch on fundus images
   video_hiera_s_512.npz      config 3 shape, shrunk: 7 slices @512², bbox on 0,2,4, 1 object
   video_hiera_t_512_2obj.npz 2 objects, object 2 absent on slice 2 (mask prompt of zeros)
   modules_hiera_t.npz        per-module known answers (memory attention / encoder, decoder)
   amg_hiera_t_1024.npz        SAM2AutomaticMaskGenerator.generate records + utils/amg.py helper answers
   func2d_hiera_t_512.npz     the 2D memory-bank validation step of func_2d/function.py:423-534 (tests/func2d_replay.py)
+  video_clicks_hiera_t_512.npz click prompts, refinement click, reverse propagation, reset_state + second session
+  postprocess_cases.npz      SAM2Transforms.postprocess_masks (hole / sprinkle) and _apply_non_overlapping_constraints
+  ingest_jpeg.npz            load_video_frames / AsyncVideoFrameLoader on a JPEG directory (JPEG bytes inside)
   cc_*.npz                   connected-component labels from a transliteration of the .cu kernels
 """
 
@@ -186,9 +189,9 @@ def golden_image_s():
     from sam2_train.sam2_image_predictor import SAM2ImagePredictor
     load_seeded(m)
     pred = SAM2ImagePredictor(m)
-    imgs, pts = fundus_images(2, 1024, 0)
+    imgs, pts = fundus_images(4, 1024, 0)          # BASELINE configs[1]: batch of 4
     pred.set_image_batch(imgs)
-    masks, ious, low = pred.predict_batch(point_coords_batch=pts, point_labels_batch=[np.array([1])] * 2,
+    masks, ious, low = pred.predict_batch(point_coords_batch=pts, point_labels_batch=[np.array([1])] * 4,
                                           multimask_output=True, return_logits=True)
     out = {"image_embed_sub": npy(sub(pred._features["image_embed"], 4)),
            "low_res": np.stack(low), "ious": np.stack(ious)}
@@ -298,6 +301,113 @@ def golden_func2d():
         out[f"{tag}/maskmem_pos_sub"] = npy(r["maskmem_pos"][..., ::2, ::2])
     np.savez_compressed(f"{OUT}/func2d_hiera_t_512.npz", **out)
     print("func2d", {k: v.shape for k, v in out.items()})
+
+
+def golden_video_clicks():
+    """Click prompts (func_3d/function.py:241-251: train_add_new_points, clear_old_points=False), a refinement click on an
+    already prompted frame (prev_sam_mask_logits path, sam2_video_predictor.py:355-372), forward AND reverse propagation
+    from a middle slice (sam2_video_predictor.py:1041-1123), then reset_state (:1424-1441) and a second session on the same
+    state with a box + a click.  hiera_t, 512^2, 6 slices, 1 object."""
+    size, T = 512, 6
+    m = load_reference("sam2_hiera_t", video=True, image_size=size)
+    load_seeded(m)
+    vol, boxes = btcv_volume(T, size, 55, 1)
+    st = m.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
+    st["device"] = st["storage_device"] = torch.device("cpu")
+    out = {}
+
+    def centre(f):
+        x0, y0, x1, y1 = boxes[f][0]
+        return [(x0 + x1) / 2.0, (y0 + y1) / 2.0]
+
+    def dump(tag, frames):
+        od = st["output_dict"]
+        for f in frames:
+            o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+            out[f"{tag}/pred_masks_{f}"] = npy(o["pred_masks"])
+            out[f"{tag}/obj_ptr_{f}"] = npy(o["obj_ptr"])
+    with torch.no_grad():
+        c2 = centre(2)
+        _, _, vr = m.train_add_new_points(inference_state=st, frame_idx=2, obj_id=1, points=torch.tensor([c2]),
+                                          labels=torch.tensor([1], dtype=torch.int32), clear_old_points=False)
+        out["a/click1_video_res_sub"] = npy(sub(vr, 4))
+        _, _, vr = m.train_add_new_points(inference_state=st, frame_idx=2, obj_id=1,
+                                          points=torch.tensor([[c2[0] + 150.0, c2[1] + 120.0]]),
+                                          labels=torch.tensor([0], dtype=torch.int32), clear_old_points=False)
+        out["a/click2_video_res_sub"] = npy(sub(vr, 4))
+        fwd = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=2)}
+        rev = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=2, reverse=True)}
+        out["a/fwd_frames"] = np.array(sorted(fwd))
+        out["a/rev_frames"] = np.array(sorted(rev))
+        out["a/video_res_sub"] = np.stack([npy(sub(fwd[f] if f in fwd else rev[f], 4)) for f in range(T)])
+        dump("a", range(T))
+        m.reset_state(st)
+        m.train_add_new_bbox(inference_state=st, frame_idx=0, obj_id=7, bbox=torch.tensor(boxes[0][0]), clear_old_points=False)
+        m.train_add_new_points(inference_state=st, frame_idx=3, obj_id=7, points=torch.tensor([centre(3)]),
+                               labels=torch.tensor([1], dtype=torch.int32), clear_old_points=False)
+        b = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0, max_frame_num_to_track=4)}
+        out["b/frames"] = np.array(sorted(b))
+        out["b/video_res_sub"] = np.stack([npy(sub(b[f], 4)) for f in sorted(b)])
+        dump("b", sorted(b))
+    np.savez_compressed(f"{OUT}/video_clicks_hiera_t_512.npz", **out)
+    print("video_clicks", out["a/fwd_frames"], out["a/rev_frames"], out["b/frames"])
+
+
+def golden_postprocess():
+    """SAM2Transforms.postprocess_masks with hole / sprinkle removal (utils/transforms.py:74-99) and
+    SAM2Base._apply_non_overlapping_constraints (modeling/sam2_base.py:812-830) on seeded logits."""
+    load_reference("sam2_hiera_t", video=False)         # installs the _C shim (scipy CC restatement)
+    from sam2_train.utils.transforms import SAM2Transforms
+    from sam2_train.modeling.sam2_base import SAM2Base
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    # smooth logits with speckle so that small holes and sprinkles exist
+    base = torch.nn.functional.interpolate(torch.randn(3, 2, 16, 16, generator=g), size=(64, 64), mode="bilinear")
+    speck = (torch.rand(3, 2, 64, 64, generator=g) < 0.04).float() * torch.randn(3, 2, 64, 64, generator=g).sign() * 3.0
+    masks = base + speck
+    out["pp/masks"] = npy(masks)
+    for tag, (ha, sa, thr) in {"h8_s4": (8.0, 4.0, 0.0), "h8_s0": (8.0, 0.0, 0.0), "h3_s6_t05": (3.0, 6.0, 0.5)}.items():
+        tr = SAM2Transforms(resolution=1024, mask_threshold=thr, max_hole_area=ha, max_sprinkle_area=sa)
+        out[f"pp/{tag}"] = npy(tr.postprocess_masks(masks.clone(), (96, 80)))
+    for n in (1, 2, 5):
+        pm = torch.randn(n, 1, 48, 40, generator=g) * 4
+        pm[:, :, :4] = pm[:1, :, :4]                     # ties between objects: argmax takes the first
+        out[f"no/in_{n}"] = npy(pm)
+        out[f"no/out_{n}"] = npy(SAM2Base._apply_non_overlapping_constraints(None, pm.clone()))
+    np.savez_compressed(f"{OUT}/postprocess_cases.npz", **out)
+    print("postprocess", {k: v.shape for k, v in out.items()})
+
+
+def golden_ingest():
+    """Frame ingest from a JPEG directory (utils/misc.py:92-212): `load_video_frames` sync and async
+    (`AsyncVideoFrameLoader`).  The JPEG files themselves are stored in the fixture (bytes), so the test recreates the
+    directory and decodes with the same PIL."""
+    import io
+    import tempfile
+    from PIL import Image
+    load_reference("sam2_hiera_t", video=False)
+    import sam2_train.utils.misc as rm
+    rm.tqdm = lambda x, **k: x
+    rng = np.random.default_rng(3)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for i in range(5):
+            yy, xx = np.mgrid[0:80, 0:96]
+            img = np.stack([(xx * 2 + i * 9) % 256, (yy * 3 + i * 5) % 256, ((xx + yy) * 2) % 256], -1).astype(np.float32)
+            img = np.clip(img + rng.normal(0, 6, img.shape), 0, 255).astype(np.uint8)
+            buf = io.BytesIO()
+            Image.fromarray(img).save(buf, format="JPEG", quality=90)
+            out[f"jpeg_{i}"] = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+            open(os.path.join(d, f"{i}.jpg"), "wb").write(buf.getvalue())
+        images, vh, vw = rm.load_video_frames(d, image_size=64, offload_video_to_cpu=True)
+        out["sync"] = npy(images)
+        out["hw"] = np.array([vh, vw])
+        lazy, vh2, vw2 = rm.load_video_frames(d, image_size=64, offload_video_to_cpu=True, async_loading_frames=True)
+        lazy.thread.join()
+        out["async"] = np.stack([npy(lazy[i]) for i in range(len(lazy))])
+        assert (vh2, vw2) == (vh, vw)
+    np.savez_compressed(f"{OUT}/ingest_jpeg.npz", **out)
+    print("ingest", out["sync"].shape, out["hw"], float(np.abs(out["sync"] - out["async"]).max()))
 
 
 # thresholds sit in gaps of the candidate statistics of the seeded random-weight model (predicted IoU: 16 values >= 0.5238, the
@@ -496,5 +606,11 @@ if __name__ == "__main__":
         golden_image_s()
     if "video_s" in which:
         golden_video("sam2_hiera_s", 512, 7, 1, (0, 2, 4), (), "video_hiera_s_512.npz", 1234)
+    if "video_clicks" in which:
+        golden_video_clicks()
+    if "postprocess" in which:
+        golden_postprocess()
+    if "ingest" in which:
+        golden_ingest()
     if "video_t2" in which:
         golden_video("sam2_hiera_t", 512, 6, 2, (0, 3), ((3, 1),), "video_hiera_t_512_2obj.npz", 77)

@@ -23,6 +23,11 @@ def _close(a, b, tol, what):
     b = np.asarray(b, np.float32)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     err = float(np.abs(a - b).max()) if a.size else 0.0
+    from conftest import _PARITY
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split("::")[-1].split(" ")[0]
+    d = _PARITY.setdefault(test, {})
+    d[what] = max(err, d.get(what, 0.0))
+    d.setdefault("tol", {})[what] = tol
     assert err <= tol, f"{what}: max abs err {err} > {tol}"
 
 

@@ -103,10 +103,10 @@ def test_image_predictor_hiera_s_batch():
     cfg = get_config("sam2_hiera_s")
     m = OracleSAM2(cfg, make_state_dict(cfg))
     p = OracleImagePredictor(m)
-    imgs, pts = fundus_images(2, 1024, 0)
+    imgs, pts = fundus_images(4, 1024, 0)
     p.set_image_batch(imgs)
     _close(p._features["image_embed"][..., ::4, ::4], z["image_embed_sub"], 5e-4, "image_embed")
-    masks, ious, low = p.predict_batch(pts, [np.array([1])] * 2, multimask_output=True, return_logits=True)
+    masks, ious, low = p.predict_batch(pts, [np.array([1])] * 4, multimask_output=True, return_logits=True)
     _close(np.stack(low), z["low_res"], 1e-4, "low_res")
     _close(np.stack(ious), z["ious"], 1e-5, "ious")
 
@@ -142,3 +142,64 @@ def test_video_predictor_matches_reference(case):
         _close(o["obj_ptr"], z[f"obj_ptr_{f}"], 1e-3, f"obj_ptr frame {f}")
         _close(o["maskmem_features"][..., ::4, ::4], z[f"maskmem_sub_{f}"], 1e-3, f"maskmem frame {f}")
         _close(outs[f][..., ::4, ::4], z["video_res_masks_sub"][f], 2e-3, f"video masks frame {f}")
+
+
+def test_video_clicks_reverse_reset_match_reference():
+    """click prompts + refinement click + forward/reverse propagation + reset_state + second session
+    (golden: video_clicks_hiera_t_512.npz, made by make_golden.py video_clicks on the real reference)."""
+    z = np.load(f"{G}/video_clicks_hiera_t_512.npz")
+    size, T = 512, 6
+    cfg = get_config("sam2_hiera_t", image_size=size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg)))
+    vol, boxes = btcv_volume(T, size, 55, 1)
+    st = vp.init_state(vol, size, size)
+
+    def centre(f):
+        x0, y0, x1, y1 = boxes[f][0]
+        return [(x0 + x1) / 2.0, (y0 + y1) / 2.0]
+    c2 = centre(2)
+    _, _, vr = vp.add_new_points(st, 2, 1, [c2], [1], clear_old_points=False)
+    _close(vr[..., ::4, ::4], z["a/click1_video_res_sub"], 2e-3, "first click")
+    _, _, vr = vp.add_new_points(st, 2, 1, [[c2[0] + 150.0, c2[1] + 120.0]], [0], clear_old_points=False)
+    _close(vr[..., ::4, ::4], z["a/click2_video_res_sub"], 2e-3, "refinement click")
+    fwd = {f: mk for f, _, mk in vp.propagate_in_video(st, start_frame_idx=2)}
+    rev = {f: mk for f, _, mk in vp.propagate_in_video(st, start_frame_idx=2, reverse=True)}
+    assert sorted(fwd) == list(z["a/fwd_frames"]) and sorted(rev) == list(z["a/rev_frames"])
+    od = st["output_dict"]
+    for f in range(T):
+        o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+        _close(o["pred_masks"], z[f"a/pred_masks_{f}"], 2e-3, f"a pred_masks {f}")
+        _close(o["obj_ptr"], z[f"a/obj_ptr_{f}"], 1e-3, f"a obj_ptr {f}")
+        _close((fwd[f] if f in fwd else rev[f])[..., ::4, ::4], z["a/video_res_sub"][f], 2e-3, f"a video res {f}")
+    vp.reset_state(st)
+    vp.add_new_bbox(st, 0, 7, boxes[0][0], clear_old_points=False)
+    vp.add_new_points(st, 3, 7, [centre(3)], [1], clear_old_points=False)
+    b = {f: mk for f, _, mk in vp.propagate_in_video(st, start_frame_idx=0, max_frame_num_to_track=4)}
+    assert sorted(b) == list(z["b/frames"])
+    for i, f in enumerate(sorted(b)):
+        o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+        _close(o["pred_masks"], z[f"b/pred_masks_{f}"], 2e-3, f"b pred_masks {f}")
+        _close(b[f][..., ::4, ::4], z["b/video_res_sub"][i], 2e-3, f"b video res {f}")
+
+
+def test_postprocess_and_non_overlap_match_reference():
+    from oracle.sam2_oracle import apply_non_overlapping_constraints, postprocess_masks
+    z = np.load(f"{G}/postprocess_cases.npz")
+    masks = torch.from_numpy(z["pp/masks"])
+    for tag, (ha, sa, thr) in {"h8_s4": (8.0, 4.0, 0.0), "h8_s0": (8.0, 0.0, 0.0), "h3_s6_t05": (3.0, 6.0, 0.5)}.items():
+        got = postprocess_masks(masks.clone(), (96, 80), thr, ha, sa)
+        _close(got, z[f"pp/{tag}"], 1e-6, f"postprocess {tag}")
+    for n in (1, 2, 5):
+        got = apply_non_overlapping_constraints(torch.from_numpy(z[f"no/in_{n}"]))
+        assert np.array_equal(got.numpy(), z[f"no/out_{n}"]), n
+
+
+def test_ingest_jpeg_matches_reference(tmp_path):
+    from oracle.sam2_oracle import load_video_frames
+    z = np.load(f"{G}/ingest_jpeg.npz")
+    for i in range(5):
+        (tmp_path / f"{i}.jpg").write_bytes(z[f"jpeg_{i}"].tobytes())
+    frames, h, w = load_video_frames(str(tmp_path), 64)
+    assert (h, w) == tuple(z["hw"])
+    _close(frames, z["sync"], 1e-6, "sync loader")
+    _close(frames, z["async"], 1e-6, "async loader")
