@@ -48,6 +48,12 @@ def parse():
     ap.add_argument("--config", default="sam2_hiera_s")
     ap.add_argument("--cpu-sample-slices", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager bf16 leg (gpu_baseline)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison outside the timed region")
+    ap.add_argument("--parity-slices", type=int, default=24, help="slices of the volume the fp32 oracle is run on for the check")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the config-5 (one long volume, strong scaling) sub-record")
+    ap.add_argument("--strong-slices", type=int, default=512)
+    ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--feature-cache", type=int, default=0, help="0 = one entry per slice (no double encode)")
     ap.add_argument("--kernel-table", default="", help="write a CUPTI per-kernel time table of one extra step here")
@@ -200,12 +206,13 @@ def main_reference(args):
         rates.append(r)
         secs.append(s)
     value = n * args.steps / sum(secs)
-    sample = (f"first {n} slices of the config-3 volume (bbox every {args.prompt_every}), oracle port of the reference, "
-              f"fp32, {cores} host threads")
+    sample = cpu_sample_text(args, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2] sample: {n} slices {args.size}^2, {args.config}, CPU"},
+            "config": {"workload": workload_text(args),
+                       "cpu_sample": f"timed on the first {n} slices of that volume (a shorter memory bank than the full volume: "
+                                     f"flatters the CPU); N>1: one CPU process on rank 0, the CPU arm does not use the GPUs"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -248,6 +255,190 @@ def main_image(args):
                                              "click each, multimask_output, masks returned to the host as numpy"}}))
 
 
+def _sync_all(world):
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def _timed(fn, steps, world):
+    """CUDA events around `steps` calls, barrier + synchronize on both sides, max over ranks -> ms."""
+    import torch.distributed as dist
+    _sync_all(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    _sync_all(world)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _build_predictor(args, T, prefetch):
+    import medsam2_b200
+    from oracle.config import get_config          # config table only (layout of the synthetic weights)
+    from oracle.weights import param_spec
+    from synth_data import seeded_weights
+    S = args.size
+    cache = args.feature_cache if args.feature_cache > 0 else T
+    model = medsam2_b200.build_sam2_video_predictor(
+        args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
+                                                      f"++model.feature_encode_batch={args.encode_batch}",
+                                                      f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}",
+                                                      f"++model.feature_prefetch={'true' if prefetch else 'false'}"])
+    model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
+    return model
+
+
+def _strong_record(args, world, rank):
+    """BASELINE configs[4] under torchrun: ONE `--strong-slices`-slice volume on all ranks — slice encoding sharded by
+    contiguous blocks + all-gather of the pyramid, memory bank dealt to the ranks (split-KV memory cross-attention, one
+    exchange of the partials per layer), all ranks track in lockstep.  Strong scaling: value = slices / max-rank time."""
+    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from synth_data import btcv_volume
+    T, S = args.strong_slices, args.size
+    model = _build_predictor(args, T, prefetch=False)
+    shard = shard_memory_attention(model)
+    vol, boxes = btcv_volume(T, S, 4321, 1)
+    vol_host = vol.pin_memory()
+    vol_dev = vol.cuda()
+    del vol
+    out_host = torch.empty((T, S, S), dtype=torch.uint8).pin_memory()
+
+    def run(v, lazy_host):
+        st = model.val_init_state(imgs_tensor=v, video_height=S, video_width=S, offload_video_to_cpu=lazy_host,
+                                  async_loading_frames=lazy_host)
+        encode_volume_sharded(model, st)                      # each rank uploads + encodes only its block of slices
+        masks = [None] * T
+        for f in prompt_frames(T, args.prompt_every):
+            model.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]),
+                                     clear_old_points=False)
+        for f, _, m in model.propagate_in_video(st, start_frame_idx=0):
+            masks[f] = m
+        return masks
+
+    def step_resident():
+        run(vol_dev, False)
+
+    def step_e2e():
+        masks = run(vol_host, True)
+        if rank == 0:
+            out_host.copy_(torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    steps = max(1, min(args.steps, args.strong_steps))
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_resident()
+    ex0 = shard.exchanges if shard is not None else 0
+    ms = _timed(step_resident, steps, world)
+    exchanges = ((shard.exchanges - ex0) // steps) if shard is not None else 0
+    step_e2e()
+    ms_e2e = _timed(step_e2e, steps, world)
+    rec = {"metric": METRIC, "value": T * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+           "ms_per_step": ms / steps, "scaling": "strong",
+           "config": {"workload": f"BASELINE configs[4]: ONE {T}-slice {S}^2 volume, {args.config}, bbox every "
+                                  f"{args.prompt_every} slices; slice encoding sharded by contiguous blocks + NCCL all-gather of "
+                                  f"the FPN pyramid; memory bank dealt to the ranks (split-KV cross-attention), lockstep tracking"},
+           "e2e": {"value": T * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": vol_host.numel() * 4, "d2h_bytes_per_step": out_host.numel(),
+                   "note": "each rank uploads only the slice block it encodes"},
+           "partial_exchanges_per_step": exchanges}
+    del model, vol_dev, vol_host
+    torch.cuda.empty_cache()
+    return rec
+
+
+def _gpu_baseline(args, steps):
+    """The reference's algorithm as a user of the reference gets it on this GPU today: the oracle port's torch modules
+    (cuBLAS / SDPA / cuDNN kernels) in eager mode under bf16 autocast (train_3d.py:28,57), same volume, same prompts.
+    -> (record, {frame: low-res logits} of the last run)."""
+    from oracle.config import get_config
+    from oracle.sam2_oracle import OracleSAM2, OracleVideoPredictor
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    cfg = get_config(args.config, image_size=args.size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg), device="cuda"))
+    vol, boxes = btcv_volume(args.slices, args.size, 1234, 1)
+    vol = vol.cuda()
+    keep = {}
+
+    def run():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            st = vp.init_state(vol, args.size, args.size)
+            for f in prompt_frames(args.slices, args.prompt_every):
+                vp.add_new_bbox(st, f, 1, boxes[f][0], clear_old_points=False)
+            for f, _, m in vp.propagate_in_video(st, start_frame_idx=0):
+                keep[f] = m
+    run()
+    ms = _timed(run, steps, 1)
+    rec = {"value": args.slices * steps / (ms * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+           "kind": "oracle port of the reference in torch eager (cuBLAS/SDPA/cuDNN), bf16 autocast, cuda:0, same volume and "
+                   "prompts (feature cache 1 as the reference: prompted slices are encoded twice)"}
+    return rec, {f: m.float() for f, m in keep.items()}
+
+
+def _parity_check(args, model, step_masks, torch_bf16_masks):
+    """Outside the timed region: (a) the masks of the benchmarked step against the torch-eager bf16 run of the same volume
+    (two bf16 implementations, free-running over the whole volume); (b) the product against the fp32 oracle on the first
+    `--parity-slices` slices of the same volume (free-running, low-res logits away from hole-filled pixels)."""
+    from oracle.config import get_config
+    from oracle.sam2_oracle import OracleSAM2, OracleVideoPredictor
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    out = {}
+    if torch_bf16_masks:
+        agree, mad = 1.0, 0.0
+        for f, ref in torch_bf16_masks.items():
+            got = step_masks[f].float()
+            agree = min(agree, float(((got > 0) == (ref > 0)).float().mean().item()))
+            mad = max(mad, float((got - ref).abs().mean().item()))
+        out["benchmarked_step_vs_torch_bf16"] = {"frames": len(torch_bf16_masks), "sign_agree_min": agree,
+                                                 "mean_abs_diff_max": mad}
+    n = min(args.parity_slices, args.slices)
+    cfg = get_config(args.config, image_size=args.size)
+    vp = OracleVideoPredictor(OracleSAM2(cfg, make_state_dict(cfg), device="cuda"))
+    vol, boxes = btcv_volume(args.slices, args.size, 1234, 1)
+    vol = vol[:n].cuda()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            st = vp.init_state(vol, args.size, args.size)
+            for f in prompt_frames(n, args.prompt_every):
+                vp.add_new_bbox(st, f, 1, boxes[f][0], clear_old_points=False)
+            for _ in vp.propagate_in_video(st, start_frame_idx=0):
+                pass
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    pst = model.val_init_state(imgs_tensor=vol, video_height=args.size, video_width=args.size)
+    for f in prompt_frames(n, args.prompt_every):
+        model.train_add_new_bbox(inference_state=pst, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+    for _ in model.propagate_in_video(pst, start_frame_idx=0):
+        pass
+    worst, agree = 0.0, 1.0
+    for f in range(n):
+        o = st["output_dict"]["cond_frame_outputs"].get(f) or st["output_dict"]["non_cond_frame_outputs"].get(f)
+        p = pst["output_dict"]["cond_frame_outputs"].get(f) or pst["output_dict"]["non_cond_frame_outputs"].get(f)
+        a, b = p["pred_masks"].float(), o["pred_masks"].float()
+        filled = ((a - 0.1).abs() < 1e-6) | ((b - 0.1).abs() < 1e-6)
+        worst = max(worst, float((a - b).abs().masked_fill(filled, 0.0).max().item()))
+        agree = min(agree, float(((a > 0) == (b > 0)).float().mean().item()))
+    tol = 1e-2 if args.dtype == "bf16" else 1e-3
+    out["vs_fp32_oracle"] = {"slices": n, "regime": "free-running", "low_res_logit_max_abs_err": worst,
+                             "sign_agree_min": agree, "tolerance": tol}
+    ok = worst <= tol and agree >= 0.995
+    if torch_bf16_masks:
+        ok = ok and out["benchmarked_step_vs_torch_bf16"]["sign_agree_min"] >= 0.98
+    return ok, out
+
+
 def main_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,22 +449,14 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import medsam2_b200
     from medsam2_b200 import native, ops
-    from oracle.config import get_config          # config table only (layout of the synthetic weights)
-    from oracle.weights import param_spec
-    from synth_data import btcv_volume, seeded_weights
+    from synth_data import btcv_volume
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     medsam2_b200.set_compute_dtype(dtype)
     T, S = args.slices, args.size
-    cache = args.feature_cache if args.feature_cache > 0 else T
-    model = medsam2_b200.build_sam2_video_predictor(
-        args.config, device="cuda", hydra_overrides_extra=[f"++model.image_size={S}", f"++model.feature_cache_size={cache}",
-                                                      f"++model.feature_encode_batch={args.encode_batch}",
-                                                      f"++model.use_cuda_graphs={'false' if args.no_graphs else 'true'}",
-                                                      f"++model.feature_prefetch={'false' if (args.no_prefetch or args.shard_encode) else 'true'}"])
-    model.load_state_dict(seeded_weights(param_spec(get_config(args.config))), strict=True)
     shard_encode = args.shard_encode and world > 1
     shard_attention = shard_encode and args.shard_attention
+    model = _build_predictor(args, T, prefetch=not (args.no_prefetch or shard_encode))
     if shard_attention:
         from medsam2_b200.parallel import shard_memory_attention
         shard_memory_attention(model)
@@ -283,26 +466,8 @@ def main_ours(args):
     vol_dev = vol.cuda()
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     def timed(fn, steps):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return _timed(fn, steps, world)
 
     def run_sharded(v):
         from medsam2_b200.parallel import encode_volume_sharded
@@ -318,12 +483,14 @@ def main_ours(args):
                 masks[f] = m
         return masks
 
+    last = {}
+
     def step_resident():
         l2_flush.zero_()
         if shard_encode:
-            run_sharded(vol_dev)
+            last["masks"] = run_sharded(vol_dev)
         else:
-            run_volume(model, vol_dev, boxes, S, args.prompt_every)
+            last["masks"] = run_volume(model, vol_dev, boxes, S, args.prompt_every)
 
     out_host = torch.empty((T, S, S), dtype=torch.uint8).pin_memory()
 
@@ -350,6 +517,7 @@ def main_ours(args):
     n0 = native.launch_count
     ms = timed(step_resident, args.steps)
     launches = native.launch_count - n0
+    step_masks = {f: m.clone() for f, m in enumerate(last["masks"]) if m is not None} if rank == 0 else {}
     for _ in range(min(args.warmup, 2)):       # the host-upload path has its own first-use allocations (1.2 GB frame
         step_e2e()                             # buffer, upload-stream pool): warm it up like the resident path
     ms_e2e = timed(step_e2e, args.steps)
@@ -384,10 +552,17 @@ def main_ours(args):
         with open(args.kernel_table, "w") as fh:
             fh.write(f"# CUPTI kernel times of one step ({T} slices); total device time {tot / 1e3:.2f} ms\n")
             fh.write("# share%   total_ms   calls   avg_us   kernel\n")
-            for e in rows[:60]:
+            for e in rows[:80]:
                 fh.write(f"{100 * e.device_time_total / tot:6.2f} {e.device_time_total / 1e3:10.3f} {e.count:7d} "
                          f"{e.device_time_total / max(e.count, 1):8.1f}   {e.key[:110]}\n")
-    clk = clocks.stop() if rank == 0 else None
+
+    # ---- config 5 under torchrun: one long volume over all ranks (strong scaling), appended to the same JSON line
+    strong = None
+    if world > 1 and not shard_encode and not args.no_strong:
+        del vol_dev, vol_host, l2_flush
+        last.clear()
+        torch.cuda.empty_cache()
+        strong = _strong_record(args, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -409,10 +584,13 @@ def main_ours(args):
         # reference's formulation of the same attention is 4*Lq*Lk*256 (SURVEY §8(d) "canonical")
         canon = achieved * (512.0 / 320.0) if name == "mem_cross_attention" else achieved
         meta = {}
-        try:      # kernel name + dram traffic of the dominant kernel from the committed ncu capture
-            meta = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json"))).get(name, {})
-        except Exception:
-            pass
+        for fn_ in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):
+            try:      # kernel name + dram traffic of the dominant kernel from the committed ncu capture
+                meta = json.load(open(os.path.join(ROOT, "profiles", fn_))).get(name, {})
+                if meta:
+                    break
+            except Exception:
+                pass
         roofline = {"bound": "tensor", "kernel": meta.get("kernel", name),
                     "achieved": achieved, "achieved_canonical_flops": canon, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
@@ -422,34 +600,57 @@ def main_ours(args):
                     "profiled_step_ms": ms_prof,
                     "all": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0),
                                 "n": v["n"]} for k, v in prof.items()}}
+    gpu_base, parity_ok, parity = None, None, None
+    if world == 1 and not shard_encode:
+        del l2_flush
+        torch_masks = {}
+        if not args.no_gpu_baseline:
+            gpu_base, torch_masks = _gpu_baseline(args, max(3, min(args.steps, 3)))
+            torch.cuda.empty_cache()
+        if not args.no_parity_check:
+            with torch.inference_mode():
+                parity_ok, parity = _parity_check(args, model, step_masks, torch_masks)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         r, secs, cores = cpu_oracle_rate(args, args.cpu_sample_slices)
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {args.cpu_sample_slices} slices of the same volume (bbox every {args.prompt_every}), "
-                         f"oracle port, fp32, {secs:.1f} s"}
+               "sample": cpu_sample_text(args, cores) + f", {secs:.1f} s"}
     total_slices = T * args.steps * (1 if shard_encode else world)
     line = {"metric": METRIC, "value": total_slices / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if shard_encode else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: {args.config} SAM2VideoPredictor.propagate_in_video, one "
-                                   f"{T}-slice {S}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, "
-                                   f"num_maskmem=7, fill_hole_area=8",
+            "config": {"workload": workload_text(args),
                        "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid; memory bank dealt to the ranks "
-                                    "(split-KV cross-attention, partials all-gathered per layer), all ranks propagate in lockstep"
+                                    "(split-KV cross-attention, partials exchanged per layer), all ranks propagate in lockstep"
                                     if shard_attention else
                                     "one volume: slice encoding sharded + NCCL all-gather of the pyramid, rank 0 propagates"
-                                    if shard_encode else "by volume, no collectives" if world > 1 else "single GPU"),
+                                    if shard_encode else "one volume per GPU (BASELINE configs[3]: by volume, no collectives)"
+                                    if world > 1 else "single GPU"),
                        "encode_batch": args.encode_batch, "cuda_graphs": not args.no_graphs,
                        "encode_prefetch": not args.no_prefetch,
                        "l2": "256 MiB flush buffer written before every step; per-step working set >> L2"},
-            "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel(), "ms_per_step": ms_e2e / args.steps,
-                    "h2d_alone_ms": h2d_ms, "h2d_alone_gbs": vol_host.numel() * 4 / h2d_ms / 1e6},
-            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": {"value": total_slices / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": vol_host_bytes(T, S),
+                    "d2h_bytes_per_step": T * S * S, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_alone_ms": h2d_ms, "h2d_alone_gbs": vol_host_bytes(T, S) / h2d_ms / 1e6},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_baseline": gpu_base, "parity_checked": parity_ok, "parity": parity, "strong": strong}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def vol_host_bytes(T, S):
+    return T * 3 * S * S * 4
+
+
+def workload_text(args):
+    return (f"BASELINE configs[2]: {args.config} SAM2VideoPredictor.propagate_in_video, one {args.slices}-slice "
+            f"{args.size}^2 volume per GPU, bbox every {args.prompt_every} slices, 1 object, num_maskmem=7, fill_hole_area=8")
+
+
+def cpu_sample_text(args, cores):
+    return (f"first {args.cpu_sample_slices} slices of the same volume (bbox every {args.prompt_every}), oracle port of the "
+            f"reference, fp32, {cores} host threads")
 
 
 if __name__ == "__main__":

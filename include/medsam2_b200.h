@@ -137,10 +137,10 @@ int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int C, ms2_str
 int ms2_patch_embed(const float* img, const float* w, const float* bias, const float* pos, float* out,
                     int B, int Hin, int Win, int Cout, ms2_stream_t stream);
 
-/* bf16 path of the same conv: NCHW fp32 image -> bf16 im2col rows [B*Ho*Wo, ldk] (taps in (ky,kx,c) order, zero
+/* bf16 path of the same conv: NCHW image (img_dt fp32 or bf16) -> bf16 im2col rows [B*Ho*Wo, ldk] (taps in (ky,kx,c) order, zero
  * beyond 147; ldk a multiple of 8 >= 152); the contraction then runs in ms2_gemm against the weight re-laid-out to
  * [Cout, ldk], with bias and the pos-embed table as the epilogue residual. */
-int ms2_patch_im2col(const float* img, void* cols, int B, int Hin, int Win, int ldk, ms2_stream_t stream);
+int ms2_patch_im2col(const void* img, int img_dt, void* cols, int B, int Hin, int Win, int ldk, ms2_stream_t stream);
 
 /* ---- elementwise family (fp32 unless noted) */
 /* y = a*x + b*z + c; x fp32 [n]; z fp32 [zn] or NULL, broadcast as z[i mod zn] (zn divides n);
@@ -215,9 +215,11 @@ int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, i
 int ms2_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float* out,
                     int B, int N, int pad, int F, int image_w, int image_h, ms2_stream_t stream);
 
-/* ---- frame ingest (utils/misc.py:215-244, transforms.py:28-42): out fp32 NCHW = (x/255 - mean)/std.
- *      x is fp32 NCHW (video tensor, in_layout 0) or uint8 NHWC (image predictor, in_layout 1). */
-int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, ms2_stream_t stream);
+/* ---- frame ingest (utils/misc.py:92-101 `_load_img_as_tensor`, :215-244 `load_video_frames_from_data`,
+ *      transforms.py:28-42): out NCHW = (x/255 - mean)/std, dtype out_dt (fp32 = the reference's frame dtype; bf16 = the
+ *      cast autocast applies in front of the patch-embed conv, fused here).  x: in_layout 0 = fp32 NCHW (video tensor),
+ *      1 = uint8 NHWC (decoded JPEG / image predictor), 2 = uint8 NCHW (uint8 video tensor). */
+int ms2_normalize_image(const void* x, int in_layout, void* out, int out_dt, int B, int H, int W, ms2_stream_t stream);
 
 /* ---- mask statistics for the stability fallback (mask_decoder.py:269-317): per (b) plane of fp32
  *      logits [N,P]: counts[n,0] = #(x>delta), counts[n,1] = #(x>-delta). */
@@ -234,6 +236,20 @@ int ms2_seg_counts(const float* pred, const float* gt, const float* thr_host, in
  *      (1-y)*x + (1+(pos_weight-1)*y)*(log1p(exp(-|x|)) + max(-x,0)); the caller divides by the element count. */
 int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_weight, double* sums, int N, long P,
                        ms2_stream_t stream);
+
+/* ---- the same scoring straight from LOW-resolution logits (reference repo root: func_3d/function.py:283-305 scores the
+ *      video-resolution logits that sam2_train/sam2_video_predictor.py:724-744 `_get_orig_video_res_output` up-samples
+ *      with F.interpolate(bilinear, align_corners=False)): low fp32 [N,h,w] device planes are up-sampled to H x W on the
+ *      fly (bit-identical to ms2_resize_bilinear), compared with gt fp32 [N,H,W]; counts int32 [N,T,3] as ms2_seg_counts,
+ *      sums fp64 [N] as ms2_bce_logits_sum (NULL: skip the loss).  W % 4 == 0.  The video-resolution logits are never
+ *      written: one pass over gt. */
+int ms2_score_lowres(const float* low, const float* gt, const float* h_thr, int T, float pos_weight, int32_t* counts,
+                     double* sums, int N, int h, int w, int H, int W, ms2_stream_t stream);
+
+/* ---- non-overlapping constraints (reference sam2_train/modeling/sam2_base.py:812-830 `_apply_non_overlapping_constraints`,
+ *      callers sam2_video_predictor.py:742-743, :850-851): in/out fp32 [n_obj, P] device planes (out != in); per pixel the
+ *      FIRST arg-max object keeps its score, every other object gets min(score, -10). */
+int ms2_non_overlap(const float* in, float* out, int n_obj, long P, ms2_stream_t stream);
 
 /* ---- automatic mask generator, per-plane statistics in one pass (automatic_mask_generator.py:300-340; utils/amg.py:158-180
  *      `calculate_stability_score`, :296-348 `batched_mask_to_box`): x fp32 logits [N,H,W]; stats int32 [N,7] =

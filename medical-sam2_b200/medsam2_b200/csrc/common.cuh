@@ -80,6 +80,15 @@ __device__ __forceinline__ float gelu_erf_tanh(float x) {
   return fmaf(hx, t, hx);
 }
 
+// bilinear blend with a fixed operation order and rounding (no compiler-chosen FMA contraction): every kernel that
+// up-samples mask logits (resize.cu, postproc.cu) produces the same bits for the same pixel
+__device__ __forceinline__ float ms2_bilerp(float v00, float v01, float v10, float v11, float lx, float ly) {
+  const float ax = __fsub_rn(1.f, lx), ay = __fsub_rn(1.f, ly);
+  const float top = __fmaf_rn(lx, v01, __fmul_rn(ax, v00));
+  const float bot = __fmaf_rn(lx, v11, __fmul_rn(ax, v10));
+  return __fmaf_rn(ly, bot, __fmul_rn(ay, top));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -321,8 +321,9 @@ dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 // NCHW fp32 image -> bf16 rows [B*Ho*Wo, ldk] of the 7x7/s4/p3 taps in (ky, kx, c) order, zero beyond 147; the
 // contraction itself then runs on the tensor-core GEMM (K = 147 padded to a 16-byte multiple).  One thread = one
 // 16-byte chunk of a row: coalesced stores, gathers served from L1.
+template <typename IN>
 __global__ void __launch_bounds__(256)
-patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ cols, long total_chunks, int Hin, int Win, int Ho,
+patch_im2col_kernel(const IN* __restrict__ img, bf16* __restrict__ cols, long total_chunks, int Hin, int Win, int Ho,
                     int Wo, int chunks) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total_chunks) return;
@@ -331,7 +332,7 @@ patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ cols, long
   const int ox = (int)(row % Wo);
   const long r2 = row / Wo;
   const int oy = (int)(r2 % Ho), b = (int)(r2 / Ho);
-  const float* base = img + (long)b * 3 * Hin * Win;
+  const IN* base = img + (long)b * 3 * Hin * Win;
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -340,7 +341,7 @@ patch_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ cols, long
     if (idx < 147) {
       const int ky = idx / 21, r = idx - ky * 21, kx = r / 3, c = r - kx * 3;
       const int sy = oy * 4 + ky - 3, sx = ox * 4 + kx - 3;
-      if (sy >= 0 && sy < Hin && sx >= 0 && sx < Win) val = __ldg(base + ((long)c * Hin + sy) * Win + sx);
+      if (sy >= 0 && sy < Hin && sx >= 0 && sx < Win) val = to_f(base[((long)c * Hin + sy) * Win + sx]);
     }
     v[e] = val;
   }
@@ -384,14 +385,14 @@ extern "C" int ms2_conv3x3s2_ln_gelu(const float* x, const float* w, const float
   return MS2_OK;
 }
 
-extern "C" int ms2_patch_im2col(const float* img, void* cols, int B, int Hin, int Win, int ldk, void* stream) {
+extern "C" int ms2_patch_im2col(const void* img, int img_dt, void* cols, int B, int Hin, int Win, int ldk, void* stream) {
   MS2_CHECK_ARG(img && cols, "patch_im2col: null pointer");
   MS2_CHECK_ARG(ldk >= 152 && ldk % 8 == 0 && ((uintptr_t)cols % 16 == 0), "patch_im2col: ldk must be a multiple of 8 >= 152");
   const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
   const long total = (long)B * Ho * Wo * (ldk / 8);
   if (!total) return MS2_OK;
-  patch_im2col_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (bf16*)cols, total, Hin, Win, Ho, Wo,
-                                                                               ldk / 8);
+  MS2_DISPATCH_DTYPE(img_dt, T, (patch_im2col_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                    (const T*)img, (bf16*)cols, total, Hin, Win, Ho, Wo, ldk / 8)));
   MS2_CHECK_LAUNCH("patch_im2col_kernel");
   return MS2_OK;
 }

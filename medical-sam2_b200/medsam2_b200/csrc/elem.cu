@@ -287,21 +287,38 @@ __global__ void point_embed_kernel(const float* __restrict__ coords, const int* 
   }
 }
 
-__global__ void normalize_image_kernel(const void* __restrict__ x, int in_layout, float* __restrict__ out, int B,
-                                       int H, int W) {
+// in_layout 0: fp32 NCHW (video tensor), 1: uint8 NHWC (decoded images), 2: uint8 NCHW (uint8 video tensor);
+// OUT = float (the reference's frame dtype) or bf16 (what the patch-embed contraction rounds the frame to anyway under
+// autocast: half the bytes written here and read there).  4 pixels of one row per thread.
+template <typename OUT>
+__global__ void __launch_bounds__(256) normalize_image_kernel(const void* __restrict__ x, int in_layout, OUT* __restrict__ out,
+                                                              int B, int H, int W) {
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
-  const long n = (long)B * 3 * H * W;
+  const int W4 = (W + 3) >> 2;
+  const long n = (long)B * 3 * H * W4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     long t = i;
-    int xw = t % W; t /= W;
-    int yh = t % H; t /= H;
-    int c = t % 3;
-    int b = t / 3;
-    float v;
-    if (in_layout == 0) v = ((const float*)x)[i];
-    else v = (float)((const uint8_t*)x)[(((long)b * H + yh) * W + xw) * 3 + c];
-    out[i] = (v / 255.0f - mean[c]) / stdv[c];
+    const int xq = t % W4; t /= W4;
+    const int yh = t % H; t /= H;
+    const int c = t % 3;
+    const int b = t / 3;
+    const long o0 = (((long)b * 3 + c) * H + yh) * W + 4 * xq;
+    const int cnt = min(4, W - 4 * xq);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (in_layout == 0) {
+      const float* p = (const float*)x + o0;
+      if (cnt == 4 && ((uintptr_t)p & 15) == 0) { const float4 q = __ldcs((const float4*)p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else for (int e = 0; e < cnt; ++e) v[e] = p[e];
+    } else if (in_layout == 2) {
+      const uint8_t* p = (const uint8_t*)x + o0;
+      if (cnt == 4 && ((uintptr_t)p & 3) == 0) { const uchar4 q = *(const uchar4*)p; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else for (int e = 0; e < cnt; ++e) v[e] = (float)p[e];
+    } else {
+      const uint8_t* p = (const uint8_t*)x + (((long)b * H + yh) * W + 4 * xq) * 3 + c;
+      for (int e = 0; e < cnt; ++e) v[e] = (float)p[3 * e];
+    }
+    for (int e = 0; e < cnt; ++e) out[o0 + e] = from_f<OUT>((v[e] / 255.0f - mean[c]) / stdv[c]);
   }
 }
 
@@ -774,11 +791,11 @@ extern "C" int ms2_point_embed(const float* coords, const int* labels, const flo
   MS2_CHECK_LAUNCH("point_embed");
   return MS2_OK;
 }
-extern "C" int ms2_normalize_image(const void* x, int in_layout, float* out, int B, int H, int W, void* stream) {
-  MS2_CHECK_ARG(x && out && (in_layout == 0 || in_layout == 1), "normalize_image: bad args");
-  long n = (long)B * 3 * H * W;
+extern "C" int ms2_normalize_image(const void* x, int in_layout, void* out, int out_dt, int B, int H, int W, void* stream) {
+  MS2_CHECK_ARG(x && out && in_layout >= 0 && in_layout <= 2, "normalize_image: bad args (layout 0 fp32 NCHW, 1 u8 NHWC, 2 u8 NCHW)");
+  long n = (long)B * 3 * H * ((W + 3) / 4);
   if (!n) return MS2_OK;
-  normalize_image_kernel<<<grid_for(n), 256, 0, ST>>>(x, in_layout, out, B, H, W);
+  MS2_DISPATCH_DTYPE(out_dt, T, (normalize_image_kernel<T><<<grid_for(n), 256, 0, ST>>>(x, in_layout, (T*)out, B, H, W)));
   MS2_CHECK_LAUNCH("normalize_image");
   return MS2_OK;
 }

@@ -23,7 +23,7 @@ __global__ void bilinear_kernel(const float* __restrict__ x, float* __restrict__
     const float* p = x + pl * (long)H * W;
     float v00 = p[(long)y0 * W + x0], v01 = p[(long)y0 * W + x1];
     float v10 = p[(long)y1 * W + x0], v11 = p[(long)y1 * W + x1];
-    y[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    y[i] = ms2_bilerp(v00, v01, v10, v11, lx, ly);
   }
 }
 
@@ -49,7 +49,7 @@ __global__ void bilinear_vec4_kernel(const float* __restrict__ x, float* __restr
       const int x0 = (int)sx, x1 = x0 + (x0 < W - 1);
       const float lx = sx - x0;
       const float v00 = p0[x0], v01 = p0[x1], v10 = p1[x0], v11 = p1[x1];
-      o[e] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+      o[e] = ms2_bilerp(v00, v01, v10, v11, lx, ly);
     }
     *(float4*)(y + 4L * i) = make_float4(o[0], o[1], o[2], o[3]);
   }

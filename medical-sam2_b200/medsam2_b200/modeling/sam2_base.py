@@ -103,6 +103,25 @@ class SAM2Base(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    # captured CUDA graphs bake in pointers to kernel-ready parameter copies: any event that can change the parameters
+    # (checkpoint load, a train()/eval() round trip as in the reference's epoch loop, .to()/.cuda()) starts a new
+    # parameter generation, and GraphRunner never replays a graph of an older one
+    def load_state_dict(self, *args, **kwargs):
+        from ..runtime import bump_generation
+        bump_generation()
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        from ..runtime import bump_generation
+        if mode != self.training:
+            bump_generation()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        from ..runtime import bump_generation
+        bump_generation()
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, *args, **kwargs):
         raise NotImplementedError("Please use the corresponding methods in SAM2VideoPredictor for inference.")
 
@@ -142,7 +161,9 @@ class SAM2Base(nn.Module):
                 fs[0] = ops.gemm(to_compute(fs[0]), w_c(d.conv_s0.weight), p32(d.conv_s0.bias))
                 fs[1] = ops.gemm(to_compute(fs[1]), w_c(d.conv_s1.weight), p32(d.conv_s1.bias))
             return fs
-        img = img_batch.float().contiguous()
+        # frames ingested as bf16 (utils/misc.py: streamed loaders in bf16 mode) feed the bf16 patch-embed im2col directly
+        keep = img_batch.dtype == torch.bfloat16 and compute_dtype() == torch.bfloat16
+        img = (img_batch if keep else img_batch.float()).contiguous()
         if self.use_cuda_graphs and not self.training and img.is_cuda and not torch.is_grad_enabled():
             feats = self._graphs.run(("image_encoder",), encode, [img])
         else:
@@ -478,11 +499,7 @@ class SAM2Base(nn.Module):
                 and (self.multimask_min_pt_num <= num_pts <= self.multimask_max_pt_num))
 
     def _apply_non_overlapping_constraints(self, pred_masks):
-        """sam2_base.py:812-830 (off in the shipped configs; plain tensor glue when enabled)."""
-        batch_size = pred_masks.size(0)
-        if batch_size == 1:
+        """sam2_base.py:812-830: one kernel (ms2_non_overlap)."""
+        if pred_masks.size(0) == 1:
             return pred_masks
-        max_obj_inds = torch.argmax(pred_masks, dim=0, keepdim=True)
-        batch_obj_inds = torch.arange(batch_size, device=pred_masks.device)[:, None, None, None]
-        keep = max_obj_inds == batch_obj_inds
-        return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
+        return ops.non_overlap(pred_masks.float().contiguous())

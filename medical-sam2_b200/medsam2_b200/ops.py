@@ -13,7 +13,7 @@ from . import native
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
-_SMS = 148
+_SMS = 148                  # B200; only sizes split-KV scratch (the kernels query the device themselves)
 # debugging aid: MS2_DISABLE=tc_gemm,small_gemm,tc_attn,small_attn,tc_win forces the fp32-accumulate SIMT
 # kernel for that family (still a CUDA kernel of this library - there is no non-native path)
 import os as _os
@@ -74,6 +74,9 @@ PROFILE = _EventProfiler()
 def _chk(t, name, dtype=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise native.NativeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.device.index != _cur_dev():
+        raise native.NativeError(f"{name}: tensor lives on cuda:{t.device.index} but the current device is cuda:{_cur_dev()} "
+                                 "(kernels launch on the current device's stream: call torch.cuda.set_device first)")
     if not t.is_contiguous():
         raise native.NativeError(f"{name}: tensor must be contiguous, got strides {t.stride()}")
     if dtype is not None and t.dtype != dtype:
@@ -326,11 +329,11 @@ def patch_embed(img, w, bias, pos):
 
 
 def patch_im2col(img, ldk=152):
-    """fp32 NCHW image [B,3,H,W] -> bf16 [B, Ho*Wo, ldk] rows of 7x7/s4/p3 taps ((ky,kx,c) order, zero padded)."""
+    """fp32 or bf16 NCHW image [B,3,H,W] -> bf16 [B, Ho*Wo, ldk] rows of 7x7/s4/p3 taps ((ky,kx,c) order, zero padded)."""
     B, _, Hin, Win = img.shape
     Ho, Wo = (Hin + 6 - 7) // 4 + 1, (Win + 6 - 7) // 4 + 1
     cols = torch.empty((B, Ho * Wo, ldk), dtype=torch.bfloat16, device=img.device)
-    native.call("ms2_patch_im2col", _chk(img, "img", torch.float32), cols.data_ptr(), B, Hin, Win, ldk, _st())
+    native.call("ms2_patch_im2col", _chk(img, "img"), _DT[img.dtype], cols.data_ptr(), B, Hin, Win, ldk, _st())
     return cols
 
 
@@ -500,20 +503,42 @@ def point_embed(coords, labels, gauss, table, pad, image_size):
     return out
 
 
-def normalize_image(x, out=None):
-    """fp32 [B,3,H,W] in 0..255 or uint8 [B,H,W,3] -> fp32 NCHW (x/255-mean)/std (optionally into `out`)."""
+def normalize_image(x, out=None, nhwc=None, out_dtype=torch.float32):
+    """(x/255 - mean)/std -> NCHW `out_dtype` (fp32, or bf16 = the cast autocast applies before the patch-embed conv).
+    x: fp32 [B,3,H,W] in 0..255 (video tensor), uint8 [B,3,H,W] (uint8 video tensor: `imgs_tensor / 255.0` of
+    utils/misc.py:233 works for any dtype) or, with nhwc=True, uint8 [B,H,W,3] (decoded images).  nhwc=None infers the
+    uint8 layout from the shape and refuses ambiguous or malformed ones instead of mis-reading them."""
+    if x.dim() != 4:
+        raise native.NativeError(f"normalize_image: expected a 4-D tensor, got {tuple(x.shape)}")
     if x.dtype == torch.uint8:
-        B, H, W, _ = x.shape
-        layout = 1
+        if nhwc is None:
+            c_first, c_last = x.shape[1] == 3, x.shape[-1] == 3
+            if c_first == c_last:
+                raise native.NativeError(f"normalize_image: cannot tell the layout of a uint8 tensor of shape "
+                                         f"{tuple(x.shape)}: pass nhwc=True ([B,H,W,3]) or nhwc=False ([B,3,H,W])")
+            nhwc = c_last
+        if nhwc:
+            if x.shape[-1] != 3:
+                raise native.NativeError(f"normalize_image: uint8 NHWC input must be [B,H,W,3], got {tuple(x.shape)}")
+            B, H, W, _ = x.shape
+            layout = 1
+        else:
+            if x.shape[1] != 3:
+                raise native.NativeError(f"normalize_image: uint8 NCHW input must be [B,3,H,W], got {tuple(x.shape)}")
+            B, _, H, W = x.shape
+            layout = 2
+        _chk(x, "x", torch.uint8)
     else:
+        if x.shape[1] != 3:
+            raise native.NativeError(f"normalize_image: expected [B,3,H,W], got {tuple(x.shape)}")
         B, _, H, W = x.shape
         layout = 0
         _chk(x, "x", torch.float32)
     if out is None:
-        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, 3, H, W), dtype=out_dtype, device=x.device)
     elif tuple(out.shape) != (B, 3, H, W):
         raise native.NativeError("normalize_image: bad `out` shape")
-    native.call("ms2_normalize_image", _chk(x, "x"), layout, _chk(out, "out", torch.float32), B, H, W, _st())
+    native.call("ms2_normalize_image", x.data_ptr(), layout, _chk(out, "out"), _DT[out.dtype], B, H, W, _st())
     return out
 
 
@@ -553,6 +578,36 @@ def bce_logits_sum(pred, gt, pos_weight):
     native.call("ms2_bce_logits_sum", _chk(pred, "pred", torch.float32), _chk(gt, "gt", torch.float32), float(pos_weight),
                 sums.data_ptr(), N, P, _st())
     return sums
+
+
+def score_lowres(low, gt, thresholds, pos_weight=None):
+    """low fp32 [N,h,w] logits, gt fp32 [N,H,W] -> (counts int32 [N,T,3], sums fp64 [N] or None): `seg_counts` and
+    `bce_logits_sum` of the bilinear up-sampling of `low` to gt's size, without materialising it."""
+    import ctypes
+    T = len(thresholds)
+    if not 1 <= T <= 8:
+        raise ValueError("score_lowres: 1..8 thresholds per call")
+    N, h, w = low.shape
+    if gt.dim() != 3 or gt.shape[0] != N:
+        raise ValueError(f"score_lowres: low {tuple(low.shape)} vs gt {tuple(gt.shape)}")
+    H, W = gt.shape[1:]
+    counts = torch.empty((N, T, 3), dtype=torch.int32, device=low.device)
+    sums = torch.empty((N,), dtype=torch.float64, device=low.device) if pos_weight is not None else None
+    thr = (ctypes.c_float * T)(*[float(t) for t in thresholds])
+    native.call("ms2_score_lowres", _chk(low, "low", torch.float32), _chk(gt, "gt", torch.float32),
+                ctypes.cast(thr, ctypes.c_void_p), T, float(pos_weight if pos_weight is not None else 1.0),
+                counts.data_ptr(), None if sums is None else sums.data_ptr(), N, h, w, H, W, _st())
+    return counts, sums
+
+
+def non_overlap(pred_masks):
+    """fp32 [n_obj, ...] scores -> same shape: per pixel the first arg-max object keeps its score, the others are
+    clamped to <= -10 (SAM2Base._apply_non_overlapping_constraints)."""
+    n = pred_masks.shape[0]
+    out = torch.empty_like(pred_masks)
+    native.call("ms2_non_overlap", _chk(pred_masks, "pred_masks", torch.float32), out.data_ptr(), n,
+                pred_masks.numel() // max(n, 1), _st())
+    return out
 
 
 def mask_stats(x, thr, off):

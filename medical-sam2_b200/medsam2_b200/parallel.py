@@ -72,7 +72,12 @@ def encode_volume_sharded(predictor, inference_state, group=None):
     levels, pos, kept_images = None, None, {}
     for f0 in range(lo, hi, nb):
         f1 = min(f0 + nb, hi)
-        batch = torch.stack([imgs[f] for f in range(f0, f1)]).to(dev).float()
+        if hasattr(imgs, "frames"):                       # host-resident volume: upload only this rank's block
+            batch = imgs.frames(f0, f1)
+        else:
+            batch = torch.stack([imgs[f] for f in range(f0, f1)]).to(dev)
+        if batch.dtype != torch.bfloat16:
+            batch = batch.float()
         out = predictor.forward_image(batch)
         fpn = [t.permute(0, 2, 3, 1) for t in out["backbone_fpn"]]          # NHWC memory of the channels-last views
         fpn = [t if t.is_contiguous() else t.contiguous() for t in fpn]
@@ -84,7 +89,7 @@ def encode_volume_sharded(predictor, inference_state, group=None):
         for i, f in enumerate(range(f0, f1)):
             kept_images[f] = batch[i: i + 1]
     if levels is None:                                    # this rank has no slices: learn the shapes from slice 0
-        out = predictor.forward_image(imgs[0].to(dev).float().unsqueeze(0))
+        out = predictor.forward_image(imgs[0].to(dev).unsqueeze(0))
         fpn = [t.permute(0, 2, 3, 1) for t in out["backbone_fpn"]]
         levels = [torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in fpn]
         pos = [p[:1] for p in out["vision_pos_enc"]]
@@ -102,8 +107,8 @@ def encode_volume_sharded(predictor, inference_state, group=None):
         owner, idx = divmod(f, per)
         fpn = [gathered[l][owner][idx: idx + 1].permute(0, 3, 1, 2) for l in range(len(levels))]
         image = kept_images.get(f)
-        if image is None:
-            image = imgs[f].to(dev).float().unsqueeze(0)
+        if image is None and not hasattr(imgs, "frames"):
+            image = imgs[f].to(dev).unsqueeze(0)             # device-resident volume: a view; host-resident: not uploaded
         cache[f] = (image, {"vision_features": fpn[-1], "vision_pos_enc": pos, "backbone_fpn": fpn})
     return hi - lo
 

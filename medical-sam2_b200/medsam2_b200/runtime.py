@@ -32,6 +32,22 @@ def compute(dtype):
         _COMPUTE = old
 
 
+# Parameter generation: bumped whenever kernel-ready parameter copies may have been re-derived (a stale cache entry was
+# rebuilt, `load_state_dict`, a train()/eval() switch, `.to()`/`_apply`).  Captured CUDA graphs bake in the device
+# pointers of those copies, so GraphRunner drops every graph of an older generation instead of replaying stale or
+# freed weights.
+_GEN = [0]
+_CAPTURE_REFS = None           # while a GraphRunner captures: the derived tensors the capture touched (kept alive with it)
+
+
+def bump_generation():
+    _GEN[0] += 1
+
+
+def generation():
+    return _GEN[0]
+
+
 class ParamCache:
     """derived tensors of parameters: get(param, key, fn) -> fn(param) cached per (version, ptr)."""
 
@@ -45,9 +61,15 @@ class ParamCache:
             hit = self._d.get(k)
             if hit is not None and hit[3] is not None:
                 if hit[0][0] == params._version and hit[0][1] == params.data_ptr() and hit[2][0]() is params:
+                    if _CAPTURE_REFS is not None:
+                        _CAPTURE_REFS.append(hit[1])
                     return hit[1]
+            if hit is not None:
+                bump_generation()                     # a derived copy is being replaced: captured graphs point at the old one
             with torch.no_grad():
                 val = fn(params)
+            if _CAPTURE_REFS is not None:
+                _CAPTURE_REFS.append(val)
             if len(self._d) > 4096:
                 self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
             self._d[k] = ((params._version, params.data_ptr(), params.dtype, str(params.device)), val,
@@ -59,9 +81,15 @@ class ParamCache:
         # id() and data_ptr() are both recycled once a model is freed: an entry is only valid while the very
         # tensor objects it was derived from are still alive (weak references), not merely "same address".
         if hit is not None and hit[0] == sig and all(r() is p for r, p in zip(hit[2], params)):
+            if _CAPTURE_REFS is not None:
+                _CAPTURE_REFS.append(hit[1])
             return hit[1]
+        if hit is not None:
+            bump_generation()
         with torch.no_grad():
             val = fn(*params)
+        if _CAPTURE_REFS is not None:
+            _CAPTURE_REFS.append(val)
         if len(self._d) > 4096:                       # drop entries whose parameters are gone
             self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
         self._d[k] = (sig, val, tuple(weakref.ref(p) for p in params), None)
@@ -145,8 +173,11 @@ class GraphRunner:
     attributes get initialised outside any capture), then the call is captured once on static copies of the
     inputs and replayed afterwards.  Inputs keep their strides (NCHW-shaped views of NHWC memory stay views);
     outputs live in the graph's private pool and are cloned out unless the caller consumes them immediately.
-    Only shapes/strides/dtypes and `key` select a graph - values never do, so the kernels must not read host
-    state that changes between calls."""
+    Shapes/strides/dtypes, `key` and the compute dtype select a graph - values never do, so the kernels must not read
+    host state that changes between calls.  A graph is only replayed while the parameter generation it was captured
+    under is current (`bump_generation`: load_state_dict, train()/eval() switches, `.to()`, a re-derived parameter
+    copy); otherwise it is dropped and re-captured after a fresh eager warm-up.  The graph entry keeps strong references
+    to every derived parameter copy its capture touched."""
 
     def __init__(self, warmup=2):
         self.warmup = warmup
@@ -160,8 +191,12 @@ class GraphRunner:
 
     def run(self, key, fn, tensors, clone=True):
         from . import native
-        full_key = (key, tuple(self._sig(t) for t in tensors))
+        full_key = (key, compute_dtype(), tuple(self._sig(t) for t in tensors))
         entry = self._graphs.get(full_key)
+        if entry is not None and entry[5] != _GEN[0]:
+            del self._graphs[full_key]                 # parameters changed since the capture: never replay stale weights
+            self._seen[full_key] = 0
+            entry = None
         if entry is None:
             n = self._seen.get(full_key, 0)
             self._seen[full_key] = n + 1
@@ -175,17 +210,23 @@ class GraphRunner:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = native.launch_count
-            global _CAPTURING
+            global _CAPTURING, _CAPTURE_REFS
             while len(_BRANCH_STREAMS) < 2:            # branch streams of par() exist before the capture starts
                 _BRANCH_STREAMS.append(torch.cuda.Stream())
             _CAPTURING = True
+            _CAPTURE_REFS = refs = []
+            gen0 = _GEN[0]
             try:
                 with torch.cuda.graph(graph):
                     static_out = fn(*static_in)
             finally:
                 _CAPTURING = False
-            entry = self._graphs[full_key] = [graph, static_in, static_out, native.launch_count - n0, None]
-        graph, static_in, static_out, launches, last = entry
+                _CAPTURE_REFS = None
+            if _GEN[0] != gen0:                        # a parameter copy was re-derived DURING the capture: do not keep it
+                self._seen[full_key] = 0
+                return fn(*tensors)
+            entry = self._graphs[full_key] = [graph, static_in, static_out, native.launch_count - n0, None, gen0, refs]
+        graph, static_in, static_out, launches, last = entry[:5]
         cur = torch.cuda.current_stream()
         if last is not None and last[0] != cur.cuda_stream:
             # the previous replay ran on another stream (slice encoding ahead of need): the static buffers are shared

@@ -55,6 +55,15 @@ class SAM2VideoPredictor(SAM2Base):
         if use_cuda_graphs is not None:
             self.use_cuda_graphs = bool(use_cuda_graphs)
 
+    def _no_autograd(self, what):
+        """The native kernels have no autograd: the `train_*` twins exist so that the reference's VALIDATION drivers
+        (which call them under `torch.no_grad()`, func_3d/function.py:237) run unchanged.  Called from a training step
+        (module in train mode with gradients enabled) they would silently train nothing — refuse instead."""
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError(
+                f"{what}: medsam2_b200 is an inference path (hand-written CUDA kernels without autograd). Use the "
+                "reference's own modules for the training step, or call this under model.eval() / torch.no_grad().")
+
     # ------------------------------------------------------------------ state construction
     def _make_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):
         dev = self.device
@@ -96,6 +105,7 @@ class SAM2VideoPredictor(SAM2Base):
 
     def train_init_state(self, imgs_tensor, video_height=None, video_width=None, offload_video_to_cpu=False,
                          offload_state_to_cpu=False, async_loading_frames=False):
+        self._no_autograd("train_init_state")
         with torch.no_grad():
             return self._init_state_from_data(imgs_tensor, video_height, video_width, offload_video_to_cpu,
                                               offload_state_to_cpu, async_loading_frames)
@@ -208,6 +218,7 @@ class SAM2VideoPredictor(SAM2Base):
 
     def train_add_new_points(self, inference_state, frame_idx, obj_id, points, labels, clear_old_points=True,
                              normalize_coords=True):
+        self._no_autograd("train_add_new_points")
         with torch.no_grad():
             return self._add_new_points(inference_state, frame_idx, obj_id, points, labels, clear_old_points,
                                         normalize_coords)
@@ -219,6 +230,7 @@ class SAM2VideoPredictor(SAM2Base):
 
     def train_add_new_bbox(self, inference_state, frame_idx, obj_id, bbox, clear_old_points=True,
                            normalize_coords=True):
+        self._no_autograd("train_add_new_bbox")
         pts, lab = self._bbox_points(bbox)
         with torch.no_grad():
             return self._add_new_points(inference_state, frame_idx, obj_id, pts, lab, clear_old_points,
@@ -252,6 +264,7 @@ class SAM2VideoPredictor(SAM2Base):
         return self._add_new_mask(inference_state, frame_idx, obj_id, mask)
 
     def train_add_new_mask(self, inference_state, frame_idx, obj_id, mask):
+        self._no_autograd("train_add_new_mask")
         with torch.no_grad():
             return self._add_new_mask(inference_state, frame_idx, obj_id, mask)
 
@@ -395,6 +408,7 @@ class SAM2VideoPredictor(SAM2Base):
         self._preflight(inference_state)
 
     def train_propagate_in_video_preflight(self, inference_state):
+        self._no_autograd("train_propagate_in_video_preflight")
         with torch.no_grad():
             self._preflight(inference_state)
 
@@ -450,6 +464,10 @@ class SAM2VideoPredictor(SAM2Base):
                 output_dict[key][frame_idx] = out
             self._add_output_per_object(st, frame_idx, out, key)
             st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+            if st.get("_ms2_yield_low_res", False):
+                # validation_sam(fused_scoring=True): the scoring kernel up-samples on the fly (ms2_score_lowres)
+                yield frame_idx, obj_ids, pred_masks.to(st["device"], non_blocking=True)
+                continue
             _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
             yield frame_idx, obj_ids, video_res_masks
 
@@ -465,6 +483,7 @@ class SAM2VideoPredictor(SAM2Base):
 
     def train_propagate_in_video(self, inference_state, start_frame_idx=None, max_frame_num_to_track=None,
                                  reverse=False):
+        self._no_autograd("train_propagate_in_video")
         gen = self._propagate(inference_state, start_frame_idx, max_frame_num_to_track, reverse)
         while True:
             with torch.no_grad():
@@ -528,9 +547,11 @@ class SAM2VideoPredictor(SAM2Base):
 
         def run():
             if len(frames) == 1:
-                images = imgs[frames[0]].to(dev).float().unsqueeze(0)
+                images = imgs[frames[0]].to(dev).unsqueeze(0)
             else:
-                images = torch.stack([imgs[f] for f in frames]).to(dev).float()
+                images = torch.stack([imgs[f] for f in frames]).to(dev)
+            if images.dtype != torch.bfloat16:               # bf16 frames (streamed ingest in bf16 mode) go in as they are
+                images = images.float()
             return images, self.forward_image(images)
 
         ev = None
@@ -610,7 +631,7 @@ class SAM2VideoPredictor(SAM2Base):
             "backbone_fpn": [f.expand(batch_size, -1, -1, -1) for f in backbone_out["backbone_fpn"]],
             "vision_pos_enc": [p.expand(batch_size, -1, -1, -1) for p in backbone_out["vision_pos_enc"]],
         }
-        return (image.expand(batch_size, -1, -1, -1),) + self._prepare_backbone_features(expanded)
+        return (None if image is None else image.expand(batch_size, -1, -1, -1),) + self._prepare_backbone_features(expanded)
 
     def _run_single_frame_inference(self, inference_state, output_dict, frame_idx, batch_size, is_init_cond_frame,
                                     point_inputs, mask_inputs, reverse, run_mem_encoder, prev_sam_mask_logits=None):

@@ -119,3 +119,26 @@ def bce_with_logits(pred, target, pos_weight=2.0):
     if pred.shape != target.shape:
         raise ValueError("bce_with_logits: expected tensors of the same shape")
     return bce_with_logits_frames(pred.reshape(1, -1), target.reshape(1, -1), pos_weight)[0]
+
+
+def score_frames_lowres(low, true_masks, threshold, pos_weight=2.0):
+    """`eval_seg_frames` + `bce_with_logits_frames` of the video-resolution logits WITHOUT materialising them: low
+    [n,1,h,w] low-resolution logits (what the tracker keeps per slice), true_masks [n,1,H,W]; the bilinear up-sampling
+    of sam2_video_predictor.py:724-744 happens inside the scoring pass (`ms2_score_lowres`, bit-identical to
+    `ms2_resize_bilinear` followed by `ms2_seg_counts`).  -> (list of eval_seg tuples, fp32 losses [n] on the device)."""
+    if low.dim() != 4 or true_masks.dim() != 4 or low.shape[:2] != true_masks.shape[:2] or low.shape[1] != 1:
+        raise ValueError("score_frames_lowres: expected [n,1,h,w] logits and [n,1,H,W] masks")
+    n = low.shape[0]
+    thr = [float(t) for t in threshold]
+    if len(thr) == 0:
+        raise ZeroDivisionError("score_frames_lowres: empty threshold tuple")
+    lo, gt = _planes(low).reshape(n, *low.shape[2:]), _planes(true_masks).reshape(n, *true_masks.shape[2:])
+    parts, sums = [], None
+    for i in range(0, len(thr), 8):
+        c, s = ops.score_lowres(lo, gt, thr[i:i + 8], pos_weight if i == 0 else None)
+        parts.append(c)
+        sums = s if i == 0 else sums
+    counts = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+    counts = counts.cpu().numpy().astype(np.int64).reshape(n, 1, len(thr), 3)
+    losses = (sums / float(gt.shape[1] * gt.shape[2])).float()
+    return [_reduce(counts[i:i + 1]) for i in range(n)], losses

@@ -60,29 +60,41 @@ def _upload_stream(device):
     return s
 
 
+def _frame_dtype(device_frames=True):
+    """dtype of DEVICE-resident normalised frames: bf16 when the GEMM operands are bf16 (the patch-embed contraction
+    rounds the frame to bf16 anyway, exactly what autocast does in the reference's train_3d.py:28,57 setting; storing
+    it that way halves the frame bytes written at ingest and read by the encoder), fp32 in exact mode and on the host."""
+    from ..runtime import compute_dtype
+    return compute_dtype() if device_frames else torch.float32
+
+
 class StreamedFrames:
     """Frames of a HOST tensor uploaded and normalised chunk by chunk on a side stream (the counterpart of the
     reference's AsyncVideoFrameLoader, utils/misc.py:92-160, for frames that are already decoded): indexing a frame
     makes the consumer's stream wait for the CUDA event of its chunk, so the host->device copy of later slices
-    overlaps the encoding / tracking of earlier ones instead of preceding it."""
+    overlaps the encoding / tracking of earlier ones instead of preceding it.  `host`: [T,3,H,W] of any dtype
+    (uint8 travels as uint8: a quarter of the fp32 bytes over PCIe) or uint8 [T,H,W,3] with nhwc=True."""
 
-    def __init__(self, host, device, chunk=8):
+    def __init__(self, host, device, chunk=8, nhwc=False):
         assert not host.is_cuda and host.dim() == 4
+        if (host.shape[-1] if nhwc else host.shape[1]) != 3:
+            raise ValueError(f"StreamedFrames: expected {'[T,H,W,3]' if nhwc else '[T,3,H,W]'} frames, got {tuple(host.shape)}")
+        if nhwc and host.dtype != torch.uint8:
+            raise ValueError("StreamedFrames: channels-last frames must be uint8")
         self.T = host.shape[0]
         self.chunk = max(1, int(chunk))
-        layout_u8 = host.dtype == torch.uint8
-        H, W = (host.shape[1], host.shape[2]) if layout_u8 else (host.shape[2], host.shape[3])
-        self.out = torch.empty((self.T, 3, H, W), dtype=torch.float32, device=device)
+        H, W = (host.shape[1], host.shape[2]) if nhwc else (host.shape[2], host.shape[3])
+        self.out = torch.empty((self.T, 3, H, W), dtype=_frame_dtype(), device=device)
         self.stream = _upload_stream(device)
         self.out.record_stream(self.stream)
         self.stream.wait_stream(torch.cuda.current_stream(device))
         self.events, self.waited = [], []
-        src = host if (layout_u8 or host.dtype == torch.float32) else host.float()
+        src = host if host.dtype in (torch.uint8, torch.float32) else host.float()
         with torch.cuda.stream(self.stream):
             for c0 in range(0, self.T, self.chunk):
                 c1 = min(c0 + self.chunk, self.T)
                 raw = src[c0:c1].to(device, non_blocking=True)
-                ops.normalize_image(raw.contiguous(), out=self.out[c0:c1])
+                ops.normalize_image(raw.contiguous(), out=self.out[c0:c1], nhwc=nhwc)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
                 self.events.append(ev)
@@ -114,38 +126,194 @@ class StreamedFrames:
         return self.out[idx]
 
 
+class LazyHostFrames:
+    """Frames that STAY on the host (`offload_video_to_cpu=True`) and are uploaded + normalised only when a frame is
+    asked for (`async_loading_frames=True`): a rank that encodes one block of a long volume (parallel.
+    encode_volume_sharded) moves only that block over PCIe.  `frames(f0, f1)` uploads a run of frames in one copy."""
+
+    def __init__(self, host, device):
+        assert not host.is_cuda and host.dim() == 4 and host.shape[1] == 3
+        self.host = host if host.dtype in (torch.uint8, torch.float32) else host.float()
+        self.device = torch.device(device)
+        self.T = host.shape[0]
+
+    def __len__(self):
+        return self.T
+
+    @property
+    def shape(self):
+        return self.host.shape
+
+    def frames(self, f0, f1):
+        raw = self.host[f0:f1].to(self.device, non_blocking=True)
+        return ops.normalize_image(raw.contiguous(), nhwc=False, out_dtype=_frame_dtype())
+
+    def __getitem__(self, idx):
+        i = int(idx) % self.T
+        return self.frames(i, i + 1)[0]
+
+
 def load_video_frames_from_data(imgs_tensor, offload_video_to_cpu=False, img_mean=(0.485, 0.456, 0.406),
                                 img_std=(0.229, 0.224, 0.225), async_loading_frames=False, device="cuda"):
-    """utils/misc.py:215-244: [T,3,S,S] in 0..255 -> normalised fp32 frames, one fused kernel on device.
-    `async_loading_frames=True` with a host tensor streams the upload (StreamedFrames)."""
+    """utils/misc.py:215-244: [T,3,S,S] in 0..255 (any dtype, like the reference's `imgs_tensor / 255.0`) -> normalised
+    fp32 frames, one fused kernel on device.  `async_loading_frames=True` with a host tensor streams the upload
+    (StreamedFrames)."""
     assert tuple(img_mean) == (0.485, 0.456, 0.406) and tuple(img_std) == (0.229, 0.224, 0.225)
     x = imgs_tensor
-    if async_loading_frames and not x.is_cuda and not offload_video_to_cpu and torch.cuda.is_available():
-        return StreamedFrames(x, device)
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"load_video_frames_from_data: expected imgs_tensor [T,3,H,W], got {tuple(x.shape)}")
+    if async_loading_frames and not x.is_cuda and torch.cuda.is_available():
+        return LazyHostFrames(x, device) if offload_video_to_cpu else StreamedFrames(x, device)
     if not x.is_cuda:
         x = x.to(device, non_blocking=True)
-    images = ops.normalize_image(x.float().contiguous() if x.dtype != torch.uint8 else x.contiguous())
+    if x.dtype == torch.uint8:
+        images = ops.normalize_image(x.contiguous(), nhwc=False)
+    else:
+        images = ops.normalize_image(x.float().contiguous())
     return images.cpu() if offload_video_to_cpu else images
 
 
-def load_video_frames(video_path, image_size, offload_video_to_cpu=False, img_mean=(0.485, 0.456, 0.406),
-                      img_std=(0.229, 0.224, 0.225), async_loading_frames=False, device="cuda"):
-    """utils/misc.py:163-212: a directory of <frame_index>.jpg files -> (frames, H, W)."""
+def _decode_jpeg(path, image_size):
+    """utils/misc.py:92-101 `_load_img_as_tensor` up to the uint8 array: PIL decode -> RGB -> PIL resize (default
+    resampling).  PIL releases the GIL while decoding / resizing, so a thread pool scales over host cores."""
     from PIL import Image
+    pil = Image.open(path)
+    arr = np.asarray(pil.convert("RGB").resize((image_size, image_size)))
+    if arr.dtype != np.uint8:
+        raise RuntimeError(f"Unknown image dtype: {arr.dtype} on {path}")
+    w, h = pil.size
+    return arr, h, w
+
+
+def _jpeg_paths(video_path):
     if not (isinstance(video_path, str) and os.path.isdir(video_path)):
         raise NotImplementedError("Only JPEG frames are supported at this moment")
     names = [p for p in os.listdir(video_path) if os.path.splitext(p)[-1] in (".jpg", ".jpeg", ".JPG", ".JPEG")]
     names.sort(key=lambda p: int(os.path.splitext(p)[0]))
     if not names:
         raise RuntimeError(f"no images found in {video_path}")
-    frames = []
-    for n in names:
-        img = Image.open(os.path.join(video_path, n))
-        W0, H0 = img.size
-        frames.append(np.array(img.convert("RGB").resize((image_size, image_size))))
-    x = torch.from_numpy(np.stack(frames)).to(device)                      # uint8 [T,S,S,3]
-    images = ops.normalize_image(x)
-    return (images.cpu() if offload_video_to_cpu else images), H0, W0
+    return [os.path.join(video_path, n) for n in names]
+
+
+class AsyncVideoFrameLoader:
+    """utils/misc.py:104-160 re-designed for a GPU consumer.  The reference decodes every frame on ONE background thread
+    into fp32 tensors and uploads them one by one from that thread.  Here a pool of host threads decodes "<index>.jpg"
+    files (PIL, GIL released) straight into ONE pinned uint8 [T,S,S,3] staging buffer; finished chunks of `chunk`
+    frames are uploaded as uint8 (a quarter of the fp32 bytes) on the upload stream and normalised there by
+    `ms2_normalize_image` (bf16 frames in bf16 mode).  All CUDA calls stay on the caller's thread (the decode threads
+    never touch CUDA, so they cannot disturb a CUDA-graph capture): `loader[i]` enqueues the uploads of every chunk that
+    finished decoding, blocks on the host only if chunk(i) is still being decoded, and makes the consumer's stream wait
+    for that chunk's CUDA event.  Frame 0 is decoded synchronously (it fills video_height / video_width, as in the
+    reference).  With `offload_video_to_cpu=True` frames stay on the host as fp32 (the reference's layout)."""
+
+    def __init__(self, img_paths, image_size, offload_video_to_cpu=False, device="cuda", chunk=8, workers=None):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.img_paths = list(img_paths)
+        self.image_size = image_size
+        self.offload_video_to_cpu = offload_video_to_cpu
+        self.device = torch.device(device)
+        self.T = len(self.img_paths)
+        self.chunk = max(1, int(chunk))
+        self.exception = None
+        on_gpu = (not offload_video_to_cpu) and self.device.type == "cuda"
+        self.staging = torch.empty((self.T, image_size, image_size, 3), dtype=torch.uint8)
+        if on_gpu:
+            self.staging = self.staging.pin_memory()
+            self.out = torch.empty((self.T, 3, image_size, image_size), dtype=_frame_dtype(), device=self.device)
+            self.stream = _upload_stream(self.device)
+            self.out.record_stream(self.stream)
+        else:
+            self.out = torch.empty((self.T, 3, image_size, image_size), dtype=torch.float32)
+        self._np = self.staging.numpy()
+        n_chunks = (self.T + self.chunk - 1) // self.chunk
+        self._left = [min(self.chunk, self.T - c * self.chunk) for c in range(n_chunks)]     # frames still decoding
+        self._decoded = [threading.Event() for _ in range(n_chunks)]
+        self._uploaded = [False] * n_chunks
+        self._events = [None] * n_chunks
+        self._waited = [set() for _ in range(n_chunks)]
+        self._lock = threading.Lock()
+        self._one(0)                                          # synchronously: video size + the frame users click first
+        workers = workers or min(8, os.cpu_count() or 1)
+        self._pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="ms2-jpeg")
+        for i in range(1, self.T):
+            self._pool.submit(self._one, i)
+        self._pool.shutdown(wait=False)
+
+    def _one(self, i):
+        try:
+            arr, h, w = _decode_jpeg(self.img_paths[i], self.image_size)
+            self._np[i] = arr
+            if i == 0:
+                self.video_height, self.video_width = h, w
+        except Exception as e:                                 # surfaces in the consumer (utils/misc.py:128-134)
+            self.exception = e
+        finally:
+            c = i // self.chunk
+            with self._lock:
+                self._left[c] -= 1
+                if self._left[c] == 0:
+                    self._decoded[c].set()
+
+    def _upload(self, c):
+        c0, c1 = c * self.chunk, min((c + 1) * self.chunk, self.T)
+        if self.offload_video_to_cpu or self.device.type != "cuda":
+            x = self.staging[c0:c1].permute(0, 3, 1, 2).float() / 255.0
+            mean = torch.tensor((0.485, 0.456, 0.406))[:, None, None]
+            std = torch.tensor((0.229, 0.224, 0.225))[:, None, None]
+            self.out[c0:c1] = (x - mean) / std
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                raw = self.staging[c0:c1].to(self.device, non_blocking=True)
+                ops.normalize_image(raw, out=self.out[c0:c1], nhwc=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self._events[c] = ev
+        self._uploaded[c] = True
+
+    def _ready(self, c):
+        if self.exception is not None:
+            raise RuntimeError("Failure in frame loading thread") from self.exception
+        for k in range(len(self._uploaded)):                   # push every finished chunk to the GPU, in order, non-blocking
+            if not self._uploaded[k] and (k == c or self._decoded[k].is_set()):
+                if k == c:
+                    self._decoded[k].wait()
+                    if self.exception is not None:
+                        raise RuntimeError("Failure in frame loading thread") from self.exception
+                self._upload(k)
+        if self._events[c] is not None:
+            cur = torch.cuda.current_stream(self.device)
+            if cur.cuda_stream not in self._waited[c]:
+                cur.wait_event(self._events[c])
+                self._waited[c].add(cur.cuda_stream)
+
+    def __getitem__(self, index):
+        i = int(index) % self.T
+        self._ready(i // self.chunk)
+        return self.out[i]
+
+    def __len__(self):
+        return self.T
+
+    @property
+    def shape(self):
+        return self.out.shape
+
+
+def load_video_frames(video_path, image_size, offload_video_to_cpu=False, img_mean=(0.485, 0.456, 0.406),
+                      img_std=(0.229, 0.224, 0.225), async_loading_frames=False, device="cuda"):
+    """utils/misc.py:163-212: a directory of "<frame_index>.jpg" files -> (frames, video_height, video_width).
+    async_loading_frames=True returns the lazy `AsyncVideoFrameLoader`; otherwise all frames are decoded (thread pool),
+    uploaded as uint8 and normalised by one kernel launch."""
+    assert tuple(img_mean) == (0.485, 0.456, 0.406) and tuple(img_std) == (0.229, 0.224, 0.225)
+    paths = _jpeg_paths(video_path)
+    lazy = AsyncVideoFrameLoader(paths, image_size, offload_video_to_cpu, device=device,
+                                 chunk=8 if async_loading_frames else len(paths))
+    if async_loading_frames:
+        return lazy, lazy.video_height, lazy.video_width
+    lazy[len(paths) - 1]                                       # decode + upload everything now
+    return lazy.out, lazy.video_height, lazy.video_width
 
 
 def concat_points(old_point_inputs, new_points, new_labels):

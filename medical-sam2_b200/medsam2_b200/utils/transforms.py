@@ -25,7 +25,7 @@ class SAM2Transforms(nn.Module):
         assert x.dtype == torch.uint8 and x.dim() == 3 and x.shape[-1] == 3, "expected an HWC uint8 RGB image"
         H, W = x.shape[:2]
         if (H, W) == (self.resolution, self.resolution):
-            return ops.normalize_image(x[None])[0]
+            return ops.normalize_image(x[None], nhwc=True)[0]
         planes = x.permute(2, 0, 1).float().contiguous()            # [3,H,W] in 0..255
         planes = ops.resize_bilinear(planes, (self.resolution, self.resolution), antialias=True)
         return ops.normalize_image(planes[None].contiguous())[0]

@@ -211,12 +211,18 @@ def fourier_pe(coords01, gauss):
     return torch.cat([torch.sin(c), torch.cos(c)], dim=-1)
 
 
-def normalize_image(x):
+def normalize_image(x, out=None, nhwc=None, out_dtype=torch.float32):
     if x.dtype == torch.uint8:
-        x = x.permute(0, 3, 1, 2).float()
+        if nhwc is None:
+            nhwc = x.shape[-1] == 3 and x.shape[1] != 3
+        x = x.permute(0, 3, 1, 2).float() if nhwc else x.float()
     mean = torch.tensor((0.485, 0.456, 0.406), device=x.device)[None, :, None, None]
     std = torch.tensor((0.229, 0.224, 0.225), device=x.device)[None, :, None, None]
-    return (x.float() / 255.0 - mean) / std
+    y = ((x.float() / 255.0 - mean) / std).to(out_dtype if out is None else out.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def mask_stability_counts(x, delta):
@@ -269,6 +275,20 @@ def bce_logits_sum(pred, gt, pos_weight):
     x, y = pred.reshape(N, -1).double(), gt.reshape(N, -1).double()
     el = (1 - y) * x + (1 + (pos_weight - 1) * y) * (torch.log1p(torch.exp(-x.abs())) + torch.clamp_min(-x, 0))
     return el.sum(1)
+
+
+def score_lowres(low, gt, thresholds, pos_weight=None):
+    up = F.interpolate(low[:, None].float(), size=gt.shape[-2:], mode="bilinear", align_corners=False)[:, 0]
+    counts = seg_counts(up.reshape(up.shape[0], -1), gt.reshape(gt.shape[0], -1), thresholds)
+    sums = None if pos_weight is None else bce_logits_sum(up.reshape(up.shape[0], -1), gt.reshape(gt.shape[0], -1), pos_weight)
+    return counts, sums
+
+
+def non_overlap(pred_masks):
+    n = pred_masks.shape[0]
+    top = torch.argmax(pred_masks, dim=0, keepdim=True)
+    keep = top == torch.arange(n, device=pred_masks.device).view(n, *([1] * (pred_masks.dim() - 1)))
+    return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
 
 
 def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):

@@ -65,10 +65,10 @@ def test_image_predictor_config2_batch(dt):
     t = TOL[dt]
     with medsam2_b200.compute(dt):
         p = medsam2_b200.SAM2ImagePredictor(_build("sam2_hiera_s", video=False))
-        imgs, pts = fundus_images(2, 1024, 0)
+        imgs, pts = fundus_images(4, 1024, 0)            # BASELINE configs[1]: batch of 4
         p.set_image_batch(imgs)
         _close(p._features["image_embed"][..., ::4, ::4], z["image_embed_sub"], t["emb"], "image_embed")
-        masks, ious, low = p.predict_batch(pts, [np.array([1])] * 2, multimask_output=True, return_logits=True)
+        masks, ious, low = p.predict_batch(pts, [np.array([1])] * 4, multimask_output=True, return_logits=True)
         _close(np.stack(low), z["low_res"], t["logit"], "low_res")
         _close(np.stack(ious), z["ious"], t["iou"], "ious")
 
@@ -312,7 +312,13 @@ def test_validation_driver_gpu():
             seen[-1][f] = logits.float().cpu().clone()
             yield f, ids, logits
     m.propagate_in_video = spy
-    loss, (iou, dice) = validation_sam(m, packs, prompt="bbox", prompt_freq=2)
+    loss, (iou, dice) = validation_sam(m, packs, prompt="bbox", prompt_freq=2, fused_scoring=False)
+    # default: scored straight from the tracker's low-res logits (up-sampling fused into the scoring pass, ms2_score_lowres):
+    # same integers -> identical metrics; the loss differs by fp32 summation order only
+    m.propagate_in_video = orig
+    loss_f, (iou_f, dice_f) = validation_sam(m, packs, prompt="bbox", prompt_freq=2)
+    assert iou_f == iou and dice_f == dice, (iou_f, iou, dice_f, dice)
+    assert abs(loss_f - loss) <= 2e-6 * abs(loss), (loss_f, loss)
     want = np.zeros(3)
     for v in range(2):
         for f in range(T):
@@ -323,3 +329,199 @@ def test_validation_driver_gpu():
     want /= 3
     assert abs(iou - want[1]) < 1e-12 and abs(dice - want[2]) < 1e-9, (iou, dice, want)
     assert abs(loss - want[0]) < 1e-6 * abs(want[0]), (loss, want[0])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_video_clicks_reverse_reset(dt):
+    """Click prompts (func_3d/function.py:241-251), a refinement click on the same slice (prev-mask-logit path),
+    forward + reverse propagation from a middle slice, reset_state and a second session — against the real
+    reference's answers (tests/golden/video_clicks_hiera_t_512.npz)."""
+    import medsam2_b200
+    z = np.load(f"{G}/video_clicks_hiera_t_512.npz")
+    size, T = 512, 6
+    t = TOL[dt]
+    f32 = dt == torch.float32
+    mtol = 3e-3 if f32 else 3e-2
+
+    def masks_close(got, ref, what):
+        got = np.asarray(got.detach().float().cpu()); ref = np.asarray(ref, np.float32)
+        filled = (np.abs(got - 0.1) < 1e-6) | (np.abs(ref - 0.1) < 1e-6)
+        d = np.abs(got - ref)
+        err = float(d[~filled].max())
+        from conftest import _PARITY
+        k = _PARITY.setdefault(f"video_clicks_reverse_reset[{'fp32' if f32 else 'bf16'}]", {})
+        k["pred_masks"] = max(err, k.get("pred_masks", 0.0))
+        assert err <= mtol, (what, err)
+        assert ((got > 0) == (ref > 0)).mean() >= 0.995, what
+    with medsam2_b200.compute(dt):
+        m = _build("sam2_hiera_t", video=True, image_size=size)
+        vol, boxes = btcv_volume(T, size, 55, 1)
+        st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=size, video_width=size)
+
+        def centre(f):
+            x0, y0, x1, y1 = boxes[f][0]
+            return [(x0 + x1) / 2.0, (y0 + y1) / 2.0]
+        c2 = centre(2)
+        _, _, vr = m.train_add_new_points(inference_state=st, frame_idx=2, obj_id=1, points=torch.tensor([c2]),
+                                          labels=torch.tensor([1], dtype=torch.int32), clear_old_points=False)
+        masks_close(vr[..., ::4, ::4], z["a/click1_video_res_sub"], "first click")
+        _, _, vr = m.train_add_new_points(inference_state=st, frame_idx=2, obj_id=1,
+                                          points=torch.tensor([[c2[0] + 150.0, c2[1] + 120.0]]),
+                                          labels=torch.tensor([0], dtype=torch.int32), clear_old_points=False)
+        masks_close(vr[..., ::4, ::4], z["a/click2_video_res_sub"], "refinement click")
+        fwd = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=2)}
+        rev = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=2, reverse=True)}
+        assert sorted(fwd) == list(z["a/fwd_frames"]) and sorted(rev) == list(z["a/rev_frames"])
+        od = st["output_dict"]
+        for f in range(T):
+            o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+            masks_close(o["pred_masks"], z[f"a/pred_masks_{f}"], f"a pred_masks {f}")
+            _close(o["obj_ptr"], z[f"a/obj_ptr_{f}"], t["ptr"], f"a obj_ptr {f}")
+            masks_close((fwd[f] if f in fwd else rev[f])[..., ::4, ::4], z["a/video_res_sub"][f], f"a video res {f}")
+        m.reset_state(st)
+        assert not st["obj_ids"] and not st["output_dict"]["cond_frame_outputs"] and "_ms2_bank" not in st["output_dict"]
+        m.train_add_new_bbox(inference_state=st, frame_idx=0, obj_id=7, bbox=torch.tensor(boxes[0][0]), clear_old_points=False)
+        m.train_add_new_points(inference_state=st, frame_idx=3, obj_id=7, points=torch.tensor([centre(3)]),
+                               labels=torch.tensor([1], dtype=torch.int32), clear_old_points=False)
+        b = {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0, max_frame_num_to_track=4)}
+        assert sorted(b) == list(z["b/frames"])
+        for i, f in enumerate(sorted(b)):
+            o = od["cond_frame_outputs"].get(f) or od["non_cond_frame_outputs"].get(f)
+            masks_close(o["pred_masks"], z[f"b/pred_masks_{f}"], f"b pred_masks {f}")
+            masks_close(b[f][..., ::4, ::4], z["b/video_res_sub"][i], f"b video res {f}")
+
+
+def test_postprocess_masks_hole_sprinkle():
+    """SAM2Transforms.postprocess_masks with hole / sprinkle removal (utils/transforms.py:74-99) through the CC kernel
+    + resize kernel against the real reference's answers (tests/golden/postprocess_cases.npz)."""
+    from medsam2_b200.utils.transforms import SAM2Transforms
+    z = np.load(f"{G}/postprocess_cases.npz")
+    masks = torch.from_numpy(z["pp/masks"]).cuda()
+    for tag, (ha, sa, thr) in {"h8_s4": (8.0, 4.0, 0.0), "h8_s0": (8.0, 0.0, 0.0), "h3_s6_t05": (3.0, 6.0, 0.5)}.items():
+        tr = SAM2Transforms(resolution=1024, mask_threshold=thr, max_hole_area=ha, max_sprinkle_area=sa)
+        _close(tr.postprocess_masks(masks.clone(), (96, 80)), z[f"pp/{tag}"], 2e-5, f"postprocess {tag}")
+
+
+def _jpeg_dir(tmp_path):
+    z = np.load(f"{G}/ingest_jpeg.npz")
+    for i in range(5):
+        (tmp_path / f"{i}.jpg").write_bytes(z[f"jpeg_{i}"].tobytes())
+    return z, str(tmp_path)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1.2e-2)])
+def test_ingest_jpeg_directory(tmp_path, dt, tol):
+    """`load_video_frames` (utils/misc.py:163-212) sync and async (`AsyncVideoFrameLoader`, :104-160) against the real
+    reference's frames for the same JPEG files (tests/golden/ingest_jpeg.npz): fp32 mode to 1e-6; bf16 mode keeps the
+    frames in bf16 (the rounding autocast applies in front of the patch-embed conv): half a bf16 ulp of |x| <= 2.7."""
+    import medsam2_b200
+    from medsam2_b200.utils.misc import AsyncVideoFrameLoader, load_video_frames
+    z, d = _jpeg_dir(tmp_path)
+    with medsam2_b200.compute(dt):
+        frames, h, w = load_video_frames(d, image_size=64, device="cuda")
+        assert (h, w) == tuple(z["hw"]) and frames.is_cuda and frames.dtype == dt
+        _close(frames, z["sync"], tol, "load_video_frames")
+        lazy, h, w = load_video_frames(d, image_size=64, async_loading_frames=True, device="cuda")
+        assert isinstance(lazy, AsyncVideoFrameLoader) and len(lazy) == 5 and (h, w) == tuple(z["hw"])
+        for i in (3, 0, 4, 1, 2):                                    # out-of-order requests
+            _close(lazy[i], z["async"][i], tol, f"async frame {i}")
+        cpu_frames, _, _ = load_video_frames(d, image_size=64, offload_video_to_cpu=True, device="cuda")
+        assert not cpu_frames.is_cuda and cpu_frames.dtype == torch.float32
+        _close(cpu_frames, z["sync"], 1e-6, "offloaded frames")
+    with pytest.raises(NotImplementedError):
+        load_video_frames(d + "/0.jpg", image_size=64)
+    (tmp_path / "9.jpg").write_bytes(b"not a jpeg")
+    with pytest.raises(RuntimeError):
+        lazy, _, _ = load_video_frames(d, image_size=64, async_loading_frames=True, device="cuda")
+        lazy[5]
+
+
+def test_init_state_from_jpeg_directory(tmp_path):
+    """`init_state(video_path, async_loading_frames=True)` (sam2_video_predictor.py:39-105): frames decoded on host
+    threads while the first prompt is processed; masks come back at the ORIGINAL video resolution (80 x 96); the lazy
+    loader and the eager one give identical masks."""
+    _, d = _jpeg_dir(tmp_path)
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    outs = []
+    for lazy in (False, True):
+        st = m.init_state(d, async_loading_frames=lazy)
+        assert (st["video_height"], st["video_width"], st["num_frames"]) == (80, 96, 5)
+        _, ids, vr = m.add_new_points_or_box(st, 0, 1, box=[20, 16, 70, 60])
+        assert tuple(vr.shape) == (1, 1, 80, 96) and ids == [1]
+        outs.append({f: mk.clone() for f, _, mk in m.propagate_in_video(st)})
+    assert sorted(outs[0]) == list(range(5))
+    for f in range(5):
+        assert torch.isfinite(outs[0][f]).all() and torch.equal(outs[0][f], outs[1][f]), f
+
+
+def test_uint8_nchw_volume_is_not_misread():
+    """a uint8 [T,3,H,W] pack (validation.py documents pack['image'] as [T,3,H,W]) must be read as NCHW — the
+    reference's `imgs_tensor / 255.0` works for any dtype — and give the masks of the same volume passed as float."""
+    from medsam2_b200 import ops as o
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    vol, boxes = btcv_volume(4, 512, 7, 1)
+    vol8 = vol.round().clamp(0, 255).to(torch.uint8)
+    res = []
+    for v in (vol8.float().cuda(), vol8.cuda(), vol8.pin_memory()):
+        st = m.val_init_state(imgs_tensor=v, video_height=512, video_width=512, async_loading_frames=not v.is_cuda)
+        assert tuple(st["images"].shape) == (4, 3, 512, 512)
+        m.train_add_new_bbox(inference_state=st, frame_idx=0, obj_id=1, bbox=torch.tensor(boxes[0][0]), clear_old_points=False)
+        res.append({f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)})
+    for f in range(4):
+        assert torch.equal(res[0][f], res[1][f]) and torch.equal(res[0][f], res[2][f]), f
+    with pytest.raises(Exception):
+        o.normalize_image(torch.zeros(2, 5, 8, 8, dtype=torch.uint8, device="cuda"))           # neither [B,3,H,W] nor [B,H,W,3]
+    with pytest.raises(Exception):
+        o.normalize_image(torch.zeros(2, 3, 8, 3, dtype=torch.uint8, device="cuda"))           # ambiguous: must be stated
+    with pytest.raises(ValueError):
+        m.val_init_state(imgs_tensor=torch.zeros(4, 512, 512, 3, dtype=torch.uint8).cuda())
+
+
+def test_cuda_graphs_follow_parameter_updates():
+    """captured graphs bake in pointers to derived parameter copies; after `load_state_dict` (or a
+    train()/eval() round trip with in-place updates) the graphs of the old generation must not be replayed."""
+    from oracle.weights import param_spec
+    from synth_data import seeded_weights
+    spec = param_spec(get_config("sam2_hiera_t"))
+
+    def run(m):
+        return _run_video(m, 512, 8, 1, (0, 4), (), 99)[1]
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    m.use_cuda_graphs = True
+    m.feature_cache_size, m.feature_encode_batch = 8, 2
+    a1 = run(m)
+    assert m._graphs.replays > 0
+    m.load_state_dict(seeded_weights(spec, seed=5), strict=True)       # new weights, same shapes
+    b_graph = run(m)
+    ref = _build("sam2_hiera_t", video=True, image_size=512)
+    ref.load_state_dict(seeded_weights(spec, seed=5), strict=True)
+    ref.use_cuda_graphs = False
+    ref.feature_cache_size, ref.feature_encode_batch = 8, 2
+    b_eager = run(ref)
+    for f in range(8):
+        assert torch.equal(b_graph[f], b_eager[f]), f"stale graph replayed on frame {f}"
+        assert not torch.equal(b_graph[f], a1[f])
+    with torch.no_grad():                                              # in-place update between train() and eval()
+        m.train()
+        for p in m.sam_mask_decoder.parameters():
+            p.mul_(1.01)
+        m.eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+    c_graph = run(m)
+    ref.load_state_dict(sd, strict=True)
+    c_eager = run(ref)
+    for f in range(8):
+        assert torch.equal(c_graph[f], c_eager[f]), f"stale graph replayed after in-place update, frame {f}"
+
+
+def test_train_twins_refuse_autograd():
+    """no autograd behind the `train_*` twins — refuse a training-mode call with gradients enabled."""
+    m = _build("sam2_hiera_t", video=True, image_size=512)
+    vol, boxes = btcv_volume(2, 512, 7, 1)
+    st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=512, video_width=512)
+    m.train()
+    with pytest.raises(RuntimeError, match="inference path"):
+        m.train_add_new_bbox(inference_state=st, frame_idx=0, obj_id=1, bbox=torch.tensor(boxes[0][0]), clear_old_points=False)
+    with torch.no_grad():
+        m.train_add_new_bbox(inference_state=st, frame_idx=0, obj_id=1, bbox=torch.tensor(boxes[0][0]), clear_old_points=False)
+    m.eval()

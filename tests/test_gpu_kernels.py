@@ -263,6 +263,33 @@ def test_attention_dv(ops, B, Lq, Lk, qs):
     assert (o.float() - r).abs().mean().item() < 2e-3
 
 
+@pytest.mark.parametrize("Lk,qs", [(209120, 1.0), (209120, 4.0), (1052736, 2.0)])
+def test_attention_dv_benchmarked_key_counts(ops, Lk, qs):
+    """memory cross-attention at the key counts of the benchmarked configurations: 209 120 = the longest bank of
+    BASELINE configs[2] as bench.py runs it (48 conditioning memories, the recent memories, pointer tokens), 1 052 736 = configs[4] (256 conditioning memories).  Checked against an fp32 torch statement evaluated in query
+    chunks on the same bf16-rounded operands; rows of probabilities over 10^5..10^6 keys make the outputs small, so the
+    bound is relative to the output scale as well as absolute."""
+    Lq = 4096
+    q = (rnd(1, Lq, 256, seed=1) * qs).to(torch.bfloat16)
+    k, v = rnd(1, Lk, 256, seed=2).to(torch.bfloat16), rnd(1, Lk, 64, seed=3).to(torch.bfloat16)
+    # a few keys every query attends to strongly, so the softmax is not flat noise
+    k[0, ::4099] = (q[0, :1].float() * 0.5).to(torch.bfloat16)
+    o = ops.attention_dv(q, k, v).float()
+    kf, vf = k[0].float(), v[0].float()
+    r = torch.empty(Lq, 64, device="cuda")
+    for c0 in range(0, Lq, 512):
+        s = (q[0, c0:c0 + 512].float() @ kf.T) / 16.0
+        r[c0:c0 + 512] = torch.softmax(s, dim=-1) @ vf
+        del s
+    err = (o[0] - r).abs()
+    scale = r.abs().max().item()
+    assert err.max().item() <= 1e-2 * max(scale, 1.0) and err.max().item() <= 8e-3 * scale + 2e-3, (err.max().item(), scale)
+    assert err.mean().item() <= 2e-3 * max(r.abs().mean().item(), 1e-3) + 2e-4, (err.mean().item(), r.abs().mean().item())
+    from conftest import record_parity
+    record_parity(f"attention_dv_Lk{Lk}_qs{qs}", {"max_abs_err": err.max().item(), "out_abs_max": scale,
+                                                  "mean_abs_err": err.mean().item(), "out_abs_mean": r.abs().mean().item()})
+
+
 @pytest.mark.parametrize("B,Lq,cuts,qs", [(1, 4096, (64, 4197, 24576), 1.0), (1, 4096, (8192,), 4.0), (2, 256, (100, 300, 1000), 3.0)])
 def test_attention_dv_partial_and_merge(ops, B, Lq, cuts, qs):
     """split-KV over several GPUs, on one GPU: partials over disjoint key ranges (plus an empty share) merged by
@@ -496,3 +523,41 @@ def test_fourier_and_normalize(ops):
     close(ops.normalize_image(x), ref_ops.normalize_image(x), 1e-5, "normalize f32")
     u = (torch.rand(2, 64, 64, 3, generator=gen(4)) * 255).to(torch.uint8).cuda()
     close(ops.normalize_image(u), ref_ops.normalize_image(u), 1e-5, "normalize u8")
+
+
+# ------------------------------------------------------------------ post-processing
+@pytest.mark.parametrize("shape", [(1, 1, 64, 64), (2, 1, 48, 40), (5, 1, 48, 40), (13, 1, 1024, 1024), (3, 1, 33, 7)])
+def test_non_overlap_bit_exact(ops, shape):
+    """ms2_non_overlap vs the torch statement of sam2_base.py:812-830 (argmax keeps the FIRST object on ties)."""
+    x = rnd(*shape, seed=3, scale=4.0)
+    x[:, :, :4] = x[:1, :, :4]                                  # ties across all objects
+    got = ops.non_overlap(x)
+    assert torch.equal(got, ref_ops.non_overlap(x)), shape
+
+
+def test_non_overlap_reference_golden(ops):
+    z = np.load(f"{G}/postprocess_cases.npz")
+    for n in (1, 2, 5):
+        x = torch.from_numpy(z[f"no/in_{n}"]).cuda()
+        from medsam2_b200.modeling.sam2_base import SAM2Base
+        got = SAM2Base._apply_non_overlapping_constraints(None, x)
+        assert np.array_equal(got.cpu().numpy(), z[f"no/out_{n}"]), n
+
+
+@pytest.mark.parametrize("N,h,H,T", [(3, 64, 256, 5), (2, 256, 1024, 5), (1, 128, 512, 8), (4, 50, 120, 1), (96, 256, 1024, 5)])
+def test_score_lowres_equals_resize_then_score(ops, N, h, H, T):
+    """ms2_score_lowres (bilinear up-sampling fused into the eval_seg counts + BCE pass) == ms2_resize_bilinear followed
+    by ms2_seg_counts (bit-exact integers) and ms2_bce_logits_sum (fp64 sums of fp32 terms, 1e-6 relative)."""
+    low = rnd(N, h, h, seed=4, scale=0.6)
+    low[0, : h // 4] = 0.1                                      # hole-fill value exactly on a threshold
+    gt = (rnd(N, H, H, seed=5) > 0.3).float()
+    thr = [0.1, 0.3, 0.5, 0.7, 0.9, -0.2, 0.0, 0.05][:T]
+    counts, sums = ops.score_lowres(low, gt, thr, pos_weight=2.0)
+    up = ops.resize_bilinear(low, (H, H))
+    assert torch.equal(counts, ops.seg_counts(up, gt, thr))
+    want = ops.bce_logits_sum(up, gt, 2.0)
+    assert ((sums - want).abs() <= 1e-6 * want.abs()).all(), (sums, want)
+    c2, s2 = ops.score_lowres(low, gt, thr)
+    assert s2 is None and torch.equal(c2, counts)
+    # and the up-sampling itself against torch (fp32 rounding only)
+    close(up, F.interpolate(low[:, None], size=(H, H), mode="bilinear", align_corners=False)[:, 0], 2e-6, "bilinear")
