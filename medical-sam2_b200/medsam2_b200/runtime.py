@@ -38,6 +38,8 @@ def compute(dtype):
 # freed weights.
 _GEN = [0]
 _CAPTURE_REFS = None           # while a GraphRunner captures: the derived tensors the capture touched (kept alive with it)
+_DERIVED_IN_CAPTURE = [False]  # a parameter copy had to be derived while capturing: its kernels were only RECORDED, so the
+                               # value is never stored in the cache and the capture is thrown away (GraphRunner.run)
 
 
 def bump_generation():
@@ -69,7 +71,9 @@ class ParamCache:
             with torch.no_grad():
                 val = fn(params)
             if _CAPTURE_REFS is not None:
+                _DERIVED_IN_CAPTURE[0] = True         # recorded, not executed: never cache it
                 _CAPTURE_REFS.append(val)
+                return val
             if len(self._d) > 4096:
                 self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
             self._d[k] = ((params._version, params.data_ptr(), params.dtype, str(params.device)), val,
@@ -89,7 +93,9 @@ class ParamCache:
         with torch.no_grad():
             val = fn(*params)
         if _CAPTURE_REFS is not None:
+            _DERIVED_IN_CAPTURE[0] = True
             _CAPTURE_REFS.append(val)
+            return val
         if len(self._d) > 4096:                       # drop entries whose parameters are gone
             self._d = {kk: v for kk, v in self._d.items() if all(r() is not None for r in v[2])}
         self._d[k] = (sig, val, tuple(weakref.ref(p) for p in params), None)
@@ -195,11 +201,14 @@ class GraphRunner:
         entry = self._graphs.get(full_key)
         if entry is not None and entry[5] != _GEN[0]:
             del self._graphs[full_key]                 # parameters changed since the capture: never replay stale weights
-            self._seen[full_key] = 0
             entry = None
         if entry is None:
-            n = self._seen.get(full_key, 0)
-            self._seen[full_key] = n + 1
+            # eager warm-up calls are counted PER parameter generation: the warm-up is what re-derives the kernel-ready
+            # parameter copies outside of any capture
+            g, n = self._seen.get(full_key, (_GEN[0], 0))
+            if g != _GEN[0]:
+                n = 0
+            self._seen[full_key] = (_GEN[0], n + 1)
             if n < self.warmup or not torch.cuda.is_available():
                 return fn(*tensors)
             # empty_like keeps the strides of dense (permuted) views and densifies expanded (stride-0) ones
@@ -215,6 +224,7 @@ class GraphRunner:
                 _BRANCH_STREAMS.append(torch.cuda.Stream())
             _CAPTURING = True
             _CAPTURE_REFS = refs = []
+            _DERIVED_IN_CAPTURE[0] = False
             gen0 = _GEN[0]
             try:
                 with torch.cuda.graph(graph):
@@ -222,8 +232,10 @@ class GraphRunner:
             finally:
                 _CAPTURING = False
                 _CAPTURE_REFS = None
-            if _GEN[0] != gen0:                        # a parameter copy was re-derived DURING the capture: do not keep it
-                self._seen[full_key] = 0
+            if _GEN[0] != gen0 or _DERIVED_IN_CAPTURE[0]:
+                # a parameter copy was (re-)derived DURING the capture: throw the capture away, warm up again
+                self._seen[full_key] = (_GEN[0], 0)
+                del graph
                 return fn(*tensors)
             entry = self._graphs[full_key] = [graph, static_in, static_out, native.launch_count - n0, None, gen0, refs]
         graph, static_in, static_out, launches, last = entry[:5]

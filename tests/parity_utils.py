@@ -68,7 +68,8 @@ def _frame_out(od, f):
 
 def compare_free_running(ost, ovid, pst, pvid, T):
     """-> dict of worst errors over all frames: low-res logits, video-res logits, sign agreement."""
-    worst = {"low_res": 0.0, "video_res": 0.0, "sign_agree_min": 1.0, "filled_mismatch": 0, "obj_ptr": 0.0}
+    worst = {"low_res": 0.0, "video_res": 0.0, "sign_agree_min": 1.0, "flipped_abs_logit_max": 0.0, "filled_mismatch": 0,
+             "obj_ptr": 0.0}
     for f in range(T):
         o, p = _frame_out(ost["output_dict"], f), _frame_out(pst["output_dict"], f)
         e, mm = _err(p["pred_masks"], o["pred_masks"])
@@ -86,7 +87,13 @@ def compare_free_running(ost, ovid, pst, pvid, T):
         else:
             d = (a - b).abs()
         worst["video_res"] = max(worst["video_res"], float(d.max().item()))
-        worst["sign_agree_min"] = min(worst["sign_agree_min"], float(((a > 0) == (b > 0)).float().mean().item()))
+        flip = (a > 0) != (b > 0)
+        worst["sign_agree_min"] = min(worst["sign_agree_min"], 1.0 - float(flip.float().mean().item()))
+        # a pixel may only change sides where the oracle's own logit is within the error bound of zero (random-weight
+        # logits crowd around zero, so the FRACTION of such pixels says little; their magnitude is the criterion)
+        flip_free = flip & ~infl if fill.any() else flip
+        if flip_free.any():
+            worst["flipped_abs_logit_max"] = max(worst["flipped_abs_logit_max"], float(b.abs()[flip_free].max().item()))
         worst["obj_ptr"] = max(worst["obj_ptr"], float((p["obj_ptr"].float() - o["obj_ptr"].float()).abs().max().item()))
     return worst
 
