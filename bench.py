@@ -297,6 +297,53 @@ def _build_predictor(args, T, prefetch):
     return model
 
 
+def _strong_selftest(world, rank):
+    """N>1 only, outside any timed region: the split-KV path (sharded slice encoding + all-gather of the pyramid + memory
+    bank dealt to the ranks + exchange/merge of the attention partials) must track a small volume to the masks ONE GPU
+    attending over the whole bank produces, and all ranks must hold identical outputs (the same checks as
+    tests/test_gpu_multi.py, which needs >= 2 GPUs and is therefore skipped on a 1-GPU test box)."""
+    import torch.distributed as dist
+    import medsam2_b200
+    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from oracle.config import get_config
+    from oracle.weights import param_spec
+    from synth_data import btcv_volume, seeded_weights
+    m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_t", device="cuda", hydra_overrides_extra=[
+        "++model.image_size=512", "++model.feature_cache_size=16", "++model.feature_encode_batch=2"])
+    m.load_state_dict(seeded_weights(param_spec(get_config("sam2_hiera_t"))), strict=True)
+    T = 10
+    vol, boxes = btcv_volume(T, 512, 5, 1)
+
+    def run(sharded):
+        st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=512, video_width=512)
+        if sharded:
+            encode_volume_sharded(m, st)
+        for f in (0, 3, 6):
+            m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+        return {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}
+    ref = run(False)
+    shard = shard_memory_attention(m)
+    got = run(True)
+    ok = shard is not None and shard.exchanges == 7 * len(m.memory_attention.layers)
+    worst = 0.0
+    for f in range(T):
+        a, b = got[f].float(), ref[f].float()
+        keep = ((a - 0.1).abs() > 1e-6) & ((b - 0.1).abs() > 1e-6)
+        worst = max(worst, float((a - b)[keep].abs().max().item()))
+        ok = ok and ((a > 0) == (b > 0)).float().mean().item() >= 0.998
+    ok = ok and worst <= 3e-2
+    mine = torch.stack([got[f] for f in range(T)]).contiguous()
+    theirs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(theirs, mine)
+    ok = ok and all(torch.equal(t, theirs[0]) for t in theirs)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    del m
+    torch.cuda.empty_cache()
+    return {"split_kv_matches_single_gpu": bool(flag.item()), "ranks_identical": bool(flag.item()),
+            "max_abs_logit_diff_vs_single_gpu": worst, "volume": "hiera_t 512^2, 10 slices, bbox on 0/3/6"}
+
+
 def _strong_record(args, world, rank):
     """BASELINE configs[4] under torchrun: ONE `--strong-slices`-slice volume on all ranks — slice encoding sharded by
     contiguous blocks + all-gather of the pyramid, memory bank dealt to the ranks (split-KV memory cross-attention, one
@@ -351,6 +398,8 @@ def _strong_record(args, world, rank):
                    "note": "each rank uploads only the slice block it encodes"},
            "partial_exchanges_per_step": exchanges}
     del model, vol_dev, vol_host
+    torch.cuda.empty_cache()
+    rec["selftest"] = _strong_selftest(world, rank)
     torch.cuda.empty_cache()
     return rec
 

@@ -44,6 +44,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (max relative error 7.6e-5, far below the bf16 rounding of P, 3.9e-3), 2^n by adding n to the exponent
+// bits.  The 1.5*2^23 constant leaves n in the low mantissa bits of t.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.05520550534f, f, 0.24261397123f);
+  p = fmaf(p, f, 0.69325476885f);
+  p = fmaf(p, f, 0.99992769957f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // D = head dim of Q/K, DV = head dim of V/O (DV < D: attention over un-projected 64-d memory values, the value
 // projection is applied to the 64-d result afterwards - softmax rows sum to 1), BKV = keys per
 // tile, KST = depth of the K ring (V ring: 2).
@@ -374,10 +387,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //   warps 6..9  softmax of stream b
 // TMEM: O_a [0,64) O_b [64,128) S_a [128,192) S_b [192,256) Q_a [256,384) Q_b [384,512); P overwrites S in place,
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
-constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64;
+constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64, T2_DEFAULT_VAR = 0;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
 
+// VAR: bit 0 = independent partial maxima / row sums (breaks the 32-deep FMNMX3 and FADD dependency chains of a row);
+//      bits 1..2 = share of the exponentials evaluated by ex2_poly on the FMA pipe instead of MUFU.EX2: 0, 1/4, 3/8, 1/2
+template <int VAR>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
@@ -557,10 +573,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
       }
       float mx = -INFINITY;
+      if (VAR & 1) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[c][i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+      }
       mx *= p.c;
       if (j == 0) {
         m_used = mx;
@@ -589,16 +614,26 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t pk[32];
       const float nm = -m_used;
+      constexpr int PM = (VAR >> 1) & 3;             // polynomial share: 0, 2/8, 3/8, 4/8 of the elements
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
-          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
-          l += p0 + p1;
+          const float x0 = fmaf(__uint_as_float(r[c][i]), p.c, nm);
+          const float x1 = fmaf(__uint_as_float(r[c][i + 1]), p.c, nm);
+          // element i of every group of 8: which pipe evaluates 2^x (compile-time pattern, interleaved with MUFU ones)
+          const int e = i & 7;
+          const bool poly0 = (PM == 1 && e == 2) || (PM == 2 && (e == 2 || e == 6)) || (PM == 3 && (e == 2 || e == 6));
+          const bool poly1 = (PM == 1 && e == 6) || (PM == 2 && e == 4) || (PM == 3 && (e == 0 || e == 4));
+          const float p0 = poly0 ? ex2_poly(x0) : ex2(x0);
+          const float p1 = poly1 ? ex2_poly(x1) : ex2(x1);
+          if (VAR & 1) l4[(i >> 1) & 3] += p0 + p1;
+          else l += p0 + p1;
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
         }
+      if (VAR & 1) l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       if (j > 0) tc::mbar_wait(&o_ready[x], (uint32_t)(j - 1) & 1u);      // observe every phase (see attn_tc_kernel)
       tc::tmem_st16(tS, &pk[0]);
       tc::tmem_st16(tS + 16, &pk[16]);
@@ -831,13 +866,25 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
+    static const int var = []() { const char* e = getenv("MS2_T2_VAR"); return e ? atoi(e) : T2_DEFAULT_VAR; }();
     static bool attr2 = false;
     if (!attr2) {
-      MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr");
+#define MS2_T2_ATTR(V) MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr")
+      MS2_T2_ATTR(0); MS2_T2_ATTR(1); MS2_T2_ATTR(2); MS2_T2_ATTR(3); MS2_T2_ATTR(4); MS2_T2_ATTR(5); MS2_T2_ATTR(6); MS2_T2_ATTR(7);
+#undef MS2_T2_ATTR
       attr2 = true;
     }
     dim3 grid2(qpairs, B * Hh, p.nsplit);
-    attn_tc2_kernel<<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p);
+    switch (var & 7) {
+      case 0: attn_tc2_kernel<0><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 1: attn_tc2_kernel<1><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 2: attn_tc2_kernel<2><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 3: attn_tc2_kernel<3><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 4: attn_tc2_kernel<4><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 5: attn_tc2_kernel<5><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 6: attn_tc2_kernel<6><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      default: attn_tc2_kernel<7><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    }
     MS2_CHECK_LAUNCH("attn_tc2_kernel");
   } else {
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }

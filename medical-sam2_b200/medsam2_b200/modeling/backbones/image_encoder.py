@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ...runtime import compute_dtype, p32, w_c
+from ...runtime import CACHE, compute_dtype, p32, w_c
 from ..sam2_utils import as_nchw_view, as_nhwc, to_compute
 
 
@@ -32,17 +32,32 @@ class FpnNeck(nn.Module):
         self.fpn_top_down_levels = list(fpn_top_down_levels)
 
     def lateral(self, i, x_nhwc, fold=None):
-        """1x1 conv of level i as a token GEMM; `fold=(W2,b2)` applies a second 1x1 conv folded in."""
+        """1x1 conv of level i as a token GEMM.  `fold` = a second 1x1 conv (nn.Conv2d) applied right after it on a
+        level that receives no top-down feature (SAM2Base.forward_image: conv_s0 / conv_s1 on the two high-resolution
+        levels, sam2_base.py:464-476): two 1x1 convs in a row are ONE linear map, W = W2 W1, b = W2 b1 + b2 (folded in
+        fp32), so the 256-channel intermediate (512 MiB per 8-slice batch at level 0) is never written, cast or read."""
         n = len(self.convs) - 1
         conv = self.convs[n - i].conv
-        return ops.gemm(to_compute(x_nhwc), w_c(conv.weight), p32(conv.bias), out_dtype=torch.float32)
+        if fold is None:
+            return ops.gemm(to_compute(x_nhwc), w_c(conv.weight), p32(conv.bias), out_dtype=torch.float32)
+        dt = compute_dtype()
 
-    def forward_tokens(self, xs):
+        def make(w1, b1, w2, b2):
+            W2, W1 = w2.detach().float().reshape(w2.shape[0], -1), w1.detach().float().reshape(w1.shape[0], -1)
+            return ((W2 @ W1).to(dt).contiguous(), (W2 @ b1.detach().float() + b2.detach().float()).contiguous())
+        W, b = CACHE.get((conv.weight, conv.bias, fold.weight, fold.bias), ("fold1x1", dt), make)
+        return ops.gemm(to_compute(x_nhwc), W, b, out_dtype=torch.float32)
+
+    def forward_tokens(self, xs, fold=None):
+        """`fold`: {level: nn.Conv2d} of 1x1 convs to fold into the lateral conv of levels without top-down input."""
         n = len(self.convs) - 1
         out = [None] * len(self.convs)
         prev = None
         for i in range(n, -1, -1):
-            lat = self.lateral(i, xs[i])
+            f = None if fold is None else fold.get(i)
+            if f is not None:
+                assert i not in self.fpn_top_down_levels, "only levels without a top-down sum can be folded"
+            lat = self.lateral(i, xs[i], f)
             if i in self.fpn_top_down_levels and prev is not None:
                 ops.upsample2x_add_(lat, prev)
             prev = lat
@@ -64,8 +79,8 @@ class ImageEncoder(nn.Module):
             f"Channel dims of trunk and neck do not match. Trunk: {self.trunk.channel_list}, "
             f"neck: {self.neck.backbone_channel_list}")
 
-    def forward_tokens(self, sample):
-        feats = self.neck.forward_tokens(self.trunk.forward_tokens(sample))
+    def forward_tokens(self, sample, fold=None):
+        feats = self.neck.forward_tokens(self.trunk.forward_tokens(sample), fold)
         if self.scalp > 0:
             feats = feats[: -self.scalp]
         return feats

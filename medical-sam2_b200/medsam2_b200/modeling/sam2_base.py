@@ -155,9 +155,15 @@ class SAM2Base(nn.Module):
     def forward_image(self, img_batch):
         """sam2_base.py:464-476: encoder + conv_s0/conv_s1 on the two high-resolution levels."""
         def encode(img):
+            d = self.sam_mask_decoder
+            neck = self.image_encoder.neck
+            # bf16 mode: conv_s0 / conv_s1 fold into the neck's lateral 1x1 convs of the two high-resolution levels
+            # (no top-down sum there); the fp32 exact mode keeps the reference's two-step evaluation order
+            if (self.use_high_res_features_in_sam and compute_dtype() == torch.bfloat16 and self.image_encoder.scalp >= 0
+                    and 0 not in neck.fpn_top_down_levels and 1 not in neck.fpn_top_down_levels and len(neck.convs) >= 3):
+                return self.image_encoder.forward_tokens(img, fold={0: d.conv_s0, 1: d.conv_s1})
             fs = self.image_encoder.forward_tokens(img)
             if self.use_high_res_features_in_sam:
-                d = self.sam_mask_decoder
                 fs[0] = ops.gemm(to_compute(fs[0]), w_c(d.conv_s0.weight), p32(d.conv_s0.bias))
                 fs[1] = ops.gemm(to_compute(fs[1]), w_c(d.conv_s1.weight), p32(d.conv_s1.bias))
             return fs
