@@ -211,15 +211,40 @@ int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, i
 
 /* ---- sparse prompt embedding in one launch (prompt_encoder.py:79-101 `_embed_points`): coords fp32 [B,N,2] in input
  *      pixels, labels int32 [B,N], gauss fp32 [2,F], table fp32 [5,2F] = [not_a_point, point_embeddings 0..3];
- *      out fp32 [B,N+pad,2F]; pad != 0 appends the padding point (label -1) used when no box is given. */
+ *      out fp32 [B,n_prefix+N+pad,2F]; pad != 0 appends the padding point (label -1) used when no box is given;
+ *      prefix fp32 [n_prefix,2F] (or NULL) is copied in front of the prompt rows of every batch entry (the mask decoder's
+ *      output tokens, mask_decoder.py:186-196: torch.cat of the tokens and the sparse prompts). */
 int ms2_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float* out,
-                    int B, int N, int pad, int F, int image_w, int image_h, ms2_stream_t stream);
+                    int B, int N, int pad, int F, int image_w, int image_h, const float* prefix, int n_prefix,
+                    ms2_stream_t stream);
 
 /* ---- frame ingest (utils/misc.py:92-101 `_load_img_as_tensor`, :215-244 `load_video_frames_from_data`,
  *      transforms.py:28-42): out NCHW = (x/255 - mean)/std, dtype out_dt (fp32 = the reference's frame dtype; bf16 = the
  *      cast autocast applies in front of the patch-embed conv, fused here).  x: in_layout 0 = fp32 NCHW (video tensor),
  *      1 = uint8 NHWC (decoded JPEG / image predictor), 2 = uint8 NCHW (uint8 video tensor). */
 int ms2_normalize_image(const void* x, int in_layout, void* out, int out_dt, int B, int H, int W, ms2_stream_t stream);
+
+/* ---- per-slice glue of the tracking step (the reference: a dozen tiny torch ops each)
+ *      ms2_bank_rows (reference sam2_train/modeling/sam2_base.py:566-637: torch.cat of the recent memories and the
+ *      object-pointer tokens, `+ maskmem_pos_enc + maskmem_tpos_enc`, cast): n <= 80 sources (HOST arrays of DEVICE
+ *      pointers: h_src[i] fp32 [B,h_rows[i],W]; h_pos[i] fp32 [h_rows[i],W] with h_pos_bs[i] = 0, or [B,h_rows[i],W] with
+ *      its batch stride, or NULL) are written back to back, in order: k_in[b] rows = src + pos, m_out[b] rows = src, both
+ *      of dtype out_dt with batch strides k_bs / m_bs (elements); either destination may be NULL.  W % 4 == 0. */
+int ms2_bank_rows(const void* const* h_src, const void* const* h_pos, const long* h_pos_bs, const int* h_rows, int n, int W,
+                  int B, void* k_in, long k_bs, void* m_out, long m_bs, int out_dt, ms2_stream_t stream);
+/*      ms2_argmax_select_rows (sam2_base.py:383-395): idx_out[b] = first arg-max of scores[b*scores_rs + 0..M) (may be NULL);
+ *      out[b,0..C) = rows[b*rows_bs + idx*rows_rs + 0..C) (rows/out may be NULL). */
+int ms2_argmax_select_rows(const float* scores, long scores_rs, int B, int M, const float* rows, long rows_bs, long rows_rs, int C,
+                           int32_t* idx_out, float* out, ms2_stream_t stream);
+/*      ms2_obj_ptr_mix (sam2_base.py:397-408): lam = soft ? sigmoid(logit) : (logit > 0);
+ *      out = (fixed ? lam*ptr : ptr) + (1-lam)*no_obj;  ptr/out fp32 [B,C], logits fp32 [B], no_obj fp32 [C]. */
+int ms2_obj_ptr_mix(const float* ptr, const float* logits, const float* no_obj, float* out, int B, int C, int soft,
+                    int fixed, ms2_stream_t stream);
+/*      ms2_stability_select (modeling/sam/mask_decoder.py:269-317 `_dynamic_multimask_via_stability`): counts int32 [B,2]
+ *      from ms2_mask_stability_counts, ious fp32 [B,M]: idx = (area_i/area_u >= thresh or area_u == 0) ? 0 :
+ *      1 + argmax(ious[b,1:]); iou_out[b] = ious[b,idx]. */
+int ms2_stability_select(const int32_t* counts, const float* ious, int B, int M, float thresh, int32_t* idx_out,
+                         float* iou_out, ms2_stream_t stream);
 
 /* ---- mask statistics for the stability fallback (mask_decoder.py:269-317): per (b) plane of fp32
  *      logits [N,P]: counts[n,0] = #(x>delta), counts[n,1] = #(x>-delta). */

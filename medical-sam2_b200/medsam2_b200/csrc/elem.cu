@@ -261,13 +261,21 @@ __global__ void fourier_pe_kernel(const float* __restrict__ coords, const float*
 // with label = -1 and xy = 0 for the padding point j == N.  Replaces ~14 element-wise torch kernels per slice.
 __global__ void point_embed_kernel(const float* __restrict__ coords, const int* __restrict__ labels,
                                    const float* __restrict__ gauss, const float* __restrict__ table,
-                                   float* __restrict__ out, int B, int N, int pad, int F, float inv_w, float inv_h) {
-  const int Np = N + (pad ? 1 : 0);
+                                   float* __restrict__ out, int B, int N, int pad, int F, float inv_w, float inv_h,
+                                   const float* __restrict__ prefix, int P) {
+  const int Np = N + (pad ? 1 : 0) + P;
   const long total = (long)B * Np * F;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int f = (int)(i % F);
     const long r = i / F;
-    const int j = (int)(r % Np), b = (int)(r / Np);
+    int j = (int)(r % Np);
+    const int b = (int)(r / Np);
+    if (j < P) {                    // constant rows in front of the prompt rows (the mask decoder's output tokens)
+      out[r * 2 * F + f] = prefix[(long)j * 2 * F + f];
+      out[r * 2 * F + F + f] = prefix[(long)j * 2 * F + F + f];
+      continue;
+    }
+    j -= P;
     float x = 0.f, y = 0.f;
     int lab = -1;
     if (j < N) {
@@ -781,13 +789,14 @@ extern "C" int ms2_fourier_pe(const float* coords, const float* gauss, float* ou
   return MS2_OK;
 }
 extern "C" int ms2_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float* out,
-                               int B, int N, int pad, int F, int image_w, int image_h, void* stream) {
-  MS2_CHECK_ARG(coords && labels && gauss && table && out && N >= 0 && F > 0 && image_w > 0 && image_h > 0,
+                               int B, int N, int pad, int F, int image_w, int image_h, const float* prefix, int n_prefix,
+                               void* stream) {
+  MS2_CHECK_ARG(coords && labels && gauss && table && out && N >= 0 && F > 0 && image_w > 0 && image_h > 0 && n_prefix >= 0,
                 "point_embed: bad args");
-  const long total = (long)B * (N + (pad ? 1 : 0)) * F;
+  const long total = (long)B * (N + (pad ? 1 : 0) + (prefix ? n_prefix : 0)) * F;
   if (!total) return MS2_OK;
   point_embed_kernel<<<grid_for(total), 256, 0, ST>>>(coords, labels, gauss, table, out, B, N, pad, F, 1.f / image_w,
-                                                      1.f / image_h);
+                                                      1.f / image_h, prefix, prefix ? n_prefix : 0);
   MS2_CHECK_LAUNCH("point_embed");
   return MS2_OK;
 }

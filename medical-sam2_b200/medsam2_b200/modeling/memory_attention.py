@@ -123,24 +123,23 @@ class MemoryAttention(nn.Module):
             x = layer.forward_tokens(x, curr_pos, mem_k_in, mem_v_in, num_obj_ptr_tokens)
         return self.norm(x)
 
-    def _project_into_bank(self, bank, row0, mem, pos_flat, n_rope_rows, Lq):
-        """mem fp32 [B,n,Cm]; pos_flat: fp32 tensor broadcast over mem as pos.flatten()[i mod numel] (or None)
-        -> per layer K (RoPE on the first n_rope_rows rows, restarting every Lq rows) and V written at bank rows
-        [row0, row0+n)."""
+    def _project_into_bank(self, bank, row0, srcs, poss, n_rope_rows, Lq):
+        """srcs: fp32 [B,rows_i,Cm] memories (in key order), poss: per source a position table [rows_i,Cm] / [B,rows_i,Cm]
+        or None -> per layer K (RoPE on the first n_rope_rows rows, restarting every Lq rows) and V written at bank rows
+        [row0, row0+n).  The concatenation, `+ pos`, and the casts are ONE kernel (ms2_bank_rows)."""
         cd = compute_dtype()
-        B, n, _ = mem.shape
+        B = srcs[0].shape[0]
+        n = sum(t.shape[1] for t in srcs)
         if bank.raw_v:
-            for b in range(B):
-                ops.cast_into(mem[b], bank.M[b, row0: row0 + n])
+            k_in, _ = ops.bank_rows(srcs, poss, cd, m_out=bank.M[:, row0: row0 + n])
             v_in = None
-            k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else to_compute(mem)
         else:
-            v_in = to_compute(mem)
-            k_in = ops.axpby(mem, 1.0, pos_flat, 1.0, out_dtype=cd) if pos_flat is not None else v_in
+            v_in = torch.empty((B, n, srcs[0].shape[2]), dtype=cd, device=srcs[0].device)
+            k_in, _ = ops.bank_rows(srcs, poss, cd, m_out=v_in)
         for l, layer in enumerate(self.layers):
             att = layer.cross_attn_image
             D = att.internal_dim // att.num_heads
-            cos, sin = att._table(Lq, mem.device)
+            cos, sin = att._table(Lq, srcs[0].device)
             for b in range(B):
                 kd = bank.K[l][b, row0: row0 + n]
                 att.k_proj(k_in[b], out_dtype=cd, out=kd)
@@ -169,7 +168,9 @@ class MemoryAttention(nn.Module):
             if not shard.owns_pointers(n_recent, n_cond):
                 ptrs = ptr_pos = None
         hw = cond[0][2].shape[1] if cond else (recent[0][2].shape[1] if recent else L)
-        n_dyn = sum(e[2].shape[1] for e in recent) + (ptrs.shape[1] if ptrs is not None else 0)
+        ptr_list = ptrs if isinstance(ptrs, list) else ([ptrs] if ptrs is not None else [])
+        n_ptr_rows = sum(t.shape[1] for t in ptr_list)
+        n_dyn = sum(e[2].shape[1] for e in recent) + n_ptr_rows
         keys = [e[0] for e in cond]
         if bank.keys != keys[: len(bank.keys)] or bank.B not in (None, B):
             bank.reset()
@@ -184,24 +185,21 @@ class MemoryAttention(nn.Module):
                     curr.device)
         new = cond[len(bank.keys):]
         if new:                                            # conditioning memories not yet resident: project once
-            mem = new[0][2] if len(new) == 1 else torch.cat([e[2] for e in new], dim=1)
-            same_pos = all(e[3] is new[0][3] for e in new)
-            pos = None
-            if keys_at_pos:
-                pos = new[0][3] if same_pos else torch.cat([e[3] for e in new], dim=0)
-            self._project_into_bank(bank, bank.n_static, mem.contiguous(), pos, mem.shape[1], L)
-            bank.n_static += mem.shape[1]
+            srcs = [e[2] for e in new]
+            poss = [e[3] if keys_at_pos else None for e in new]
+            self._project_into_bank(bank, bank.n_static, srcs, poss, sum(t.shape[1] for t in srcs), L)
+            bank.n_static += sum(t.shape[1] for t in srcs)
             bank.keys = keys
             bank.refs = [e[1] for e in cond]               # keep the sources alive: id() keys stay unique
         row0 = bank.n_static
         if n_dyn:
-            mems = [e[2] for e in recent] + ([ptrs] if ptrs is not None else [])
-            mem = mems[0] if len(mems) == 1 else torch.cat(mems, dim=1)
-            pos = None
+            srcs = [e[2] for e in recent] + ptr_list
             if keys_at_pos:
-                poss = [e[3][None].expand(B, -1, -1) for e in recent] + ([ptr_pos] if ptrs is not None else [])
-                pos = (poss[0] if len(poss) == 1 else torch.cat(poss, dim=1)).contiguous()
-            self._project_into_bank(bank, row0, mem.contiguous(), pos, sum(e[2].shape[1] for e in recent), L)
+                poss = [e[3] for e in recent] + ([ptr_pos] if (ptr_pos is not None and not isinstance(ptrs, list))
+                                                 else [None] * len(ptr_list))
+            else:
+                poss = [None] * len(srcs)
+            self._project_into_bank(bank, row0, srcs, poss, sum(e[2].shape[1] for e in recent), L)
         Lk = row0 + n_dyn
         x = ops.axpby(curr, 1.0, curr_pos, 0.1) if (self.pos_enc_at_input and curr_pos is not None) else curr
         for l, layer in enumerate(self.layers):

@@ -64,7 +64,7 @@ class MaskDecoder(nn.Module):
         from ...runtime import CACHE
         return CACHE.get(tuple(parts), "out_tokens", lambda *ts: torch.cat([t.float() for t in ts], 0).contiguous())
 
-    def predict_tokens(self, src, pos, sparse, feat_s0, feat_s1):
+    def predict_tokens(self, src, pos, sparse, feat_s0, feat_s1, tokens=None):
         """src fp32 [B,HW,C] (image embedding + dense prompt); pos fp32 [B,HW,C]; sparse fp32 [B,Ns,C];
         feat_s0 NHWC [B,4h,4w,C/8], feat_s1 NHWC [B,2h,2w,C/4] (or None)
         -> masks fp32 [B,4,4h,4w], iou [B,4], mask tokens fp32 [B,4,C], obj logits [B,1]."""
@@ -73,7 +73,8 @@ class MaskDecoder(nn.Module):
         h = w = int(round(HW ** 0.5))
         s = 1 if self.pred_obj_scores else 0
         out_tok = self._output_tokens()
-        tokens = torch.cat((out_tok.unsqueeze(0).expand(B, -1, -1), sparse), dim=1).contiguous()
+        if tokens is None:                 # `tokens`: output tokens + sparse prompts already in one buffer (prompt encoder)
+            tokens = torch.cat((out_tok.unsqueeze(0).expand(B, -1, -1), sparse), dim=1).contiguous()
         hs, keys = self.transformer.forward_tokens(src, pos, tokens)
         Nt = hs.shape[1]
         mask_tokens_out = hs[:, s + 1: s + 1 + self.num_mask_tokens, :]
@@ -155,17 +156,13 @@ class MaskDecoder(nn.Module):
         return masks_o, iou_o, sam_tokens
 
     def _dynamic_multimask_via_stability(self, all_mask_logits, all_iou_scores):
-        B = all_mask_logits.shape[0]
+        """mask_decoder.py:269-317: threshold counts of the single-mask logits, then stability test, best multimask index
+        and its IoU in one launch; the chosen plane is gathered on device (no host synchronisation)."""
         single = all_mask_logits[:, 0:1].contiguous()
-        counts = ops.mask_stability_counts(single, self.dynamic_multimask_stability_delta).float()
-        area_i, area_u = counts[:, 0], counts[:, 1]
-        stability = torch.where(area_u > 0, area_i / area_u, torch.ones_like(area_u))
-        is_stable = stability >= self.dynamic_multimask_stability_thresh
-        best = torch.argmax(all_iou_scores[:, 1:], dim=-1) + 1
-        idx = torch.where(is_stable, torch.zeros_like(best), best).to(torch.int32)
-        masks_o = ops.select_plane(all_mask_logits.contiguous(), idx)
-        iou_o = torch.gather(all_iou_scores, 1, idx.long()[:, None])
-        return masks_o, iou_o
+        counts = ops.mask_stability_counts(single, self.dynamic_multimask_stability_delta)
+        idx, iou_o = ops.stability_select(counts, all_iou_scores.float().contiguous(),
+                                          self.dynamic_multimask_stability_thresh)
+        return ops.select_plane(all_mask_logits.contiguous(), idx), iou_o
 
     # ------------------------------------------------------------------ reference signature
     def forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
@@ -197,7 +194,13 @@ class MaskDecoder(nn.Module):
             f0, f1 = (as_nhwc(f.float()) for f in high_res_features)
             if f0.shape[0] != B:
                 f0, f1 = f0.expand(B, -1, -1, -1).contiguous(), f1.expand(B, -1, -1, -1).contiguous()
+        tokens = getattr(sparse_prompt_embeddings, "_ms2_tokens", None)
+        n_out = self.num_mask_tokens + 1 + (1 if self.pred_obj_scores else 0)
+        if tokens is not None and not (tokens.dtype == torch.float32 and tokens.is_contiguous() and tokens.shape[0] == B
+                                       and tokens.shape[1] == n_out + sparse_prompt_embeddings.shape[1]):
+            tokens = None
         masks, iou_pred, mask_tokens_out, obj = self.predict_tokens(
-            src.view(B, h * w, C), pos, sparse_prompt_embeddings.float().contiguous(), f0, f1)
+            src.view(B, h * w, C), pos, None if tokens is not None else sparse_prompt_embeddings.float().contiguous(),
+            f0, f1, tokens=tokens)
         masks_o, iou_o, sam_tokens = self.select_outputs(masks, iou_pred, mask_tokens_out, multimask_output)
         return masks_o, iou_o, sam_tokens, obj

@@ -80,10 +80,11 @@ class PromptEncoder(nn.Module):
         ps = (self.not_a_point_embed.weight,) + tuple(e.weight for e in self.point_embeddings)
         return CACHE.get(ps, "label_table", lambda *ts: torch.cat([t.float() for t in ts], 0).contiguous())
 
-    def _embed_points(self, points, labels, pad):
+    def _embed_points(self, points, labels, pad, prefix=None):
         if points.dim() == 3 and labels.dim() == 2 and not labels.dtype.is_floating_point:
             return ops.point_embed(points, labels, p32(self.pe_layer.positional_encoding_gaussian_matrix),
-                                   self._label_table(), pad, self.input_image_size)
+                                   self._label_table(), pad, self.input_image_size, prefix)
+        assert prefix is None
         points = points.float() + 0.5
         if pad:
             points = torch.cat([points, torch.zeros((points.shape[0], 1, 2), device=points.device)], dim=1)
@@ -108,8 +109,11 @@ class PromptEncoder(nn.Module):
         x = n1(x, out_dtype=cd, act=ops.ACT_GELU)
         return ops.gemm(x, w_c(c2.weight), p32(c2.bias), out_dtype=torch.float32)
 
-    def forward(self, points, boxes, masks, batch_size=-1):
-        """-> (sparse [B,N,C] fp32, dense NCHW-shaped [B,C,h,w] fp32)."""
+    def forward(self, points, boxes, masks, batch_size=-1, token_prefix=None):
+        """-> (sparse [B,N,C] fp32, dense NCHW-shaped [B,C,h,w] fp32).  `token_prefix` (fp32 [P,C], optional, not in the
+        reference): the click embeddings are written behind P constant rows of ONE buffer and `sparse` is the view past
+        them; the buffer rides along as `sparse._ms2_tokens` so that the mask decoder can use it as its token matrix
+        (output tokens + sparse prompts, mask_decoder.py:186-196) without a concatenation kernel."""
         if points is not None:
             bs = points[0].shape[0]
         elif boxes is not None:
@@ -119,12 +123,22 @@ class PromptEncoder(nn.Module):
         else:
             bs = 1
         dev = self.no_mask_embed.weight.device
-        sparse = torch.empty((bs, 0, self.embed_dim), device=dev)
+        sparse = None
         if points is not None:
             coords, labels = points
-            sparse = torch.cat([sparse, self._embed_points(coords, labels, pad=(boxes is None))], dim=1)
+            fused = (token_prefix is not None and boxes is None and coords.dim() == 3 and labels.dim() == 2
+                     and not labels.dtype.is_floating_point)
+            emb = self._embed_points(coords, labels, pad=(boxes is None), prefix=token_prefix if fused else None)
+            if fused:
+                sparse = emb[:, token_prefix.shape[0]:]
+                sparse._ms2_tokens = emb
+            else:
+                sparse = emb
         if boxes is not None:
-            sparse = torch.cat([sparse, self._embed_boxes(boxes)], dim=1)
+            be = self._embed_boxes(boxes)
+            sparse = be if sparse is None else torch.cat([sparse, be], dim=1)
+        if sparse is None:
+            sparse = torch.empty((bs, 0, self.embed_dim), device=dev)
         if masks is not None:
             B, _, H, W = masks.shape
             dense = as_nchw_view(self.embed_masks_tokens(masks.float().contiguous().view(B, H, W, 1)))

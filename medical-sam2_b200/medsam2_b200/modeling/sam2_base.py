@@ -62,6 +62,7 @@ class SAM2Base(nn.Module):
         self.use_cuda_graphs = os.environ.get("MS2_CUDA_GRAPHS", "0") == "1"
         from ..runtime import GraphRunner
         self._graphs = GraphRunner()
+        self._no_prompt = {}
         self.maskmem_tpos_enc = nn.Parameter(torch.zeros(num_maskmem, 1, 1, self.mem_dim))
         trunc_normal_(self.maskmem_tpos_enc, std=0.02)
         self.no_mem_embed = nn.Parameter(torch.zeros(1, 1, self.hidden_dim))
@@ -223,8 +224,12 @@ class SAM2Base(nn.Module):
             sam_point_labels = point_inputs["point_labels"]
             assert sam_point_coords.size(0) == B and sam_point_labels.size(0) == B
         else:
-            sam_point_coords = torch.zeros(B, 1, 2, device=device)
-            sam_point_labels = -torch.ones(B, 1, dtype=torch.int32, device=device)
+            # the "no prompt" padding point (sam2_base.py:300-303) is a constant: built once per (B, device)
+            key = (B, str(device))
+            if key not in self._no_prompt:
+                self._no_prompt[key] = (torch.zeros(B, 1, 2, device=device),
+                                        -torch.ones(B, 1, dtype=torch.int32, device=device))
+            sam_point_coords, sam_point_labels = self._no_prompt[key]
         if mask_inputs is not None:
             assert len(mask_inputs.shape) == 4 and mask_inputs.shape[:2] == (B, 1)
             if tuple(mask_inputs.shape[-2:]) != tuple(self.sam_prompt_encoder.mask_input_size):
@@ -234,35 +239,36 @@ class SAM2Base(nn.Module):
                 sam_mask_prompt = mask_inputs
         else:
             sam_mask_prompt = None
+        # the decoder's output tokens ride in front of the sparse prompt rows (one buffer, no concatenation kernel)
         sparse, dense = self.sam_prompt_encoder(points=(sam_point_coords, sam_point_labels), boxes=None,
-                                                masks=sam_mask_prompt)
+                                                masks=sam_mask_prompt, token_prefix=self.sam_mask_decoder._output_tokens())
         low_res_multimasks, ious, sam_output_tokens, object_score_logits = self.sam_mask_decoder(
             image_embeddings=backbone_features, image_pe=self.sam_prompt_encoder.get_dense_pe(),
             sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=multimask_output,
             repeat_image=False, high_res_features=high_res_features)
         low_res_multimasks = low_res_multimasks.float().contiguous()
-        best = torch.argmax(ious, dim=-1) if multimask_output else None
+        best = tok_best = None
+        if multimask_output:
+            # best mask by predicted IoU and (when the decoder returns one token per mask) its output token: one launch
+            multi_tok = sam_output_tokens if sam_output_tokens.size(1) > 1 else None
+            best, tok_best = ops.argmax_select_rows(ious.float(), None if multi_tok is None else multi_tok.float())
+        obj_flat = object_score_logits.float().contiguous().view(-1)
 
         def mask_side():
             lr = low_res_multimasks
             if self.pred_obj_scores:
-                lr = ops.gate_rows(lr, object_score_logits.float().contiguous().view(-1), NO_OBJ_SCORE)
+                lr = ops.gate_rows(lr, obj_flat, NO_OBJ_SCORE)
             hr = ops.resize_bilinear(lr, (self.image_size, self.image_size))
             if multimask_output:
-                idx = best.to(torch.int32)
-                return lr, hr, ops.select_plane(lr, idx), ops.select_plane(hr, idx)
+                return lr, hr, ops.select_plane(lr, best), ops.select_plane(hr, best)
             return lr, hr, lr, hr
 
         def pointer_side():
-            tok = sam_output_tokens[:, 0]
-            if multimask_output and sam_output_tokens.size(1) > 1:
-                tok = sam_output_tokens[torch.arange(B, device=device), best]
+            tok = tok_best if tok_best is not None else sam_output_tokens[:, 0]
             ptr = self.obj_ptr_proj(tok.contiguous())
             if self.pred_obj_scores:
-                lam = object_score_logits.sigmoid() if self.soft_no_obj_ptr else (object_score_logits > 0).float()
-                if self.fixed_no_obj_ptr:
-                    ptr = lam * ptr
-                ptr = ptr + (1 - lam) * p32(self.no_obj_ptr)
+                ptr = ops.obj_ptr_mix(ptr.float().contiguous(), obj_flat, p32(self.no_obj_ptr).view(-1),
+                                      self.soft_no_obj_ptr, self.fixed_no_obj_ptr)
             return ptr
 
         # the mask path (gating, x4 up-sampling, plane selection) and the object pointer do not depend on each other
@@ -288,12 +294,11 @@ class SAM2Base(nn.Module):
                 backbone_features=backbone_features, mask_inputs=down.view(B, 1, H // 4, W // 4),
                 high_res_features=high_res_features)
         counts = ops.mask_stability_counts(mask_f, 0.0)
-        lam = (counts[:, 0:1] > 0).float()
-        object_score_logits = out_scale * lam + out_bias
+        # object present <=> any mask pixel > 0: logits = +10 / -10 (sam2_base.py:447-452)
+        object_score_logits = ops.axpby(counts[:, 0:1].float().clamp_(max=1.0).contiguous(), out_scale, None, 0.0, out_bias)
         if self.pred_obj_scores:
-            if self.fixed_no_obj_ptr:
-                obj_ptr = lam * obj_ptr
-            obj_ptr = obj_ptr + (1 - lam) * p32(self.no_obj_ptr)
+            obj_ptr = ops.obj_ptr_mix(obj_ptr.float().contiguous(), object_score_logits.view(-1), p32(self.no_obj_ptr).view(-1),
+                                      False, self.fixed_no_obj_ptr)
         return low_res_masks, high_res_masks, ious, low_res_masks, high_res_masks, obj_ptr, object_score_logits
 
     # ------------------------------------------------------------------ memory conditioning
@@ -307,10 +312,11 @@ class SAM2Base(nn.Module):
             return (t + tp[slot].float().reshape(1, -1)).contiguous()
         return CACHE.get(self.maskmem_tpos_enc, ("mem_pos", h, w, slot, str(device)), make)
 
-    def _memory_entries(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device):
+    def _memory_entries(self, frame_idx, output_dict, num_frames, track_in_reverse, B, device, lazy_ptrs=False):
         """sam2_base.py:518-637, un-concatenated: -> (cond, recent, ptrs, ptr_pos) where cond / recent are lists of
         (key, feats [B,hw,mem_dim] fp32 token-major, pos table [hw,mem_dim]) for the conditioning memories
-        (t_pos = 0) and the <= num_maskmem-1 recent ones, and ptrs / ptr_pos are [B,n_tok,mem_dim] or None."""
+        (t_pos = 0) and the <= num_maskmem-1 recent ones, and ptrs / ptr_pos are [B,n_tok,mem_dim] or None
+        (lazy_ptrs: ptrs is a LIST of [B,C/mem_dim,mem_dim] views, one per pointer, ptr_pos None = zero)."""
         C = self.hidden_dim
         cond_outputs = output_dict["cond_frame_outputs"]
         assert len(cond_outputs) > 0
@@ -356,6 +362,12 @@ class SAM2Base(nn.Module):
                     pos_and_ptrs.append((t_diff, o["obj_ptr"]))
             if pos_and_ptrs:
                 pos_list, ptrs_list = zip(*pos_and_ptrs)
+                if lazy_ptrs and not self.add_tpos_enc_to_obj_ptrs and self.mem_dim < C and C % self.mem_dim == 0:
+                    # banked path: the pointer tensors go into the bank's staging rows one by one (ms2_bank_rows), no
+                    # torch.stack / zeros / repeat_interleave; their position code is zero (sam2_base.py:627)
+                    rr = C // self.mem_dim
+                    ptrs = [p.float().contiguous().view(B, rr, self.mem_dim) for p in ptrs_list]
+                    return cond, recent, ptrs, None
                 ptrs = torch.stack([p.float() for p in ptrs_list], dim=1)                # [B,P,C]
                 P = ptrs.shape[1]
                 if self.add_tpos_enc_to_obj_ptrs:
@@ -410,7 +422,7 @@ class SAM2Base(nn.Module):
             # conditioning memories are frame-invariant after projection: keep their per-layer
             # K (RoPE applied) / V resident and only project the <= 6 recent memories + object pointers per frame
             cond, recent, ptrs, obj_pos = self._memory_entries(frame_idx, output_dict, num_frames, track_in_reverse,
-                                                               B, device)
+                                                               B, device, lazy_ptrs=True)
             bank = output_dict.get("_ms2_bank")
             if bank is None:
                 from .memory_attention import MemoryBank

@@ -490,17 +490,104 @@ def fourier_pe(coords01, gauss):
     return out
 
 
-def point_embed(coords, labels, gauss, table, pad, image_size):
-    """coords fp32 [B,N,2] (input pixels), labels int [B,N] -> sparse prompt embeddings fp32 [B,N+pad,2F]."""
+def point_embed(coords, labels, gauss, table, pad, image_size, prefix=None):
+    """coords fp32 [B,N,2] (input pixels), labels int [B,N] -> sparse prompt embeddings fp32 [B,P+N+pad,2F]; `prefix`
+    fp32 [P,2F]: constant rows written in front of the prompt rows of every batch entry."""
     B, N, _ = coords.shape
     Fh = gauss.shape[1]
-    out = torch.empty((B, N + (1 if pad else 0), 2 * Fh), dtype=torch.float32, device=coords.device)
+    P = 0 if prefix is None else prefix.shape[0]
+    out = torch.empty((B, P + N + (1 if pad else 0), 2 * Fh), dtype=torch.float32, device=coords.device)
     lab = labels if labels.dtype == torch.int32 else labels.to(torch.int32)
-    native.call("ms2_point_embed", _chk(coords.float().contiguous(), "coords", torch.float32),
-                _chk(lab.contiguous(), "labels", torch.int32), _chk(gauss, "gauss", torch.float32),
+    cf = coords if (coords.dtype == torch.float32 and coords.is_contiguous()) else coords.float().contiguous()
+    native.call("ms2_point_embed", _chk(cf, "coords", torch.float32),
+                _chk(lab if lab.is_contiguous() else lab.contiguous(), "labels", torch.int32), _chk(gauss, "gauss", torch.float32),
                 _chk(table, "table", torch.float32), out.data_ptr(), B, N, 1 if pad else 0, Fh, int(image_size[1]),
-                int(image_size[0]), _st())
+                int(image_size[0]), None if prefix is None else _chk(prefix, "prefix", torch.float32), P, _st())
     return out
+
+
+def bank_rows(srcs, poss, out_dtype, k_out=None, m_out=None):
+    """srcs: list of fp32 [B,rows_i,W] contiguous tensors; poss: per source None, an fp32 [rows_i,W] table or an fp32
+    [B,rows_i,W] tensor.  Writes the sources back to back (in order) as k_out[b] = src + pos and m_out[b] = src, both
+    `out_dtype` [B,total,W] (row-strided views of a larger buffer are fine: unit inner stride, rows contiguous);
+    allocates k_out when None, m_out stays optional.  -> (k_out, m_out)."""
+    import ctypes
+    n = len(srcs)
+    B, _, W = srcs[0].shape
+    total = sum(t.shape[1] for t in srcs)
+    if k_out is None:
+        k_out = torch.empty((B, total, W), dtype=out_dtype, device=srcs[0].device)
+    if n > 80:                                   # the kernel takes its source pointers by value: 80 per launch
+        r0 = 0
+        for c0 in range(0, n, 80):
+            rows_c = sum(t.shape[1] for t in srcs[c0:c0 + 80])
+            bank_rows(srcs[c0:c0 + 80], poss[c0:c0 + 80], out_dtype, k_out[:, r0:r0 + rows_c],
+                      None if m_out is None else m_out[:, r0:r0 + rows_c])
+            r0 += rows_c
+        return k_out, m_out
+    for d in (k_out, m_out):
+        if d is not None and (tuple(d.shape) != (B, total, W) or d.dtype != out_dtype or d.stride(2) != 1 or d.stride(1) != W):
+            raise native.NativeError("bank_rows: destination must be [B,total,W] with contiguous rows")
+    src_p, pos_p, pos_bs, rows = [], [], [], []
+    for t, q in zip(srcs, poss):
+        if t.shape[0] != B or t.shape[2] != W:
+            raise native.NativeError("bank_rows: sources must share B and W")
+        src_p.append(_chk(t, "src", torch.float32))
+        rows.append(t.shape[1])
+        if q is None:
+            pos_p.append(None); pos_bs.append(0)
+        else:
+            if q.dim() == 3 and q.shape[0] == B and q.stride(0) != 0:
+                pos_bs.append(q.stride(0))
+            else:
+                q = q[0] if q.dim() == 3 else q
+                pos_bs.append(0)
+            if q.stride(-1) != 1 or q.stride(-2) != W or tuple(q.shape[-2:]) != (t.shape[1], W) or q.dtype != torch.float32:
+                raise native.NativeError("bank_rows: position tensor must be fp32 [rows,W] / [B,rows,W] with contiguous rows")
+            pos_p.append(q.data_ptr())
+    native.call("ms2_bank_rows", (ctypes.c_void_p * n)(*src_p), (ctypes.c_void_p * n)(*pos_p), (ctypes.c_long * n)(*pos_bs),
+                (ctypes.c_int * n)(*rows), n, W, B, k_out.data_ptr(), k_out.stride(0),
+                None if m_out is None else m_out.data_ptr(), 0 if m_out is None else m_out.stride(0), _DT[out_dtype], _st())
+    return k_out, m_out
+
+
+def argmax_select_rows(scores, rows=None):
+    """scores fp32 [B,M] -> (idx int32 [B] = first arg-max, rows[b, idx[b]] fp32 [B,C] or None); rows [B,M,C] may be a
+    strided view with unit inner stride."""
+    B, M = scores.shape
+    idx = torch.empty((B,), dtype=torch.int32, device=scores.device)
+    out = None
+    rp, bs, rs, C = None, 0, 0, 0
+    if rows is not None:
+        if rows.dtype != torch.float32 or rows.stride(-1) != 1 or rows.shape[0] != B or rows.shape[1] < M:
+            raise native.NativeError("argmax_select_rows: rows must be fp32 [B,>=M,C] with unit inner stride")
+        C = rows.shape[2]
+        out = torch.empty((B, C), dtype=torch.float32, device=scores.device)
+        rp, bs, rs = rows.data_ptr(), rows.stride(0), rows.stride(1)
+    if not scores.is_cuda or scores.dtype != torch.float32 or scores.stride(1) != 1:
+        raise native.NativeError("argmax_select_rows: scores must be fp32 CUDA [B,M] with unit inner stride")
+    native.call("ms2_argmax_select_rows", scores.data_ptr(), scores.stride(0), B, M, rp, bs, rs, C, idx.data_ptr(),
+                None if out is None else out.data_ptr(), _st())
+    return idx, out
+
+
+def obj_ptr_mix(ptr, logits, no_obj, soft, fixed):
+    """(fixed ? lam*ptr : ptr) + (1-lam)*no_obj with lam = sigmoid(logit) (soft) or (logit > 0)."""
+    B, C = ptr.shape
+    out = torch.empty_like(ptr)
+    native.call("ms2_obj_ptr_mix", _chk(ptr, "ptr", torch.float32), _chk(logits, "logits", torch.float32),
+                _chk(no_obj, "no_obj", torch.float32), out.data_ptr(), B, C, int(bool(soft)), int(bool(fixed)), _st())
+    return out
+
+
+def stability_select(counts, ious, thresh):
+    """counts int32 [B,2] (mask_stability_counts), ious fp32 [B,M] -> (idx int32 [B], iou fp32 [B,1])."""
+    B, M = ious.shape
+    idx = torch.empty((B,), dtype=torch.int32, device=ious.device)
+    iou = torch.empty((B, 1), dtype=torch.float32, device=ious.device)
+    native.call("ms2_stability_select", _chk(counts, "counts", torch.int32), _chk(ious, "ious", torch.float32), B, M,
+                float(thresh), idx.data_ptr(), iou.data_ptr(), _st())
+    return idx, iou
 
 
 def normalize_image(x, out=None, nhwc=None, out_dtype=torch.float32):

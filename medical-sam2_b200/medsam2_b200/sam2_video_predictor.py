@@ -292,15 +292,33 @@ class SAM2VideoPredictor(SAM2Base):
         else:
             ch = cw = self.image_size // 4
             mask_key = "pred_masks"
-        cons = {
-            "maskmem_features": None, "maskmem_pos_enc": None,
-            mask_key: torch.full((batch_size, 1, ch, cw), NO_OBJ_SCORE, dtype=torch.float32,
-                                 device=st["storage_device"]),
-            "obj_ptr": torch.full((batch_size, self.hidden_dim), NO_OBJ_SCORE, dtype=torch.float32,
-                                  device=st["device"]),
-        }
+        single = None
+        if batch_size == 1:
+            # one object with an output on this frame (the common case): its mask / pointer ARE the consolidated ones —
+            # no NO_OBJ_SCORE fill (4 MiB at video resolution) and no copy into it
+            single = st["temp_output_dict_per_obj"][0][key].get(frame_idx, None)
+            if single is None:
+                single = st["output_dict_per_obj"][0]["cond_frame_outputs"].get(frame_idx, None)
+            if single is None:
+                single = st["output_dict_per_obj"][0]["non_cond_frame_outputs"].get(frame_idx, None)
+        if single is not None:
+            obj_mask = single["pred_masks"].to(st["device"]).float()
+            if tuple(obj_mask.shape[-2:]) != (ch, cw):
+                obj_mask = ops.resize_bilinear(obj_mask.contiguous(), (ch, cw))
+            cons = {"maskmem_features": None, "maskmem_pos_enc": None,
+                    mask_key: obj_mask.to(st["storage_device"]), "obj_ptr": single["obj_ptr"].float()}
+            batch_iter = ()
+        else:
+            cons = {
+                "maskmem_features": None, "maskmem_pos_enc": None,
+                mask_key: torch.full((batch_size, 1, ch, cw), NO_OBJ_SCORE, dtype=torch.float32,
+                                     device=st["storage_device"]),
+                "obj_ptr": torch.full((batch_size, self.hidden_dim), NO_OBJ_SCORE, dtype=torch.float32,
+                                      device=st["device"]),
+            }
+            batch_iter = range(batch_size)
         empty_mask_ptr = None
-        for obj_idx in range(batch_size):
+        for obj_idx in batch_iter:
             out = st["temp_output_dict_per_obj"][obj_idx][key].get(frame_idx, None)
             if out is None:
                 out = st["output_dict_per_obj"][obj_idx]["cond_frame_outputs"].get(frame_idx, None)

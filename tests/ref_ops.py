@@ -291,6 +291,40 @@ def non_overlap(pred_masks):
     return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
 
 
+def bank_rows(srcs, poss, out_dtype, k_out=None, m_out=None):
+    ks = []
+    for t, q in zip(srcs, poss):
+        ks.append(t if q is None else t + (q if q.dim() == 3 else q[None]))
+    k = torch.cat(ks, dim=1).to(out_dtype)
+    m = torch.cat(list(srcs), dim=1).to(out_dtype)
+    if k_out is None:
+        k_out = k
+    else:
+        k_out.copy_(k)
+    if m_out is not None:
+        m_out.copy_(m)
+    return k_out, m_out
+
+
+def argmax_select_rows(scores, rows=None):
+    idx = torch.argmax(scores, dim=-1)
+    out = None if rows is None else rows[torch.arange(scores.shape[0], device=scores.device), idx].contiguous()
+    return idx.to(torch.int32), out
+
+
+def obj_ptr_mix(ptr, logits, no_obj, soft, fixed):
+    lam = (torch.sigmoid(logits) if soft else (logits > 0).float()).reshape(-1, 1)
+    return (lam * ptr if fixed else ptr) + (1 - lam) * no_obj.reshape(1, -1)
+
+
+def stability_select(counts, ious, thresh):
+    c = counts.float()
+    stab = torch.where(c[:, 1] > 0, c[:, 0] / c[:, 1], torch.ones_like(c[:, 1]))
+    best = torch.argmax(ious[:, 1:], dim=-1) + 1
+    idx = torch.where(stab >= thresh, torch.zeros_like(best), best)
+    return idx.to(torch.int32), torch.gather(ious, 1, idx[:, None])
+
+
 def conv3x3s2_ln_gelu(x, w, bias, gamma, beta, eps, out_dtype=torch.float32, pre=0, pre_scale=1.0, pre_bias=0.0):
     xi = x.float()
     if pre == 1:
@@ -353,7 +387,7 @@ def attention_merge(parts, B, Lq, DV=64):
     return (num / den[:, None]).view(B, Lq, DV).to(torch.bfloat16)
 
 
-def point_embed(coords, labels, gauss, table, pad, image_size):
+def point_embed(coords, labels, gauss, table, pad, image_size, prefix=None):
     pts = coords.float() + 0.5
     lab = labels.long()
     if pad:
@@ -364,7 +398,10 @@ def point_embed(coords, labels, gauss, table, pad, image_size):
     c[:, :, 1] = c[:, :, 1] / image_size[0]
     pe = fourier_pe(c.contiguous(), gauss)
     keep = (lab != -1).to(pe.dtype).unsqueeze(-1)
-    return pe * keep + table[(lab + 1).clamp(0, 4)]
+    out = pe * keep + table[(lab + 1).clamp(0, 4)]
+    if prefix is not None:
+        out = torch.cat([prefix[None].expand(out.shape[0], -1, -1), out], dim=1).contiguous()
+    return out
 
 
 def patch_im2col(img, ldk=152):

@@ -561,3 +561,51 @@ def test_score_lowres_equals_resize_then_score(ops, N, h, H, T):
     assert s2 is None and torch.equal(c2, counts)
     # and the up-sampling itself against torch (fp32 rounding only)
     close(up, F.interpolate(low[:, None], size=(H, H), mode="bilinear", align_corners=False)[:, 0], 2e-6, "bilinear")
+
+
+# ------------------------------------------------------------------ per-slice glue kernels (csrc/glue.cu)
+@pytest.mark.parametrize("B,dt", [(1, torch.bfloat16), (2, torch.bfloat16), (1, torch.float32)])
+def test_bank_rows(ops, B, dt):
+    """recent memories + pointer tokens, concatenated / position-coded / cast in one launch == the torch statement;
+    destinations may be row ranges of a larger bank; > 80 sources are chunked."""
+    W = 64
+    srcs = [rnd(B, 4096, W, seed=i) for i in range(3)] + [rnd(B, 4, W, seed=10 + i) for i in range(5)]
+    table = rnd(4096, W, seed=20)
+    per_b = rnd(B, 4, W, seed=21)
+    poss = [table, None, table, per_b, None, None, per_b.expand(B, 4, W)[:1].expand(B, 4, W), None]
+    total = sum(t.shape[1] for t in srcs)
+    bank = torch.zeros(B, total + 100, W, dtype=dt, device="cuda")
+    k, m = ops.bank_rows(srcs, poss, dt, m_out=bank[:, 37:37 + total])
+    rk, rm = ref_ops.bank_rows(srcs, poss, dt, m_out=torch.empty(B, total, W, dtype=dt, device="cuda"))
+    assert torch.equal(k, rk) and torch.equal(bank[:, 37:37 + total], rm)
+    assert not bank[:, :37].any() and not bank[:, 37 + total:].any()
+    many = [rnd(B, 4, W, seed=100 + i) for i in range(173)]
+    k2, _ = ops.bank_rows(many, [None] * 173, dt)
+    assert torch.equal(k2, torch.cat(many, dim=1).to(dt))
+
+
+def test_sam_head_glue(ops):
+    B, M, C = 5, 3, 256
+    ious = rnd(B, 4, seed=1)
+    ious[1, 1] = ious[1, 2] = 9.0                                    # tie: the first maximum wins
+    hs = rnd(B, 9, C, seed=2)
+    idx, rows = ops.argmax_select_rows(ious[:, 1:], hs[:, 2:5])      # strided views, as the decoder hands them over
+    ridx, rrows = ref_ops.argmax_select_rows(ious[:, 1:], hs[:, 2:5])
+    assert torch.equal(idx, ridx) and torch.equal(rows, rrows)
+    idx2, none = ops.argmax_select_rows(ious.contiguous())
+    assert none is None and torch.equal(idx2, torch.argmax(ious, -1).int())
+    ptr, logits, no_obj = rnd(B, C, seed=3), torch.tensor([3.0, -2.0, 0.0, 1e-3, -7.0]).cuda(), rnd(C, seed=4)
+    for soft in (False, True):
+        for fixed in (False, True):
+            close(ops.obj_ptr_mix(ptr, logits, no_obj, soft, fixed), ref_ops.obj_ptr_mix(ptr, logits, no_obj, soft, fixed),
+                  2e-6, f"obj_ptr_mix soft={soft} fixed={fixed}")
+    counts = torch.tensor([[98, 100], [99, 100], [0, 0], [5, 10], [100, 100]], dtype=torch.int32).cuda()
+    i3, iou3 = ops.stability_select(counts, ious.contiguous(), 0.98)
+    r3, riou3 = ref_ops.stability_select(counts, ious.contiguous(), 0.98)
+    assert torch.equal(i3, r3) and torch.equal(iou3, riou3)
+    # point embedding with constant rows in front (the decoder's output tokens)
+    gauss, table, prefix = rnd(2, 128, seed=5), rnd(5, 256, seed=6), rnd(6, 256, seed=7)
+    coords = (torch.rand(B, 2, 2, generator=gen(8)) * 1024).cuda()
+    labels = torch.tensor([[2, 3]] * B, dtype=torch.int32).cuda()
+    close(ops.point_embed(coords, labels, gauss, table, True, (1024, 1024), prefix),
+          ref_ops.point_embed(coords, labels, gauss, table, True, (1024, 1024), prefix), 2e-4, "point_embed + prefix")
