@@ -71,6 +71,7 @@ struct Loader {
 template <typename T, int D, int BK, int R>
 __global__ void __launch_bounds__(128)
 attn_simt_kernel(const AttnP p) {
+  MS2_PDL_WAIT();
   constexpr int KPL = BK / 32;
   constexpr int DI = (D + 31) / 32;
   constexpr int NW = 4;
@@ -177,7 +178,7 @@ int launch_d(const AttnP& p, int nbatch, cudaStream_t st) {
   auto kern = attn_simt_kernel<T, D, BK, R>;
   MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attn attr");
   dim3 grid(ceil_div(p.Lq, 4 * R), p.Hh, nbatch);
-  kern<<<grid, 128, smem, st>>>(p);
+  ms2_launch(kern, grid, 128, smem, st, p);
   MS2_CHECK_LAUNCH("attn_simt_kernel");
   return MS2_OK;
 }

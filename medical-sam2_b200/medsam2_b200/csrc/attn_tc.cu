@@ -128,6 +128,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  MS2_PDL_WAIT();      // barriers, tensor-memory allocation and descriptor prefetch above overlap the preceding kernel
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -447,6 +448,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  MS2_PDL_WAIT();      // barriers, tensor-memory allocation and descriptor prefetch above overlap the preceding kernel
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -701,6 +703,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attn_combine_kernel(const float* __restrict__ opart, const float* __restrict__ ml, bf16* __restrict__ o, long o_bs,
                     long o_hs, long o_ts, int Hh, int Lq, int nsplit, long rows) {
+  MS2_PDL_WAIT();
   constexpr int TPR = D / 8;                  // threads per row, 8 columns each
   constexpr int RPB = 128 / TPR > 0 ? 128 / TPR : 1;
   const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
@@ -742,6 +745,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attn_reduce_partials_kernel(const float* __restrict__ opart, const float* __restrict__ ml, float* __restrict__ out_o,
                             float* __restrict__ out_ml, int nsplit, long rows) {
+  MS2_PDL_WAIT();
   constexpr int TPR = D / 8, RPB = 128 / TPR;
   const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
   const int cg = threadIdx.x % TPR;
@@ -771,6 +775,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attn_merge_kernel(const float* __restrict__ parts_o, const float* __restrict__ parts_ml, long part_stride,
                   bf16* __restrict__ o, long o_bs, long o_ts, int Lq, int nparts, long rows) {
+  MS2_PDL_WAIT();
   constexpr int TPR = D / 8, RPB = 128 / TPR;
   const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
   const int cg = threadIdx.x % TPR;
@@ -876,14 +881,14 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     }
     dim3 grid2(qpairs, B * Hh, p.nsplit);
     switch (var & 7) {
-      case 0: attn_tc2_kernel<0><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 1: attn_tc2_kernel<1><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 2: attn_tc2_kernel<2><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 3: attn_tc2_kernel<3><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 4: attn_tc2_kernel<4><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 5: attn_tc2_kernel<5><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 6: attn_tc2_kernel<6><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      default: attn_tc2_kernel<7><<<grid2, T2_THREADS, T2_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 0: ms2_launch(attn_tc2_kernel<0>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 1: ms2_launch(attn_tc2_kernel<1>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 2: ms2_launch(attn_tc2_kernel<2>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 3: ms2_launch(attn_tc2_kernel<3>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 4: ms2_launch(attn_tc2_kernel<4>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 5: ms2_launch(attn_tc2_kernel<5>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      case 6: ms2_launch(attn_tc2_kernel<6>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
+      default: ms2_launch(attn_tc2_kernel<7>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
     }
     MS2_CHECK_LAUNCH("attn_tc2_kernel");
   } else {
@@ -895,18 +900,18 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
       attr_set = true;
     }
     dim3 grid(qtiles, B * Hh, p.nsplit);
-    kern<<<grid, NUM_THREADS, C::SMEM, st>>>(tmQ, tmK, tmV, p);
+    ms2_launch(kern, grid, NUM_THREADS, C::SMEM, st, tmQ, tmK, tmV, p);
     MS2_CHECK_LAUNCH("attn_tc_kernel");
   }
   if (part_o) {
     if (p.nsplit > 1) {
       constexpr int TPR = DV / 8, RPB = 128 / TPR;
-      attn_reduce_partials_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, part_o, part_ml, p.nsplit, rows);
+      ms2_launch(attn_reduce_partials_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, p.opart, p.ml, part_o, part_ml, p.nsplit, rows);
       MS2_CHECK_LAUNCH("attn_reduce_partials_kernel");
     }
   } else if (p.nsplit > 1) {
     constexpr int TPR = DV / 8, RPB = 128 / TPR;
-    attn_combine_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
+    ms2_launch(attn_combine_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, p.opart, p.ml, (bf16*)o, o_bs, o_hs, o_ts, Hh, Lq,
                                                                  p.nsplit, rows);
     MS2_CHECK_LAUNCH("attn_combine_kernel");
   }
@@ -966,7 +971,7 @@ int ms2_attention_merge_launch(const float* parts_o, const float* parts_ml, long
                 "attention_merge: alignment");
   const long rows = (long)B * Lq;
   constexpr int DV = 64, TPR = DV / 8, RPB = 128 / TPR;
-  attn_merge_kernel<DV><<<ceil_div(rows, RPB), 128, 0, st>>>(parts_o, parts_ml, part_stride, (bf16*)o, o_bs, o_ts, Lq,
+  ms2_launch(attn_merge_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, parts_o, parts_ml, part_stride, (bf16*)o, o_bs, o_ts, Lq,
                                                              nparts, rows);
   MS2_CHECK_LAUNCH("attn_merge_kernel");
   return MS2_OK;

@@ -67,6 +67,7 @@ template <bool SCORES>
 __global__ void __launch_bounds__(1024, 1)
 cc_smem_kernel(Src<SCORES> src, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
                float* __restrict__ filled, int H, int W, int max_area, float fill_value) {
+  MS2_PDL_WAIT();
   extern __shared__ int smem[];
   const int BW = W >> 1, BH = H >> 1, NB = BW * BH;
   int* lab = smem;
@@ -140,6 +141,7 @@ cc_smem_kernel(Src<SCORES> src, int32_t* __restrict__ labels, int32_t* __restric
 
 // ---------------- global-memory path (large images); the union-find array is `ws` indexed by block id
 __global__ void ccg_init(const uint8_t* __restrict__ mask, int32_t* __restrict__ ws, int H, int W) {
+  MS2_PDL_WAIT();
   const int BW = W >> 1, NB = BW * (H >> 1);
   const long img = (long)blockIdx.z * H * W;
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +154,7 @@ __device__ __forceinline__ unsigned g_bits(const uint8_t* m, int by, int bx, int
   return block_bits(s, (long)(2 * by) * W + 2 * bx, W);
 }
 __global__ void ccg_merge(const uint8_t* __restrict__ mask, int32_t* __restrict__ ws, int H, int W) {
+  MS2_PDL_WAIT();
   const int BW = W >> 1, NB = BW * (H >> 1);
   const long img = (long)blockIdx.z * H * W;
   const uint8_t* m = mask + img;
@@ -169,6 +172,7 @@ __global__ void ccg_merge(const uint8_t* __restrict__ mask, int32_t* __restrict_
   if (bx > 0 && (me & 5u) && (g_bits(m, by, bx - 1, W) & 10u)) uf_union(lab, b, b - 1);
 }
 __global__ void ccg_compress_count(const uint8_t* __restrict__ mask, int32_t* __restrict__ ws, int H, int W) {
+  MS2_PDL_WAIT();
   const int BW = W >> 1, NB = BW * (H >> 1);
   const long img = (long)blockIdx.z * H * W;
   int* lab = ws + img;
@@ -183,6 +187,7 @@ __global__ void ccg_compress_count(const uint8_t* __restrict__ mask, int32_t* __
 }
 __global__ void ccg_final(const uint8_t* __restrict__ mask, const int32_t* __restrict__ ws,
                           int32_t* __restrict__ labels, int32_t* __restrict__ counts, int H, int W) {
+  MS2_PDL_WAIT();
   const int BW = W >> 1, NB = BW * (H >> 1);
   const long img = (long)blockIdx.z * H * W;
   const int* lab = ws + img;
@@ -219,16 +224,16 @@ extern "C" int ms2_cc_label(const uint8_t* mask, int32_t* labels, int32_t* count
     MS2_CUDA(cudaFuncSetAttribute(cc_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
              "cc_label attr");
     Src<false> s{mask, 0.f};
-    cc_smem_kernel<false><<<N, 1024, sm, stream>>>(s, labels, counts, nullptr, H, W, 0, 0.f);
+    ms2_launch(cc_smem_kernel<false>, N, 1024, sm, stream, s, labels, counts, nullptr, H, W, 0, 0.f);
     MS2_CHECK_LAUNCH("cc_smem_kernel");
     return MS2_OK;
   }
   MS2_CHECK_ARG(workspace != nullptr, "cc_label: workspace required for %dx%d", H, W);
   dim3 grid(ceil_div(NB, 256), 1, N);
-  ccg_init<<<grid, 256, 0, stream>>>(mask, workspace, H, W);
-  ccg_merge<<<grid, 256, 0, stream>>>(mask, workspace, H, W);
-  ccg_compress_count<<<grid, 256, 0, stream>>>(mask, workspace, H, W);
-  ccg_final<<<grid, 256, 0, stream>>>(mask, workspace, labels, counts, H, W);
+  ms2_launch(ccg_init, grid, 256, 0, stream, mask, workspace, H, W);
+  ms2_launch(ccg_merge, grid, 256, 0, stream, mask, workspace, H, W);
+  ms2_launch(ccg_compress_count, grid, 256, 0, stream, mask, workspace, H, W);
+  ms2_launch(ccg_final, grid, 256, 0, stream, mask, workspace, labels, counts, H, W);
   MS2_CHECK_LAUNCH("cc global path");
   return MS2_OK;
 }
@@ -243,6 +248,7 @@ constexpr int kLocalMaxArea = 32;
 __global__ void __launch_bounds__(256)
 fill_holes_local_kernel(const float* __restrict__ in, float* __restrict__ out, long total, int H, int W, float thresh,
                         int max_area, float fill_value) {
+  MS2_PDL_WAIT();
   const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
   const int hw = H * W;
@@ -289,7 +295,7 @@ extern "C" int ms2_fill_holes(const float* in, float* out, int N, int H, int W, 
   MS2_CHECK_ARG(in && out, "fill_holes: null pointer");
   if (max_area <= kLocalMaxArea && H < 65536 && W < 65536) {
     const long total = (long)N * H * W;
-    fill_holes_local_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(in, out, total, H, W, thresh, max_area, fill_value);
+    ms2_launch(fill_holes_local_kernel, ceil_div(total, 256), 256, 0, stream, in, out, total, H, W, thresh, max_area, fill_value);
     MS2_CHECK_LAUNCH("fill_holes_local_kernel");
     return MS2_OK;
   }
@@ -299,7 +305,7 @@ extern "C" int ms2_fill_holes(const float* in, float* out, int N, int H, int W, 
   MS2_CUDA(cudaFuncSetAttribute(cc_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
            "fill_holes attr");
   Src<true> s{in, thresh};
-  cc_smem_kernel<true><<<N, 1024, sm, stream>>>(s, nullptr, nullptr, out, H, W, max_area, fill_value);
+  ms2_launch(cc_smem_kernel<true>, N, 1024, sm, stream, s, nullptr, nullptr, out, H, W, max_area, fill_value);
   MS2_CHECK_LAUNCH("cc_smem_kernel<fill>");
   return MS2_OK;
 }

@@ -44,6 +44,37 @@ extern "C" void ms2_set_error(const char* fmt, ...);
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL).  The tracked-frame path is a chain of ~200 dependent kernels of 2-20 us each;
+// with plain stream order kernel N+1 is only scheduled after kernel N has drained.  Every kernel of this library is
+// launched with programmaticStreamSerialization and starts with MS2_PDL_WAIT(): `griddepcontrol.wait` blocks until the
+// preceding kernel of the stream has COMPLETED and its writes are visible (so no kernel ever reads or overwrites data the
+// previous one still uses), `griddepcontrol.launch_dependents` then lets the NEXT kernel be scheduled right away: its
+// launch latency, block scheduling and (where the wait sits behind it) barrier / tensor-memory set-up overlap this
+// kernel's execution.  Without the launch attribute (MS2_PDL=0) both instructions are no-ops.
+#define MS2_PDL_WAIT() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
+
+#include <stdlib.h>
+#include <utility>
+static inline bool ms2_pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("MS2_PDL"); return !e || atoi(e) != 0; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ms2_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ms2_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

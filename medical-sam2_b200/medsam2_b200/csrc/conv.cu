@@ -15,6 +15,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ pos, float* __restrict__ out, int Hin, int Win, int Ho, int Wo) {
+  MS2_PDL_WAIT();
   extern __shared__ float sm[];
   float* ws = sm;                                  // [147][COUT]
   float* patch = sm + 147 * COUT;                  // [3][35][36]
@@ -85,6 +86,7 @@ patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, c
 template <typename T>
 __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ cols, int B, int H, int W, int Cin, int k,
                               int stride, int pad, int Ho, int Wo, int pre, float pre_scale, float pre_bias) {
+  MS2_PDL_WAIT();
   const int KK = k * k * Cin;
   const long n = (long)B * Ho * Wo * KK;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -112,6 +114,7 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ cols,
 __global__ void __launch_bounds__(256)
 im2col_vec8_kernel(const float* __restrict__ x, bf16* __restrict__ cols, long total, int H, int W, int Cin, int k,
                    int stride, int pad, int Ho, int Wo) {
+  MS2_PDL_WAIT();
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int c8 = Cin >> 3;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(128)
 conv3x3s2_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ gamma, const float* __restrict__ beta, TO* __restrict__ y, int B,
                          int H, int W, int Ho, int Wo, float eps, int pre, float pre_scale, float pre_bias) {
+  MS2_PDL_WAIT();
   __shared__ __align__(16) float ws[9 * CIN * COUT];   // [tap][ci][co]
   __shared__ float sb[3 * COUT];
   // conv weight [Cout, Cin, 3, 3] -> [tap][ci][co]: read in SOURCE order with 16-byte loads that are all issued before
@@ -257,6 +261,7 @@ constexpr int DW_T = 8, DW_C = 32, DW_IN = DW_T + 6;
 __global__ void __launch_bounds__(DW_T * DW_C)
 dwconv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y, int B, int H, int W, int C) {
+  MS2_PDL_WAIT();
   __shared__ __align__(16) float tile[DW_IN][DW_IN][DW_C];
   __shared__ float ws[49][DW_C];
   const int tilesx = (W + DW_T - 1) / DW_T;
@@ -325,6 +330,7 @@ template <typename IN>
 __global__ void __launch_bounds__(256)
 patch_im2col_kernel(const IN* __restrict__ img, bf16* __restrict__ cols, long total_chunks, int Hin, int Win, int Ho,
                     int Wo, int chunks) {
+  MS2_PDL_WAIT();
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total_chunks) return;
   const int ch = (int)(t % chunks);
@@ -367,10 +373,10 @@ extern "C" int ms2_conv3x3s2_ln_gelu(const float* x, const float* w, const float
 #define MS2_C3(CI, CO)                                                                                               \
   do {                                                                                                               \
     if (y_dt == MS2_F32)                                                                                             \
-      conv3x3s2_ln_gelu_kernel<CI, CO, float><<<grid, 128, 0, st>>>(x, w, bias, gamma, beta, (float*)y, B, H, W, Ho, Wo, \
+      ms2_launch(conv3x3s2_ln_gelu_kernel<CI, CO, float>, grid, 128, 0, st, x, w, bias, gamma, beta, (float*)y, B, H, W, Ho, Wo, \
                                                                     eps, pre, pre_scale, pre_bias);                  \
     else                                                                                                             \
-      conv3x3s2_ln_gelu_kernel<CI, CO, bf16><<<grid, 128, 0, st>>>(x, w, bias, gamma, beta, (bf16*)y, B, H, W, Ho, Wo,  \
+      ms2_launch(conv3x3s2_ln_gelu_kernel<CI, CO, bf16>, grid, 128, 0, st, x, w, bias, gamma, beta, (bf16*)y, B, H, W, Ho, Wo,  \
                                                                    eps, pre, pre_scale, pre_bias);                   \
   } while (0)
   if (Cin == 1 && Cout == 4) MS2_C3(1, 4);
@@ -391,7 +397,7 @@ extern "C" int ms2_patch_im2col(const void* img, int img_dt, void* cols, int B, 
   const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
   const long total = (long)B * Ho * Wo * (ldk / 8);
   if (!total) return MS2_OK;
-  MS2_DISPATCH_DTYPE(img_dt, T, (patch_im2col_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  MS2_DISPATCH_DTYPE(img_dt, T, (ms2_launch(patch_im2col_kernel<T>, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, 
                                     (const T*)img, (bf16*)cols, total, Hin, Win, Ho, Wo, ldk / 8)));
   MS2_CHECK_LAUNCH("patch_im2col_kernel");
   return MS2_OK;
@@ -407,7 +413,7 @@ extern "C" int ms2_patch_embed(const float* img, const float* w, const float* bi
   MS2_CUDA(cudaFuncSetAttribute(patch_embed_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
            "patch_embed attr");
   dim3 grid(ceil_div(Wo, PE_T), ceil_div(Ho, PE_T), B);
-  patch_embed_kernel<96><<<grid, 256, smem, (cudaStream_t)stream>>>(img, w, bias, pos, out, Hin, Win, Ho, Wo);
+  ms2_launch(patch_embed_kernel<96>, grid, 256, smem, (cudaStream_t)stream, img, w, bias, pos, out, Hin, Win, Ho, Wo);
   MS2_CHECK_LAUNCH("patch_embed");
   return MS2_OK;
 }
@@ -420,14 +426,14 @@ extern "C" int ms2_im2col(const float* x, void* cols, int dt, int B, int H, int 
   if (!n) return MS2_OK;
   if (dt == MS2_BF16 && pre == 0 && Cin % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)cols % 16 == 0)) {
     const long total = n / 8;
-    im2col_vec8_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)cols, total, H, W, Cin, k, stride,
+    ms2_launch(im2col_vec8_kernel, ceil_div(total, 256), 256, 0, (cudaStream_t)stream, x, (bf16*)cols, total, H, W, Cin, k, stride,
                                                                                pad, Ho, Wo);
     MS2_CHECK_LAUNCH("im2col_vec8");
     return MS2_OK;
   }
   long blocks = (n + 255) / 256;
   int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
-  MS2_DISPATCH_DTYPE(dt, T, (im2col_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(
+  MS2_DISPATCH_DTYPE(dt, T, (ms2_launch(im2col_kernel<T>, g, 256, 0, (cudaStream_t)stream, 
                                 x, (T*)cols, B, H, W, Cin, k, stride, pad, Ho, Wo, pre, pre_scale, pre_bias)));
   MS2_CHECK_LAUNCH("im2col");
   return MS2_OK;
@@ -439,7 +445,7 @@ extern "C" int ms2_dwconv7x7(const float* x, const float* w, const float* bias, 
   long npix = (long)B * H * W;
   if (!npix) return MS2_OK;
   dim3 grid(ceil_div(W, DW_T) * ceil_div(H, DW_T), ceil_div(C, DW_C), B);
-  dwconv7x7_kernel<<<grid, DW_T * DW_C, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C);
+  ms2_launch(dwconv7x7_kernel, grid, DW_T * DW_C, 0, (cudaStream_t)stream, x, w, bias, y, B, H, W, C);
   MS2_CHECK_LAUNCH("dwconv7x7");
   return MS2_OK;
 }

@@ -13,6 +13,7 @@ inline int grid_for(long n, int threads = 256) {
 template <typename TO>
 __global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ z, float b, float c,
                              TO* __restrict__ y, long n, long zn) {
+  MS2_PDL_WAIT();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = from_f<TO>(a * x[i] + (z ? b * z[i % zn] : 0.f) + c);
 }
@@ -30,6 +31,7 @@ __device__ __forceinline__ void store4(bf16* y, long i, float4 v) {
 template <typename TO>
 __global__ void axpby_vec4_kernel(const float* __restrict__ x, float a, const float* __restrict__ z, float b, float c,
                                   TO* __restrict__ y, unsigned n4, unsigned zn4) {
+  MS2_PDL_WAIT();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const float4 xv = *(const float4*)(x + 4L * i);
     float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -40,18 +42,21 @@ __global__ void axpby_vec4_kernel(const float* __restrict__ x, float a, const fl
 }
 template <typename TO>
 __global__ void cast_vec4_kernel(const float* __restrict__ x, TO* __restrict__ y, unsigned n4) {
+  MS2_PDL_WAIT();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
     store4(y, 4L * i, *(const float4*)(x + 4L * i));
 }
 
 __global__ void gate_rows_kernel(const float* __restrict__ x, const float* __restrict__ gate, float fill,
                                  float* __restrict__ y, long n, long P) {
+  MS2_PDL_WAIT();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = gate[i / P] > 0.f ? x[i] : fill;
 }
 
 __global__ void select_plane_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
                                     float* __restrict__ y, int B, int M, long P) {
+  MS2_PDL_WAIT();
   const long n = (long)B * P;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     long b = i / P, p = i - b * P;
@@ -63,17 +68,20 @@ __global__ void select_plane_kernel(const float* __restrict__ x, const int32_t* 
 
 __global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ v, float s,
                                   float* __restrict__ y, long n, int C) {
+  MS2_PDL_WAIT();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = x[i] + s * v[i % C];
 }
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long n) {
+  MS2_PDL_WAIT();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = from_f<TO>(to_f(x[i]));
 }
 
 __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, long n, int act) {
+  MS2_PDL_WAIT();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float v = x[i];
     if (act == 1) v = gelu_erf(v);
@@ -85,6 +93,7 @@ __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, l
 
 __global__ void upsample2x_add_kernel(float* __restrict__ fine, const float* __restrict__ coarse, int B, int H,
                                       int W, int C) {
+  MS2_PDL_WAIT();
   const long n = (long)B * H * W * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int c = i % C;
@@ -98,6 +107,7 @@ __global__ void upsample2x_add_kernel(float* __restrict__ fine, const float* __r
 
 // tiled transpose of [R, Cc] -> [Cc, R] per batch (NHWC<->NCHW with R=H*W)
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, long R, int Cc) {
+  MS2_PDL_WAIT();
   __shared__ float tile[32][33];
   const long b = blockIdx.z;
   const float* xb = x + b * R * Cc;
@@ -118,6 +128,7 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict_
 }
 
 __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  MS2_PDL_WAIT();
   const int Ho = H / 2, Wo = W / 2;
   const long n = (long)B * Ho * Wo * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -134,6 +145,7 @@ __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict
 // 4 channels per thread (16-byte loads / stores), 32-bit indices: C % 4 == 0 and < 2^31 input elements
 __global__ void maxpool2x2_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned n4, unsigned H,
                                        unsigned W, unsigned C4) {
+  MS2_PDL_WAIT();
   const unsigned Ho = H / 2, Wo = W / 2;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned c4 = i % C4;
@@ -151,6 +163,7 @@ __global__ void maxpool2x2_vec4_kernel(const float* __restrict__ x, float* __res
 __global__ void pixel_shuffle_add_kernel(const float* __restrict__ g, const float* __restrict__ bias,
                                          const float* __restrict__ skip, float* __restrict__ out, int B, int H,
                                          int W, int C, int act) {
+  MS2_PDL_WAIT();
   const long n = (long)B * 2 * H * 2 * W * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int c = i % C;
@@ -171,6 +184,7 @@ __global__ void pixel_shuffle_add_kernel(const float* __restrict__ g, const floa
 __global__ void pixel_shuffle_add_vec4_kernel(const float* __restrict__ g, const float* __restrict__ bias,
                                               const float* __restrict__ skip, float* __restrict__ out, unsigned n4,
                                               unsigned H, unsigned W, unsigned C4, int act) {
+  MS2_PDL_WAIT();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned c4 = i % C4;
     unsigned t = i / C4;
@@ -195,6 +209,7 @@ __global__ void pixel_shuffle_add_vec4_kernel(const float* __restrict__ g, const
 // one warp per pixel: lanes own channels, Mk dot products reduced by shuffles
 __global__ void hyper_mask_kernel(const float* __restrict__ up, const float* __restrict__ hyper,
                                   float* __restrict__ masks, int B, int P, int C, int Mk) {
+  MS2_PDL_WAIT();
   __shared__ float hs[8 * 64];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < Mk * C; i += blockDim.x) hs[i] = hyper[(long)b * Mk * C + i];
@@ -219,6 +234,7 @@ __global__ void hyper_mask_kernel(const float* __restrict__ up, const float* __r
 // per pixel: 17 us for 8 MB)
 __global__ void __launch_bounds__(128)
 hyper_mask_c32m4_kernel(const float* __restrict__ up, const float* __restrict__ hyper, float* __restrict__ masks, int P) {
+  MS2_PDL_WAIT();
   __shared__ float4 hs[4 * 8];
   const int b = blockIdx.y;
   if (threadIdx.x < 32) hs[threadIdx.x] = *(const float4*)(hyper + (long)b * 128 + threadIdx.x * 4);
@@ -243,6 +259,7 @@ hyper_mask_c32m4_kernel(const float* __restrict__ up, const float* __restrict__ 
 
 __global__ void fourier_pe_kernel(const float* __restrict__ coords, const float* __restrict__ gauss,
                                   float* __restrict__ out, int n, int F) {
+  MS2_PDL_WAIT();
   const long total = (long)n * F;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int f = i % F;
@@ -263,6 +280,7 @@ __global__ void point_embed_kernel(const float* __restrict__ coords, const int* 
                                    const float* __restrict__ gauss, const float* __restrict__ table,
                                    float* __restrict__ out, int B, int N, int pad, int F, float inv_w, float inv_h,
                                    const float* __restrict__ prefix, int P) {
+  MS2_PDL_WAIT();
   const int Np = N + (pad ? 1 : 0) + P;
   const long total = (long)B * Np * F;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -301,6 +319,7 @@ __global__ void point_embed_kernel(const float* __restrict__ coords, const int* 
 template <typename OUT>
 __global__ void __launch_bounds__(256) normalize_image_kernel(const void* __restrict__ x, int in_layout, OUT* __restrict__ out,
                                                               int B, int H, int W) {
+  MS2_PDL_WAIT();
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
   const int W4 = (W + 3) >> 2;
@@ -339,6 +358,7 @@ struct SegThr { float v[8]; };
 template <int T, bool VEC>
 __global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                          SegThr thr, int32_t* __restrict__ counts, long P) {
+  MS2_PDL_WAIT();
   __shared__ int sh[3 * T];
   const int n = blockIdx.y;
   const float* pp = pred + (long)n * P;
@@ -399,7 +419,7 @@ void seg_counts_launch2(cudaStream_t st, const float* pred, const float* gt, con
   long per_plane = slots / N, by_size = (P + 8191) / 8192;
   if (per_plane > by_size) per_plane = by_size;
   dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
-  seg_counts_kernel<T, VEC><<<grid, 256, 0, st>>>(pred, gt, thr, counts, P);
+  ms2_launch(seg_counts_kernel<T, VEC>, grid, 256, 0, st, pred, gt, thr, counts, P);
 }
 template <int T>
 void seg_counts_launch(bool vec, cudaStream_t st, const float* pred, const float* gt, const SegThr& thr, int32_t* counts,
@@ -414,6 +434,7 @@ void seg_counts_launch(bool vec, cudaStream_t st, const float* pred, const float
 template <bool VEC>
 __global__ void __launch_bounds__(256) bce_logits_sum_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                              float pwm1, double* __restrict__ sums, long P) {
+  MS2_PDL_WAIT();
   __shared__ double sh[8];
   const int n = blockIdx.y;
   const float* pp = pred + (long)n * P;
@@ -450,6 +471,7 @@ __global__ void __launch_bounds__(256) bce_logits_sum_kernel(const float* __rest
 // max/min reductions over every [H,W] logit plane; here ONE pass (4 B/pixel) yields per plane
 // (#(x > thr+off), #(x > thr-off), #(x > thr), min col, min row, max col, max row of x > thr).
 __global__ void mask_stats_init_kernel(int32_t* __restrict__ out, int N, int H, int W) {
+  MS2_PDL_WAIT();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   int32_t* o = out + (long)n * 7;
@@ -458,6 +480,7 @@ __global__ void mask_stats_init_kernel(int32_t* __restrict__ out, int N, int H, 
 }
 __global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int H, int W,
                                                          float thr, float off, bool vec) {
+  MS2_PDL_WAIT();
   const int n = blockIdx.y;
   const float* xp = x + (long)n * H * W;
   const float hi = thr + off, lo = thr - off;
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict
 // uint8, out is [K, OW, OH] and zero outside the crop.  32x32 shared-memory tiles: coalesced reads and writes.
 __global__ void mask_binarize_t_kernel(const float* __restrict__ x, const int32_t* __restrict__ sel, uint8_t* __restrict__ out,
                                        int H, int W, float thr, int OH, int OW, int x0, int y0) {
+  MS2_PDL_WAIT();
   __shared__ uint8_t tile[32][33];
   const int k = blockIdx.z;
   const float* xp = x + (long)sel[k] * H * W;
@@ -570,6 +594,7 @@ __global__ void mask_binarize_t_kernel(const float* __restrict__ x, const int32_
 // sorted.  cnt[k] is the TOTAL number of transitions; positions beyond `cap` are dropped (the caller re-runs with a larger cap).
 __global__ void __launch_bounds__(1024) rle_transitions_kernel(const uint8_t* __restrict__ m, long L, int32_t* __restrict__ pos,
                                                                int32_t* __restrict__ cnt, int cap, bool vec) {
+  MS2_PDL_WAIT();
   __shared__ int warp_tot[32];
   __shared__ int base_sh;
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -630,6 +655,7 @@ __global__ void __launch_bounds__(1024) rle_transitions_kernel(const uint8_t* __
 }
 
 __global__ void stability_counts_kernel(const float* __restrict__ x, int32_t* __restrict__ counts, long P, float delta) {
+  MS2_PDL_WAIT();
   const int nidx = blockIdx.y;
   const float* xp = x + (long)nidx * P;
   int hi = 0, lo = 0;
@@ -658,10 +684,10 @@ extern "C" int ms2_axpby(const float* x, float a, const float* z, float b, float
   const bool vec = n % 4 == 0 && n < (1L << 31) && (!z || zn % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
                    ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0);
   if (vec) {
-    MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_vec4_kernel<TO><<<grid_for(n / 4), 256, 0, ST>>>(
+    MS2_DISPATCH_DTYPE(y_dt, TO, (ms2_launch(axpby_vec4_kernel<TO>, grid_for(n / 4), 256, 0, ST, 
                                      x, a, z, b, c, (TO*)y, (unsigned)(n / 4), (unsigned)(z ? zn / 4 : 1))));
   } else {
-    MS2_DISPATCH_DTYPE(y_dt, TO, (axpby_kernel<TO><<<grid_for(n), 256, 0, ST>>>(x, a, z, b, c, (TO*)y, n, z ? zn : 1)));
+    MS2_DISPATCH_DTYPE(y_dt, TO, (ms2_launch(axpby_kernel<TO>, grid_for(n), 256, 0, ST, x, a, z, b, c, (TO*)y, n, z ? zn : 1)));
   }
   MS2_CHECK_LAUNCH("axpby");
   return MS2_OK;
@@ -670,7 +696,7 @@ extern "C" int ms2_gate_rows(const float* x, const float* gate, float fill, floa
   MS2_CHECK_ARG(x && gate && y, "gate_rows: null");
   long n = (long)B * P;
   if (!n) return MS2_OK;
-  gate_rows_kernel<<<grid_for(n), 256, 0, ST>>>(x, gate, fill, y, n, P);
+  ms2_launch(gate_rows_kernel, grid_for(n), 256, 0, ST, x, gate, fill, y, n, P);
   MS2_CHECK_LAUNCH("gate_rows");
   return MS2_OK;
 }
@@ -678,7 +704,7 @@ extern "C" int ms2_select_plane(const float* x, const int32_t* idx, float* y, in
   MS2_CHECK_ARG(x && idx && y && M > 0, "select_plane: bad args");
   long n = (long)B * P;
   if (!n) return MS2_OK;
-  select_plane_kernel<<<grid_for(n), 256, 0, ST>>>(x, idx, y, B, M, P);
+  ms2_launch(select_plane_kernel, grid_for(n), 256, 0, ST, x, idx, y, B, M, P);
   MS2_CHECK_LAUNCH("select_plane");
   return MS2_OK;
 }
@@ -686,9 +712,9 @@ extern "C" int ms2_add_rowvec(const float* x, const float* v, float s, float* y,
   MS2_CHECK_ARG(x && v && y && M >= 0 && C > 0, "add_rowvec: bad args");
   if (!M) return MS2_OK;
   if (C % 4 == 0 && M * C < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)v % 16 == 0))
-    axpby_vec4_kernel<float><<<grid_for(M * C / 4), 256, 0, ST>>>(x, 1.f, v, s, 0.f, y, (unsigned)(M * C / 4), (unsigned)(C / 4));
+    ms2_launch(axpby_vec4_kernel<float>, grid_for(M * C / 4), 256, 0, ST, x, 1.f, v, s, 0.f, y, (unsigned)(M * C / 4), (unsigned)(C / 4));
   else
-    add_rowvec_kernel<<<grid_for(M * C), 256, 0, ST>>>(x, v, s, y, M * C, C);
+    ms2_launch(add_rowvec_kernel, grid_for(M * C), 256, 0, ST, x, v, s, y, M * C, C);
   MS2_CHECK_LAUNCH("add_rowvec");
   return MS2_OK;
 }
@@ -698,11 +724,11 @@ extern "C" int ms2_cast(const void* x, int x_dt, void* y, int y_dt, long n, void
   int g = grid_for(n);
   const bool vec = n % 4 == 0 && n < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
   if (x_dt == MS2_F32 && y_dt == MS2_BF16 && vec)
-    cast_vec4_kernel<bf16><<<grid_for(n / 4), 256, 0, ST>>>((const float*)x, (bf16*)y, (unsigned)(n / 4));
-  else if (x_dt == MS2_F32 && y_dt == MS2_BF16) cast_kernel<float, bf16><<<g, 256, 0, ST>>>((const float*)x, (bf16*)y, n);
-  else if (x_dt == MS2_BF16 && y_dt == MS2_F32) cast_kernel<bf16, float><<<g, 256, 0, ST>>>((const bf16*)x, (float*)y, n);
-  else if (x_dt == MS2_F32 && y_dt == MS2_F32) cast_kernel<float, float><<<g, 256, 0, ST>>>((const float*)x, (float*)y, n);
-  else if (x_dt == MS2_BF16 && y_dt == MS2_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, ST>>>((const bf16*)x, (bf16*)y, n);
+    ms2_launch(cast_vec4_kernel<bf16>, grid_for(n / 4), 256, 0, ST, (const float*)x, (bf16*)y, (unsigned)(n / 4));
+  else if (x_dt == MS2_F32 && y_dt == MS2_BF16) ms2_launch(cast_kernel<float, bf16>, g, 256, 0, ST, (const float*)x, (bf16*)y, n);
+  else if (x_dt == MS2_BF16 && y_dt == MS2_F32) ms2_launch(cast_kernel<bf16, float>, g, 256, 0, ST, (const bf16*)x, (float*)y, n);
+  else if (x_dt == MS2_F32 && y_dt == MS2_F32) ms2_launch(cast_kernel<float, float>, g, 256, 0, ST, (const float*)x, (float*)y, n);
+  else if (x_dt == MS2_BF16 && y_dt == MS2_BF16) ms2_launch(cast_kernel<bf16, bf16>, g, 256, 0, ST, (const bf16*)x, (bf16*)y, n);
   else { ms2_set_error("cast: bad dtype"); return MS2_ERR_ARG; }
   MS2_CHECK_LAUNCH("cast");
   return MS2_OK;
@@ -710,7 +736,7 @@ extern "C" int ms2_cast(const void* x, int x_dt, void* y, int y_dt, long n, void
 extern "C" int ms2_activation(const float* x, float* y, long n, int act, void* stream) {
   MS2_CHECK_ARG(x && y && n >= 0, "activation: bad args");
   if (!n) return MS2_OK;
-  act_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n, act);
+  ms2_launch(act_kernel, grid_for(n), 256, 0, ST, x, y, n, act);
   MS2_CHECK_LAUNCH("activation");
   return MS2_OK;
 }
@@ -718,14 +744,14 @@ extern "C" int ms2_upsample2x_add(float* fine, const float* coarse, int B, int H
   MS2_CHECK_ARG(fine && coarse && (H % 2 == 0) && (W % 2 == 0), "upsample2x_add: bad args");
   long n = (long)B * H * W * C;
   if (!n) return MS2_OK;
-  upsample2x_add_kernel<<<grid_for(n), 256, 0, ST>>>(fine, coarse, B, H, W, C);
+  ms2_launch(upsample2x_add_kernel, grid_for(n), 256, 0, ST, fine, coarse, B, H, W, C);
   MS2_CHECK_LAUNCH("upsample2x_add");
   return MS2_OK;
 }
 static int transpose_launch(const float* x, float* y, int B, long R, int Cc, cudaStream_t st) {
   if (!B || !R || !Cc) return MS2_OK;
   dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), B), block(32, 8);
-  transpose_kernel<<<grid, block, 0, st>>>(x, y, R, Cc);
+  ms2_launch(transpose_kernel, grid, block, 0, st, x, y, R, Cc);
   MS2_CHECK_LAUNCH("transpose");
   return MS2_OK;
 }
@@ -738,7 +764,7 @@ extern "C" int ms2_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, i
   // input viewed as [C, HW] -> output [HW, C]
   if (!B) return MS2_OK;
   dim3 grid(ceil_div((long)H * W, 32), ceil_div(C, 32), B), block(32, 8);
-  transpose_kernel<<<grid, block, 0, ST>>>(x, y, (long)C, H * W);
+  ms2_launch(transpose_kernel, grid, block, 0, ST, x, y, (long)C, H * W);
   MS2_CHECK_LAUNCH("transpose");
   return MS2_OK;
 }
@@ -747,9 +773,9 @@ extern "C" int ms2_maxpool2x2(const float* x, float* y, int B, int H, int W, int
   long n = (long)B * (H / 2) * (W / 2) * C;
   if (!n) return MS2_OK;
   if (C % 4 == 0 && (long)B * H * W * C < (1L << 31) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0))
-    maxpool2x2_vec4_kernel<<<grid_for(n / 4), 256, 0, ST>>>(x, y, (unsigned)(n / 4), (unsigned)H, (unsigned)W, (unsigned)(C / 4));
+    ms2_launch(maxpool2x2_vec4_kernel, grid_for(n / 4), 256, 0, ST, x, y, (unsigned)(n / 4), (unsigned)H, (unsigned)W, (unsigned)(C / 4));
   else
-    maxpool2x2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, B, H, W, C);
+    ms2_launch(maxpool2x2_kernel, grid_for(n), 256, 0, ST, x, y, B, H, W, C);
   MS2_CHECK_LAUNCH("maxpool2x2");
   return MS2_OK;
 }
@@ -760,10 +786,10 @@ extern "C" int ms2_pixel_shuffle_add(const float* g, const float* bias, const fl
   if (!n) return MS2_OK;
   if (C % 4 == 0 && n < (1L << 31) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
       (!bias || (uintptr_t)bias % 16 == 0) && (!skip || (uintptr_t)skip % 16 == 0))
-    pixel_shuffle_add_vec4_kernel<<<grid_for(n / 4), 256, 0, ST>>>(g, bias, skip, out, (unsigned)(n / 4), (unsigned)H,
+    ms2_launch(pixel_shuffle_add_vec4_kernel, grid_for(n / 4), 256, 0, ST, g, bias, skip, out, (unsigned)(n / 4), (unsigned)H,
                                                                    (unsigned)W, (unsigned)(C / 4), act);
   else
-    pixel_shuffle_add_kernel<<<grid_for(n), 256, 0, ST>>>(g, bias, skip, out, B, H, W, C, act);
+    ms2_launch(pixel_shuffle_add_kernel, grid_for(n), 256, 0, ST, g, bias, skip, out, B, H, W, C, act);
   MS2_CHECK_LAUNCH("pixel_shuffle_add");
   return MS2_OK;
 }
@@ -773,10 +799,10 @@ extern "C" int ms2_hyper_mask(const float* up, const float* hyper, float* masks,
   if (!B || !P) return MS2_OK;
   if (C == 32 && Mk == 4 && ((uintptr_t)up % 16 == 0) && ((uintptr_t)hyper % 16 == 0)) {
     dim3 grid1((P + 127) / 128, B);
-    hyper_mask_c32m4_kernel<<<grid1, 128, 0, ST>>>(up, hyper, masks, P);
+    ms2_launch(hyper_mask_c32m4_kernel, grid1, 128, 0, ST, up, hyper, masks, P);
   } else {
     dim3 grid(148 * 4, B);
-    hyper_mask_kernel<<<grid, 256, 0, ST>>>(up, hyper, masks, B, P, C, Mk);
+    ms2_launch(hyper_mask_kernel, grid, 256, 0, ST, up, hyper, masks, B, P, C, Mk);
   }
   MS2_CHECK_LAUNCH("hyper_mask");
   return MS2_OK;
@@ -784,7 +810,7 @@ extern "C" int ms2_hyper_mask(const float* up, const float* hyper, float* masks,
 extern "C" int ms2_fourier_pe(const float* coords, const float* gauss, float* out, int n, int F, void* stream) {
   MS2_CHECK_ARG(coords && gauss && out, "fourier_pe: null");
   if (!n) return MS2_OK;
-  fourier_pe_kernel<<<grid_for((long)n * F), 256, 0, ST>>>(coords, gauss, out, n, F);
+  ms2_launch(fourier_pe_kernel, grid_for((long)n * F), 256, 0, ST, coords, gauss, out, n, F);
   MS2_CHECK_LAUNCH("fourier_pe");
   return MS2_OK;
 }
@@ -795,7 +821,7 @@ extern "C" int ms2_point_embed(const float* coords, const int* labels, const flo
                 "point_embed: bad args");
   const long total = (long)B * (N + (pad ? 1 : 0) + (prefix ? n_prefix : 0)) * F;
   if (!total) return MS2_OK;
-  point_embed_kernel<<<grid_for(total), 256, 0, ST>>>(coords, labels, gauss, table, out, B, N, pad, F, 1.f / image_w,
+  ms2_launch(point_embed_kernel, grid_for(total), 256, 0, ST, coords, labels, gauss, table, out, B, N, pad, F, 1.f / image_w,
                                                       1.f / image_h, prefix, prefix ? n_prefix : 0);
   MS2_CHECK_LAUNCH("point_embed");
   return MS2_OK;
@@ -804,7 +830,7 @@ extern "C" int ms2_normalize_image(const void* x, int in_layout, void* out, int 
   MS2_CHECK_ARG(x && out && in_layout >= 0 && in_layout <= 2, "normalize_image: bad args (layout 0 fp32 NCHW, 1 u8 NHWC, 2 u8 NCHW)");
   long n = (long)B * 3 * H * ((W + 3) / 4);
   if (!n) return MS2_OK;
-  MS2_DISPATCH_DTYPE(out_dt, T, (normalize_image_kernel<T><<<grid_for(n), 256, 0, ST>>>(x, in_layout, (T*)out, B, H, W)));
+  MS2_DISPATCH_DTYPE(out_dt, T, (ms2_launch(normalize_image_kernel<T>, grid_for(n), 256, 0, ST, x, in_layout, (T*)out, B, H, W)));
   MS2_CHECK_LAUNCH("normalize_image");
   return MS2_OK;
 }
@@ -813,7 +839,7 @@ extern "C" int ms2_mask_stability_counts(const float* x, int32_t* counts, int N,
   if (!N) return MS2_OK;
   MS2_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 2 * N, ST), "stability memset");
   dim3 grid(64, N);
-  stability_counts_kernel<<<grid, 256, 0, ST>>>(x, counts, P, delta);
+  ms2_launch(stability_counts_kernel, grid, 256, 0, ST, x, counts, P, delta);
   MS2_CHECK_LAUNCH("stability_counts");
   return MS2_OK;
 }
@@ -854,8 +880,8 @@ extern "C" int ms2_bce_logits_sum(const float* pred, const float* gt, float pos_
   long per_plane = (148L * 6) / N, by_size = (P + 8191) / 8192;      // one resident wave (6 CTAs of 256 threads per SM)
   if (per_plane > by_size) per_plane = by_size;
   dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
-  if (vec) bce_logits_sum_kernel<true><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
-  else bce_logits_sum_kernel<false><<<grid, 256, 0, ST>>>(pred, gt, pos_weight - 1.f, sums, P);
+  if (vec) ms2_launch(bce_logits_sum_kernel<true>, grid, 256, 0, ST, pred, gt, pos_weight - 1.f, sums, P);
+  else ms2_launch(bce_logits_sum_kernel<false>, grid, 256, 0, ST, pred, gt, pos_weight - 1.f, sums, P);
   MS2_CHECK_LAUNCH("bce_logits_sum");
   return MS2_OK;
 }
@@ -863,14 +889,14 @@ extern "C" int ms2_mask_stats(const float* x, int32_t* stats, int N, int H, int 
   MS2_CHECK_ARG(N >= 0 && H >= 0 && W >= 0, "mask_stats: bad sizes");
   if (!N) return MS2_OK;
   MS2_CHECK_ARG(stats && N <= 65535, "mask_stats: stats is null or more than 65535 planes");
-  mask_stats_init_kernel<<<(N + 255) / 256, 256, 0, ST>>>(stats, N, H, W);
+  ms2_launch(mask_stats_init_kernel, (N + 255) / 256, 256, 0, ST, stats, N, H, W);
   MS2_CHECK_LAUNCH("mask_stats_init");
   if (!H || !W) return MS2_OK;
   MS2_CHECK_ARG(x, "mask_stats: x is null");
   long per_plane = (148L * 8) / N;                        // one resident wave of 256-thread CTAs, at most one per row
   if (per_plane > H) per_plane = H;
   dim3 grid((unsigned)(per_plane < 1 ? 1 : per_plane), N);
-  mask_stats_kernel<<<grid, 256, 0, ST>>>(x, stats, H, W, thr, off, W % 4 == 0 && (uintptr_t)x % 16 == 0);
+  ms2_launch(mask_stats_kernel, grid, 256, 0, ST, x, stats, H, W, thr, off, W % 4 == 0 && (uintptr_t)x % 16 == 0);
   MS2_CHECK_LAUNCH("mask_stats");
   return MS2_OK;
 }
@@ -884,7 +910,7 @@ extern "C" int ms2_mask_binarize_t(const float* x, const int32_t* sel, uint8_t* 
   if (!H || !W) return MS2_OK;
   MS2_CHECK_ARG(x && sel, "mask_binarize_t: null input");
   dim3 grid((W + 31) / 32, (H + 31) / 32, K), block(32, 8);
-  mask_binarize_t_kernel<<<grid, block, 0, ST>>>(x, sel, out, H, W, thr, OH, OW, x0, y0);
+  ms2_launch(mask_binarize_t_kernel, grid, block, 0, ST, x, sel, out, H, W, thr, OH, OW, x0, y0);
   MS2_CHECK_LAUNCH("mask_binarize_t");
   return MS2_OK;
 }
@@ -893,7 +919,7 @@ extern "C" int ms2_rle_transitions(const uint8_t* m, int32_t* pos, int32_t* cnt,
   if (!K) return MS2_OK;
   MS2_CHECK_ARG(cnt && (pos || !cap) && (m || !L), "rle_transitions: null pointer");
   const bool vec = (L % 16 == 0) && ((uintptr_t)m % 16 == 0);
-  rle_transitions_kernel<<<K, 1024, 0, ST>>>(m, L, pos, cnt, cap, vec);
+  ms2_launch(rle_transitions_kernel, K, 1024, 0, ST, m, L, pos, cnt, cap, vec);
   MS2_CHECK_LAUNCH("rle_transitions");
   return MS2_OK;
 }

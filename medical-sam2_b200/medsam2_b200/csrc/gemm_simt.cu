@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, long lda, const TW* __restrict__ W, const float* __restrict__ bias,
                  const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
                  TO* __restrict__ out, long ldo, int M, int N, int K, int act) {
+  MS2_PDL_WAIT();
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -88,7 +89,7 @@ template <typename TI, typename TO>
 int launch(const void* A, long lda, const void* W, const float* bias, const float* colscale, const float* residual,
            long ldr, void* out, long ldo, int M, int N, int K, int act, cudaStream_t st) {
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  gemm_simt_kernel<TI, TI, TO><<<grid, 256, 0, st>>>((const TI*)A, lda, (const TI*)W, bias, colscale, residual, ldr,
+  ms2_launch(gemm_simt_kernel<TI, TI, TO>, grid, 256, 0, st, (const TI*)A, lda, (const TI*)W, bias, colscale, residual, ldr,
                                                      (TO*)out, ldo, M, N, K, act);
   MS2_CHECK_LAUNCH("gemm_simt_kernel");
   return MS2_OK;

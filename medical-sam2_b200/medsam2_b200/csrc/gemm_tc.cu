@@ -87,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  MS2_PDL_WAIT();      // barriers, tensor-memory allocation and descriptor prefetch above overlap the preceding kernel
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -387,7 +388,7 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
       MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL), "gemm_tc attr"); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    kern<<<grid, 64 + p.epi_warps * 32, smem, st>>>(tmA, tmW, tmO, p);                                         \
+    ms2_launch(kern, grid, 64 + p.epi_warps * 32, smem, st, tmA, tmW, tmO, p);                                         \
   } while (0)
 #define MS2_GEMM_TC_ACT(F, R)                                                                                  \
   do {                                                                                                         \

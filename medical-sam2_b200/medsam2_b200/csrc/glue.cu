@@ -23,6 +23,7 @@ struct BankRowsP {
 template <typename T>
 __global__ void __launch_bounds__(256) bank_rows_kernel(const __grid_constant__ BankRowsP p, T* __restrict__ k_in,
                                                         T* __restrict__ m_out) {
+  MS2_PDL_WAIT();
   const int s = blockIdx.y, b = blockIdx.z;
   const int rows = p.rows[s], W = p.W, W4 = W >> 2;
   const long n4 = (long)rows * W4;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) bank_rows_kernel(const __grid_constant__ 
 __global__ void argmax_select_rows_kernel(const float* __restrict__ scores, long srs, int M, const float* __restrict__ rows,
                                           long rows_bs, long rows_rs, int C, int32_t* __restrict__ idx_out,
                                           float* __restrict__ out) {
+  MS2_PDL_WAIT();
   const int b = blockIdx.x;
   int best = 0;
   float bv = scores[(long)b * srs];
@@ -70,6 +72,7 @@ __global__ void argmax_select_rows_kernel(const float* __restrict__ scores, long
 
 __global__ void obj_ptr_mix_kernel(const float* __restrict__ ptr, const float* __restrict__ logits,
                                    const float* __restrict__ no_obj, float* __restrict__ out, int C, int soft, int fixed) {
+  MS2_PDL_WAIT();
   const int b = blockIdx.x;
   const float l = logits[b];
   const float lam = soft ? 1.f / (1.f + __expf(-l)) : (l > 0.f ? 1.f : 0.f);
@@ -82,6 +85,7 @@ __global__ void obj_ptr_mix_kernel(const float* __restrict__ ptr, const float* _
 
 __global__ void stability_select_kernel(const int32_t* __restrict__ counts, const float* __restrict__ ious, int M,
                                         float thresh, int32_t* __restrict__ idx_out, float* __restrict__ iou_out, int B) {
+  MS2_PDL_WAIT();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float ai = (float)counts[2 * b], au = (float)counts[2 * b + 1];
@@ -123,8 +127,8 @@ extern "C" int ms2_bank_rows(const void* const* h_src, const void* const* h_pos,
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, n, B);
-  if (out_dt == MS2_BF16) bank_rows_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(p, (bf16*)k_in, (bf16*)m_out);
-  else if (out_dt == MS2_F32) bank_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p, (float*)k_in, (float*)m_out);
+  if (out_dt == MS2_BF16) ms2_launch(bank_rows_kernel<bf16>, grid, 256, 0, (cudaStream_t)stream, p, (bf16*)k_in, (bf16*)m_out);
+  else if (out_dt == MS2_F32) ms2_launch(bank_rows_kernel<float>, grid, 256, 0, (cudaStream_t)stream, p, (float*)k_in, (float*)m_out);
   else MS2_CHECK_ARG(false, "bank_rows: bad dtype");
   MS2_CHECK_LAUNCH("bank_rows");
   return MS2_OK;
@@ -134,7 +138,7 @@ extern "C" int ms2_argmax_select_rows(const float* scores, long scores_rs, int B
                                       int C, int32_t* idx_out, float* out, void* stream) {
   MS2_CHECK_ARG(scores && M >= 1 && (idx_out || out), "argmax_select_rows: bad args");
   if (!B) return MS2_OK;
-  argmax_select_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(scores, scores_rs, M, rows, rows_bs, rows_rs, C, idx_out, out);
+  ms2_launch(argmax_select_rows_kernel, B, 128, 0, (cudaStream_t)stream, scores, scores_rs, M, rows, rows_bs, rows_rs, C, idx_out, out);
   MS2_CHECK_LAUNCH("argmax_select_rows");
   return MS2_OK;
 }
@@ -143,7 +147,7 @@ extern "C" int ms2_obj_ptr_mix(const float* ptr, const float* logits, const floa
                                int soft, int fixed, void* stream) {
   MS2_CHECK_ARG(ptr && logits && no_obj && out, "obj_ptr_mix: null pointer");
   if (!B) return MS2_OK;
-  obj_ptr_mix_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(ptr, logits, no_obj, out, C, soft, fixed);
+  ms2_launch(obj_ptr_mix_kernel, B, 128, 0, (cudaStream_t)stream, ptr, logits, no_obj, out, C, soft, fixed);
   MS2_CHECK_LAUNCH("obj_ptr_mix");
   return MS2_OK;
 }
@@ -152,7 +156,7 @@ extern "C" int ms2_stability_select(const int32_t* counts, const float* ious, in
                                     float* iou_out, void* stream) {
   MS2_CHECK_ARG(counts && ious && idx_out && iou_out && M >= 2, "stability_select: bad args");
   if (!B) return MS2_OK;
-  stability_select_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(counts, ious, M, thresh, idx_out, iou_out, B);
+  ms2_launch(stability_select_kernel, (B + 127) / 128, 128, 0, (cudaStream_t)stream, counts, ious, M, thresh, idx_out, iou_out, B);
   MS2_CHECK_LAUNCH("stability_select");
   return MS2_OK;
 }

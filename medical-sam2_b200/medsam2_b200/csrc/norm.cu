@@ -18,6 +18,7 @@ template <typename TO, int G>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
                  const float* __restrict__ beta, TO* __restrict__ y, long M, int C, float eps, int act) {
+  MS2_PDL_WAIT();
   const int lane_in_group = threadIdx.x % G;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const bool active = row < M;
@@ -51,6 +52,7 @@ template <typename TO, int VPT>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TO* __restrict__ y, long M, int C, float eps, int act) {
+  MS2_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -111,6 +113,7 @@ template <typename TO, int VPT, int ROWS>
 __global__ void __launch_bounds__(256)
 layernorm_vec_rows_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
                           const float* __restrict__ beta, TO* __restrict__ y, long M, int C, float eps, int act) {
+  MS2_PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const long row0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS;
   if (row0 >= M) return;
@@ -187,12 +190,12 @@ int launch_ln(const float* x, const float* add, const float* gamma, const float*
   if (C % 4 == 0 && C >= 32 && C <= 1024 && aligned) {
     const int vpt = (C / 4 + 31) / 32;
     const int grid = ceil_div(M * 32, threads);
-#define LN_VEC(V) layernorm_vec_kernel<TO, V><<<grid, threads, 0, st>>>(x, add, gamma, beta, y, M, C, eps, act)
+#define LN_VEC(V) ms2_launch(layernorm_vec_kernel<TO, V>, grid, threads, 0, st, x, add, gamma, beta, y, M, C, eps, act)
     if (vpt == 1 && M >= 4096) {
-      layernorm_vec_rows_kernel<TO, 1, 4><<<ceil_div(ceil_div(M, 4) * 32, threads), threads, 0, st>>>(x, add, gamma, beta, y, M,
+      ms2_launch(layernorm_vec_rows_kernel<TO, 1, 4>, ceil_div(ceil_div(M, 4) * 32, threads), threads, 0, st, x, add, gamma, beta, y, M,
                                                                                                   C, eps, act);
     } else if (vpt == 2 && M >= 4096) {
-      layernorm_vec_rows_kernel<TO, 2, 2><<<ceil_div(ceil_div(M, 2) * 32, threads), threads, 0, st>>>(x, add, gamma, beta, y, M,
+      ms2_launch(layernorm_vec_rows_kernel<TO, 2, 2>, ceil_div(ceil_div(M, 2) * 32, threads), threads, 0, st, x, add, gamma, beta, y, M,
                                                                                                   C, eps, act);
     } else if (vpt == 1) LN_VEC(1);
     else if (vpt == 2) LN_VEC(2);
@@ -203,7 +206,7 @@ int launch_ln(const float* x, const float* add, const float* gamma, const float*
     return MS2_OK;
   }
 #define LN_LAUNCH(G)                                                                            \
-  layernorm_kernel<TO, G><<<ceil_div(M * G, threads), threads, 0, st>>>(x, add, gamma, beta, y, M, C, eps, act)
+  ms2_launch(layernorm_kernel<TO, G>, ceil_div(M * G, threads), threads, 0, st, x, add, gamma, beta, y, M, C, eps, act)
   if (C <= 4) LN_LAUNCH(4);
   else if (C <= 8) LN_LAUNCH(8);
   else if (C <= 16) LN_LAUNCH(16);

@@ -15,6 +15,7 @@ namespace {
 // ------------------------------------------------------------------ non-overlapping constraints
 __global__ void __launch_bounds__(256) non_overlap_kernel(const float* __restrict__ in, float* __restrict__ out, int n_obj,
                                                           long P4) {
+  MS2_PDL_WAIT();
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += stride) {
     float4 best = __ldg((const float4*)in + i);
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) non_overlap_kernel(const float* __restric
   }
 }
 __global__ void non_overlap_scalar_kernel(const float* __restrict__ in, float* __restrict__ out, int n_obj, long P) {
+  MS2_PDL_WAIT();
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
     float best = in[i];
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(256) score_lowres_kernel(const float* __restri
                                                            ScoreThr thr, float pwm1, int32_t* __restrict__ counts,
                                                            double* __restrict__ sums, int h, int w, int H, int W,
                                                            float sh, float sw) {
+  MS2_PDL_WAIT();
   __shared__ int shc[3 * T];
   __shared__ double shs[8];
   const int n = blockIdx.y;
@@ -135,8 +138,8 @@ void score_launch(cudaStream_t st, const float* low, const float* gt, const Scor
   if (per_plane < 1) per_plane = 1;
   dim3 grid((unsigned)per_plane, N);
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
-  if (sums) score_lowres_kernel<T, true><<<grid, 256, 0, st>>>(low, gt, thr, pwm1, counts, sums, h, w, H, W, sh, sw);
-  else score_lowres_kernel<T, false><<<grid, 256, 0, st>>>(low, gt, thr, pwm1, counts, sums, h, w, H, W, sh, sw);
+  if (sums) ms2_launch(score_lowres_kernel<T, true>, grid, 256, 0, st, low, gt, thr, pwm1, counts, sums, h, w, H, W, sh, sw);
+  else ms2_launch(score_lowres_kernel<T, false>, grid, 256, 0, st, low, gt, thr, pwm1, counts, sums, h, w, H, W, sh, sw);
 }
 
 }  // namespace
@@ -149,11 +152,11 @@ extern "C" int ms2_non_overlap(const float* in, float* out, int n_obj, long P, v
   if (P % 4 == 0 && (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0) {
     long b = (P / 4 + 255) / 256;
     if (b > 148L * 8) b = 148L * 8;
-    non_overlap_kernel<<<(int)b, 256, 0, st>>>(in, out, n_obj, P / 4);
+    ms2_launch(non_overlap_kernel, (int)b, 256, 0, st, in, out, n_obj, P / 4);
   } else {
     long b = (P + 255) / 256;
     if (b > 148L * 8) b = 148L * 8;
-    non_overlap_scalar_kernel<<<(int)b, 256, 0, st>>>(in, out, n_obj, P);
+    ms2_launch(non_overlap_scalar_kernel, (int)b, 256, 0, st, in, out, n_obj, P);
   }
   MS2_CHECK_LAUNCH("non_overlap");
   return MS2_OK;

@@ -9,6 +9,7 @@ namespace {
 
 __global__ void bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int Ho,
                                 int Wo, float sh, float sw) {
+  MS2_PDL_WAIT();
   const long n = (long)N * Ho * Wo;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int xo = i % Wo;
@@ -31,6 +32,7 @@ __global__ void bilinear_kernel(const float* __restrict__ x, float* __restrict__
 // Wo % 4 == 0 and < 2^31 output elements
 __global__ void bilinear_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned n4, int H, int W,
                                      unsigned Ho, unsigned Wo4, float sh, float sw) {
+  MS2_PDL_WAIT();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned xq = i % Wo4;
     unsigned t = i / Wo4;
@@ -66,6 +68,7 @@ __device__ __forceinline__ void aa_bounds(int o, float scale, int in, float& cen
 
 __global__ void bilinear_aa_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int Ho,
                                    int Wo, float sh, float sw) {
+  MS2_PDL_WAIT();
   const long n = (long)N * Ho * Wo;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int xo = i % Wo;
@@ -105,14 +108,14 @@ extern "C" int ms2_resize_bilinear(const float* x, float* y, int N, int H, int W
   long blocks = (n + 255) / 256;
   int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
   float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
-  if (antialias) bilinear_aa_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, Ho, Wo, sh, sw);
+  if (antialias) ms2_launch(bilinear_aa_kernel, g, 256, 0, (cudaStream_t)stream, x, y, N, H, W, Ho, Wo, sh, sw);
   else if (Wo % 4 == 0 && (long)N * Ho * Wo < (1L << 31) && ((uintptr_t)y % 16 == 0)) {
     const long n4 = (long)N * Ho * Wo / 4;
     long b = (n4 + 255) / 256;
     if (b > 148L * 16) b = 148L * 16;
-    bilinear_vec4_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, y, (unsigned)n4, H, W, (unsigned)Ho,
+    ms2_launch(bilinear_vec4_kernel, (int)b, 256, 0, (cudaStream_t)stream, x, y, (unsigned)n4, H, W, (unsigned)Ho,
                                                                   (unsigned)(Wo / 4), sh, sw);
-  } else bilinear_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, Ho, Wo, sh, sw);
+  } else ms2_launch(bilinear_kernel, g, 256, 0, (cudaStream_t)stream, x, y, N, H, W, Ho, Wo, sh, sw);
   MS2_CHECK_LAUNCH("resize_bilinear");
   return MS2_OK;
 }

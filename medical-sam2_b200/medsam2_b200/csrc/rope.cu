@@ -8,6 +8,7 @@ namespace {
 template <typename T>
 __global__ void rope_kernel(T* __restrict__ x, long batch_stride, long row_stride, int B, int rows, int n_rope_rows,
                             int D, const float* __restrict__ cos_t, const float* __restrict__ sin_t, int table_len) {
+  MS2_PDL_WAIT();
   const int half = D / 2;
   const long n = (long)B * n_rope_rows * half;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -27,6 +28,7 @@ __global__ void rope_kernel(T* __restrict__ x, long batch_stride, long row_strid
 __global__ void rope_bf16_vec_kernel(bf16* __restrict__ x, long batch_stride, long row_stride, unsigned n4,
                                      unsigned n_rope_rows, unsigned q4, const float* __restrict__ cos_t,
                                      const float* __restrict__ sin_t, unsigned table_len) {
+  MS2_PDL_WAIT();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const unsigned p4 = i % q4;                       // group of 4 pairs inside the row
     unsigned t = i / q4;
@@ -59,7 +61,7 @@ extern "C" int ms2_rope(void* x, int dt, long batch_stride, long row_stride, int
     const long n4 = n / 4;
     long b4 = (n4 + 255) / 256;
     if (b4 > 148L * 32) b4 = 148L * 32;
-    rope_bf16_vec_kernel<<<(int)b4, 256, 0, (cudaStream_t)stream>>>((bf16*)x, batch_stride, row_stride, (unsigned)n4,
+    ms2_launch(rope_bf16_vec_kernel, (int)b4, 256, 0, (cudaStream_t)stream, (bf16*)x, batch_stride, row_stride, (unsigned)n4,
                                                                    (unsigned)n_rope_rows, (unsigned)(D / 8), cos_t, sin_t,
                                                                    (unsigned)table_len);
     MS2_CHECK_LAUNCH("rope");
@@ -67,7 +69,7 @@ extern "C" int ms2_rope(void* x, int dt, long batch_stride, long row_stride, int
   }
   long blocks = (n + 255) / 256;
   int g = (int)(blocks > 148L * 32 ? 148L * 32 : blocks);
-  MS2_DISPATCH_DTYPE(dt, T, (rope_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(
+  MS2_DISPATCH_DTYPE(dt, T, (ms2_launch(rope_kernel<T>, g, 256, 0, (cudaStream_t)stream, 
                                 (T*)x, batch_stride, row_stride, B, rows, n_rope_rows, D, cos_t, sin_t, table_len)));
   MS2_CHECK_LAUNCH("rope");
   return MS2_OK;

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(SMK_WARPS * 32)
 gemm_smallm_kernel(const T* __restrict__ A, long lda, const T* __restrict__ W, const float* __restrict__ bias,
                    const float* __restrict__ colscale, const float* __restrict__ residual, long ldr,
                    TO* __restrict__ out, long ldo, int M, int N, int K, int act, int rows_per_pass) {
+  MS2_PDL_WAIT();
   constexpr int CPW = 32 / KL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = lane / KL, kl = lane % KL;
@@ -171,6 +172,7 @@ struct GroupedP {
 template <typename T, typename TO, int NCH>
 __global__ void __launch_bounds__(SM_WARPS * 32)
 gemm_smallm_grouped_kernel(const GroupedP<T> p, int M, int K, int rows_per_pass) {
+  MS2_PDL_WAIT();
   const int g = blockIdx.y;
   const int N = p.N[g];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(256)
 attn_fewk_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
                  long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
                  long o_bs, long o_hs, long o_ts, int Hh, int Lq, int Lk, float scale) {
+  MS2_PDL_WAIT();
   extern __shared__ float smf[];
   const int HS = Lk * D + 4;             // head stride, padded: heads land in different banks
   float* Ks = smf;                       // [Hh][Lk][D] (+4 per head)
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(FQ_THREADS)
 attn_fewq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
                  long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
                  long o_bs, long o_hs, long o_ts, int Lq, int Lk, float scale) {
+  MS2_PDL_WAIT();
   extern __shared__ float smf[];
   float* S = smf;                                   // [Lq][Lk]
   float* Qs = S + (long)Lq * Lk;                    // [Lq][D]
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(FS_THREADS)
 attn_fewq_split_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, float* __restrict__ part,
                        long q_bs, long q_hs, long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts,
                        int Lq, int Lk, int chunk, float scale) {
+  MS2_PDL_WAIT();
   __shared__ float S[FQ_MAXQ][FS_MAXCHUNK];
   __shared__ float Vs[FS_MAXCHUNK][D + 1];
   __shared__ float Qs[FQ_MAXQ][D];
@@ -429,6 +434,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(256)
 attn_fewq_combine_kernel(const float* __restrict__ part, T* __restrict__ o, long o_bs, long o_hs, long o_ts,
                          int Hh, int Lq, int ns, int nrows) {
+  MS2_PDL_WAIT();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= nrows) return;
   const int bh = row / Lq, qi = row - bh * Lq;
@@ -489,13 +495,13 @@ int ms2_gemm_smallm_launch(const void* A, int a_dt, long lda, const void* W, con
 #define MS2_SMALLM(TA, TO)                                                                                          \
   do {                                                                                                              \
     if (wide)                                                                                                       \
-      gemm_smallm_kernel<TA, TO, 32, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+      ms2_launch(gemm_smallm_kernel<TA, TO, 32, 8>, grid, SMK_WARPS * 32, smem, st, (const TA*)A, lda, (const TA*)W, bias, colscale, \
                                                                          residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);  \
     else if (K <= 256)                                                                                              \
-      gemm_smallm_kernel<TA, TO, 8, 4><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+      ms2_launch(gemm_smallm_kernel<TA, TO, 8, 4>, grid, SMK_WARPS * 32, smem, st, (const TA*)A, lda, (const TA*)W, bias, colscale, \
                                                                         residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
     else                                                                                                            \
-      gemm_smallm_kernel<TA, TO, 8, 8><<<grid, SMK_WARPS * 32, smem, st>>>((const TA*)A, lda, (const TA*)W, bias, colscale, \
+      ms2_launch(gemm_smallm_kernel<TA, TO, 8, 8>, grid, SMK_WARPS * 32, smem, st, (const TA*)A, lda, (const TA*)W, bias, colscale, \
                                                                         residual, ldr, (TO*)out, ldo, M, N, K, act, rpp);   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_SMALLM(bf16, bf16);
@@ -541,8 +547,8 @@ extern "C" int ms2_gemm_smallm_grouped(int groups, const void* const* h_A, const
       p.out[g] = h_out[g]; p.lda[g] = h_lda[g]; p.ldo[g] = h_ldo[g]; p.N[g] = h_N[g];              \
       p.act[g] = h_act ? h_act[g] : 0;                                                             \
     }                                                                                              \
-    if (K <= 256) gemm_smallm_grouped_kernel<TA, TO, 4><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);         \
-    else gemm_smallm_grouped_kernel<TA, TO, 8><<<grid, SM_WARPS * 32, smem, st>>>(p, M, K, rpp);                   \
+    if (K <= 256) ms2_launch(gemm_smallm_grouped_kernel<TA, TO, 4>, grid, SM_WARPS * 32, smem, st, p, M, K, rpp);         \
+    else ms2_launch(gemm_smallm_grouped_kernel<TA, TO, 8>, grid, SM_WARPS * 32, smem, st, p, M, K, rpp);                   \
   } while (0)
   if (a_dt == MS2_BF16 && o_dt == MS2_BF16) MS2_GROUPED(bf16, bf16);
   else if (a_dt == MS2_BF16 && o_dt == MS2_F32) MS2_GROUPED(bf16, float);
@@ -571,10 +577,10 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
   if (Lk <= 32 && (size_t)2 * Hh * (Lk * D + 4) * 4 <= 48 * 1024) {
     const size_t smem = (size_t)2 * Hh * (Lk * D + 4) * 4;
     dim3 grid(ceil_div((long)Lq * Hh, 256), B);
-    if (dt == MS2_BF16 && D == 16) attn_fewk_kernel<bf16, 16><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
-    else if (dt == MS2_BF16 && D == 32) attn_fewk_kernel<bf16, 32><<<grid, 256, smem, st>>>(MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
-    else if (dt == MS2_F32 && D == 16) attn_fewk_kernel<float, 16><<<grid, 256, smem, st>>>(MS2_ARGS_T(float), Hh, Lq, Lk, scale);
-    else if (dt == MS2_F32 && D == 32) attn_fewk_kernel<float, 32><<<grid, 256, smem, st>>>(MS2_ARGS_T(float), Hh, Lq, Lk, scale);
+    if (dt == MS2_BF16 && D == 16) ms2_launch(attn_fewk_kernel<bf16, 16>, grid, 256, smem, st, MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
+    else if (dt == MS2_BF16 && D == 32) ms2_launch(attn_fewk_kernel<bf16, 32>, grid, 256, smem, st, MS2_ARGS_T(bf16), Hh, Lq, Lk, scale);
+    else if (dt == MS2_F32 && D == 16) ms2_launch(attn_fewk_kernel<float, 16>, grid, 256, smem, st, MS2_ARGS_T(float), Hh, Lq, Lk, scale);
+    else if (dt == MS2_F32 && D == 32) ms2_launch(attn_fewk_kernel<float, 32>, grid, 256, smem, st, MS2_ARGS_T(float), Hh, Lq, Lk, scale);
     else return 0;
     MS2_CHECK_LAUNCH("attn_fewk_kernel");
     return 1;
@@ -587,9 +593,9 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
       dim3 grid(Hh, B, ns);
 #define MS2_FEWQS(T, DD)                                                                                              \
   do {                                                                                                                \
-    attn_fewq_split_kernel<T, DD><<<grid, FS_THREADS, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (float*)ws, q_bs, \
+    ms2_launch(attn_fewq_split_kernel<T, DD>, grid, FS_THREADS, 0, st, (const T*)q, (const T*)k, (const T*)v, (float*)ws, q_bs, \
                                                                q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, Lq, Lk, chunk, scale); \
-    attn_fewq_combine_kernel<T, DD><<<ceil_div((long)B * Hh * Lq, 8), 256, 0, st>>>((const float*)ws, (T*)o, o_bs, o_hs, o_ts, Hh, Lq, ns, B * Hh * Lq); \
+    ms2_launch(attn_fewq_combine_kernel<T, DD>, ceil_div((long)B * Hh * Lq, 8), 256, 0, st, (const float*)ws, (T*)o, o_bs, o_hs, o_ts, Hh, Lq, ns, B * Hh * Lq); \
   } while (0)
       if (dt == MS2_BF16 && D == 16) MS2_FEWQS(bf16, 16);
       else if (dt == MS2_BF16 && D == 32) MS2_FEWQS(bf16, 32);
@@ -612,7 +618,7 @@ int ms2_attention_small(const void* q, const void* k, const void* v, void* o, in
       MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "fewq attr"); \
       attr = 200 * 1024;                                                                                        \
     }                                                                                                           \
-    kern<<<grid, FQ_THREADS, smem, st>>>(MS2_ARGS_T(T), Lq, Lk, scale);                                         \
+    ms2_launch(kern, grid, FQ_THREADS, smem, st, MS2_ARGS_T(T), Lq, Lk, scale);                                         \
   } while (0)
     if (dt == MS2_BF16 && D == 16) MS2_FEWQ(bf16, 16);
     else if (dt == MS2_BF16 && D == 32) MS2_FEWQ(bf16, 32);

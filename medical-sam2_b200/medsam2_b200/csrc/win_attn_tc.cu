@@ -114,6 +114,7 @@ win_attn_tc_kernel(const WinP p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  MS2_PDL_WAIT();      // barriers, tensor-memory allocation and descriptor prefetch above overlap the preceding kernel
   const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)p.o_col;
 
   // Q row table of query tile qt (4 source positions with the 2x2 max-pool, 1 without)
@@ -411,7 +412,7 @@ int ms2_window_attention_tc_launch(const void* qkv, const float* qkv_bias, void*
                "win_attn_tc attr");
       attr2 = smem;
     }
-    win_attn_tc_kernel<2><<<grid, NT, smem, st>>>(p);
+    ms2_launch(win_attn_tc_kernel<2>, grid, NT, smem, st, p);
   } else {
     static size_t attr4 = 0;
     if (smem > attr4) {
@@ -419,7 +420,7 @@ int ms2_window_attention_tc_launch(const void* qkv, const float* qkv_bias, void*
                "win_attn_tc attr");
       attr4 = smem;
     }
-    win_attn_tc_kernel<4><<<grid, NT, smem, st>>>(p);
+    ms2_launch(win_attn_tc_kernel<4>, grid, NT, smem, st, p);
   }
   MS2_CHECK_LAUNCH("win_attn_tc_kernel");
   return MS2_OK;

@@ -30,3 +30,11 @@ for dt in (torch.float32, torch.bfloat16):
               "frac>0.01", float((d > 0.01).mean()))
         lo = st["temp_output_dict_per_obj"][0]["cond_frame_outputs"][2]["pred_masks"].float().cpu().numpy()
         print("   low-res filled px", int((np.abs(lo - 0.1) < 1e-6).sum()), "range", lo.min(), lo.max())
+        print("second click")
+        _, _, vr = m.train_add_new_points(inference_state=st, frame_idx=2, obj_id=1,
+                                          points=torch.tensor([[c2[0] + 150.0, c2[1] + 120.0]]),
+                                          labels=torch.tensor([0], dtype=torch.int32), clear_old_points=False)
+        lo = st["temp_output_dict_per_obj"][0]["cond_frame_outputs"][2]["pred_masks"].float().cpu().numpy()
+        d = np.abs(lo - z["a/pred_masks_2"])
+        print(dt, "click2 low-res err quantiles 50/90/99/99.9/max", [float(np.quantile(d, q)) for q in (0.5, 0.9, 0.99, 0.999, 1.0)],
+              "frac>0.01", float((d > 0.01).mean()))
