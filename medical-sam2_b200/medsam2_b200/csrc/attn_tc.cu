@@ -389,6 +389,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // TMEM: O_a [0,64) O_b [64,128) S_a [128,192) S_b [192,256) Q_a [256,384) Q_b [384,512); P overwrites S in place,
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
 constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64, T2_DEFAULT_VAR = 0;
+constexpr bool MC_DEFAULT_ON = true;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
 
@@ -698,6 +699,320 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Memory cross-attention on CTA PAIRS (thread-block cluster of 2, D = 256 keys, DV = 64 values, 128-key tiles).
+// attn_tc2 shares every K/V tile between two query tiles of ONE CTA; its price is tensor memory: O_a O_b S_a S_b Q_a Q_b
+// fill all 512 columns, so P has to overwrite S in place and S_x(j+1) cannot start before P V_x(j) has finished — the
+// per-stream chain S -> softmax -> P V is serial (ncu: tensor pipe 54 % active).  Here the two query tiles live in the
+// two CTAs of a cluster and share K/V through TMA MULTICAST: each CTA fetches half of every tile and the hardware
+// writes it into both shared memories, so the L2 -> SM operand traffic per FLOP is that of attn_tc2, while each SM
+// holds ONE stream with room for a double-buffered S:  O [0,64)  S0 [64,192)  S1 [192,320)  Q [320,448).
+// S(j+1) = Q K^T is issued before P V(j) and runs under the softmax of tile j; 128-key tiles halve the barrier round
+// trips per key.  Empty-slot signals (tcgen05.commit) are multicast to both CTAs: a slot is refilled only when both
+// CTAs' tensor pipes have finished reading it.  Q is staged through K slot 1 (one cluster barrier orders that).
+constexpr int MC_BKV = 128, MC_KST = 2, MC_THREADS = 320;
+constexpr int MC_K_BYTES = 4 * MC_BKV * 128, MC_V_BYTES = MC_BKV * 128;
+constexpr int MC_SMEM = MC_KST * MC_K_BYTES + 2 * MC_V_BYTES + 1024 + 4096;
+constexpr int MC_S_COL = 64, MC_Q_COL = 320;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MC_THREADS, 1)
+attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
+  constexpr int BKV = MC_BKV, KST = MC_KST, D = 256, DV = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sQ = sK + MC_K_BYTES;               // Q staging = K slot 1 (free until the cluster barrier below)
+  uint8_t* sV = sK + KST * MC_K_BYTES;
+  uint64_t* bars = (uint64_t*)(sV + 2 * MC_V_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2 (one arrival per CTA of the pair)
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2 (one arrival per CTA)
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* p_full = bars + 11;       // 1 (8 softmax warps)
+  uint64_t* o_ready = bars + 12;      // 1
+  uint64_t* q_tmem = bars + 13;       // 1 (8 softmax warps)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 14);
+  float* mxbuf = (float*)(bars + 16);    // [tile parity][half][128 rows]
+  float* lbuf = mxbuf + 512;             // [half][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int q0 = blockIdx.x * BQ;
+  const int bh = blockIdx.y, b = bh / p.Hh, h = bh - b * p.Hh;
+  const int split = blockIdx.z;
+  const int t_begin = split * p.tiles_per_split;
+  int n = p.ntiles - t_begin;
+  if (n > p.tiles_per_split) n = p.tiles_per_split;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmQ);
+    tc::prefetch_tmap(&tmK);
+    tc::prefetch_tmap(&tmV);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&k_full[s], 1);
+      tc::mbar_init(&k_empty[s], 2);
+      tc::mbar_init(&v_full[s], 1);
+      tc::mbar_init(&v_empty[s], 2);
+      tc::mbar_init(&s_full[s], 1);
+    }
+    tc::mbar_init(p_full, 8);
+    tc::mbar_init(o_ready, 1);
+    tc::mbar_init(q_tmem, 8);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  tc::tc_fence_before();
+  __syncwarp();
+  tc::cluster_arrive();               // both CTAs' barriers exist before anybody multicasts into them
+  tc::cluster_wait();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  MS2_PDL_WAIT();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // every tile is loaded as two half-tiles of 64 keys: this CTA fetches half `rank` and multicasts it to both CTAs
+    auto load_k = [&](int j) {
+      const int ks = j & 1;
+      tc::mbar_wait(&k_empty[ks], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      tc::mbar_arrive_expect_tx(&k_full[ks], MC_K_BYTES);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tc::tma_load_4d_mc(sK + ks * MC_K_BYTES + c * BKV * 128 + rank * 64 * 128, &tmK, &k_full[ks], c * 64,
+                           (t_begin + j) * BKV + (int)rank * 64, h, b, (uint16_t)3);
+    };
+    auto load_v = [&](int j) {
+      const int st = j & 1;
+      tc::mbar_wait(&v_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      tc::mbar_arrive_expect_tx(&v_full[st], MC_V_BYTES);
+      tc::tma_load_4d_mc(sV + st * MC_V_BYTES + rank * 64 * 128, &tmV, &v_full[st], 0, (t_begin + j) * BKV + (int)rank * 64,
+                         h, b, (uint16_t)3);
+    };
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(q_full, 4 * BQ * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
+      load_k(0);
+    }
+    __syncwarp();
+    tc::cluster_arrive();             // Q of BOTH CTAs has left K slot 1 (see the softmax warps)
+    tc::cluster_wait();
+    if (tc::elect_one()) {
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) load_k(j + 1);
+        load_v(j);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
+    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
+    const uint32_t tO = tmem_base, tS = tmem_base + MC_S_COL, tQ = tmem_base + MC_Q_COL;
+    auto issue_qk = [&](int j) {
+      const int st = j & 1, ks = j & 1;
+      // S[st] still holds P of tile j-2: P V of tile j-2 must have finished READING it before this MMA writes
+      if (j >= 2) tc::mbar_wait(o_ready, (uint32_t)(j - 2) & 1u);
+      tc::mbar_wait(&k_full[ks], (uint32_t)(j >> 1) & 1u);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t db = tc::desc_kmajor_sw128(aK + ks * MC_K_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
+          tc::umma_bf16_ts(tS + st * BKV, tQ + kk * 8, db, idesc_qk, kk ? 1u : 0u);
+        }
+        // the slot is refilled by BOTH CTAs' producers: tell both (only if somebody will wait for it)
+        if (j + KST < n) tc::umma_commit_mc(&k_empty[ks], (uint16_t)3);
+        tc::umma_commit(&s_full[st]);
+      }
+      __syncwarp();
+    };
+    tc::cluster_arrive();
+    tc::cluster_wait();
+    tc::mbar_wait(q_tmem, 0);
+    tc::tc_fence_after();
+    issue_qk(0);
+    for (int j = 0; j < n; ++j) {
+      if (j + 1 < n) issue_qk(j + 1);
+      const int st = j & 1;
+      tc::mbar_wait(&v_full[st], (uint32_t)(j >> 1) & 1u);
+      tc::mbar_wait(p_full, (uint32_t)j & 1u);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * MC_V_BYTES + kk * 2048, BKV * 128);
+          tc::umma_bf16_ts(tO, tS + st * BKV + kk * 8, db, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+        if (j + 2 < n) tc::umma_commit_mc(&v_empty[st], (uint16_t)3);
+        tc::umma_commit(o_ready);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..9) =====================
+    constexpr int HC = BKV / 2;                     // S columns per warp
+    const int qtr = warp & 3, half = (warp - 2) >> 2;
+    const int row = qtr * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+    const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + MC_S_COL;
+    float m_used = 0.f, l = 0.f;
+    const int last_valid = p.Lk - (p.ntiles - 1) * BKV;
+
+    {  // Q: swizzled staging tile (K slot 1) -> tensor memory; the two warps of a quarter take alternate blocks
+      tc::mbar_wait(q_full, 0);
+      const uint32_t aQ = tc::smem_u32(sQ);
+#pragma unroll
+      for (int blk = 0; blk < 8; ++blk) {
+        if ((blk & 1) != half) continue;
+        const int ch = blk >> 1, g0 = (blk & 1) * 4;
+        uint32_t w[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 v = tc::lds128(aQ + ch * BQ * 128 + row * 128 + (((g0 + g) ^ (row & 7)) << 4));
+          w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+        }
+        tc::tmem_st16(tmem_base + lane_addr + MC_Q_COL + blk * 16, w);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(q_tmem);
+      tc::cluster_arrive();           // K slot 1 may now be overwritten — by either CTA's multicast
+      tc::cluster_wait();
+    }
+
+    for (int j = 0; j < n; ++j) {
+      const int st = j & 1;
+      tc::mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1u);
+      tc::tc_fence_after();
+      uint32_t r[HC / 32][32];
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c) tc::tmem_ld32(tS + st * BKV + half * HC + c * 32, r[c]);
+      tc::tmem_ld_wait();
+      if ((t_begin + j == p.ntiles - 1) && (last_valid < BKV)) {
+#pragma unroll
+        for (int c = 0; c < HC / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (half * HC + c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+      mx *= p.c;
+      float* mslot = mxbuf + (j & 1) * 256;
+      mslot[half * 128 + row] = mx;
+      tc::named_bar_sync(1 + qtr, 64);
+      mx = fmaxf(mx, mslot[(half ^ 1) * 128 + row]);
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = mx > m_used + p.tau;
+        if (__any_sync(0xffffffffu, need)) {
+          tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);
+          tc::tc_fence_after();
+          float alpha = 1.f;
+          if (need) {
+            alpha = ex2(m_used - mx);
+            m_used = mx;
+            l *= alpha;
+          }
+          if (half == 0) {                             // DV = 64: two 32-column blocks, one warp of the quarter each
+            uint32_t o[32];
+            tc::tmem_ld32(tO, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tO, o);
+          } else {
+            uint32_t o[32];
+            tc::tmem_ld32(tO + 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tO + 32, o);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      uint32_t pk[HC / 2];
+      const float nm = -m_used;
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
+          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
+          l += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
+        }
+      if (j > 0) tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);      // observe every phase (see attn_tc_kernel)
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c) tc::tmem_st16(tS + st * BKV + half * (HC / 2) + c * 16, &pk[c * 16]);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+
+    lbuf[half * 128 + row] = l;
+    tc::named_bar_sync(1 + qtr, 64);
+    l += lbuf[(half ^ 1) * 128 + row];
+    tc::mbar_wait(o_ready, (uint32_t)(n - 1) & 1u);
+    tc::tc_fence_after();
+    const int qi = q0 + row;
+    uint32_t o[32];
+    tc::tmem_ld32(tO + half * 32, o);                // this warp's 32 of the 64 output columns
+    tc::tmem_ld_wait();
+    if (p.nsplit == 1 && !p.force_part) {
+      const float inv = 1.f / l;
+      bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
+      if (qi < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv,
+                                                      __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
+            vv[i] = *(uint32_t*)&hh;
+          }
+          *(uint4*)(orow + half * 32 + g * 8) = v;
+        }
+      }
+    } else {
+      const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
+      float* orow = p.opart + rix * DV;
+      if (qi < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *(float4*)(orow + half * 32 + g * 4) =
+              make_float4(__uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]), __uint_as_float(o[g * 4 + 2]),
+                          __uint_as_float(o[g * 4 + 3]));
+        if (half == 0) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncwarp();
+  tc::cluster_arrive();               // neither CTA leaves while the other may still signal its barriers
+  tc::cluster_wait();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // merge the split-KV partials: O = sum_s 2^(m_s - m*) O_s / sum_s 2^(m_s - m*) l_s
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -864,7 +1179,32 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
   p.force_part = part_o ? 1 : 0;
 
   static const bool two_tiles_ok = []() { const char* e = getenv("MS2_ATTN_TWO_TILES"); return !e || atoi(e) != 0; }();
-  if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
+  static const bool mc_ok = []() { const char* e = getenv("MS2_ATTN_MC"); return e ? atoi(e) != 0 : MC_DEFAULT_ON; }();
+  if (D == 256 && DV == 64 && qtiles % 2 == 0 && mc_ok) {
+    // CTA pairs sharing K/V through TMA multicast, 128-key tiles (attn_mc_kernel)
+    CUtensorMap tmK2, tmV2;
+    auto mk2 = [&](CUtensorMap* m, const void* base, long bs, long hs, long ts, int L, int rows, int width) {
+      const uint64_t dims[4] = {(uint64_t)width, (uint64_t)L, (uint64_t)Hh, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)ts, (uint64_t)(Hh > 1 ? hs : ts * (long)L), (uint64_t)(B > 1 ? bs : ts * (long)L * Hh)};
+      const uint32_t box[4] = {64, (uint32_t)rows, 1, 1};
+      return tc::make_tmap_bf16(m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    if ((rc = mk2(&tmK2, k, k_bs, k_hs, k_ts, Lk, 64, D))) return rc;
+    if ((rc = mk2(&tmV2, v, v_bs, v_hs, v_ts, Lk, 64, DV))) return rc;
+    p.ntiles = (Lk + MC_BKV - 1) / MC_BKV;
+    p.nsplit = ws ? pick_nsplit(qtiles * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
+    p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
+    p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
+    if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
+    static bool attr_mc = false;
+    if (!attr_mc) {
+      MS2_CUDA(cudaFuncSetAttribute(attn_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
+      attr_mc = true;
+    }
+    dim3 gridm(qtiles, B * Hh, p.nsplit);
+    ms2_launch(attn_mc_kernel, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
+    MS2_CHECK_LAUNCH("attn_mc_kernel");
+  } else if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
     // two query tiles per CTA share every K/V tile (half the L2->SM operand traffic per FLOP)
     const int qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);
     p.nsplit = ws ? pick_nsplit(qpairs * B * Hh, p.ntiles, per_split, ws_bytes) : 1;
