@@ -72,7 +72,7 @@ struct Cfg {
   static constexpr int Q_COL = D == 256 ? 384 : 128;    // Q (A operand of S = Q K^T) resident in TMEM, D/2 columns
 };
 
-template <int D, int DV, int BKV, int KST>
+template <int D, int DV, int BKV, int KST, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
@@ -295,12 +295,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // p = 2^(s*c - m_used), row sum in fp32, pack to bf16 pairs
       uint32_t pk[HC / 2];
       const float nm = -m_used;
+      // D = 96 (Hiera global blocks): per 128x128 tile the tensor pipe needs 768 cycles, the 16384 exponentials 1024
+      // MUFU cycles -> a share of them (p.poly eighths, 0..4) is evaluated by ex2_poly on the FMA pipe instead
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
-          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
+          const float x0 = fmaf(__uint_as_float(r[c][i]), p.c, nm);
+          const float x1 = fmaf(__uint_as_float(r[c][i + 1]), p.c, nm);
+          const int e = i & 7;
+          const bool poly0 = D == 96 && ((POLY >= 1 && e == 2) || (POLY >= 3 && e == 6));
+          const bool poly1 = D == 96 && ((POLY >= 2 && e == 4) || (POLY >= 4 && e == 0));
+          const float p0 = poly0 ? ex2_poly(x0) : ex2(x0);
+          const float p1 = poly1 ? ex2_poly(x1) : ex2(x1);
           l += p0 + p1;
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
@@ -390,6 +397,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
 constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64, T2_DEFAULT_VAR = 0;
 constexpr bool MC_DEFAULT_ON = true;
+constexpr int ATTN_D96_POLY = 2;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
 
@@ -1233,11 +1241,21 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     MS2_CHECK_LAUNCH("attn_tc2_kernel");
   } else {
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
-    auto kern = attn_tc_kernel<D, DV, BKV, KST>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const int poly = []() { const char* e = getenv("MS2_ATTN_POLY"); return e ? atoi(e) : ATTN_D96_POLY; }();
+    auto kern = attn_tc_kernel<D, DV, BKV, KST, 0>;
+    if (D == 96) {
+      switch (poly) {
+        case 1: kern = attn_tc_kernel<D, DV, BKV, KST, 1>; break;
+        case 2: kern = attn_tc_kernel<D, DV, BKV, KST, 2>; break;
+        case 3: kern = attn_tc_kernel<D, DV, BKV, KST, 3>; break;
+        case 4: kern = attn_tc_kernel<D, DV, BKV, KST, 4>; break;
+        default: break;
+      }
+    }
+    static decltype(kern) attr_set = nullptr;
+    if (attr_set != kern) {
       MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM), "attn_tc attr");
-      attr_set = true;
+      attr_set = kern;
     }
     dim3 grid(qtiles, B * Hh, p.nsplit);
     ms2_launch(kern, grid, NUM_THREADS, C::SMEM, st, tmQ, tmK, tmV, p);
