@@ -59,20 +59,37 @@ static inline bool ms2_pdl_enabled() {
   static const bool on = []() { const char* e = getenv("MS2_PDL"); return !e || atoi(e) != 0; }();
   return on;
 }
+// cluster_x > 1: launch as thread-block clusters of cluster_x CTAs along x (kernels without __cluster_dims__)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t ms2_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                     Args&&... args) {
+static inline cudaError_t ms2_launch_cluster(void (*kern)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem,
+                                             cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (ms2_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = ms2_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ms2_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  return ms2_launch_cluster(kern, 1, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ float to_f(float x) { return x; }

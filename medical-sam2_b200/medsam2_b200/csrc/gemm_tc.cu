@@ -29,6 +29,7 @@ struct GemmP {
   const float* residual;
   long ldr;
   int M, N, K, BN, tiles_n, tiles, num_kb, stages, epi_warps, epi_bufs;
+  int pair;       // CTA pairs (cluster of 2) share every W tile through TMA multicast; tiles (2*mp + rank, n)
 };
 
 template <int ACT, bool F32OUT>
@@ -67,6 +68,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr = (uint32_t*)(acc_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // i-th tile of this CTA (-1: none).  Plain: tiles blockIdx.x, +gridDim.x, ...  Pair mode: cluster cl works on the
+  // tile pairs cl, cl + #clusters, ...; pair tp = (m-tile pair mp, n-tile) and this CTA takes m-tile 2*mp + rank, so
+  // the two CTAs of a cluster always need the SAME W tile at the same time.
+  const uint32_t rank = p.pair ? tc::cluster_ctarank() : 0u;
+  const int ncl = p.pair ? (int)(gridDim.x >> 1) : 0, cl = (int)(blockIdx.x >> 1);
+  const int pair_tiles = p.tiles >> 1;
+  auto tile_of = [&](int i) -> int {
+    if (!p.pair) {
+      const long t = (long)blockIdx.x + (long)i * gridDim.x;
+      return t < p.tiles ? (int)t : -1;
+    }
+    const long tp = (long)cl + (long)i * ncl;
+    if (tp >= pair_tiles) return -1;
+    const int mp = (int)(tp / p.tiles_n), n = (int)(tp - (long)mp * p.tiles_n);
+    return (2 * mp + (int)rank) * p.tiles_n + n;
+  };
+  int my_tiles = 0;
+  while (tile_of(my_tiles) >= 0) ++my_tiles;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -74,7 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::prefetch_tmap(&tmO);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&empty[s], p.pair ? 2 : 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       tc::mbar_init(&acc_full[s], 1);
@@ -84,7 +103,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, TMEM_COLS);
   tc::tc_fence_before();
-  __syncthreads();
+  if (p.pair) {                       // both CTAs' barriers exist before anybody multicasts into them
+    __syncwarp();
+    tc::cluster_arrive();
+    tc::cluster_wait();
+  } else {
+    __syncthreads();
+  }
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   MS2_PDL_WAIT();      // barriers, tensor-memory allocation and descriptor prefetch above overlap the preceding kernel
@@ -94,14 +119,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      const int half_rows = p.BN >> 1;
+      for (int i = 0, t; (t = tile_of(i)) >= 0; ++i) {
         const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * p.BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           tc::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
           tc::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-          tc::tma_load_2d(sa + A_STAGE_BYTES, &tmW, &full[stage], kb * BK, n0);
+          if (p.pair)      // this CTA fetches half `rank` of the W tile; the hardware writes it into both CTAs
+            tc::tma_load_2d_mc(sa + A_STAGE_BYTES + rank * half_rows * 128, &tmW, &full[stage], kb * BK,
+                               n0 + (int)rank * half_rows, (uint16_t)3);
+          else
+            tc::tma_load_2d(sa + A_STAGE_BYTES, &tmW, &full[stage], kb * BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -111,7 +141,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = tc::make_idesc_bf16(BM, p.BN, 0, 0);
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    long it = 0;                                     // k-block iterations issued so far
+    const long it_total = (long)my_tiles * p.num_kb;
+    for (int i = 0; tile_of(i) >= 0; ++i) {
       tc::mbar_wait(&acc_empty[as], aphase ^ 1);
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
@@ -126,10 +158,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc::umma_bf16(d_tmem, tc::desc_kmajor_sw128(sa + k * 32), tc::desc_kmajor_sw128(sb + k * 32), idesc,
                           (kb | k) ? 1u : 0u);
           }
-          tc::umma_commit(&empty[stage]);
+          // pair mode: the slot is refilled by both CTAs' multicasts, so both must hear about it — unless nobody
+          // will wait for this slot again (the peer may be gone by the time a trailing signal lands)
+          if (!p.pair) tc::umma_commit(&empty[stage]);
+          else if (it + p.stages < it_total) tc::umma_commit_mc(&empty[stage], (uint16_t)3);
           if (kb == p.num_kb - 1) tc::umma_commit(&acc_full[as]);
         }
         __syncwarp();
+        ++it;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
@@ -167,11 +203,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // the chunk this warp handles after (t, c): same tile, or the first one of a later tile (groups rotate per tile)
-    auto next_chunk = [&](int t, int c, int rot, int& tn, int& cn) -> bool {
-      tn = t; cn = c + ngrp;
-      while (cn >= tile_nch(tn)) {
-        tn += gridDim.x;
-        if (tn >= p.tiles) return false;
+    // (ti = index into this CTA's tile sequence, tile_of(ti) = the tile)
+    auto next_chunk = [&](int ti, int c, int rot, int& tin, int& cn) -> bool {
+      tin = ti; cn = c + ngrp;
+      while (cn >= tile_nch(tile_of(tin))) {
+        ++tin;
+        if (tile_of(tin) < 0) return false;
         rot = (rot + 1 == ngrp) ? 0 : rot + 1;
         cn = rot;
       }
@@ -182,10 +219,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     bool fetched = false;                          // the residual of the upcoming chunk is already on its way
     if (has_res && nbuf > 1) {
-      int t0 = blockIdx.x, c0 = rot - ngrp, tn, cn;   // "chunk before the first": next_chunk finds the first one
-      if (t0 < p.tiles && next_chunk(t0, c0, rot, tn, cn)) { fetch_residual(tn, cn, sbuf0); fetched = true; }
+      int c0 = rot - ngrp, tin, cn;                   // "chunk before the first": next_chunk finds the first one
+      if (tile_of(0) >= 0 && next_chunk(0, c0, rot, tin, cn)) { fetch_residual(tile_of(tin), cn, sbuf0); fetched = true; }
     }
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    for (int ti = 0, t; (t = tile_of(ti)) >= 0; ++ti) {
       const int m0 = (t / p.tiles_n) * BM + q * 32, n0 = (t % p.tiles_n) * p.BN;
       const int nch = tile_nch(t);
       bool waited = false;
@@ -204,10 +241,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (has_res) {
             if (!fetched) fetch_residual(t, c, sbuf);          // (only when the look-ahead found nothing)
-            int tn, cn;
-            const bool more = next_chunk(t, c, rot, tn, cn);
+            int tin, cn;
+            const bool more = next_chunk(ti, c, rot, tin, cn);
             if (more) {
-              fetch_residual(tn, cn, sbuf0 + ((it + 1) & 1) * EPI_BUF_BYTES);
+              fetch_residual(tile_of(tin), cn, sbuf0 + ((it + 1) & 1) * EPI_BUF_BYTES);
               asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
               asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -290,7 +327,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tc::elect_one()) tc::tma_store_wait<0>();
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (p.pair) {                       // neither CTA leaves while the other may still multicast into it
+    __syncwarp();
+    tc::cluster_arrive();
+    tc::cluster_wait();
+  } else {
+    __syncthreads();
+  }
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -377,7 +420,26 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
     }
     if (rc) return rc;
   }
-  const int grid = p.tiles < tc::sm_count() ? p.tiles : tc::sm_count();
+  // CTA pairs: worth it where the W tile dominates the L2 -> SM operand traffic of a tile (wide N tile, K >= 256) and
+  // there is more than one wave of tiles; MS2_GEMM_PAIR=0 disables, =2 forces (whenever the shape allows it)
+  static const int pair_env = []() { const char* e = getenv("MS2_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const int tiles_m = (M + BM - 1) / BM;
+  const bool pair_possible = tiles_m % 2 == 0 && p.BN % 16 == 0 && p.tiles >= 2;
+  p.pair = 0;
+  if (pair_possible && pair_env == 2) p.pair = 1;
+  else if (pair_possible && pair_env == 1 && p.BN >= 128 && K >= 4096 && p.tiles >= 2 * tc::sm_count()) p.pair = 1;
+  CUtensorMap tmWp;
+  if (p.pair) {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K};
+    const uint32_t box[2] = {BK, (uint32_t)(p.BN / 2)};
+    if ((rc = tc::make_tmap_bf16(&tmWp, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  int grid = p.tiles < tc::sm_count() ? p.tiles : tc::sm_count();
+  if (p.pair) {
+    int ncl = tc::sm_count() / 2;
+    if (ncl > p.tiles / 2) ncl = p.tiles / 2;
+    grid = 2 * ncl;
+  }
   const bool res = residual || colscale;
   MS2_CHECK_ARG(!residual || o_dt == MS2_F32, "gemm_tc: a residual needs an fp32 output");
 #define MS2_GEMM_TC(F, A, R)                                                                                   \
@@ -388,7 +450,7 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
       MS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL), "gemm_tc attr"); \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    ms2_launch(kern, grid, 64 + p.epi_warps * 32, smem, st, tmA, tmW, tmO, p);                                         \
+    ms2_launch_cluster(kern, p.pair ? 2 : 1, grid, 64 + p.epi_warps * 32, smem, st, tmA, p.pair ? tmWp : tmW, tmO, p);  \
   } while (0)
 #define MS2_GEMM_TC_ACT(F, R)                                                                                  \
   do {                                                                                                         \
