@@ -116,6 +116,23 @@ int ms2_attention_dv_partial(const void* q, const void* k, const void* v, float*
 int ms2_attention_merge(const float* parts_o, const float* parts_ml, long part_stride, void* o, int dt,
                         long o_bs, long o_ts, int B, int Lq, int DV, int nparts, ms2_stream_t stream);
 
+/* ---- the same exchange WITHOUT a collective call (fused compute + transfer over NVLink peer memory; replaces the
+ *      dist.all_gather of the packed partial).  Every rank owns a gather buffer of `world` packed partials
+ *      ([rows*64] un-normalised O then [rows*2] (m,l) per rank) and `world` uint32 flag words, both in peer-accessible
+ *      (symmetric) device memory.  ms2_attention_dv_partial_push computes this rank's partial over its Lk keys (Lk == 0:
+ *      the empty partial) and its last kernel stores it into slot `rank` of EVERY rank's buffer — h_dst[r] / h_flag[r] are
+ *      HOST arrays of the DEVICE addresses of this rank's slot / flag word in rank r's memory — then publishes `step` in
+ *      the flags (st.release.sys after a grid-wide fence; `counter` = one zeroed uint32 of local device memory).
+ *      ms2_attention_merge_wait spins until all `world` local flags show `step` (ld.acquire.sys) and merges the local
+ *      gather buffer `parts` (stride `part_stride` floats between ranks) into bf16 o [B,Lq,64].  Two buffers used
+ *      alternately make back-to-back exchanges safe.  workspace: >= B*Lq*66*4 bytes. */
+int ms2_attention_dv_partial_push(const void* q, const void* k, const void* v, int dt, long q_bs, long q_ts, long k_bs,
+                                  long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk, int D, int DV, float scale,
+                                  void* workspace, long workspace_bytes, const void* const* h_dst, const void* const* h_flag,
+                                  int world, int step, void* counter, ms2_stream_t stream);
+int ms2_attention_merge_wait(const float* parts, long part_stride, const void* flags, int step, int world, void* o, int dt,
+                             long o_bs, long o_ts, int B, int Lq, int DV, ms2_stream_t stream);
+
 /* ---- Hiera windowed attention with window partition / zero-pad-as-bias-key / q max-pool /
  *      unpartition+crop folded into the loads and stores (hieradet.py:58-83,136-159,
  *      backbones/utils.py:16-62).  qkv [B,H,W,3,heads,D] dtype dt (the qkv Linear output on the

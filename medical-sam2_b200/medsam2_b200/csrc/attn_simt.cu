@@ -251,6 +251,36 @@ extern "C" int ms2_attention_merge(const float* parts_o, const float* parts_ml, 
   return ms2_attention_merge_launch(parts_o, parts_ml, part_stride, o, o_bs, o_ts, B, Lq, nparts, (cudaStream_t)stream);
 }
 
+int ms2_attention_dv_partial_push_launch(const void* q, const void* k, const void* v, long q_bs, long q_ts, long k_bs,
+                                         long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk, float scale, void* ws,
+                                         long ws_bytes, const void* const* h_dst, const void* const* h_flag, int world,
+                                         unsigned step, void* counter, cudaStream_t st);
+int ms2_attention_merge_wait_launch(const float* parts, long part_stride, const void* flags, unsigned step, int world, void* o,
+                                    long o_bs, long o_ts, int B, int Lq, cudaStream_t st);
+
+extern "C" int ms2_attention_dv_partial_push(const void* q, const void* k, const void* v, int dt, long q_bs, long q_ts,
+                                             long k_bs, long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk, int D,
+                                             int DV, float scale, void* workspace, long workspace_bytes,
+                                             const void* const* h_dst, const void* const* h_flag, int world, int step,
+                                             void* counter, void* stream) {
+  MS2_CHECK_ARG(B > 0 && Lq > 0 && Lk >= 0 && D == 256 && DV == 64 && dt == MS2_BF16,
+                "attention_dv_partial_push: bf16, D=256, DV=64 only");
+  MS2_CHECK_ARG(Lk == 0 || (q && k && v), "attention_dv_partial_push: null pointer");
+  MS2_CHECK_ARG(Lk == 0 || ms2_attention_tc_supported(dt, 256, q_ts, 256, k_ts, 64, v_ts, 64, 64, 1, Lq, Lk, D, DV),
+                "attention_dv_partial_push: unsupported shape/stride (Lq, Lk >= 64)");
+  return ms2_attention_dv_partial_push_launch(q, k, v, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, Lq, Lk, scale, workspace,
+                                              workspace_bytes, h_dst, h_flag, world, (unsigned)step, counter,
+                                              (cudaStream_t)stream);
+}
+
+extern "C" int ms2_attention_merge_wait(const float* parts, long part_stride, const void* flags, int step, int world, void* o,
+                                        int dt, long o_bs, long o_ts, int B, int Lq, int DV, void* stream) {
+  MS2_CHECK_ARG(dt == MS2_BF16 && DV == 64, "attention_merge_wait: bf16 output with DV = 64 only");
+  if (B == 0 || Lq == 0) return MS2_OK;
+  return ms2_attention_merge_wait_launch(parts, part_stride, flags, (unsigned)step, world, o, o_bs, o_ts, B, Lq,
+                                         (cudaStream_t)stream);
+}
+
 extern "C" int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs,
                                 long q_ts, long k_bs, long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs,
                                 long o_hs, long o_ts, int B, int Hh, int Lq, int Lk, int D, float scale, int impl,

@@ -397,6 +397,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
 constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64, T2_DEFAULT_VAR = 0;
 constexpr bool MC_DEFAULT_ON = true;
+constexpr int MC_DEFAULT_POLY = 0;
 constexpr int ATTN_D96_POLY = 2;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
@@ -723,6 +724,7 @@ constexpr int MC_K_BYTES = 4 * MC_BKV * 128, MC_V_BYTES = MC_BKV * 128;
 constexpr int MC_SMEM = MC_KST * MC_K_BYTES + 2 * MC_V_BYTES + 1024 + 4096;
 constexpr int MC_S_COL = 64, MC_Q_COL = 320;
 
+template <int POLY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MC_THREADS, 1)
 attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
@@ -957,8 +959,13 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[c][i]), p.c, nm));
-          const float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), p.c, nm));
+          const float x0 = fmaf(__uint_as_float(r[c][i]), p.c, nm);
+          const float x1 = fmaf(__uint_as_float(r[c][i + 1]), p.c, nm);
+          const int e = i & 7;                       // POLY eighths of the exponentials on the FMA pipe (ex2_poly)
+          const bool poly0 = (POLY >= 1 && e == 2) || (POLY >= 3 && e == 6);
+          const bool poly1 = (POLY >= 2 && e == 4) || (POLY >= 4 && e == 0);
+          const float p0 = poly0 ? ex2_poly(x0) : ex2(x0);
+          const float p1 = poly1 ? ex2_poly(x1) : ex2(x1);
           l += p0 + p1;
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
@@ -1130,6 +1137,115 @@ attn_merge_kernel(const float* __restrict__ parts_o, const float* __restrict__ p
   *(uint4*)(o + b * o_bs + (long)qi * o_ts + cg * 8) = v;
 }
 
+// ---- split-KV across GPUs without a collective call: the kernel that folds this rank's local splits into ONE partial
+//      writes it straight into EVERY rank's gather buffer (peer memory over NVLink: plain stores to addresses of the
+//      peers' symmetric allocation; slot = this rank) and, when the last CTA has fenced its stores, raises this rank's
+//      flag on every peer (st.release.sys).  The consumer is attn_merge_wait_kernel on each rank: it spins on the flags
+//      of all ranks (ld.acquire.sys) and merges.  One exchange = (world-1) x 1.03 MiB of NVLink writes per rank.
+struct PushP {
+  float* dst[8];          // per destination rank: base of MY slot in that rank's gather buffer ([rows*DV] O then [rows*2] (m,l))
+  unsigned* flag[8];      // per destination rank: MY flag word there
+  unsigned* counter;      // local, zero between launches: CTAs that have fenced their stores
+  int world;
+  unsigned step;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_reduce_push_kernel(const float* __restrict__ opart, const float* __restrict__ ml, int nsplit, long rows, const PushP pp) {
+  MS2_PDL_WAIT();
+  constexpr int TPR = D / 8, RPB = 128 / TPR;
+  const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int cg = threadIdx.x % TPR;
+  if (rix < rows) {
+    float mstar = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mstar = fmaxf(mstar, ml[((long)s * rows + rix) * 2]);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float lsum = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float2 v = *(const float2*)(ml + ((long)s * rows + rix) * 2);
+      const float w = exp2f(v.x - mstar);
+      lsum += w * v.y;
+      const float4* src = (const float4*)(opart + ((long)s * rows + rix) * D + cg * 8);
+      const float4 a = src[0], bq = src[1];
+      acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+      acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+    }
+    const float4 o0 = make_float4(acc[0], acc[1], acc[2], acc[3]), o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    for (int r = 0; r < pp.world; ++r) {
+      float4* dst = (float4*)(pp.dst[r] + rix * D + cg * 8);
+      dst[0] = o0;
+      dst[1] = o1;
+      if (cg == 0) *(float2*)(pp.dst[r] + rows * D + rix * 2) = make_float2(mstar, lsum);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(pp.counter, 1u);
+    if (prev == gridDim.x - 1) {                    // every CTA's stores are fenced: publish
+      *pp.counter = 0u;
+      __threadfence_system();
+      for (int r = 0; r < pp.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flag[r]), "r"(pp.step) : "memory");
+    }
+  }
+}
+
+// merge of the `world` partials of one exchange step once every rank's flag shows that step (or a later one)
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_merge_wait_kernel(const float* __restrict__ parts, long part_stride, const unsigned* __restrict__ flags, unsigned step,
+                       int world, bf16* __restrict__ o, long o_bs, long o_ts, int Lq, long rows) {
+  MS2_PDL_WAIT();
+  if (threadIdx.x == 0) {
+    const uint64_t t0 = tc::globaltimer_ns();
+    for (int r = 0; r < world; ++r) {
+      unsigned v;
+      uint32_t spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if ((int)(v - step) >= 0) break;
+        if ((++spins & 0xfffu) == 0 && tc::globaltimer_ns() - t0 > 20000000000ull) {
+          printf("medsam2_b200: partial of rank %d (step %u, have %u) never arrived\n", r, step, v);
+          __trap();
+        }
+      } while (true);
+    }
+  }
+  __syncthreads();
+  constexpr int TPR = D / 8, RPB = 128 / TPR;
+  const long rix = (long)blockIdx.x * RPB + threadIdx.x / TPR;
+  const int cg = threadIdx.x % TPR;
+  if (rix >= rows) return;
+  // peers wrote these lines: read them past the (non-coherent) L1
+  float mstar = -INFINITY;
+  for (int r = 0; r < world; ++r) mstar = fmaxf(mstar, __ldcg(parts + (long)r * part_stride + rows * D + rix * 2));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float lsum = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float2 v = __ldcg((const float2*)(parts + (long)r * part_stride + rows * D + rix * 2));
+    if (v.y <= 0.f) continue;                                  // empty share
+    const float w = exp2f(v.x - mstar);
+    lsum += w * v.y;
+    const float4* src = (const float4*)(parts + (long)r * part_stride + rix * D + cg * 8);
+    const float4 a = __ldcg(src), bq = __ldcg(src + 1);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * bq.x; acc[5] += w * bq.y; acc[6] += w * bq.z; acc[7] += w * bq.w;
+  }
+  const float inv = 1.f / lsum;
+  const long b = rix / Lq;
+  const int qi = (int)(rix - b * Lq);
+  uint4 v;
+  uint32_t* vv = (uint32_t*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+    vv[i] = *(uint32_t*)&hh;
+  }
+  *(uint4*)(o + b * o_bs + (long)qi * o_ts + cg * 8) = v;
+}
+
 int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long ws_bytes) {
   const int sms = tc::sm_count();
   if (qtiles_total >= 2 * sms || ntiles < 4) return 1;
@@ -1152,8 +1268,13 @@ int pick_nsplit(int qtiles_total, int ntiles, long ws_rows_bytes_per_split, long
 template <int D, int DV, int BKV, int KST>
 int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long q_hs, long q_ts, long k_bs, long k_hs,
            long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts, int B, int Hh, int Lq, int Lk,
-           float scale, void* ws, long ws_bytes, cudaStream_t st, float* part_o = nullptr, float* part_ml = nullptr) {
+           float scale, void* ws, long ws_bytes, cudaStream_t st, float* part_o = nullptr, float* part_ml = nullptr,
+           const PushP* push = nullptr) {
   using C = Cfg<D, DV, BKV, KST>;
+  // `push`: the folded partial goes to every rank's gather buffer (attn_reduce_push_kernel) instead of part_o: the
+  // attention kernel then always leaves its split partials in the workspace (also when there is a single split)
+  float* const ws_ml1 = ws ? (float*)ws + (long)B * Hh * Lq * DV : nullptr;
+  if (push) { part_o = (float*)ws; part_ml = ws_ml1; }
   static_assert(C::SMEM <= 227 * 1024, "attention tile does not fit shared memory");
   static_assert(KST >= 2 && KST <= 4, "K ring depth");
   CUtensorMap tmQ, tmK, tmV;
@@ -1204,13 +1325,22 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
+    static const int mc_poly = []() { const char* e = getenv("MS2_MC_POLY"); return e ? atoi(e) : MC_DEFAULT_POLY; }();
+    auto kmc = attn_mc_kernel<0>;
+    switch (mc_poly) {
+      case 1: kmc = attn_mc_kernel<1>; break;
+      case 2: kmc = attn_mc_kernel<2>; break;
+      case 3: kmc = attn_mc_kernel<3>; break;
+      case 4: kmc = attn_mc_kernel<4>; break;
+      default: break;
+    }
     static bool attr_mc = false;
     if (!attr_mc) {
-      MS2_CUDA(cudaFuncSetAttribute(attn_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
+      MS2_CUDA(cudaFuncSetAttribute(kmc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
       attr_mc = true;
     }
     dim3 gridm(qtiles, B * Hh, p.nsplit);
-    ms2_launch(attn_mc_kernel, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
+    ms2_launch(kmc, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
     MS2_CHECK_LAUNCH("attn_mc_kernel");
   } else if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
     // two query tiles per CTA share every K/V tile (half the L2->SM operand traffic per FLOP)
@@ -1261,7 +1391,12 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     ms2_launch(kern, grid, NUM_THREADS, C::SMEM, st, tmQ, tmK, tmV, p);
     MS2_CHECK_LAUNCH("attn_tc_kernel");
   }
-  if (part_o) {
+  if (push) {
+    constexpr int TPR = DV / 8, RPB = 128 / TPR;
+    ms2_launch(attn_reduce_push_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, (const float*)p.opart, (const float*)p.ml,
+               p.nsplit, rows, *push);
+    MS2_CHECK_LAUNCH("attn_reduce_push_kernel");
+  } else if (part_o) {
     if (p.nsplit > 1) {
       constexpr int TPR = DV / 8, RPB = 128 / TPR;
       ms2_launch(attn_reduce_partials_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, p.opart, p.ml, part_o, part_ml, p.nsplit, rows);
@@ -1332,5 +1467,43 @@ int ms2_attention_merge_launch(const float* parts_o, const float* parts_ml, long
   ms2_launch(attn_merge_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, parts_o, parts_ml, part_stride, (bf16*)o, o_bs, o_ts, Lq,
                                                              nparts, rows);
   MS2_CHECK_LAUNCH("attn_merge_kernel");
+  return MS2_OK;
+}
+
+int ms2_attention_dv_partial_push_launch(const void* q, const void* k, const void* v, long q_bs, long q_ts, long k_bs,
+                                         long k_ts, long v_bs, long v_ts, int B, int Lq, int Lk, float scale, void* ws,
+                                         long ws_bytes, const void* const* h_dst, const void* const* h_flag, int world,
+                                         unsigned step, void* counter, cudaStream_t st) {
+  MS2_CHECK_ARG(world >= 1 && world <= 8 && h_dst && h_flag && counter, "attention_dv_partial_push: 1..8 ranks");
+  const long rows = (long)B * Lq;
+  MS2_CHECK_ARG(ws && ws_bytes >= rows * (64 + 2) * 4 && (uintptr_t)ws % 16 == 0, "attention_dv_partial_push: workspace too small");
+  PushP pp;
+  pp.world = world; pp.step = step; pp.counter = (unsigned*)counter;
+  for (int r = 0; r < world; ++r) {
+    MS2_CHECK_ARG(h_dst[r] && h_flag[r] && (uintptr_t)h_dst[r] % 16 == 0, "attention_dv_partial_push: bad destination %d", r);
+    pp.dst[r] = (float*)h_dst[r];
+    pp.flag[r] = (unsigned*)h_flag[r];
+  }
+  if (Lk <= 0) {                                    // no keys on this rank: the empty partial (0, -inf, 0)
+    constexpr int DV = 64, TPR = DV / 8, RPB = 128 / TPR;
+    ms2_launch(attn_reduce_push_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, (const float*)ws, (const float*)ws, 0, rows, pp);
+    MS2_CHECK_LAUNCH("attn_reduce_push_kernel");
+    return MS2_OK;
+  }
+  MS2_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0),
+                "attention_dv_partial_push: pointers must be 16-byte aligned");
+  return launch<256, 64, 64, 4>(q, k, v, nullptr, q_bs, 256, q_ts, k_bs, 256, k_ts, v_bs, 64, v_ts, 0, 0, 0, B, 1, Lq, Lk,
+                                scale, ws, ws_bytes, st, nullptr, nullptr, &pp);
+}
+
+int ms2_attention_merge_wait_launch(const float* parts, long part_stride, const void* flags, unsigned step, int world, void* o,
+                                    long o_bs, long o_ts, int B, int Lq, cudaStream_t st) {
+  MS2_CHECK_ARG(parts && flags && o && world >= 1 && world <= 8 && (uintptr_t)parts % 16 == 0 && part_stride % 4 == 0 &&
+                    (uintptr_t)o % 16 == 0 && o_ts % 8 == 0, "attention_merge_wait: bad args");
+  const long rows = (long)B * Lq;
+  constexpr int DV = 64, TPR = DV / 8, RPB = 128 / TPR;
+  ms2_launch(attn_merge_wait_kernel<DV>, ceil_div(rows, RPB), 128, 0, st, parts, part_stride, (const unsigned*)flags, step, world,
+             (bf16*)o, o_bs, o_ts, Lq, rows);
+  MS2_CHECK_LAUNCH("attn_merge_wait_kernel");
   return MS2_OK;
 }

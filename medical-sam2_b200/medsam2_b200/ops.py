@@ -295,6 +295,46 @@ def attention_merge(parts, B, Lq, DV=64):
     return o
 
 
+def attention_dv_partial_push(q, k, v, dst_ptrs, flag_ptrs, step, counter, scale=None):
+    """This rank's share of a split-KV memory cross-attention, pushed into EVERY rank's gather buffer over peer
+    memory by the kernel that folds the local splits (no collective call): q [B,Lq,256], k [B,Lk,256], v [B,Lk,64]
+    bf16 (k = None or Lk == 0: the empty partial).  dst_ptrs[r] / flag_ptrs[r]: device address of this rank's slot /
+    flag word in rank r's symmetric memory; `counter`: zeroed int32 [1] on this device."""
+    import ctypes
+    B, Lq, D = q.shape
+    DV = 64
+    rows = B * Lq
+    world = len(dst_ptrs)
+    Lk = 0 if k is None else k.shape[1]
+    if Lk:
+        for t, n in ((q, "q"), (k, "k"), (v, "v")):
+            if not t.is_cuda or t.stride(-1) != 1 or t.dtype != torch.bfloat16:
+                raise native.NativeError(f"attention_dv_partial_push: {n} must be a bf16 CUDA tensor with unit inner stride")
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    per_split = rows * (DV + 2) * 4
+    qtiles = B * ((Lq + 127) // 128)
+    nsplit = max(2, min(32, (4 * _SMS) // qtiles, (256 << 20) // per_split)) if Lk >= 512 else 1
+    ws = torch.empty(nsplit * per_split, dtype=torch.uint8, device=q.device)
+    ev = PROFILE.begin("mem_cross_attention")
+    native.call("ms2_attention_dv_partial_push", q.data_ptr(), None if not Lk else k.data_ptr(), None if not Lk else v.data_ptr(),
+                BF16, q.stride(0), q.stride(1), 0 if not Lk else k.stride(0), 0 if not Lk else k.stride(1),
+                0 if not Lk else v.stride(0), 0 if not Lk else v.stride(1), B, Lq, Lk, D, DV, float(scale), ws.data_ptr(),
+                ws.numel(), (ctypes.c_void_p * world)(*dst_ptrs), (ctypes.c_void_p * world)(*flag_ptrs), world, int(step),
+                _chk(counter, "counter", torch.int32), _st())
+    PROFILE.end("mem_cross_attention", ev, 2.0 * B * Lq * Lk * (D + DV))
+
+
+def attention_merge_wait(parts, flags, step, B, Lq, DV=64):
+    """parts fp32 [world, B*Lq*(DV+2)] (this rank's gather buffer, filled by the peers' attention_dv_partial_push),
+    flags int32 [world]: waits on the device until every flag shows `step`, then merges -> bf16 [B,Lq,DV]."""
+    world = parts.shape[0]
+    o = torch.empty((B, Lq, DV), dtype=torch.bfloat16, device=parts.device)
+    native.call("ms2_attention_merge_wait", _chk(parts, "parts", torch.float32), parts.stride(0), _chk(flags, "flags", torch.int32),
+                int(step), world, o.data_ptr(), BF16, o.stride(0), o.stride(1), B, Lq, DV, _st())
+    return o
+
+
 def window_attention(qkv, qkv_bias, B, H, W, heads, D, ws, qpool, impl=0):
     """qkv [B,H,W,3*heads*D] -> [B,Ho,Wo,heads*D]."""
     Ho, Wo = (H // 2, W // 2) if qpool else (H, W)

@@ -114,11 +114,23 @@ def encode_volume_sharded(predictor, inference_state, group=None):
 
 
 class KVShard:
-    """Placement of the memory bank's keys over the ranks of `group` and the exchange of the attention partials."""
+    """Placement of the memory bank's keys over the ranks of `group` and the exchange of the attention partials.
 
-    def __init__(self, rank, world, group=None):
+    Exchange (`exchange="p2p"`, default when peer memory is available): every rank owns two gather buffers of `world`
+    packed partials + flag words in symmetric (peer-mapped) device memory (`torch.distributed._symmetric_memory`, used
+    for allocation and address exchange only).  The kernel that folds a rank's local splits stores the partial straight
+    into every rank's buffer over NVLink and publishes a step counter (`ms2_attention_dv_partial_push`); the merge kernel
+    spins on the flags (`ms2_attention_merge_wait`).  No collective call, no host synchronisation: one exchange per layer
+    per frame = (world-1) x 1.03 MiB of peer writes per rank.  `exchange="nccl"`: one all_gather_into_tensor per layer."""
+
+    def __init__(self, rank, world, group=None, exchange=None):
+        import os
         self.rank, self.world, self.group = int(rank), int(world), group
         self.exchanges = 0
+        self.exchange = exchange or os.environ.get("MS2_KV_EXCHANGE", "p2p")
+        self._symm = None
+        self.step = 0
+        self.nvlink_bytes = 0
 
     def owns_cond(self, i):
         """conditioning memory number i (arrival order) lives on rank i mod world (rank 0 always owns the first)."""
@@ -133,11 +145,50 @@ class KVShard:
         memory when there is none, so that no rank ends up with a few rows only."""
         return self.owns_recent(0, n_cond) if n_recent else self.rank == 0
 
+    def _symmetric(self, part_numel, device):
+        """two gather buffers [2, world, part_numel] fp32 + flags [2, world] int32 in peer-mapped memory; None when the
+        platform cannot provide it (falls back to NCCL)."""
+        if self._symm is not None and self._symm["numel"] == part_numel:
+            return self._symm
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((2 * self.world * part_numel,), dtype=torch.float32, device=device)
+            flg = symm_mem.empty((64,), dtype=torch.int32, device=device)
+            flg.zero_()
+            hb = symm_mem.rendezvous(buf, grp)
+            hf = symm_mem.rendezvous(flg, grp)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._symm = {"numel": part_numel, "buf": buf, "flags": flg, "buf_ptrs": list(hb.buffer_ptrs),
+                          "flag_ptrs": list(hf.buffer_ptrs), "counter": torch.zeros(1, dtype=torch.int32, device=device),
+                          "handles": (hb, hf)}
+        except Exception as e:                          # no peer access / symmetric memory on this platform
+            import warnings
+            warnings.warn(f"KVShard: peer-memory exchange unavailable ({e}); using NCCL all-gather")
+            self.exchange = "nccl"
+            self._symm = None
+        return self._symm
+
     def attend(self, q, k, v):
         """q [B,L,256] (identical on all ranks), k/v: this rank's keys / raw values (None or Lk = 0: no share)
         -> softmax(q K_all^T) V_all [B,L,64], identical on all ranks."""
         from . import ops
         B, L, _ = q.shape
+        part_numel = B * L * 66
+        if self.world > 1 and self.exchange == "p2p":
+            sm = self._symmetric(part_numel, q.device)
+            if sm is not None:
+                self.step += 1
+                b = self.step & 1
+                dst = [sm["buf_ptrs"][r] + ((b * self.world + self.rank) * part_numel) * 4 for r in range(self.world)]
+                flg = [sm["flag_ptrs"][r] + (b * self.world + self.rank) * 4 for r in range(self.world)]
+                ops.attention_dv_partial_push(q, k, v, dst, flg, self.step, sm["counter"])
+                parts = sm["buf"].view(2, self.world, part_numel)[b]
+                flags = sm["flags"][b * self.world: (b + 1) * self.world]
+                self.exchanges += 1
+                self.nvlink_bytes += (self.world - 1) * part_numel * 4
+                return ops.attention_merge_wait(parts, flags, self.step, B, L)
         part = ops.attention_dv_partial(q, k, v)
         if self.world == 1:
             parts = part[None]
