@@ -186,11 +186,11 @@ def main_torch_gpu(args):
         n = run()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / args.steps
-    print(json.dumps({"impl": "torch_eager_gpu", "metric": METRIC, "value": n / dt, "unit": UNIT, "n_gpus": 1,
+    emit({"impl": "torch_eager_gpu", "metric": METRIC, "value": n / dt, "unit": UNIT, "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
                       "dtype": "bf16 autocast", "data": "synthetic",
                       "config": {"workload": f"BASELINE configs[2]: {args.config}, {args.slices} slices {args.size}^2, oracle port in "
-                                             f"torch eager on cuda:0 (feature cache 1 as the reference: prompted slices encoded twice)"}}))
+                                             f"torch eager on cuda:0 (feature cache 1 as the reference: prompted slices encoded twice)"}})
 
 
 def main_reference(args):
@@ -216,7 +216,7 @@ def main_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main_image(args):
@@ -248,11 +248,11 @@ def main_image(args):
         step()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / args.steps
-    print(json.dumps({"metric": "images/sec SAM2ImagePredictor set_image_batch+predict_batch (hiera_s, 1024^2, batch 4)",
+    emit({"metric": "images/sec SAM2ImagePredictor set_image_batch+predict_batch (hiera_s, 1024^2, batch 4)",
                       "value": 4 / dt, "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
                       "ms_per_step": 1e3 * dt, "higher_is_better": True, "dtype": args.dtype, "data": "synthetic",
                       "config": {"workload": "BASELINE configs[1]: 4 fundus-shaped uint8 images from host memory, one positive "
-                                             "click each, multimask_output, masks returned to the host as numpy"}}))
+                                             "click each, multimask_output, masks returned to the host as numpy"}})
 
 
 def _sync_all(world):
@@ -352,7 +352,7 @@ def _strong_record(args, world, rank):
     from synth_data import btcv_volume
     T, S = args.strong_slices, args.size
     model = _build_predictor(args, T, prefetch=False)
-    shard = shard_memory_attention(model)
+    shard = shard_memory_attention(model) if world > 1 else None
     vol, boxes = btcv_volume(T, S, 4321, 1)
     vol_host = vol.pin_memory()
     vol_dev = vol.cuda()
@@ -391,15 +391,24 @@ def _strong_record(args, world, rank):
     rec = {"metric": METRIC, "value": T * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
            "ms_per_step": ms / steps, "scaling": "strong",
            "config": {"workload": f"BASELINE configs[4]: ONE {T}-slice {S}^2 volume, {args.config}, bbox every "
-                                  f"{args.prompt_every} slices; slice encoding sharded by contiguous blocks + NCCL all-gather of "
-                                  f"the FPN pyramid; memory bank dealt to the ranks (split-KV cross-attention), lockstep tracking"},
+                                  f"{args.prompt_every} slices" + (
+                                      "; slice encoding sharded by contiguous blocks + NCCL all-gather of the FPN pyramid; "
+                                      "memory bank dealt to the ranks (split-KV cross-attention), lockstep tracking"
+                                      if world > 1 else "; one GPU: the reference point of the strong-scaling runs")},
            "e2e": {"value": T * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": vol_host.numel() * 4, "d2h_bytes_per_step": out_host.numel(),
                    "note": "each rank uploads only the slice block it encodes"},
-           "partial_exchanges_per_step": exchanges}
+           "partial_exchanges_per_step": exchanges,
+           "exchange": (shard.exchange if shard is not None else None),
+           "exchange_note": ("p2p = the kernel folding a rank's local split-KV partials stores the 1.03 MiB partial into every "
+                             "rank's gather buffer over NVLink peer memory and raises a flag; the merge kernel waits on the "
+                             "flags: no collective call on the data path" if shard is not None and shard.exchange == "p2p"
+                             else "NCCL all_gather_into_tensor per layer"),
+           "nvlink_bytes_per_step_per_rank": ((shard.nvlink_bytes // max(1, steps + 1 + max(1, min(args.warmup, 2))))
+                                              if shard is not None else 0)}
     del model, vol_dev, vol_host
     torch.cuda.empty_cache()
-    rec["selftest"] = _strong_selftest(world, rank)
+    rec["selftest"] = _strong_selftest(world, rank) if world > 1 else None
     torch.cuda.empty_cache()
     return rec
 
@@ -607,9 +616,10 @@ def main_ours(args):
 
     # ---- config 5 under torchrun: one long volume over all ranks (strong scaling), appended to the same JSON line
     strong = None
-    if world > 1 and not shard_encode and not args.no_strong:
+    if not shard_encode and not args.no_strong:
         del vol_dev, vol_host, l2_flush
         last.clear()
+        step_resident = step_e2e = None
         torch.cuda.empty_cache()
         strong = _strong_record(args, world, rank)
 
@@ -651,7 +661,6 @@ def main_ours(args):
                                 "n": v["n"]} for k, v in prof.items()}}
     gpu_base, parity_ok, parity = None, None, None
     if world == 1 and not shard_encode:
-        del l2_flush
         torch_masks = {}
         if not args.no_gpu_baseline:
             gpu_base, torch_masks = _gpu_baseline(args, max(3, min(args.steps, 3)))
@@ -683,7 +692,7 @@ def main_ours(args):
                     "h2d_alone_ms": h2d_ms, "h2d_alone_gbs": vol_host_bytes(T, S) / h2d_ms / 1e6},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_baseline": gpu_base, "parity_checked": parity_ok, "parity": parity, "strong": strong}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -702,7 +711,24 @@ def cpu_sample_text(args, cores):
             f"reference, fp32, {cores} host threads")
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of this run, on the process's original stdout (libraries that print to stdout — NCCL's version
+    banner, for one — are diverted to stderr for the whole run)."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         main_reference(a)

@@ -76,6 +76,9 @@ def _kv_worker(rank, world, port, out):
     shard = shard_memory_attention(m)
     got, st = run(True)
     ok = shard is not None and shard.exchanges == 7 * len(m.memory_attention.layers)   # 7 tracked frames x 4 layers
+    # the exchange ran over peer memory (ms2_attention_dv_partial_push / _merge_wait), not as an NCCL collective
+    want = os.environ.get("MS2_KV_EXCHANGE", "p2p")
+    ok &= shard.exchange == want and (shard.nvlink_bytes > 0) == (want == "p2p")
     bank = st["output_dict"]["_ms2_bank"]
     ok &= bank.n_static == 1024 * len([i for i in range(3) if i % world == rank])       # only this rank's cond memories
     for f in range(T):
