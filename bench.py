@@ -304,7 +304,7 @@ def _strong_selftest(world, rank):
     tests/test_gpu_multi.py, which needs >= 2 GPUs and is therefore skipped on a 1-GPU test box)."""
     import torch.distributed as dist
     import medsam2_b200
-    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from medsam2_b200.parallel import add_prompts_sharded, encode_volume_sharded, shard_memory_attention
     from oracle.config import get_config
     from oracle.weights import param_spec
     from synth_data import btcv_volume, seeded_weights
@@ -318,8 +318,10 @@ def _strong_selftest(world, rank):
         st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=512, video_width=512)
         if sharded:
             encode_volume_sharded(m, st)
-        for f in (0, 3, 6):
-            m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+            add_prompts_sharded(m, st, [(f, 1, boxes[f][0]) for f in (0, 3, 6)])
+        else:
+            for f in (0, 3, 6):
+                m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
         return {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}
     ref = run(False)
     shard = shard_memory_attention(m)
@@ -348,7 +350,7 @@ def _strong_record(args, world, rank):
     """BASELINE configs[4] under torchrun: ONE `--strong-slices`-slice volume on all ranks — slice encoding sharded by
     contiguous blocks + all-gather of the pyramid, memory bank dealt to the ranks (split-KV memory cross-attention, one
     exchange of the partials per layer), all ranks track in lockstep.  Strong scaling: value = slices / max-rank time."""
-    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from medsam2_b200.parallel import add_prompts_sharded, encode_volume_sharded, shard_memory_attention
     from synth_data import btcv_volume
     T, S = args.strong_slices, args.size
     model = _build_predictor(args, T, prefetch=False)
@@ -364,9 +366,8 @@ def _strong_record(args, world, rank):
                                   async_loading_frames=lazy_host)
         encode_volume_sharded(model, st)                      # each rank uploads + encodes only its block of slices
         masks = [None] * T
-        for f in prompt_frames(T, args.prompt_every):
-            model.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]),
-                                     clear_old_points=False)
+        # prompted slices are independent: each rank runs the prompt step of the slices whose memory it will own
+        add_prompts_sharded(model, st, [(f, 1, boxes[f][0]) for f in prompt_frames(T, args.prompt_every)])
         for f, _, m in model.propagate_in_video(st, start_frame_idx=0):
             masks[f] = m
         return masks
@@ -393,6 +394,7 @@ def _strong_record(args, world, rank):
            "config": {"workload": f"BASELINE configs[4]: ONE {T}-slice {S}^2 volume, {args.config}, bbox every "
                                   f"{args.prompt_every} slices" + (
                                       "; slice encoding sharded by contiguous blocks + NCCL all-gather of the FPN pyramid; "
+                                      "prompt step and memory encoding of a prompted slice on the rank that owns its memory; "
                                       "memory bank dealt to the ranks (split-KV cross-attention), lockstep tracking"
                                       if world > 1 else "; one GPU: the reference point of the strong-scaling runs")},
            "e2e": {"value": T * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,

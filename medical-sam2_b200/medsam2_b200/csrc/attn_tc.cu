@@ -395,9 +395,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //   warps 6..9  softmax of stream b
 // TMEM: O_a [0,64) O_b [64,128) S_a [128,192) S_b [192,256) Q_a [256,384) Q_b [384,512); P overwrites S in place,
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
-constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64, T2_DEFAULT_VAR = 0;
+constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64;
 constexpr bool MC_DEFAULT_ON = true;
-constexpr int MC_DEFAULT_POLY = 0;
 constexpr int ATTN_D96_POLY = 2;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
@@ -1325,15 +1324,8 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
-    static const int mc_poly = []() { const char* e = getenv("MS2_MC_POLY"); return e ? atoi(e) : MC_DEFAULT_POLY; }();
+    // (polynomial share of the exponentials, measured at Lk = 209120: 433 / 443 / 460 / 495 us for 0, 1/8, 1/4, 3/8)
     auto kmc = attn_mc_kernel<0>;
-    switch (mc_poly) {
-      case 1: kmc = attn_mc_kernel<1>; break;
-      case 2: kmc = attn_mc_kernel<2>; break;
-      case 3: kmc = attn_mc_kernel<3>; break;
-      case 4: kmc = attn_mc_kernel<4>; break;
-      default: break;
-    }
     static bool attr_mc = false;
     if (!attr_mc) {
       MS2_CUDA(cudaFuncSetAttribute(kmc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
@@ -1349,31 +1341,22 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
-    static const int var = []() { const char* e = getenv("MS2_T2_VAR"); return e ? atoi(e) : T2_DEFAULT_VAR; }();
+    // (softmax variants <1..7>: independent partial maxima / sums and a polynomial share of the exponentials were
+    //  measured at Lk = 209120: 525 us for <0> and <1>, 532 / 556 / 575 us with 1/4, 3/8, 1/2 of the exponentials on the
+    //  FMA pipe — one softmax warp's instruction stream, not MUFU throughput, is this kernel's critical path)
     static bool attr2 = false;
     if (!attr2) {
-#define MS2_T2_ATTR(V) MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr")
-      MS2_T2_ATTR(0); MS2_T2_ATTR(1); MS2_T2_ATTR(2); MS2_T2_ATTR(3); MS2_T2_ATTR(4); MS2_T2_ATTR(5); MS2_T2_ATTR(6); MS2_T2_ATTR(7);
-#undef MS2_T2_ATTR
+      MS2_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM), "attn_tc2 attr");
       attr2 = true;
     }
     dim3 grid2(qpairs, B * Hh, p.nsplit);
-    switch (var & 7) {
-      case 0: ms2_launch(attn_tc2_kernel<0>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 1: ms2_launch(attn_tc2_kernel<1>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 2: ms2_launch(attn_tc2_kernel<2>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 3: ms2_launch(attn_tc2_kernel<3>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 4: ms2_launch(attn_tc2_kernel<4>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 5: ms2_launch(attn_tc2_kernel<5>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      case 6: ms2_launch(attn_tc2_kernel<6>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-      default: ms2_launch(attn_tc2_kernel<7>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p); break;
-    }
+    ms2_launch(attn_tc2_kernel<0>, grid2, T2_THREADS, T2_SMEM, st, tmQ, tmK, tmV, p);
     MS2_CHECK_LAUNCH("attn_tc2_kernel");
   } else {
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
     static const int poly = []() { const char* e = getenv("MS2_ATTN_POLY"); return e ? atoi(e) : ATTN_D96_POLY; }();
     auto kern = attn_tc_kernel<D, DV, BKV, KST, 0>;
-    if (D == 96) {
+    if constexpr (D == 96) {
       switch (poly) {
         case 1: kern = attn_tc_kernel<D, DV, BKV, KST, 1>; break;
         case 2: kern = attn_tc_kernel<D, DV, BKV, KST, 2>; break;

@@ -47,11 +47,20 @@ class MemoryAttentionLayer(nn.Module):
         q = self.cross_attn_image.project_q(t)
         if kv is not None and kv[2]:
             attend = kv[3] if len(kv) > 3 else ops.attention_dv          # kv[3]: split-KV over several GPUs (KVShard.attend)
-            o = self.cross_attn_image.v_proj(attend(q, kv[0], kv[1]), out_dtype=cd)             # deferred value projection
+            # deferred value projection and output projection are two linear maps in a row on the [L,64] attention
+            # result: ONE GEMM with W = Wo Wv [256,64], b = Wo bv + bo (folded in fp32), residual in the epilogue
+            att = self.cross_attn_image
+
+            def fold(wv, bv, wo, bo):
+                Wo, Wv = wo.detach().float(), wv.detach().float()
+                return (Wo @ Wv).to(cd).contiguous(), (Wo @ bv.detach().float() + bo.detach().float()).contiguous()
+            from ..runtime import CACHE
+            W, b = CACHE.get((att.v_proj.weight, att.v_proj.bias, att.out_proj.weight, att.out_proj.bias), ("vo_fold", cd), fold)
+            x = ops.gemm(attend(q, kv[0], kv[1]), W, b, out_dtype=torch.float32, residual=x)
         else:
             k, v = kv[:2] if kv is not None else self.cross_attn_image.project_kv(mem_k_in, mem_v_in, L, num_k_exclude_rope)
             o = ops.attention(q, k, v, self.cross_attn_image.num_heads)
-        x = self.cross_attn_image.out_proj(o, out_dtype=torch.float32, residual=x)
+            x = self.cross_attn_image.out_proj(o, out_dtype=torch.float32, residual=x)
         t = self.norm3(x, out_dtype=cd)
         h = self.linear1(t, out_dtype=cd, act=ops.ACT_RELU)
         return self.linear2(h, out_dtype=torch.float32, residual=x)

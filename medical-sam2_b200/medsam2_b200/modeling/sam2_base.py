@@ -340,6 +340,12 @@ class SAM2Base(nn.Module):
             if prev is None:
                 continue
             src = prev["maskmem_features"]
+            if src is None:
+                # a conditioning memory that lives on another rank (split-KV bank, parallel.add_prompts_sharded): keep its
+                # place in the list (ownership goes by position), MemoryAttention drops it before use
+                assert t_pos == 0 and self.memory_attention.kv_shard is not None, "memory features are missing"
+                cond.append(((t, None), None, None, None))
+                continue
             feats = src.to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
             h, w = feats.shape[-2:]
             item = ((t, id(src)), src, as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim),

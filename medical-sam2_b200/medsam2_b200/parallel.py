@@ -150,6 +150,9 @@ class KVShard:
         platform cannot provide it (falls back to NCCL)."""
         if self._symm is not None and self._symm["numel"] == part_numel:
             return self._symm
+        if torch.device(device).type != "cuda":          # gloo / CPU host-logic tests
+            self.exchange = "nccl"
+            return None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             grp = self.group if self.group is not None else dist.group.WORLD
@@ -197,6 +200,71 @@ class KVShard:
             dist.all_gather_into_tensor(parts.view(-1), part, group=self.group)      # the exchange step
             self.exchanges += 1
         return ops.attention_merge(parts, B, L)
+
+
+@torch.no_grad()
+def add_prompts_sharded(predictor, inference_state, prompts, group=None):
+    """Prompt phase of ONE long volume on several GPUs (config 5).  `prompts`: [(frame_idx, obj_id, bbox), ...] of a single
+    object, as func_3d/function.py:236-267 issues them.  The prompted frames are independent of each other (no memory
+    is attended to on an initial conditioning frame), so instead of every rank running all of them in lockstep, rank r
+    runs the prompt step (prompt encoder + mask decoder) only for the frames whose conditioning memory it will own
+    (`KVShard.owns_cond`: the i-th prompted frame, in frame order, lives on rank i mod world); ONE all-gather of the
+    low-resolution logits (256 KiB) and object pointers (1 KiB) per frame gives every rank the same per-frame outputs.
+    The memory encoder of a prompted frame then also runs on its owner only (`propagate_in_video_preflight`): nobody else
+    ever reads that frame's memory features.  Needs `shard_memory_attention(predictor)`; without a process group it
+    is the plain loop."""
+    st = inference_state
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    shard = predictor.memory_attention.kv_shard
+    if world == 1 or shard is None:
+        for f, obj_id, bbox in prompts:
+            predictor.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=obj_id, bbox=torch.as_tensor(bbox),
+                                         clear_old_points=False)
+        return
+    obj_ids = {o for _, o, _ in prompts}
+    if len(obj_ids) != 1 or st["obj_ids"] and set(st["obj_ids"]) != obj_ids:
+        raise ValueError("add_prompts_sharded handles the prompts of ONE object on a fresh state")
+    obj_id = next(iter(obj_ids))
+    order = sorted(prompts, key=lambda p: p[0])
+    if len({p[0] for p in order}) != len(order):
+        raise ValueError("add_prompts_sharded: one prompt per frame")
+    owner = {p[0]: i % world for i, p in enumerate(order)}          # == KVShard.owns_cond(i) of the consolidated bank
+    per = (len(order) + world - 1) // world
+    dev = st["device"]
+    lo = predictor.image_size // 4
+    pm = torch.zeros((per, 1, 1, lo, lo), dtype=torch.float32, device=dev)
+    ptr = torch.zeros((per, 1, predictor.hidden_dim), dtype=torch.float32, device=dev)
+    slot = {}
+    for i, (f, _, bbox) in enumerate(order):
+        slot[f] = i // world
+        if owner[f] != rank:
+            continue
+        predictor.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=obj_id, bbox=torch.as_tensor(bbox),
+                                     clear_old_points=False)
+        out = st["temp_output_dict_per_obj"][predictor._obj_id_to_idx(st, obj_id)]["cond_frame_outputs"][f]
+        pm[slot[f]] = out["pred_masks"]
+        ptr[slot[f]] = out["obj_ptr"]
+    pm_all = torch.empty((world,) + tuple(pm.shape), dtype=pm.dtype, device=dev)
+    ptr_all = torch.empty((world,) + tuple(ptr.shape), dtype=ptr.dtype, device=dev)
+    dist.all_gather_into_tensor(pm_all.view(-1), pm.view(-1), group=group)          # the exchange step of the prompt phase
+    dist.all_gather_into_tensor(ptr_all.view(-1), ptr.view(-1), group=group)
+    obj_idx = predictor._obj_id_to_idx(st, obj_id)
+    for f, _, bbox in order:
+        if owner[f] == rank:
+            continue
+        # the bookkeeping `_add_new_points` does, without the compute
+        pts, lab = predictor._bbox_points(torch.as_tensor(bbox))
+        pts = pts / torch.tensor([st["video_width"], st["video_height"]]).to(pts.device)
+        st["point_inputs_per_obj"][obj_idx][f] = {"point_coords": (pts * predictor.image_size).to(dev),
+                                                  "point_labels": lab.to(dev)}
+        st["mask_inputs_per_obj"][obj_idx].pop(f, None)
+        st["temp_output_dict_per_obj"][obj_idx]["cond_frame_outputs"][f] = {
+            "maskmem_features": None, "maskmem_pos_enc": None, "pred_masks": pm_all[owner[f], slot[f]],
+            "obj_ptr": ptr_all[owner[f], slot[f]]}
+    st["_ms2_prompt_owner"] = owner
+    st["_ms2_rank"] = rank
 
 
 def shard_memory_attention(predictor, group=None):

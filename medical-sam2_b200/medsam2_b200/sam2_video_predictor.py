@@ -335,6 +335,13 @@ class SAM2VideoPredictor(SAM2Base):
                 obj_mask = ops.resize_bilinear(obj_mask.to(st["device"]).float().contiguous(), (ch, cw))
             cons[mask_key][obj_idx: obj_idx + 1] = obj_mask
             cons["obj_ptr"][obj_idx: obj_idx + 1] = out["obj_ptr"]
+        owner = st.get("_ms2_prompt_owner", {}).get(frame_idx) if is_cond else None
+        if run_mem_encoder and owner is not None and owner != st.get("_ms2_rank", owner):
+            # parallel.add_prompts_sharded: this prompted frame's memory lives on another rank (split-KV memory bank):
+            # its memory features are never read here, so they are not computed here either
+            if deferred_mem_enc is not None:
+                deferred_mem_enc.append((frame_idx, cons, None))
+            return cons
         if run_mem_encoder:
             high_res_masks = ops.resize_bilinear(cons["pred_masks"].to(st["device"], non_blocking=True).contiguous(),
                                                  (self.image_size, self.image_size))
@@ -353,8 +360,9 @@ class SAM2VideoPredictor(SAM2Base):
         masks)), several frames per pass: the frames are independent, and one frame alone (4096 tokens) leaves most of
         the GPU idle.  Per-sample arithmetic is that of `_run_memory_encoder`."""
         per = max(1, self.feature_encode_batch // max(batch_size, 1))
-        for c0 in range(0, len(pending), per):
-            chunk = pending[c0: c0 + per]
+        todo = [p for p in pending if p[2] is not None]            # (None: the frame's memory belongs to another rank)
+        for c0 in range(0, len(todo), per):
+            chunk = todo[c0: c0 + per]
             if len(chunk) == 1:
                 f, cons, hr = chunk[0]
                 cons["maskmem_features"], cons["maskmem_pos_enc"] = self._run_memory_encoder(

@@ -51,7 +51,7 @@ def test_sharded_encode_nccl_matches_local():
 def _kv_worker(rank, world, port, out):
     import torch.distributed as dist
     import medsam2_b200
-    from medsam2_b200.parallel import encode_volume_sharded, shard_memory_attention
+    from medsam2_b200.parallel import add_prompts_sharded, encode_volume_sharded, shard_memory_attention
     from oracle.config import get_config
     from oracle.weights import make_state_dict
     from synth_data import btcv_volume
@@ -68,8 +68,10 @@ def _kv_worker(rank, world, port, out):
         st = m.val_init_state(imgs_tensor=vol.cuda(), video_height=512, video_width=512)
         if sharded:
             encode_volume_sharded(m, st)
-        for f in (0, 3, 6):
-            m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
+            add_prompts_sharded(m, st, [(f, 1, boxes[f][0]) for f in (0, 3, 6)])
+        else:
+            for f in (0, 3, 6):
+                m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=1, bbox=torch.tensor(boxes[f][0]), clear_old_points=False)
         return {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}, st
 
     ref, _ = run(False)

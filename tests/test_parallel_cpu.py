@@ -145,6 +145,66 @@ def test_split_kv_memory_attention_two_ranks():
     assert out[0] and out[1], dict(out)
 
 
+def _prompt_worker(rank, world, port, out):
+    """sharded prompt phase + split-KV tracking on 2 gloo ranks == the single-process run (host logic; torch statements)"""
+    import pytest
+    import medsam2_b200
+    import ref_ops
+    from medsam2_b200.parallel import add_prompts_sharded, encode_volume_sharded, shard_memory_attention
+    from oracle.config import get_config
+    from oracle.weights import make_state_dict
+    from synth_data import btcv_volume
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mp_ = pytest.MonkeyPatch()
+    ref_ops.install(mp_)
+    ok = True
+    size, T, prompts_at = 128, 7, (0, 2, 4, 5)
+    with medsam2_b200.compute(torch.bfloat16), torch.no_grad():
+        m = medsam2_b200.build_sam2_video_predictor("sam2_hiera_t", device="cpu", hydra_overrides_extra=[
+            f"++model.image_size={size}", "++model.feature_cache_size=16", "++model.feature_encode_batch=2"])
+        m.load_state_dict(make_state_dict(get_config("sam2_hiera_t")), strict=True)
+        vol, boxes = btcv_volume(T, size, 5, 1)
+
+        def run(sharded):
+            st = m.val_init_state(imgs_tensor=vol, video_height=size, video_width=size)
+            st["device"] = st["storage_device"] = torch.device("cpu")
+            prompts = [(f, 1, boxes[f][0]) for f in prompts_at]
+            if sharded:
+                encode_volume_sharded(m, st)
+                add_prompts_sharded(m, st, prompts)
+            else:
+                for f, o, b in prompts:
+                    m.train_add_new_bbox(inference_state=st, frame_idx=f, obj_id=o, bbox=torch.tensor(b), clear_old_points=False)
+            return {f: mk.clone() for f, _, mk in m.propagate_in_video(st, start_frame_idx=0)}, st
+        ref, _ = run(False)
+        shard_memory_attention(m)
+        got, st = run(True)
+        # every rank ran the prompt step / memory encoder only for the prompted frames it owns ...
+        mine = [f for i, f in enumerate(prompts_at) if i % world == rank]
+        cond = st["output_dict"]["cond_frame_outputs"]
+        ok &= sorted(f for f in cond if cond[f]["maskmem_features"] is not None) == mine
+        # ... and tracks the volume to the single-process masks (bf16 operands; split-KV changes the summation order)
+        for f in range(T):
+            a, b = got[f].float(), ref[f].float()
+            keep = ((a - 0.1).abs() > 1e-6) & ((b - 0.1).abs() > 1e-6)
+            ok &= bool((a - b)[keep].abs().max().item() <= 5e-2)
+        mine_t = torch.stack([got[f] for f in range(T)]).contiguous()
+        theirs = [torch.empty_like(mine_t) for _ in range(world)]
+        dist.all_gather(theirs, mine_t)
+        ok &= all(torch.equal(t, theirs[0]) for t in theirs)
+    mp_.undo()
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_prompt_phase_two_ranks():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_prompt_worker, args=(2, 29737, out), nprocs=2, join=True)
+    assert out[0] and out[1], dict(out)
+
+
 def test_kv_shard_partition_is_exact():
     """every conditioning / recent memory and the pointer tokens belong to exactly one rank, rank 0 owns the first
     conditioning memory, and the pointer tokens never sit alone on a rank."""
