@@ -263,6 +263,46 @@ int ms2_obj_ptr_mix(const float* ptr, const float* logits, const float* no_obj, 
 int ms2_stability_select(const int32_t* counts, const float* ious, int B, int M, float thresh, int32_t* idx_out,
                          float* iou_out, ms2_stream_t stream);
 
+/* ---- memory-attention stack driven from ONE call per tracked frame (reference sam2_train/modeling/memory_attention.py:15-169,
+ *      modeling/sam/transformer.py:266-331): host-side orchestration only — these entry points launch the kernels above in
+ *      the reference's order (LN -> fused qkv GEMM -> RoPE -> self-attention -> out-proj + residual -> LN -> q GEMM + RoPE ->
+ *      cross-attention over the memory bank -> folded value/output projection + residual -> LN -> FFN), so that the
+ *      latency-bound tracked-frame path is not bound by the caller's per-launch overhead.  Shipped configuration only
+ *      (one head of C = 256 over Cm = 64-d memories, bf16 operands, ReLU FFN).  `layers` points to `n_layers` consecutive
+ *      ms2_memattn_layer_w records (device pointers: weights bf16 [N,K] row-major, everything else fp32). */
+typedef struct ms2_memattn_layer_w {
+  const float *norm1_g, *norm1_b, *norm2_g, *norm2_b, *norm3_g, *norm3_b;
+  const void* qkv_w; const float* qkv_b;   /* self-attention q|k|v fused [3C, C] */
+  const void* so_w; const float* so_b;     /* self-attention out_proj [C, C] */
+  const void* cq_w; const float* cq_b;     /* cross-attention q_proj [C, C] */
+  const void* ck_w; const float* ck_b;     /* cross-attention k_proj [C, Cm] */
+  const void* vo_w; const float* vo_b;     /* cross-attention out_proj . v_proj folded [C, Cm] */
+  const void* f1_w; const float* f1_b;     /* FFN linear1 [F, C] */
+  const void* f2_w; const float* f2_b;     /* FFN linear2 [C, F] */
+  const float *rope_cos, *rope_sin;        /* axial RoPE table [rope_len, C/2] */
+  float eps1, eps2, eps3;
+  int C, Cm, F, rope_len;
+} ms2_memattn_layer_w;
+long ms2_memattn_workspace_bytes(int B, int L, int C, int Cm, int F);
+/*      x fp32 [B,L,C] (in place) -> ... -> q bf16 [B,L,C] (RoPE applied) of the layer's cross-attention */
+int ms2_memattn_layer_pre(const void* layer, float* x, void* q_out, void* workspace, long workspace_bytes, int B, int L,
+                          ms2_stream_t stream);
+/*      att bf16 [B,L,Cm] = softmax(q K^T) M  ->  x updated in place through the rest of the layer */
+int ms2_memattn_layer_post(const void* layer, float* x, const void* att, void* workspace, long workspace_bytes, int B, int L,
+                           ms2_stream_t stream);
+/*      per-frame rows of the memory bank (reference sam2_base.py:566-637): sources as in ms2_bank_rows -> raw values into
+ *      m_bank rows [row0, row0+n), per layer K = k_proj(src + pos) into h_K[l] rows [row0, row0+n) (HOST array of device
+ *      pointers, batch stride k_bs elements), RoPE on the first n_rope_rows of them */
+int ms2_memattn_bank_project(const void* layers, int n_layers, const void* const* h_src, const void* const* h_pos,
+                             const long* h_pos_bs, const int* h_rows, int n_src, int B, int n_rope_rows, int Lq,
+                             void* const* h_K, long k_bs, int row0, void* m_bank, long m_bs, void* workspace,
+                             long workspace_bytes, ms2_stream_t stream);
+/*      the whole stack on one GPU: x = curr + pos_scale * curr_pos (curr_pos may be NULL); layers; final LayerNorm -> out */
+int ms2_memattn_forward(const void* layers, int n_layers, const float* curr, const float* curr_pos, float pos_scale,
+                        void* const* h_K, long k_bs, const void* m_bank, long m_bs, int Lk, const float* norm_g,
+                        const float* norm_b, float norm_eps, float* x, float* out, void* workspace, long workspace_bytes,
+                        int B, int L, ms2_stream_t stream);
+
 /* ---- mask statistics for the stability fallback (mask_decoder.py:269-317): per (b) plane of fp32
  *      logits [N,P]: counts[n,0] = #(x>delta), counts[n,1] = #(x>-delta). */
 int ms2_mask_stability_counts(const float* x, int32_t* counts, int N, long P, float delta, ms2_stream_t stream);

@@ -346,10 +346,19 @@ class SAM2Base(nn.Module):
                 assert t_pos == 0 and self.memory_attention.kv_shard is not None, "memory features are missing"
                 cond.append(((t, None), None, None, None))
                 continue
-            feats = src.to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
-            h, w = feats.shape[-2:]
-            item = ((t, id(src)), src, as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim),
-                    self._mem_pos_table(h, w, self.num_maskmem - t_pos - 1, device))
+            # the per-memory item (token-major view + position table) depends on the stored frame output and the slot only:
+            # cached ON that output (a tracked frame walks over every conditioning memory; 48 frames x 50 memories x a
+            # handful of torch view calls was 12 % of the host time of a step)
+            slot = self.num_maskmem - t_pos - 1
+            ck = prev.get("_ms2_item")
+            if ck is not None and ck[0] is src and ck[1] == (slot, B, str(device)):
+                item = ck[2]
+            else:
+                feats = src if src.device == device else src.to(device, non_blocking=True)       # NCHW-shaped [B,Cm,h,w]
+                h, w = feats.shape[-2:]
+                item = ((t, id(src)), src, as_nhwc(feats.float()).reshape(B, h * w, self.mem_dim),
+                        self._mem_pos_table(h, w, slot, device))
+                prev["_ms2_item"] = (src, (slot, B, str(device)), item)
             (cond if t_pos == 0 else recent).append(item)
         ptrs = obj_pos = None
         if self.use_obj_ptrs_in_encoder:
@@ -358,22 +367,29 @@ class SAM2Base(nn.Module):
                 ptr_cond = {t: o for t, o in selected.items() if (t >= frame_idx if track_in_reverse else t <= frame_idx)}
             else:
                 ptr_cond = selected
-            pos_and_ptrs = [(abs(frame_idx - t), o["obj_ptr"]) for t, o in ptr_cond.items()]
+            ptr_outs = [(abs(frame_idx - t), o) for t, o in ptr_cond.items()]
             for t_diff in range(1, max_ptrs):
                 t = frame_idx + t_diff if track_in_reverse else frame_idx - t_diff
                 if t < 0 or (num_frames is not None and t >= num_frames):
                     break
                 o = output_dict["non_cond_frame_outputs"].get(t, unselected.get(t, None))
                 if o is not None:
-                    pos_and_ptrs.append((t_diff, o["obj_ptr"]))
+                    ptr_outs.append((t_diff, o))
+            if ptr_outs and lazy_ptrs and not self.add_tpos_enc_to_obj_ptrs and self.mem_dim < C and C % self.mem_dim == 0:
+                # banked path: the pointer tensors go into the bank's staging rows one by one (ms2_bank_rows), no
+                # torch.stack / zeros / repeat_interleave; their position code is zero (sam2_base.py:627).  The
+                # [B, C/mem_dim, mem_dim] view of a pointer is cached on its frame output.
+                rr = C // self.mem_dim
+                ptrs = []
+                for _, o in ptr_outs:
+                    v = o.get("_ms2_ptr_view")
+                    if v is None or v[0] is not o["obj_ptr"]:
+                        v = o["_ms2_ptr_view"] = (o["obj_ptr"], o["obj_ptr"].float().contiguous().view(B, rr, self.mem_dim))
+                    ptrs.append(v[1])
+                return cond, recent, ptrs, None
+            pos_and_ptrs = [(d, o["obj_ptr"]) for d, o in ptr_outs]
             if pos_and_ptrs:
                 pos_list, ptrs_list = zip(*pos_and_ptrs)
-                if lazy_ptrs and not self.add_tpos_enc_to_obj_ptrs and self.mem_dim < C and C % self.mem_dim == 0:
-                    # banked path: the pointer tensors go into the bank's staging rows one by one (ms2_bank_rows), no
-                    # torch.stack / zeros / repeat_interleave; their position code is zero (sam2_base.py:627)
-                    rr = C // self.mem_dim
-                    ptrs = [p.float().contiguous().view(B, rr, self.mem_dim) for p in ptrs_list]
-                    return cond, recent, ptrs, None
                 ptrs = torch.stack([p.float() for p in ptrs_list], dim=1)                # [B,P,C]
                 P = ptrs.shape[1]
                 if self.add_tpos_enc_to_obj_ptrs:

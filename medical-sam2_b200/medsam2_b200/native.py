@@ -34,9 +34,10 @@ def parse_header(path=None):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//.*", "", src)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int|void)\s+(ms2_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const\s+char\s*\*|int|long|void)\s+(ms2_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        restype = ctypes.c_char_p if "char" in ret else (None if ret == "void" else ctypes.c_int)
+        restype = (ctypes.c_char_p if "char" in ret else None if ret == "void" else ctypes.c_long if ret == "long"
+                   else ctypes.c_int)
         argtypes, argnames = [], []
         if args and args != "void":
             for a in args.split(","):
