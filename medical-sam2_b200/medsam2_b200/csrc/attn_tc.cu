@@ -57,6 +57,17 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): one issue slot for two elements of the softmax inner loop
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %4};\nmov.b64 rc, {%5, %5};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n.reg .b64 ra, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rd, {%0, %1};\nadd.rn.f32x2 rd, rd, ra;\nmov.b64 {%0, %1}, rd;\n}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 // D = head dim of Q/K, DV = head dim of V/O (DV < D: attention over un-projected 64-d memory values, the value
 // projection is applied to the 64-d result afterwards - softmax rows sum to 1), BKV = keys per
 // tile, KST = depth of the K ring (V ring: 2).
@@ -954,21 +965,21 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       uint32_t pk[HC / 2];
       const float nm = -m_used;
+      // p = 2^(s*c - m): scale-subtract and the row sum on packed fp32 pairs (FFMA2 / FADD2): the softmax warps'
+      // instruction stream, not MUFU throughput, is what the tensor pipe waits for in this kernel
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float x0 = fmaf(__uint_as_float(r[c][i]), p.c, nm);
-          const float x1 = fmaf(__uint_as_float(r[c][i + 1]), p.c, nm);
-          const int e = i & 7;                       // POLY eighths of the exponentials on the FMA pipe (ex2_poly)
-          const bool poly0 = (POLY >= 1 && e == 2) || (POLY >= 3 && e == 6);
-          const bool poly1 = (POLY >= 2 && e == 4) || (POLY >= 4 && e == 0);
-          const float p0 = poly0 ? ex2_poly(x0) : ex2(x0);
-          const float p1 = poly1 ? ex2_poly(x1) : ex2(x1);
-          l += p0 + p1;
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1]), p.c, nm);
+          const float p0 = ex2(x0), p1 = ex2(x1);
+          fadd2(l0, l1, p0, p1);
           __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
           pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
         }
+      l += l0 + l1;
       if (j > 0) tc::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);      // observe every phase (see attn_tc_kernel)
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c) tc::tmem_st16(tS + st * BKV + half * (HC / 2) + c * 16, &pk[c * 16]);

@@ -377,7 +377,8 @@ int ms2_gemm_tc_launch(const void* A, long lda, const void* W, const float* bias
   GemmP p;
   p.bias = bias; p.colscale = colscale; p.residual = residual; p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
-  p.BN = pick_bn(M, N, K, o_dt);
+  static const int bn_env = []() { const char* e = getenv("MS2_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning aid
+  p.BN = bn_env > 0 ? bn_env : pick_bn(M, N, K, o_dt);
   p.tiles_n = (N + p.BN - 1) / p.BN;
   p.tiles = ((M + BM - 1) / BM) * p.tiles_n;
   p.num_kb = (K + BK - 1) / BK;
