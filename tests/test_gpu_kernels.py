@@ -256,7 +256,10 @@ def test_attention_tc(ops, B, H, Lq, Lk, D, qs):
 def test_attention_dv(ops, B, Lq, Lk, qs):
     """D=256 queries/keys over 64-d values (memory cross-attention with un-projected memory values)."""
     q = (rnd(B, Lq, 256, seed=1) * qs).to(torch.bfloat16)
-    k, v = rnd(B, Lk, 256, seed=2).to(torch.bfloat16), rnd(B, Lk, 64, seed=3).to(torch.bfloat16)
+    k, v = rnd(B, Lk, 256, seed=2), rnd(B, Lk, 64, seed=3).to(torch.bfloat16)
+    if qs == 3.0:     # key norm ramps x9 along the bank: the row maximum outgrows the lazy-rescale threshold repeatedly
+        k = k * (1 + 8 * torch.arange(Lk, device=k.device)[None, :, None] / Lk)
+    k = k.to(torch.bfloat16)
     o = ops.attention_dv(q, k, v)
     r = F.scaled_dot_product_attention(q.float()[:, None], k.float()[:, None], v.float()[:, None])[:, 0]
     close_rel(o, r, 1e-2, 8e-3, "attention_dv")
@@ -325,6 +328,14 @@ def test_attention_tc_rescale_every_tile(ops, monkeypatch):
         "    q=(torch.randn(B,Lq,H*D,generator=g)*qs).cuda().bfloat16(); k=torch.randn(B,Lk,H*D,generator=g).cuda().bfloat16(); v=torch.randn(B,Lk,H*D,generator=g).cuda().bfloat16()\n"
         "    o=ops.attention(q,k,v,H,impl=2); r=ref_ops.attention(q.float(),k.float(),v.float(),H)\n"
         "    e=((o.float()-r).abs()-8e-3*r.abs()).max().item(); assert e<=1e-2,(B,H,Lq,Lk,D,e)\n"
+        # memory cross-attention (64-d values): with tau = 0 the speculative exponentials of a tile are redone whenever
+        # the row maximum grew; the second case ramps the key norm so the maximum keeps growing along the bank
+        "import torch.nn.functional as F\n"
+        "for (B,Lq,Lk,qs,ramp) in [(1,4096,28736,4.0,0.0),(2,300,5000,2.0,6.0),(1,256,200,1.0,0.0)]:\n"
+        "    q=(torch.randn(B,Lq,256,generator=g)*qs).cuda().bfloat16(); k=torch.randn(B,Lk,256,generator=g).cuda()\n"
+        "    k=(k*(1+ramp*torch.arange(Lk,device='cuda')[None,:,None]/Lk)).bfloat16(); v=torch.randn(B,Lk,64,generator=g).cuda().bfloat16()\n"
+        "    o=ops.attention_dv(q,k,v); r=F.scaled_dot_product_attention(q.float()[:,None],k.float()[:,None],v.float()[:,None])[:,0]\n"
+        "    e=((o.float()-r).abs()-8e-3*r.abs()).max().item(); assert e<=1e-2,('dv',B,Lq,Lk,e)\n"
         "print('ok')\n") % (os.path.join(os.path.dirname(__file__), "..", "medical-sam2_b200"), os.path.dirname(__file__))
     env = dict(os.environ, MS2_LAZY_TAU="0")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
