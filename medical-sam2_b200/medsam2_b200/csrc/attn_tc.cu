@@ -408,7 +408,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
 constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64;
 constexpr bool MC_DEFAULT_ON = true;
-constexpr int MC_DEFAULT_MODE = 1;       // 1 = attn_mc_kernel, 2 = attn_ma_kernel (softmax warps split by tile)
 constexpr int ATTN_D96_POLY = 2;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
@@ -885,11 +884,7 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         MS2_TRACE(j, 13);
 #endif
         // the slot is refilled by BOTH CTAs' producers: tell both (only if somebody will wait for it)
-#ifdef MS2_EXP_LOCAL_COMMIT
-        if (j + KST < n) { tc::umma_commit(&k_empty[ks]); tc::umma_commit(&k_empty[ks]); }
-#else
         if (j + KST < n) tc::umma_commit_mc(&k_empty[ks], (uint16_t)3);
-#endif
       }
       __syncwarp();
     };
@@ -913,11 +908,7 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc::umma_bf16_ts(tO, tP + kk * 8, db, idesc_pv, (j | kk) ? 1u : 0u);
         }
         tc::umma_commit(o_ready);
-#ifdef MS2_EXP_LOCAL_COMMIT
-        if (j + 2 < n) { tc::umma_commit(&v_empty[st]); tc::umma_commit(&v_empty[st]); }
-#else
         if (j + 2 < n) tc::umma_commit_mc(&v_empty[st], (uint16_t)3);
-#endif
       }
       __syncwarp();
       if (j + 2 < n) issue_qk(j + 2);
@@ -1099,345 +1090,6 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           *(float4*)(orow + half * 32 + g * 4) =
               make_float4(__uint_as_float(o[g * 4]), __uint_as_float(o[g * 4 + 1]), __uint_as_float(o[g * 4 + 2]),
                           __uint_as_float(o[g * 4 + 3]));
-        if (half == 0) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
-      }
-    }
-    tc::tc_fence_before();
-  }
-  __syncwarp();
-  tc::cluster_arrive();               // neither CTA leaves while the other may still signal its barriers
-  tc::cluster_wait();
-  if (warp == 1) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// attn_ma_kernel: attn_mc with the softmax warps split by TILE instead of by column.
-// In attn_mc the two warps of a TMEM lane quarter share every tile (64 columns each): they run the same phases in lock
-// step (row maximum -> exchange through shared memory + named barrier -> exponentials), so the MUFU pipe of their SM
-// sub-partition idles during every maximum phase, and the measured softmax chain (~2100 clk per 128-key tile) is what
-// the tensor pipe waits for (tools/ubench/mufu.cu: the exponential loop alone is 1100 clk per tile per sub-partition).
-// Here warps 2..5 own the even tiles and warps 6..9 the odd tiles; a thread owns one full 128-column row, so the row
-// maximum needs no cross-warp exchange, and while one group's exponentials keep the MUFU pipe busy the other group
-// reads its next S tile and takes its maximum.  The two groups share ONE accumulator O and one running maximum:
-// group g continues from the maximum the other group published for tile j-1 (one named-barrier hand-off per tile,
-// off the MUFU critical path), keeps its own row sum, and the sums are brought to the final maximum in the epilogue.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MC_THREADS, 1)
-attn_ma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
-  constexpr int BKV = MC_BKV, KST = MC_KST, D = 256, DV = 64;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sK = smem;
-  uint8_t* sQ = sK + MC_K_BYTES;               // Q staging = K slot 1 (free until the cluster barrier below)
-  uint8_t* sV = sK + KST * MC_K_BYTES;
-  uint64_t* bars = (uint64_t*)(sV + 2 * MC_V_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 2
-  uint64_t* k_empty = bars + 3;       // 2 (one arrival per CTA of the pair)
-  uint64_t* v_full = bars + 5;        // 2
-  uint64_t* v_empty = bars + 7;       // 2 (one arrival per CTA)
-  uint64_t* s_full = bars + 9;        // 2
-  uint64_t* p_full = bars + 11;       // 1 (the 4 warps of the tile's group)
-  uint64_t* o_ready = bars + 12;      // 2 (tile parity): a group only ever waits for the OTHER group's tiles
-  uint64_t* q_tmem = bars + 14;       // 1 (8 softmax warps)
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 15);
-  float* mpub = (float*)(bars + 16);     // [group][128 rows] running max after the group's latest tile
-  float2* lbuf = (float2*)(mpub + 256);  // [group][128 rows] (max the row sum is scaled to, row sum)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = tc::cluster_ctarank();
-  const int q0 = blockIdx.x * BQ;
-  const int bh = blockIdx.y, b = bh / p.Hh, h = bh - b * p.Hh;
-  const int split = blockIdx.z;
-  const int t_begin = split * p.tiles_per_split;
-  int n = p.ntiles - t_begin;
-  if (n > p.tiles_per_split) n = p.tiles_per_split;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmQ);
-    tc::prefetch_tmap(&tmK);
-    tc::prefetch_tmap(&tmV);
-    tc::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&k_full[s], 1);
-      tc::mbar_init(&k_empty[s], 2);
-      tc::mbar_init(&v_full[s], 1);
-      tc::mbar_init(&v_empty[s], 2);
-      tc::mbar_init(&s_full[s], 1);
-    }
-    tc::mbar_init(p_full, 4);
-    tc::mbar_init(&o_ready[0], 1);
-    tc::mbar_init(&o_ready[1], 1);
-    tc::mbar_init(q_tmem, 8);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
-  tc::tc_fence_before();
-  __syncwarp();
-  tc::cluster_arrive();               // both CTAs' barriers exist before anybody multicasts into them
-  tc::cluster_wait();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  MS2_PDL_WAIT();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    // every tile is loaded as two half-tiles of 64 keys: this CTA fetches half `rank` and multicasts it to both CTAs
-    auto load_k = [&](int j) {
-      const int ks = j & 1;
-      tc::mbar_wait(&k_empty[ks], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-      tc::mbar_arrive_expect_tx(&k_full[ks], MC_K_BYTES);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        tc::tma_load_4d_mc(sK + ks * MC_K_BYTES + c * BKV * 128 + rank * 64 * 128, &tmK, &k_full[ks], c * 64,
-                           (t_begin + j) * BKV + (int)rank * 64, h, b, (uint16_t)3);
-    };
-    auto load_v = [&](int j) {
-      const int st = j & 1;
-      tc::mbar_wait(&v_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-      tc::mbar_arrive_expect_tx(&v_full[st], MC_V_BYTES);
-      tc::tma_load_4d_mc(sV + st * MC_V_BYTES + rank * 64 * 128, &tmV, &v_full[st], 0, (t_begin + j) * BKV + (int)rank * 64,
-                         h, b, (uint16_t)3);
-    };
-    if (tc::elect_one()) {
-      tc::mbar_arrive_expect_tx(q_full, 4 * BQ * 128);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
-      load_k(0);
-    }
-    __syncwarp();
-    tc::cluster_arrive();             // Q of BOTH CTAs has left K slot 1 (see the softmax warps)
-    tc::cluster_wait();
-    if (tc::elect_one()) {
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) load_k(j + 1);
-        load_v(j);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
-    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
-    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
-    const uint32_t tO = tmem_base, tP = tmem_base + MC_P_COL, tS = tmem_base + MC_S_COL, tQ = tmem_base + MC_Q_COL;
-    auto issue_qk = [&](int j) {
-      const int st = j & 1, ks = j & 1;
-      // S[st] was last read by the softmax of tile j-2 (observed through p_full before P V(j-2) was issued); P has its
-      // own columns, so this MMA does not wait for any P V to finish
-      tc::mbar_wait(&k_full[ks], (uint32_t)(j >> 1) & 1u);
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t db = tc::desc_kmajor_sw128(aK + ks * MC_K_BYTES + (kk >> 2) * BKV * 128 + (kk & 3) * 32);
-          tc::umma_bf16_ts(tS + st * BKV, tQ + kk * 8, db, idesc_qk, kk ? 1u : 0u);
-        }
-        // local signal first: commits retire in order, and the multicast one takes several hundred cycles
-        tc::umma_commit(&s_full[st]);
-        // the slot is refilled by BOTH CTAs' producers: tell both (only if somebody will wait for it)
-        if (j + KST < n) tc::umma_commit_mc(&k_empty[ks], (uint16_t)3);
-      }
-      __syncwarp();
-    };
-    tc::cluster_arrive();
-    tc::cluster_wait();
-    tc::mbar_wait(q_tmem, 0);
-    tc::tc_fence_after();
-    issue_qk(0);
-    if (n > 1) issue_qk(1);
-    for (int j = 0; j < n; ++j) {
-      const int st = j & 1;
-      tc::mbar_wait(&v_full[st], (uint32_t)(j >> 1) & 1u);
-      tc::mbar_wait(p_full, (uint32_t)j & 1u);
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t db = tc::desc_mnmajor_sw128(aV + st * MC_V_BYTES + kk * 2048, BKV * 128);
-          tc::umma_bf16_ts(tO, tP + kk * 8, db, idesc_pv, (j | kk) ? 1u : 0u);
-        }
-        tc::umma_commit(&o_ready[st]);
-        if (j + 2 < n) tc::umma_commit_mc(&v_empty[st], (uint16_t)3);
-      }
-      __syncwarp();
-      if (j + 2 < n) issue_qk(j + 2);
-    }
-  } else {
-    // ===================== softmax / correction / epilogue =====================
-    // group g = warps 2..5 / 6..9 owns the tiles of parity g; a thread owns one full 128-column S row of its tiles
-    const int qtr = warp & 3, g = (warp - 2) >> 2;
-    const int row = qtr * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
-    const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + MC_S_COL + g * BKV;
-    const uint32_t tP = tmem_base + lane_addr + MC_P_COL;
-    float m_known = 0.f, l = 0.f;                   // l is the row sum of THIS group's tiles, scaled to m_known
-    const int last_valid = p.Lk - (p.ntiles - 1) * BKV;
-
-    {  // Q: swizzled staging tile (K slot 1) -> tensor memory; the two warps of a quarter take alternate blocks
-      tc::mbar_wait(q_full, 0);
-      const uint32_t aQ = tc::smem_u32(sQ);
-#pragma unroll
-      for (int blk = 0; blk < 8; ++blk) {
-        if ((blk & 1) != g) continue;
-        const int ch = blk >> 1, g0 = (blk & 1) * 4;
-        uint32_t w[16];
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const uint4 v = tc::lds128(aQ + ch * BQ * 128 + row * 128 + (((g0 + gg) ^ (row & 7)) << 4));
-          w[gg * 4] = v.x; w[gg * 4 + 1] = v.y; w[gg * 4 + 2] = v.z; w[gg * 4 + 3] = v.w;
-        }
-        tc::tmem_st16(tmem_base + lane_addr + MC_Q_COL + blk * 16, w);
-      }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(q_tmem);
-      tc::cluster_arrive();           // K slot 1 may now be overwritten — by either CTA's multicast
-      tc::cluster_wait();
-    }
-
-    for (int j = g; j < n; j += 2) {
-      const bool masked = (t_begin + j == p.ntiles - 1) && (last_valid < BKV);
-      tc::mbar_wait(&s_full[g], (uint32_t)(j >> 1) & 1u);
-      tc::tc_fence_after();
-      // ---- pass 1: row maximum (S stays in tensor memory: P has its own columns, so pass 2 reads S again) ----
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        uint32_t r[2][32];
-        tc::tmem_ld32(tS + hb * 64, r[0]);
-        tc::tmem_ld32(tS + hb * 64 + 32, r[1]);
-        tc::tmem_ld_wait();
-        if (masked) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (hb * 64 + c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(r[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(r[1][i]));
-        }
-      }
-      const float mx = fmaxf(mx0, mx1) * p.c;
-      // ---- running max: continue from what the other group decided for tile j-1 ----
-      float m_new = mx, m_prev = mx;
-      bool need = false;
-      if (j > 0) {
-        tc::named_bar_sync(1 + qtr * 2 + (g ^ 1), 64);          // the partner warp has published m_used(j-1)
-        m_prev = mpub[(g ^ 1) * 128 + row];
-        need = mx > m_prev + p.tau;
-        m_new = need ? mx : m_prev;
-      }
-      mpub[g * 128 + row] = m_new;
-      if (j + 1 < n) tc::named_bar_arrive(1 + qtr * 2 + g, 64);
-      if (m_new != m_known) {                                   // (also catches the other group's rescales)
-        if (l > 0.f) l *= ex2(m_known - m_new);
-        m_known = m_new;
-      }
-      if (__any_sync(0xffffffffu, need)) {
-        tc::mbar_wait(&o_ready[g ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
-        tc::tc_fence_after();
-        const float alpha = need ? ex2(m_prev - m_new) : 1.f;
-#pragma unroll 1
-        for (int c = 0; c < DV / 32; ++c) {
-          uint32_t o[32];
-          tc::tmem_ld32(tO + c * 32, o);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc::tmem_st32(tO + c * 32, o);
-        }
-        tc::tmem_st_wait();
-      }
-      // ---- pass 2: p = 2^(s*c - m) on packed fp32 pairs (FFMA2 / FADD2), MUFU.EX2 is the pipe that bounds it ----
-      const float nm = -m_new;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        uint32_t r[2][32];
-        tc::tmem_ld32(tS + hb * 64, r[0]);
-        tc::tmem_ld32(tS + hb * 64 + 32, r[1]);
-        tc::tmem_ld_wait();
-        if (masked) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (hb * 64 + c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
-        }
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float x0, x1;
-            ffma2(x0, x1, __uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1]), p.c, nm);
-            const float p0 = ex2(x0), p1 = ex2(x1);
-            fadd2(l0, l1, p0, p1);
-            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-            pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
-          }
-        // P V(j-1) (the other group's tile) must have finished reading P before it is overwritten
-        if (hb == 0 && j > 0) tc::mbar_wait(&o_ready[g ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
-        tc::tmem_st16(tP + hb * 32, &pk[0]);
-        tc::tmem_st16(tP + hb * 32 + 16, &pk[16]);
-      }
-      l += l0 + l1;
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_full);
-    }
-
-    // the group that did NOT own the last tile has observed every phase of that tile's o_ready barrier
-    const int gl = (n - 1) & 1;
-    if (g != gl) tc::mbar_wait(&o_ready[gl], (uint32_t)((n - 1) >> 1) & 1u);
-    tc::tc_fence_before();
-    lbuf[g * 128 + row] = make_float2(m_known, l);
-    tc::named_bar_sync(9 + qtr, 64);
-    tc::tc_fence_after();
-    const float m_fin = mpub[gl * 128 + row];
-    const float2 other = lbuf[(g ^ 1) * 128 + row];
-    l = (l > 0.f ? l * ex2(m_known - m_fin) : 0.f) + (other.y > 0.f ? other.y * ex2(other.x - m_fin) : 0.f);
-    const float m_used = m_fin;
-    const int half = g;
-    const int qi = q0 + row;
-    uint32_t o[32];
-    tc::tmem_ld32(tO + half * 32, o);                // this warp's 32 of the 64 output columns
-    tc::tmem_ld_wait();
-    if (p.nsplit == 1 && !p.force_part) {
-      const float inv = 1.f / l;
-      bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
-      if (qi < p.Lq) {
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          uint4 v;
-          uint32_t* vv = (uint32_t*)&v;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[gg * 8 + 2 * i]) * inv,
-                                                      __uint_as_float(o[gg * 8 + 2 * i + 1]) * inv);
-            vv[i] = *(uint32_t*)&hh;
-          }
-          *(uint4*)(orow + half * 32 + gg * 8) = v;
-        }
-      }
-    } else {
-      const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
-      float* orow = p.opart + rix * DV;
-      if (qi < p.Lq) {
-#pragma unroll
-        for (int gg = 0; gg < 8; ++gg)
-          *(float4*)(orow + half * 32 + gg * 4) =
-              make_float4(__uint_as_float(o[gg * 4]), __uint_as_float(o[gg * 4 + 1]), __uint_as_float(o[gg * 4 + 2]),
-                          __uint_as_float(o[gg * 4 + 3]));
         if (half == 0) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
       }
     }
@@ -1742,7 +1394,6 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
       const uint32_t box[4] = {64, (uint32_t)rows, 1, 1};
       return tc::make_tmap_bf16(m, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     };
-    static const int mc_mode = []() { const char* e = getenv("MS2_ATTN_MC"); return e ? atoi(e) : MC_DEFAULT_MODE; }();
     if ((rc = mk2(&tmK2, k, k_bs, k_hs, k_ts, Lk, 64, D))) return rc;
     if ((rc = mk2(&tmV2, v, v_bs, v_hs, v_ts, Lk, 64, DV))) return rc;
     p.ntiles = (Lk + MC_BKV - 1) / MC_BKV;
@@ -1750,16 +1401,6 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
-    if (mc_mode == 2) {
-      static bool attr_ma = false;
-      if (!attr_ma) {
-        MS2_CUDA(cudaFuncSetAttribute(attn_ma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_ma attr");
-        attr_ma = true;
-      }
-      dim3 gridm(qtiles, B * Hh, p.nsplit);
-      ms2_launch(attn_ma_kernel, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
-      MS2_CHECK_LAUNCH("attn_ma_kernel");
-    } else {
     // (polynomial share of the exponentials, measured at Lk = 209120: 433 / 443 / 460 / 495 us for 0, 1/8, 1/4, 3/8)
     auto kmc = attn_mc_kernel<0>;
     static bool attr_mc = false;
@@ -1770,7 +1411,6 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     dim3 gridm(qtiles, B * Hh, p.nsplit);
     ms2_launch(kmc, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
     MS2_CHECK_LAUNCH("attn_mc_kernel");
-    }
   } else if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
     // two query tiles per CTA share every K/V tile (half the L2->SM operand traffic per FLOP)
     const int qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);
