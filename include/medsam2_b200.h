@@ -263,6 +263,11 @@ int ms2_obj_ptr_mix(const float* ptr, const float* logits, const float* no_obj, 
 int ms2_stability_select(const int32_t* counts, const float* ious, int B, int M, float thresh, int32_t* idx_out,
                          float* iou_out, ms2_stream_t stream);
 
+/*      ms2_multi_copy: n device-to-device copies (h_src[i] -> h_dst[i], h_bytes[i] bytes; the three tables are HOST arrays)
+ *      in one launch per 16 items.  No reference counterpart: it replaces the per-tensor `copy_` / `clone` that a CUDA-graph
+ *      replay of the SAM heads (sam2_base.py:249-412) and the memory encoder (:720-760) needs around its static buffers. */
+int ms2_multi_copy(const void* const* h_src, void* const* h_dst, const long* h_bytes, int n, ms2_stream_t stream);
+
 /* ---- memory-attention stack driven from ONE call per tracked frame (reference sam2_train/modeling/memory_attention.py:15-169,
  *      modeling/sam/transformer.py:266-331): host-side orchestration only — these entry points launch the kernels above in
  *      the reference's order (LN -> fused qkv GEMM -> RoPE -> self-attention -> out-proj + residual -> LN -> q GEMM + RoPE ->

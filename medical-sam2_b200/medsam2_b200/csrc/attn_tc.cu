@@ -408,7 +408,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // so S_x(j+1) is only issued after P V_x(j) has completed (o_ready_x), and every softmax warp observes every phase.
 constexpr int T2_THREADS = 320, T2_KST = 4, T2_BKV = 64;
 constexpr bool MC_DEFAULT_ON = true;
-constexpr int MC_DEFAULT_MODE = 1;       // 1 = attn_mc_kernel, 2 = attn_mt_kernel (softmax warps split by tile)
 constexpr int ATTN_D96_POLY = 2;
 constexpr int T2_Q_BYTES = 4 * BQ * 128, T2_K_BYTES = 4 * T2_BKV * 128, T2_V_BYTES = T2_BKV * 128;
 constexpr int T2_SMEM = T2_Q_BYTES + T2_KST * T2_K_BYTES + 2 * T2_V_BYTES + 1024 + 1024;
@@ -756,8 +755,6 @@ constexpr int MC_BKV = 128, MC_KST = 2, MC_THREADS = 320;
 constexpr int MC_K_BYTES = 4 * MC_BKV * 128, MC_V_BYTES = MC_BKV * 128;
 constexpr int MC_SMEM = MC_KST * MC_K_BYTES + 2 * MC_V_BYTES + 1024 + 4096;
 constexpr int MC_P_COL = 64, MC_S_COL = 128, MC_Q_COL = 384;
-constexpr int MT_KST = 3;                  // attn_mt: 3-deep K ring (a K tile takes ~2400 clk from request to arrival)
-constexpr int MT_SMEM = MT_KST * MC_K_BYTES + 2 * MC_V_BYTES + 1024 + 256 + 1024;
 
 template <int POLY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MC_THREADS, 1)
@@ -1107,385 +1104,6 @@ attn_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// attn_mt_kernel: attn_mc with the softmax warps split by TILE instead of by column.
-// In attn_mc the two warps of a TMEM lane quarter share every tile (64 columns each) and run the same phases in lock
-// step, so the MUFU pipe of their SM sub-partition idles while both load S, exchange the row maximum, store P and signal
-// (tools/ubench/attn_trace.cu: ~1900 clk per 128-key tile, of which the exponentials need 1100; the tensor pipe 1280).
-// Here warps 2..5 own the even tiles and warps 6..9 the odd tiles, so the two warps of a sub-partition work in
-// anti-phase: while one keeps the MUFU pipe busy the other loads, takes its maximum, stores and signals.
-//   * a thread owns one full 128-column row: it loads the row into registers ONCE, releases the S buffer at once
-//     (s_free) so that S(j+2) is issued ~1.5 tiles ahead, and needs no cross-warp exchange for the row maximum;
-//   * the two groups share ONE accumulator O, one P buffer and one running maximum: group g continues from the maximum
-//     the other group fixed for tile j-1 (one named-barrier hand-off per tile, long satisfied when it is reached),
-//     rescales O in tensor memory when the maximum grows by more than tau, keeps its own row sum, and the sums are
-//     brought to the final maximum in the epilogue;
-//   * issue order of the MMA warp: S(j+2) when tile j's row is in registers, P V(j-1) when P(j-1) is stored.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MC_THREADS, 1)
-attn_mt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const AttnTcP p) {
-  constexpr int BKV = MC_BKV, KST = MT_KST, D = 256, DV = 64;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sK = smem;
-  uint8_t* sQ = sK + MC_K_BYTES;               // Q staging = K slot 1 (free until the cluster barrier below)
-  uint8_t* sV = sK + KST * MC_K_BYTES;
-  uint64_t* bars = (uint64_t*)(sV + 2 * MC_V_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 3
-  uint64_t* k_empty = bars + 4;       // 3 (one arrival per CTA of the pair)
-  uint64_t* v_full = bars + 7;        // 2
-  uint64_t* v_empty = bars + 9;       // 2 (one arrival per CTA)
-  uint64_t* s_full = bars + 11;       // 2
-  uint64_t* p_full = bars + 13;       // 1 (the 4 warps of the tile's group)
-  uint64_t* o_ready = bars + 14;      // 2 (tile parity): a group only ever waits for the OTHER group's tiles
-  uint64_t* q_tmem = bars + 16;       // 1 (8 softmax warps)
-  uint64_t* s_free = bars + 17;       // 2 (the 4 warps of the buffer's group): the S row is in registers
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 19);
-  float* mpub = (float*)(bars + 20);     // [group][128 rows] running max after the group's latest tile
-  float2* lbuf = (float2*)sK;            // [group][128 rows] (max the row sum is scaled to, row sum): epilogue only,
-                                         // over K slot 0 (every K tile of both CTAs has been consumed by then)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = tc::cluster_ctarank();
-  const int q0 = blockIdx.x * BQ;
-  const int bh = blockIdx.y, b = bh / p.Hh, h = bh - b * p.Hh;
-  const int split = blockIdx.z;
-  const int t_begin = split * p.tiles_per_split;
-  int n = p.ntiles - t_begin;
-  if (n > p.tiles_per_split) n = p.tiles_per_split;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmQ);
-    tc::prefetch_tmap(&tmK);
-    tc::prefetch_tmap(&tmV);
-    tc::mbar_init(q_full, 1);
-    for (int s = 0; s < KST; ++s) {
-      tc::mbar_init(&k_full[s], 1);
-      tc::mbar_init(&k_empty[s], 2);
-    }
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&v_full[s], 1);
-      tc::mbar_init(&v_empty[s], 2);
-      tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&s_free[s], 4);
-      tc::mbar_init(&o_ready[s], 1);
-    }
-    tc::mbar_init(p_full, 4);
-    tc::mbar_init(q_tmem, 8);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
-  tc::tc_fence_before();
-  __syncwarp();
-  tc::cluster_arrive();               // both CTAs' barriers exist before anybody multicasts into them
-  tc::cluster_wait();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  MS2_PDL_WAIT();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    // every tile is loaded as two half-tiles of 64 keys: this CTA fetches half `rank` and multicasts it to both CTAs
-    auto load_k = [&](int j) {
-      const int ks = j % KST;
-      MS2_TRACE(j, 14);
-      tc::mbar_arrive_expect_tx(&k_full[ks], MC_K_BYTES);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        tc::tma_load_4d_mc(sK + ks * MC_K_BYTES + c * BKV * 128 + rank * 64 * 128, &tmK, &k_full[ks], c * 64,
-                           (t_begin + j) * BKV + (int)rank * 64, h, b, (uint16_t)3);
-    };
-    auto load_v = [&](int j) {
-      const int st = j & 1;
-      MS2_TRACE(j, 15);
-      tc::mbar_arrive_expect_tx(&v_full[st], MC_V_BYTES);
-      tc::tma_load_4d_mc(sV + st * MC_V_BYTES + rank * 64 * 128, &tmV, &v_full[st], 0, (t_begin + j) * BKV + (int)rank * 64,
-                         h, b, (uint16_t)3);
-    };
-    if (tc::elect_one()) {
-      tc::mbar_arrive_expect_tx(q_full, 4 * BQ * 128);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tma_load_4d(sQ + c * BQ * 128, &tmQ, q_full, c * 64, q0, h, b);
-      load_k(0);
-      if (n > 2) load_k(2);           // slot 2 is free from the start; slot 1 still stages Q
-    }
-    __syncwarp();
-    tc::cluster_arrive();             // Q of BOTH CTAs has left K slot 1 (see the softmax warps)
-    tc::cluster_wait();
-    if (tc::elect_one()) {
-      // K and V slots free up independently (S tiles run ahead of the P V they belong to, and the MMA warp issues
-      // whichever is ready): poll both rings and refill whichever slot is empty
-      int jk = 3, jv = 0;
-      if (n > 1) load_k(1);
-      while (jk < n || jv < n) {
-        if (jv < n && tc::mbar_test_wait(&v_empty[jv & 1], ((uint32_t)(jv >> 1) & 1u) ^ 1u)) {
-          load_v(jv);
-          ++jv;
-        }
-        if (jk < n && tc::mbar_test_wait(&k_empty[jk % KST], ((uint32_t)(jk / KST) & 1u) ^ 1u)) {
-          load_k(jk);
-          ++jk;
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = tc::make_idesc_bf16(BQ, BKV, 0, 0);
-    constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, DV, 0, 1);
-    const uint32_t aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
-    const uint32_t tO = tmem_base, tP = tmem_base + MC_P_COL, tS = tmem_base + MC_S_COL, tQ = tmem_base + MC_Q_COL;
-    tc::cluster_arrive();
-    tc::cluster_wait();
-    tc::mbar_wait(q_tmem, 0);
-    tc::tc_fence_after();
-    // One thread runs an event loop over the two kinds of work.  tcgen05.mma issue blocks while the (shallow) MMA queue
-    // is full, i.e. for about as long as the pipe executes, so a fixed program order S(j+2), P V(j-1) delays P V(j-1)
-    // — which the NEXT tile's P store waits for — by up to a whole S tile.  Here P V goes first whenever its P and V are
-    // there, and S tiles are issued four k-steps at a time in between (different accumulators: any interleaving is legal).
-    if (tc::elect_one()) {
-      int js = 0, kk = 0, jp = 0;                   // S tile being issued, its next k-step, next P V tile
-      bool s_ok = false;                            // buffer and K tile of S(js) observed free / full
-      while (jp < n) {
-        const int pst = jp & 1;
-        if (tc::mbar_test_wait(p_full, (uint32_t)jp & 1u) && tc::mbar_test_wait(&v_full[pst], (uint32_t)(jp >> 1) & 1u)) {
-          tc::tc_fence_after();
-          MS2_TRACE(jp, 3);
-#pragma unroll
-          for (int q = 0; q < BKV / 16; ++q) {
-            const uint64_t db = tc::desc_mnmajor_sw128(aV + pst * MC_V_BYTES + q * 2048, BKV * 128);
-            tc::umma_bf16_ts(tO, tP + q * 8, db, idesc_pv, (jp | q) ? 1u : 0u);
-          }
-          tc::umma_commit(&o_ready[pst]);
-#ifdef MS2_EXP_LOCAL_COMMIT
-          if (jp + 2 < n) { tc::umma_commit(&v_empty[pst]); tc::umma_commit(&v_empty[pst]); }
-#else
-          if (jp + 2 < n) tc::umma_commit_mc(&v_empty[pst], (uint16_t)3);
-#endif
-          MS2_TRACE(jp, 12);
-          ++jp;
-          continue;
-        }
-        if (js < n) {
-          const int st = js & 1, ks = js % KST;
-          if (!s_ok) {
-            // S[st] was last read by the softmax of tile js-2 (s_free: its row is in registers); P has its own columns,
-            // so S does not wait for any P V to finish
-            s_ok = (js < 2 || tc::mbar_test_wait(&s_free[st], (uint32_t)((js - 2) >> 1) & 1u)) &&
-                   tc::mbar_test_wait(&k_full[ks], (uint32_t)(js / KST) & 1u);
-            if (s_ok) {
-              tc::tc_fence_after();
-              MS2_TRACE(js, 10);
-            }
-          }
-          if (s_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int k4 = kk + q;
-              const uint64_t db = tc::desc_kmajor_sw128(aK + ks * MC_K_BYTES + (k4 >> 2) * BKV * 128 + (k4 & 3) * 32);
-              tc::umma_bf16_ts(tS + st * BKV, tQ + k4 * 8, db, idesc_qk, k4 ? 1u : 0u);
-            }
-            kk += 4;
-            if (kk == D / 16) {
-              // local signal first: commits retire in order, and the multicast one takes several hundred cycles
-              tc::umma_commit(&s_full[st]);
-              // the slot is refilled by BOTH CTAs' producers: tell both (only if somebody will wait for it)
-#ifdef MS2_EXP_LOCAL_COMMIT
-              if (js + KST < n) { tc::umma_commit(&k_empty[ks]); tc::umma_commit(&k_empty[ks]); }
-#else
-              if (js + KST < n) tc::umma_commit_mc(&k_empty[ks], (uint16_t)3);
-#endif
-              MS2_TRACE(js, 2);
-              ++js;
-              kk = 0;
-              s_ok = false;
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== softmax / correction / epilogue =====================
-    // group g = warps 2..5 / 6..9 owns the tiles of parity g; a thread owns one full 128-column S row of its tiles
-    const int qtr = warp & 3, g = (warp - 2) >> 2;
-    const int row = qtr * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
-    const uint32_t tO = tmem_base + lane_addr, tS = tmem_base + lane_addr + MC_S_COL + g * BKV;
-    const uint32_t tP = tmem_base + lane_addr + MC_P_COL;
-    float m_known = 0.f, l = 0.f;                   // l is the row sum of THIS group's tiles, scaled to m_known
-    const int last_valid = p.Lk - (p.ntiles - 1) * BKV;
-
-    {  // Q: swizzled staging tile (K slot 1) -> tensor memory; the two warps of a quarter take alternate blocks
-      tc::mbar_wait(q_full, 0);
-      const uint32_t aQ = tc::smem_u32(sQ);
-#pragma unroll
-      for (int blk = 0; blk < 8; ++blk) {
-        if ((blk & 1) != g) continue;
-        const int ch = blk >> 1, g0 = (blk & 1) * 4;
-        uint32_t w[16];
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const uint4 v = tc::lds128(aQ + ch * BQ * 128 + row * 128 + (((g0 + gg) ^ (row & 7)) << 4));
-          w[gg * 4] = v.x; w[gg * 4 + 1] = v.y; w[gg * 4 + 2] = v.z; w[gg * 4 + 3] = v.w;
-        }
-        tc::tmem_st16(tmem_base + lane_addr + MC_Q_COL + blk * 16, w);
-      }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(q_tmem);
-      tc::cluster_arrive();           // K slot 1 may now be overwritten — by either CTA's multicast
-      tc::cluster_wait();
-    }
-
-    for (int j = g; j < n; j += 2) {
-      const bool masked = (t_begin + j == p.ntiles - 1) && (last_valid < BKV);
-      if (qtr == 2) MS2_TRACE(j, 4);
-      tc::mbar_wait(&s_full[g], (uint32_t)(j >> 1) & 1u);
-      tc::tc_fence_after();
-      if (qtr == 2) MS2_TRACE(j, 5);
-      // the whole 128-column row -> registers, then the S buffer goes back to the MMA warp at once
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tmem_ld32(tS + c * 32, r[c]);
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_free[g]);
-      if (qtr == 2) MS2_TRACE(j, 6);
-      if (masked) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= last_valid) r[c][i] = 0xff800000u;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(r[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(r[1][i]));
-        mx2 = fmaxf(mx2, __uint_as_float(r[2][i]));
-        mx3 = fmaxf(mx3, __uint_as_float(r[3][i]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.c;
-      // ---- running max: continue from what the other group fixed for tile j-1 ----
-      float m_new = mx, m_prev = mx;
-      bool need = false;
-      if (j > 0) {
-        tc::named_bar_sync(1 + qtr * 2 + (g ^ 1), 64);          // the partner warp has published m_used(j-1)
-        m_prev = mpub[(g ^ 1) * 128 + row];
-        need = mx > m_prev + p.tau;
-        m_new = need ? mx : m_prev;
-      }
-      mpub[g * 128 + row] = m_new;
-      if (j + 1 < n) tc::named_bar_arrive(1 + qtr * 2 + g, 64);
-      if (qtr == 2) MS2_TRACE(j, 7);
-      if (m_new != m_known) {                                   // (also catches the other group's rescales)
-        if (l > 0.f) l *= ex2(m_known - m_new);
-        m_known = m_new;
-      }
-      if (__any_sync(0xffffffffu, need)) {
-        tc::mbar_wait(&o_ready[g ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
-        tc::tc_fence_after();
-        const float alpha = need ? ex2(m_prev - m_new) : 1.f;
-#pragma unroll 1
-        for (int c = 0; c < DV / 32; ++c) {
-          uint32_t o[32];
-          tc::tmem_ld32(tO + c * 32, o);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc::tmem_st32(tO + c * 32, o);
-        }
-        tc::tmem_st_wait();
-      }
-      // ---- p = 2^(s*c - m) on packed fp32 pairs (FFMA2 / FADD2); MUFU.EX2 is the pipe that bounds this loop ----
-      const float nm = -m_new;
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float x0, x1;
-          ffma2(x0, x1, __uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1]), p.c, nm);
-          const float p0 = ex2(x0), p1 = ex2(x1);
-          fadd2(l0, l1, p0, p1);
-          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-          pk[(c * 32 + i) >> 1] = *(uint32_t*)&hh;
-        }
-      l += l0 + l1;
-      if (qtr == 2) MS2_TRACE(j, 8);
-      // P V(j-1) (the other group's tile) must have finished reading P before it is overwritten
-      if (j > 0) tc::mbar_wait(&o_ready[g ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tmem_st16(tP + c * 16, &pk[c * 16]);
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_full);
-      if (qtr == 2) MS2_TRACE(j, 9);
-    }
-
-    // the group that did NOT own the last tile has observed every phase of that tile's o_ready barrier
-    const int gl = (n - 1) & 1;
-    if (g != gl) tc::mbar_wait(&o_ready[gl], (uint32_t)((n - 1) >> 1) & 1u);
-    tc::tc_fence_before();
-    lbuf[g * 128 + row] = make_float2(m_known, l);
-    tc::named_bar_sync(9 + qtr, 64);
-    tc::tc_fence_after();
-    const float m_fin = mpub[gl * 128 + row];
-    const float2 other = lbuf[(g ^ 1) * 128 + row];
-    l = (l > 0.f ? l * ex2(m_known - m_fin) : 0.f) + (other.y > 0.f ? other.y * ex2(other.x - m_fin) : 0.f);
-    const float m_used = m_fin;
-    const int half = g;
-    const int qi = q0 + row;
-    uint32_t o[32];
-    tc::tmem_ld32(tO + half * 32, o);                // this warp's 32 of the 64 output columns
-    tc::tmem_ld_wait();
-    if (p.nsplit == 1 && !p.force_part) {
-      const float inv = 1.f / l;
-      bf16* orow = (bf16*)p.o + (long)b * p.o_bs + (long)h * p.o_hs + (long)qi * p.o_ts;
-      if (qi < p.Lq) {
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          uint4 v;
-          uint32_t* vv = (uint32_t*)&v;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(o[gg * 8 + 2 * i]) * inv,
-                                                      __uint_as_float(o[gg * 8 + 2 * i + 1]) * inv);
-            vv[i] = *(uint32_t*)&hh;
-          }
-          *(uint4*)(orow + half * 32 + gg * 8) = v;
-        }
-      }
-    } else {
-      const long rix = ((long)split * gridDim.y + bh) * p.Lq + qi;
-      float* orow = p.opart + rix * DV;
-      if (qi < p.Lq) {
-#pragma unroll
-        for (int gg = 0; gg < 8; ++gg)
-          *(float4*)(orow + half * 32 + gg * 4) =
-              make_float4(__uint_as_float(o[gg * 4]), __uint_as_float(o[gg * 4 + 1]), __uint_as_float(o[gg * 4 + 2]),
-                          __uint_as_float(o[gg * 4 + 3]));
-        if (half == 0) *(float2*)(p.ml + rix * 2) = make_float2(m_used, l);
-      }
-    }
-    tc::tc_fence_before();
-  }
-  __syncwarp();
-  tc::cluster_arrive();               // neither CTA leaves while the other may still signal its barriers
-  tc::cluster_wait();
-  if (warp == 1) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // merge the split-KV partials: O = sum_s 2^(m_s - m*) O_s / sum_s 2^(m_s - m*) l_s
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -1783,27 +1401,16 @@ int launch(const void* q, const void* k, const void* v, void* o, long q_bs, long
     p.tiles_per_split = (p.ntiles + p.nsplit - 1) / p.nsplit;
     p.ml = p.nsplit > 1 ? (float*)ws + (long)p.nsplit * rows * DV : nullptr;
     if (part_o && p.nsplit == 1) { p.opart = part_o; p.ml = part_ml; }
-    static const int mc_mode = []() { const char* e = getenv("MS2_ATTN_MC"); return e ? atoi(e) : MC_DEFAULT_MODE; }();
-    dim3 gridm(qtiles, B * Hh, p.nsplit);
-    if (mc_mode == 2) {
-      static bool attr_mt = false;
-      if (!attr_mt) {
-        MS2_CUDA(cudaFuncSetAttribute(attn_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM), "attn_mt attr");
-        attr_mt = true;
-      }
-      ms2_launch(attn_mt_kernel, gridm, MC_THREADS, MT_SMEM, st, tmQ, tmK2, tmV2, p);
-      MS2_CHECK_LAUNCH("attn_mt_kernel");
-    } else {
-      // (polynomial share of the exponentials, measured at Lk = 209120: 433 / 443 / 460 / 495 us for 0, 1/8, 1/4, 3/8)
-      auto kmc = attn_mc_kernel<0>;
-      static bool attr_mc = false;
-      if (!attr_mc) {
-        MS2_CUDA(cudaFuncSetAttribute(kmc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
-        attr_mc = true;
-      }
-      ms2_launch(kmc, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
-      MS2_CHECK_LAUNCH("attn_mc_kernel");
+    // (polynomial share of the exponentials, measured at Lk = 209120: 433 / 443 / 460 / 495 us for 0, 1/8, 1/4, 3/8)
+    auto kmc = attn_mc_kernel<0>;
+    static bool attr_mc = false;
+    if (!attr_mc) {
+      MS2_CUDA(cudaFuncSetAttribute(kmc, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_SMEM), "attn_mc attr");
+      attr_mc = true;
     }
+    dim3 gridm(qtiles, B * Hh, p.nsplit);
+    ms2_launch(kmc, gridm, MC_THREADS, MC_SMEM, st, tmQ, tmK2, tmV2, p);
+    MS2_CHECK_LAUNCH("attn_mc_kernel");
   } else if (D == 256 && DV == 64 && Lq >= 2 * BQ && two_tiles_ok) {
     // two query tiles per CTA share every K/V tile (half the L2->SM operand traffic per FLOP)
     const int qpairs = (Lq + 2 * BQ - 1) / (2 * BQ);

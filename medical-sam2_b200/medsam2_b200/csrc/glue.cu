@@ -160,3 +160,59 @@ extern "C" int ms2_stability_select(const int32_t* counts, const float* ious, in
   MS2_CHECK_LAUNCH("stability_select");
   return MS2_OK;
 }
+
+// ------------------------------------------------------------------ several device-to-device copies in ONE launch
+// The graph runner moves the inputs of a captured sub-pipeline into its static buffers and its results out of the graph's
+// pool on every replay: 6-13 copies of 4 B..8 MB per slice, each 2-4 us of stream time as a separate memcpy node.
+namespace {
+constexpr int MC_MAX = 16;
+struct MultiCopyP {
+  const uint8_t* src[MC_MAX];
+  uint8_t* dst[MC_MAX];
+  long bytes[MC_MAX];
+};
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ MultiCopyP p) {
+  MS2_PDL_WAIT();
+  const int s = blockIdx.y;
+  const uint8_t* src = p.src[s];
+  uint8_t* dst = p.dst[s];
+  const long n = p.bytes[s];
+  const long stride = (long)gridDim.x * blockDim.x, t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const long n16 = n >> 4;
+    for (long i = t; i < n16; i += stride) ((uint4*)dst)[i] = __ldg((const uint4*)src + i);
+    for (long i = (n16 << 4) + t; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (long i = t; i < n; i += stride) dst[i] = src[i];
+  }
+}
+}  // namespace
+
+extern "C" int ms2_multi_copy(const void* const* h_src, void* const* h_dst, const long* h_bytes, int n, void* stream) {
+  MS2_CHECK_ARG(n >= 0 && (n == 0 || (h_src && h_dst && h_bytes)), "multi_copy: null tables");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i0 = 0; i0 < n; i0 += MC_MAX) {
+    MultiCopyP p;
+    int m = 0;
+    long big = 0;
+    for (int i = i0; i < n && m < MC_MAX; ++i) {
+      MS2_CHECK_ARG(h_bytes[i] >= 0, "multi_copy: negative size");
+      if (!h_bytes[i]) continue;
+      MS2_CHECK_ARG(h_src[i] && h_dst[i], "multi_copy: null pointer in item %d", i);
+      p.src[m] = (const uint8_t*)h_src[i];
+      p.dst[m] = (uint8_t*)h_dst[i];
+      p.bytes[m] = h_bytes[i];
+      if (h_bytes[i] > big) big = h_bytes[i];
+      ++m;
+    }
+    if (!m) continue;
+    for (int i = m; i < MC_MAX; ++i) { p.src[i] = nullptr; p.dst[i] = nullptr; p.bytes[i] = 0; }
+    long bx = (big / 16 + 255) / 256;                 // one 16-byte piece per thread for the largest item ...
+    const long cap = (148L * 8 + m - 1) / m;          // ... capped so that the whole launch is ~8 CTAs per SM
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    ms2_launch(multi_copy_kernel, dim3((unsigned)bx, m), 256, 0, st, p);
+    MS2_CHECK_LAUNCH("multi_copy");
+  }
+  return MS2_OK;
+}

@@ -273,7 +273,7 @@ class MemoryAttention(nn.Module):
             bank.refs = [e[1] for e in cond]               # keep the sources alive: id() keys stay unique
         row0 = bank.n_static
         # (per-launch CUDA-event profiling of bench.py needs the tensor-level calls: it switches the native driver off)
-        fast = (raw_v and curr_pos is not None and self._native_ok(L) and (ptr_pos is None or isinstance(ptrs, list))
+        fast = (raw_v and curr.is_cuda and curr_pos is not None and self._native_ok(L) and (ptr_pos is None or isinstance(ptrs, list))
                 and ops.PROFILE.names is None and not _NO_NATIVE)
         Lk = row0 + n_dyn
         if fast:

@@ -630,6 +630,45 @@ def stability_select(counts, ious, thresh):
     return idx, iou
 
 
+def _dense(t):
+    """the tensor covers its storage span exactly once (contiguous up to a permutation of the dimensions)"""
+    if t.is_contiguous():
+        return True
+    expect = 1
+    for st, sz in sorted((st, sz) for sz, st in zip(t.shape, t.stride()) if sz != 1):
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+def multi_copy(pairs):
+    """[(dst, src), ...]: dst.copy_(src) for every pair, in ONE launch per 16 pairs when both tensors of a pair are dense
+    with the same dtype and strides (then the copy is a byte copy of the storage span); other pairs fall back to copy_."""
+    import ctypes
+    fast = []
+    for d, s in pairs:
+        if (d.dtype == s.dtype and d.shape == s.shape and d.stride() == s.stride() and d.is_cuda and s.is_cuda
+                and d.device == s.device and _dense(d)):
+            if d.numel():
+                fast.append((d, s))
+        else:
+            d.copy_(s)
+    if not fast:
+        return
+    n = len(fast)
+    if n == 1:
+        fast[0][0].copy_(fast[0][1])
+        return
+    srcs = (ctypes.c_void_p * n)(*[s.data_ptr() for _, s in fast])
+    dsts = (ctypes.c_void_p * n)(*[d.data_ptr() for d, _ in fast])
+    sizes = (ctypes.c_long * n)(*[d.numel() * d.element_size() for d, _ in fast])
+    if fast[0][0].device.index != _cur_dev():
+        raise native.NativeError("multi_copy: tensors live on another device than the current one")
+    native.call("ms2_multi_copy", ctypes.cast(srcs, ctypes.c_void_p), ctypes.cast(dsts, ctypes.c_void_p),
+                ctypes.cast(sizes, ctypes.c_void_p), n, _st())
+
+
 def normalize_image(x, out=None, nhwc=None, out_dtype=torch.float32):
     """(x/255 - mean)/std -> NCHW `out_dtype` (fp32, or bf16 = the cast autocast applies before the patch-embed conv).
     x: fp32 [B,3,H,W] in 0..255 (video tensor), uint8 [B,3,H,W] (uint8 video tensor: `imgs_tensor / 255.0` of

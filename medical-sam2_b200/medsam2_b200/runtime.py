@@ -196,7 +196,7 @@ class GraphRunner:
         return None if t is None else (tuple(t.shape), tuple(t.stride()), t.dtype)
 
     def run(self, key, fn, tensors, clone=True):
-        from . import native
+        from . import native, ops
         full_key = (key, compute_dtype(), tuple(self._sig(t) for t in tensors))
         entry = self._graphs.get(full_key)
         if entry is not None and entry[5] != _GEN[0]:
@@ -243,9 +243,8 @@ class GraphRunner:
         if last is not None and last[0] != cur.cuda_stream:
             # the previous replay ran on another stream (slice encoding ahead of need): the static buffers are shared
             cur.wait_event(last[1])
-        for s, t in zip(static_in, tensors):
-            if s is not None:
-                s.copy_(t)
+        # all inputs move into the static buffers in one launch (they keep the callers' strides: byte copies)
+        ops.multi_copy([(s, t) for s, t in zip(static_in, tensors) if s is not None])
         graph.replay()
         self.replays += 1
         native.launch_count += launches            # kernels of this library executed by the replay
@@ -256,18 +255,28 @@ class GraphRunner:
         return out
 
 
-def _clone_tree(x, memo=None):
+def _clone_tree(x, memo=None, pairs=None):
     """clone every tensor of a nested result ONCE (the SAM heads return the same mask tensor under two names when a
-    single mask is requested: two 4 MB copies per slice otherwise)."""
-    if memo is None:
-        memo = {}
+    single mask is requested: two 4 MB copies per slice otherwise); all clones are filled by one ms2_multi_copy launch."""
+    from . import ops
+    top = memo is None
+    if top:
+        memo, pairs = {}, []
     if isinstance(x, torch.Tensor):
         k = id(x)
         if k not in memo:
-            memo[k] = x.clone()
-        return memo[k]
-    if isinstance(x, (list, tuple)):
-        return type(x)(_clone_tree(v, memo) for v in x)
-    if isinstance(x, dict):
-        return {k: _clone_tree(v, memo) for k, v in x.items()}
-    return x
+            if x.is_cuda and ops._dense(x):
+                memo[k] = torch.empty_like(x)          # preserve_format: same strides for dense tensors
+                pairs.append((memo[k], x))
+            else:
+                memo[k] = x.clone()
+        out = memo[k]
+    elif isinstance(x, (list, tuple)):
+        out = type(x)(_clone_tree(v, memo, pairs) for v in x)
+    elif isinstance(x, dict):
+        out = {k: _clone_tree(v, memo, pairs) for k, v in x.items()}
+    else:
+        out = x
+    if top and pairs:
+        ops.multi_copy(pairs)
+    return out

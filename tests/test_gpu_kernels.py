@@ -620,3 +620,21 @@ def test_sam_head_glue(ops):
     labels = torch.tensor([[2, 3]] * B, dtype=torch.int32).cuda()
     close(ops.point_embed(coords, labels, gauss, table, True, (1024, 1024), prefix),
           ref_ops.point_embed(coords, labels, gauss, table, True, (1024, 1024), prefix), 2e-4, "point_embed + prefix")
+
+
+def test_multi_copy(ops):
+    """several device-to-device copies in one launch (graph runner inputs / result clones): dense tensors of mixed
+    dtypes, sizes from 4 B to 8 MB, unaligned storage offsets, a channels-last view, more than 16 items, an empty one;
+    a strided (non-dense) pair takes the copy_ fall-back."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    srcs = [torch.randn(n, device="cuda", generator=g) for n in (1, 7, 1024, 2 * 1024 * 1024, 333)]
+    srcs += [torch.randint(0, 255, (n,), device="cuda", dtype=torch.uint8, generator=g) for n in (5, 4099)]
+    srcs.append(torch.randn(1000, device="cuda", generator=g)[3:])                    # 12-byte storage offset
+    srcs.append(torch.randn(2, 8, 16, 16, device="cuda", generator=g).permute(0, 3, 1, 2))   # dense, not contiguous
+    srcs += [torch.randn(64 + i, device="cuda", generator=g).to(torch.bfloat16) for i in range(20)]
+    srcs.append(torch.empty(0, device="cuda"))
+    srcs.append(torch.randn(16, 16, device="cuda", generator=g)[:, ::2])              # not dense -> copy_
+    dsts = [torch.empty_like(s) if i != len(srcs) - 1 else torch.empty(16, 8, device="cuda") for i, s in enumerate(srcs)]
+    ops.multi_copy(list(zip(dsts, srcs)))
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)

@@ -7,9 +7,6 @@
 #include <cstdlib>
 
 int main() {
-#ifdef TRACE_MT
-  setenv("MS2_ATTN_MC", "2", 1);
-#endif
   const int Lq = 4096, Lk = 209120;
   std::vector<uint16_t> hq((size_t)Lq * 256), hk((size_t)Lk * 256), hv((size_t)Lk * 64);
   auto rnd = [](std::vector<uint16_t>& v) {
@@ -33,15 +30,9 @@ int main() {
   long long h[32 * 16];
   cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
   const long long t0 = h[0 * 16 + 3];
-#ifdef TRACE_MT
-  setenv("MS2_ATTN_MC", "2", 1);
-  const char* names[16] = {"sfree.wait", "sfree.ok", "S+2.issued", "PV.pfull.ok", "sm.wait.S", "sm.S.ok", "sm.ld.done", "sm.handoff",
-                           "sm.exp.ok", "sm.P.done", "S.kfull.ok", "PV.vfull.ok", "PV.issued", "-", "K.load", "V.load"};
-#else
   const char* names[16] = {"S.issue.begin", "S.kfull.ok", "PV.vfull.ok", "PV.pfull.ok", "w2.wait.S", "w2.S.ok", "w2.max.ok",
                            "w2.exp.ok", "w2.P.done", "w6.wait.S", "w6.S.ok", "w6.max.ok", "w6.exp.ok", "w6.P.done", "K.load",
                            "V.load"};
-#endif
   printf("%4s", "tile");
   for (int e = 0; e < 16; ++e) printf(" %13s", names[e]);
   printf("\n");
