@@ -263,6 +263,21 @@ int ms2_obj_ptr_mix(const float* ptr, const float* logits, const float* no_obj, 
 int ms2_stability_select(const int32_t* counts, const float* ious, int B, int M, float thresh, int32_t* idx_out,
                          float* iou_out, ms2_stream_t stream);
 
+/* ---- row-complete GEMM tiles for the 256-wide memory-attention stream (csrc/gemm_row.cu): A bf16 [M,K] (lda), W bf16 [N,K],
+ *      bias fp32 [N] or NULL; M a multiple of 128, K of 8.
+ *      ms2_gemm_res_ln (memory_attention.py:58-99,166 `tgt = tgt + ...; tgt2 = self.norm_k(tgt)`), N = 256:
+ *          x_out = residual + A W^T + bias (fp32 [M,256], may alias residual) and
+ *          t_out = LayerNorm(x_out) * gamma + beta (biased variance, eps), t_dt MS2_BF16 or MS2_F32.
+ *      ms2_gemm_rope (transformer.py:288-318 q_proj / k_proj + position_encoding.py:185-216 apply_rotary_enc), N a multiple
+ *          of 256: out bf16 [M,N] = A W^T + bias rounded to bf16; the 256-wide column tiles below `rope_cols` are then
+ *          rotated like ms2_rope with D = 256: row r uses table position ((r mod L) mod table_len), cos/sin fp32
+ *          [table_len,128]. */
+int ms2_gemm_res_ln(const void* A, long lda, const void* W, const float* bias, const float* residual, long ldr,
+                    float* x_out, long ldx, const float* gamma, const float* beta, float eps, void* t_out, int t_dt,
+                    long ldt, int M, int K, ms2_stream_t stream);
+int ms2_gemm_rope(const void* A, long lda, const void* W, const float* bias, void* out, long ldo, int M, int N, int K,
+                  int L, int rope_cols, const float* cos_t, const float* sin_t, int table_len, ms2_stream_t stream);
+
 /*      ms2_multi_copy: n device-to-device copies (h_src[i] -> h_dst[i], h_bytes[i] bytes; the three tables are HOST arrays)
  *      in one launch per 16 items.  No reference counterpart: it replaces the per-tensor `copy_` / `clone` that a CUDA-graph
  *      replay of the SAM heads (sam2_base.py:249-412) and the memory encoder (:720-760) needs around its static buffers. */

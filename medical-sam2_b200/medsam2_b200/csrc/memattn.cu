@@ -21,6 +21,11 @@ int ms2_attention_ws(const void* q, const void* k, const void* v, void* o, int d
 int ms2_attention_dv(const void* q, const void* k, const void* v, void* o, int dt, long q_bs, long q_hs, long q_ts, long k_bs,
                      long k_hs, long k_ts, long v_bs, long v_hs, long v_ts, long o_bs, long o_hs, long o_ts, int B, int Hh,
                      int Lq, int Lk, int D, int DV, float scale, void* workspace, long workspace_bytes, void* stream);
+int ms2_gemm_res_ln(const void* A, long lda, const void* W, const float* bias, const float* residual, long ldr,
+                    float* x_out, long ldx, const float* gamma, const float* beta, float eps, void* t_out, int t_dt,
+                    long ldt, int M, int K, void* stream);
+int ms2_gemm_rope(const void* A, long lda, const void* W, const float* bias, void* out, long ldo, int M, int N, int K,
+                  int L, int rope_cols, const float* cos_t, const float* sin_t, int table_len, void* stream);
 int ms2_axpby(const float* x, float a, const float* z, float b, float c, void* y, int y_dt, long n, long zn, void* stream);
 int ms2_bank_rows(const void* const* h_src, const void* const* h_pos, const long* h_pos_bs, const int* h_rows, int n, int W,
                   int B, void* k_in, long k_bs, void* m_out, long m_bs, int out_dt, void* stream);
@@ -87,23 +92,45 @@ long split_budget(long avail, int B, int Lq, int Lk, int DV) {
     if (rc__) return rc__;  \
   } while (0)
 
-// x (fp32 [R,C], in place) through LN1 -> self-attention (RoPE on q,k) -> +residual -> LN2 -> q projection (+RoPE) -> q
-int layer_pre(const LayerW& w, float* x, void* q_out, const Ws& s, int B, int L, void* st) {
+// Row-complete fused tiles (csrc/gemm_row.cu) for the shipped geometry: projection + RoPE and GEMM + residual + LayerNorm
+// as one kernel each, 8 instead of 13 dependent kernels per layer.  OFF by default (MS2_MEMATTN_FUSED=1 enables): measured
+// on the bench step 409 vs 421 slices/s — a 128 x 256 row-complete tile leaves 32 CTAs for 4096 rows, each of which has to
+// pull its whole A and W panels through one SM's ~70 B/clk TMA ingest (1.5 MB for the FFN's second GEMM = 11 us), while
+// the one-op-per-kernel chain spreads the same bytes over 128+ CTAs and overlaps its prologues through programmatic
+// dependent launch (~4-5 us per kernel in the chain).
+bool fused_ok(const LayerW& w, long R) {
+  static const bool on = []() { const char* e = getenv("MS2_MEMATTN_FUSED"); return e && atoi(e) != 0; }();
+  return on && w.C == 256 && R % 128 == 0 && w.Cm % 8 == 0 && w.Cm >= 16 && w.F % 8 == 0;
+}
+
+// x (fp32 [R,C], in place) through LN1 -> self-attention (RoPE on q,k) -> +residual -> LN2 -> q projection (+RoPE) -> q.
+// t_ready: s.t already holds LN1(x) (written by the previous layer's fused FFN epilogue).
+int layer_pre(const LayerW& w, float* x, void* q_out, const Ws& s, int B, int L, void* st, bool t_ready = false) {
   const int C = w.C;
   const long R = (long)B * L;
-  MS2_TRY(ms2_layernorm(x, nullptr, w.norm1_g, w.norm1_b, s.t, MS2_BF16, (int)R, C, w.eps1, 0, st));
-  MS2_TRY(ms2_gemm(s.t, MS2_BF16, C, w.qkv_w, MS2_BF16, w.qkv_b, nullptr, nullptr, 0, s.qkv, MS2_BF16, 3 * C, (int)R, 3 * C, C,
-                   0, 0, st));
+  const bool fused = fused_ok(w, R);
+  if (!t_ready) MS2_TRY(ms2_layernorm(x, nullptr, w.norm1_g, w.norm1_b, s.t, MS2_BF16, (int)R, C, w.eps1, 0, st));
   bf16* qkv = (bf16*)s.qkv;
-  if (B == 1) {   // q and k of the fused projection in one launch: "batch" 0 = q columns, 1 = k columns of the same rows
-    MS2_TRY(ms2_rope(qkv, MS2_BF16, C, 3 * C, 2, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+  if (fused) {
+    MS2_TRY(ms2_gemm_rope(s.t, C, w.qkv_w, w.qkv_b, qkv, 3 * C, (int)R, 3 * C, C, L, 2 * C, w.rope_cos, w.rope_sin, w.rope_len, st));
   } else {
-    MS2_TRY(ms2_rope(qkv, MS2_BF16, (long)L * 3 * C, 3 * C, B, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
-    MS2_TRY(ms2_rope(qkv + C, MS2_BF16, (long)L * 3 * C, 3 * C, B, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+    MS2_TRY(ms2_gemm(s.t, MS2_BF16, C, w.qkv_w, MS2_BF16, w.qkv_b, nullptr, nullptr, 0, s.qkv, MS2_BF16, 3 * C, (int)R, 3 * C, C,
+                     0, 0, st));
+    if (B == 1) {   // q and k of the fused projection in one launch: "batch" 0 = q columns, 1 = k columns of the same rows
+      MS2_TRY(ms2_rope(qkv, MS2_BF16, C, 3 * C, 2, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+    } else {
+      MS2_TRY(ms2_rope(qkv, MS2_BF16, (long)L * 3 * C, 3 * C, B, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+      MS2_TRY(ms2_rope(qkv + C, MS2_BF16, (long)L * 3 * C, 3 * C, B, L, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+    }
   }
   MS2_TRY(ms2_attention_ws(qkv, qkv + C, qkv + 2 * C, s.o, MS2_BF16, (long)L * 3 * C, C, 3 * C, (long)L * 3 * C, C, 3 * C,
                            (long)L * 3 * C, C, 3 * C, (long)L * C, C, C, B, 1, L, L, C, 1.0f / sqrtf((float)C), 0, s.split,
                            split_budget(s.split_bytes, B, L, L, C), st));
+  if (fused) {
+    MS2_TRY(ms2_gemm_res_ln(s.o, C, w.so_w, w.so_b, x, C, x, C, w.norm2_g, w.norm2_b, w.eps2, s.t, MS2_BF16, C, (int)R, C, st));
+    MS2_TRY(ms2_gemm_rope(s.t, C, w.cq_w, w.cq_b, q_out, C, (int)R, C, C, L, C, w.rope_cos, w.rope_sin, w.rope_len, st));
+    return MS2_OK;
+  }
   MS2_TRY(ms2_gemm(s.o, MS2_BF16, C, w.so_w, MS2_BF16, w.so_b, nullptr, x, C, x, MS2_F32, C, (int)R, C, C, 0, 0, st));
   MS2_TRY(ms2_layernorm(x, nullptr, w.norm2_g, w.norm2_b, s.t, MS2_BF16, (int)R, C, w.eps2, 0, st));
   MS2_TRY(ms2_gemm(s.t, MS2_BF16, C, w.cq_w, MS2_BF16, w.cq_b, nullptr, nullptr, 0, q_out, MS2_BF16, C, (int)R, C, C, 0, 0, st));
@@ -111,13 +138,23 @@ int layer_pre(const LayerW& w, float* x, void* q_out, const Ws& s, int B, int L,
   return MS2_OK;
 }
 
-// att (bf16 [R,Cm] = softmax(q K^T) M) -> x += att (Wo Wv)^T + b -> LN3 -> FFN(ReLU) -> +residual (x in place)
-int layer_post(const LayerW& w, float* x, const void* att, const Ws& s, int B, int L, void* st) {
+// att (bf16 [R,Cm] = softmax(q K^T) M) -> x += att (Wo Wv)^T + b -> LN3 -> FFN(ReLU) -> +residual (x in place).
+// next_g != null (fused geometry only): the LayerNorm that follows (the next layer's norm1, or the stack's final norm) is
+// written by the FFN's epilogue into t_next (t_next_dt).
+int layer_post(const LayerW& w, float* x, const void* att, const Ws& s, int B, int L, void* st, const float* next_g = nullptr,
+               const float* next_b = nullptr, float next_eps = 0.f, void* t_next = nullptr, int t_next_dt = MS2_BF16) {
   const int C = w.C;
   const long R = (long)B * L;
-  MS2_TRY(ms2_gemm(att, MS2_BF16, w.Cm, w.vo_w, MS2_BF16, w.vo_b, nullptr, x, C, x, MS2_F32, C, (int)R, C, w.Cm, 0, 0, st));
-  MS2_TRY(ms2_layernorm(x, nullptr, w.norm3_g, w.norm3_b, s.t, MS2_BF16, (int)R, C, w.eps3, 0, st));
+  const bool fused = fused_ok(w, R);
+  if (fused) {
+    MS2_TRY(ms2_gemm_res_ln(att, w.Cm, w.vo_w, w.vo_b, x, C, x, C, w.norm3_g, w.norm3_b, w.eps3, s.t, MS2_BF16, C, (int)R, w.Cm, st));
+  } else {
+    MS2_TRY(ms2_gemm(att, MS2_BF16, w.Cm, w.vo_w, MS2_BF16, w.vo_b, nullptr, x, C, x, MS2_F32, C, (int)R, C, w.Cm, 0, 0, st));
+    MS2_TRY(ms2_layernorm(x, nullptr, w.norm3_g, w.norm3_b, s.t, MS2_BF16, (int)R, C, w.eps3, 0, st));
+  }
   MS2_TRY(ms2_gemm(s.t, MS2_BF16, C, w.f1_w, MS2_BF16, w.f1_b, nullptr, nullptr, 0, s.h, MS2_BF16, w.F, (int)R, w.F, C, 2, 0, st));
+  if (fused && next_g)
+    return ms2_gemm_res_ln(s.h, w.F, w.f2_w, w.f2_b, x, C, x, C, next_g, next_b, next_eps, t_next, t_next_dt, C, (int)R, w.F, st);
   MS2_TRY(ms2_gemm(s.h, MS2_BF16, w.F, w.f2_w, MS2_BF16, w.f2_b, nullptr, x, C, x, MS2_F32, C, (int)R, C, w.F, 0, 0, st));
   return MS2_OK;
 }
@@ -203,12 +240,17 @@ extern "C" int ms2_memattn_forward(const void* layers, int n_layers, const float
   MS2_CHECK_ARG(s.ok, "memattn_forward: workspace too small (ms2_memattn_workspace_bytes)");
   if (curr_pos) MS2_TRY(ms2_axpby(curr, 1.0f, curr_pos, pos_scale, 0.0f, x, MS2_F32, R * C, R * C, stream));
   else MS2_CUDA(cudaMemcpyAsync(x, curr, R * C * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "memattn_forward copy");
+  const bool fused = fused_ok(w[0], R) && out != x;
   for (int l = 0; l < n_layers; ++l) {
-    MS2_TRY(layer_pre(w[l], x, s.q, s, B, L, stream));
+    MS2_TRY(layer_pre(w[l], x, s.q, s, B, L, stream, fused && l > 0));
     MS2_TRY(ms2_attention_dv(s.q, h_K[l], m_bank, s.att, MS2_BF16, (long)L * C, C, C, k_bs, C, C, m_bs, Cm, Cm, (long)L * Cm, Cm,
                              Cm, B, 1, L, Lk, C, Cm, 1.0f / sqrtf((float)C), s.split, split_budget(s.split_bytes, B, L, Lk, Cm),
                              stream));
-    MS2_TRY(layer_post(w[l], x, s.att, s, B, L, stream));
+    if (!fused) MS2_TRY(layer_post(w[l], x, s.att, s, B, L, stream));
+    else if (l + 1 < n_layers)      // the FFN epilogue writes the next layer's LN1 (bf16) ...
+      MS2_TRY(layer_post(w[l], x, s.att, s, B, L, stream, w[l + 1].norm1_g, w[l + 1].norm1_b, w[l + 1].eps1, s.t, MS2_BF16));
+    else                            // ... or the stack's final LayerNorm (fp32) straight into `out`
+      return layer_post(w[l], x, s.att, s, B, L, stream, norm_g, norm_b, norm_eps, out, MS2_F32);
   }
   return ms2_layernorm(x, nullptr, norm_g, norm_b, out, MS2_F32, (int)R, C, norm_eps, 0, stream);
 }

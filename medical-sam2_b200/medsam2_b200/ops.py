@@ -630,6 +630,30 @@ def stability_select(counts, ious, thresh):
     return idx, iou
 
 
+def gemm_res_ln(a, w, bias, residual, gamma, beta, eps, out_dtype=torch.bfloat16, x_out=None):
+    """x = residual + a @ w.T + bias (fp32, written to x_out or in place over residual) and t = LayerNorm(x):
+    a bf16 [M,K], w bf16 [256,K], residual fp32 [M,256] -> (x fp32 [M,256], t out_dtype [M,256]); M % 128 == 0."""
+    M, K = a.shape
+    x = residual if x_out is None else x_out
+    t = torch.empty((M, 256), dtype=out_dtype, device=a.device)
+    native.call("ms2_gemm_res_ln", _chk(a, "a", torch.bfloat16), K, _chk(w, "w", torch.bfloat16), _opt(bias, "bias"),
+                _chk(residual, "residual", torch.float32), 256, _chk(x, "x_out", torch.float32), 256,
+                _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32), float(eps), t.data_ptr(), _DT[t.dtype],
+                256, M, K, _st())
+    return x, t
+
+
+def gemm_rope(a, w, bias, L, rope_cols, cos_t, sin_t):
+    """bf16 [M,N] = a @ w.T + bias with the 256-wide column tiles below rope_cols rotated (row r: position r mod L)."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    native.call("ms2_gemm_rope", _chk(a, "a", torch.bfloat16), K, _chk(w, "w", torch.bfloat16), _opt(bias, "bias"),
+                out.data_ptr(), N, M, N, K, int(L), int(rope_cols), _chk(cos_t, "cos", torch.float32),
+                _chk(sin_t, "sin", torch.float32), cos_t.shape[0], _st())
+    return out
+
+
 def _dense(t):
     """the tensor covers its storage span exactly once (contiguous up to a permutation of the dimensions)"""
     if t.is_contiguous():

@@ -638,3 +638,43 @@ def test_multi_copy(ops):
     ops.multi_copy(list(zip(dsts, srcs)))
     for d, s in zip(dsts, srcs):
         assert torch.equal(d, s)
+
+
+@pytest.mark.parametrize("M,K,out_dtype", [(4096, 256, torch.bfloat16), (4096, 64, torch.bfloat16), (4096, 2048, torch.bfloat16),
+                                           (128, 256, torch.float32), (8192, 2048, torch.float32)])
+def test_gemm_res_ln(ops, M, K, out_dtype):
+    """x = residual + A W^T + b and t = LayerNorm(x) in one kernel (memory_attention.py:58-99,166) vs the fp32 statement
+    on the same bf16-rounded operands: x to fp32 accumulation-order accuracy, t to the output rounding."""
+    a = rnd(M, K, seed=1).to(torch.bfloat16)
+    w = (rnd(256, K, seed=2) / K ** 0.5).to(torch.bfloat16)
+    b, g, be = rnd(256, seed=3), 1 + 0.1 * rnd(256, seed=4), 0.1 * rnd(256, seed=5)
+    res = rnd(M, 256, seed=6) * 3 + 5                         # a mean well away from zero
+    x_ref = res + a.float() @ w.float().T + b
+    t_ref = F.layer_norm(x_ref, (256,), g, be, 1e-5)
+    x, t = ops.gemm_res_ln(a, w, b, res.clone(), g, be, 1e-5, out_dtype=out_dtype, x_out=torch.empty_like(res))
+    assert t.dtype == out_dtype
+    close(x, x_ref, 2e-5 * max(1.0, K ** 0.5 / 8), "gemm_res_ln x")
+    close(t, t_ref, 1e-4 if out_dtype == torch.float32 else 2e-2, "gemm_res_ln t")
+    # in place over the residual, and the same LayerNorm as the stand-alone kernel on the same x
+    r2 = res.clone()
+    x2, t2 = ops.gemm_res_ln(a, w, b, r2, g, be, 1e-5, out_dtype=out_dtype)
+    assert x2.data_ptr() == r2.data_ptr() and torch.equal(x2, x)
+    close(t2, ops.layernorm(x, g, be, 1e-5, out_dtype=out_dtype), 1e-5 if out_dtype == torch.float32 else 3.2e-2, "vs ms2_layernorm")   # one bf16 ulp of |t| < 8
+
+
+@pytest.mark.parametrize("B,L,N,rope_cols,K", [(1, 4096, 256, 256, 256), (1, 4096, 768, 512, 256), (2, 1024, 768, 512, 256),
+                                              (1, 128, 256, 0, 64)])
+def test_gemm_rope(ops, B, L, N, rope_cols, K):
+    """projection + rotary encoding in one kernel == ms2_gemm (bf16 out) followed by ms2_rope on the rotated column
+    tiles, bit for bit (the kernel rounds the projection to bf16 before rotating, like the two-kernel path)."""
+    a = rnd(B * L, K, seed=1).to(torch.bfloat16)
+    w = (rnd(N, K, seed=2) / K ** 0.5).to(torch.bfloat16)
+    b = rnd(N, seed=3)
+    T = min(L, 4096)
+    ang = rnd(T, 128, seed=4) * 3
+    cos_t, sin_t = torch.cos(ang).contiguous(), torch.sin(ang).contiguous()
+    got = ops.gemm_rope(a, w, b, L, rope_cols, cos_t, sin_t)
+    ref = ops.gemm(a, w, b, out_dtype=torch.bfloat16)
+    for c0 in range(0, rope_cols, 256):
+        ops.rope_(ref[:, c0:], B, L, L, 256, cos_t, sin_t, batch_stride=L * N, row_stride=N)
+    assert torch.equal(got, ref), (got.float() - ref.float()).abs().max().item()
