@@ -258,6 +258,20 @@ fill_holes_local_kernel(const float* __restrict__ in, float* __restrict__ out, l
   const float v = img[pix];
   float res = v;
   if (v <= thresh) {
+    // every background pixel of the 3x3 neighbourhood is an 8-neighbour of this one, i.e. in its component: more than
+    // max_area of them settle the question without a flood fill (almost every pixel of a real mask: max_area = 8 < 9)
+    int near = 1;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int dy = (d < 3) ? -1 : (d < 5 ? 0 : 1);
+      const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 1 || d == 6) ? 0 : 1);
+      const int ny = y0 + dy, nx = x0 + dx;
+      if (ny >= 0 && ny < H && nx >= 0 && nx < W) near += (img[ny * W + nx] <= thresh) ? 1 : 0;
+    }
+    if (near > max_area) {
+      out[p] = v;
+      return;
+    }
     int q[kLocalMaxArea];
     q[0] = (y0 << 16) | x0;
     int cnt = 1, head = 0;

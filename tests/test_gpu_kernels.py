@@ -678,3 +678,12 @@ def test_gemm_rope(ops, B, L, N, rope_cols, K):
     for c0 in range(0, rope_cols, 256):
         ops.rope_(ref[:, c0:], B, L, L, 256, cos_t, sin_t, batch_stride=L * N, row_stride=N)
     assert torch.equal(got, ref), (got.float() - ref.float()).abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W,dt", [(1, 1024, 1024, torch.float32), (2, 512, 520, torch.bfloat16), (1, 28, 300, torch.float32)])
+def test_patch_im2col_tiled(ops, B, H, W, dt):
+    """the shared-memory tiled patch gather (64 output pixels per CTA, partial last tile, bf16 frames) == the statement"""
+    img = rnd(B, 3, H, W, seed=5).to(dt)
+    got = ops.patch_im2col(img)
+    ref = ref_ops.patch_im2col(img.float())
+    assert got.shape == ref.shape and torch.equal(got.float(), ref.float())
