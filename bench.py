@@ -124,9 +124,10 @@ def prompt_frames(T, every):
     return list(range(0, T, every))
 
 
-def run_volume(predictor, vol, boxes, size, every):
+def run_volume(predictor, vol, boxes, size, every, sink=None):
     """The timed unit: func_3d/function.py:226-274's call order on one volume.  A host (pinned) volume is uploaded
-    through the predictor's own async frame loading (`async_loading_frames=True`, a reference API flag)."""
+    through the predictor's own async frame loading (`async_loading_frames=True`, a reference API flag).  `sink(f, m)` is
+    the caller's per-slice consumer (the validation loop thresholds every mask as it is yielded, function.py:283-293)."""
     st = predictor.val_init_state(imgs_tensor=vol, video_height=size, video_width=size,
                                   async_loading_frames=not vol.is_cuda)
     for f in prompt_frames(vol.shape[0], every):
@@ -135,7 +136,36 @@ def run_volume(predictor, vol, boxes, size, every):
     masks = [None] * vol.shape[0]
     for f, _, m in predictor.propagate_in_video(st, start_frame_idx=0):
         masks[f] = m
+        if sink is not None:
+            sink(f, m)
     return masks
+
+
+class MaskSink:
+    """Per-slice consumer of the end-to-end arm: binarise the yielded video-resolution logits into a device uint8 volume
+    and send it to pinned host memory in blocks of `block` slices on a side stream, so the device->host read of the result
+    overlaps the tracking of the following slices instead of trailing the step."""
+
+    def __init__(self, out_host, block=16):
+        self.out_host, self.block = out_host, block
+        self.out_dev = torch.empty(out_host.shape, dtype=torch.uint8, device="cuda")
+        self.stream = torch.cuda.Stream()
+        self.done = 0
+
+    def __call__(self, f, m):
+        torch.gt(m[0, 0], 0, out=self.out_dev[f].view(torch.bool))
+        T = self.out_host.shape[0]
+        if f + 1 == self.done + self.block or f + 1 == T:          # slices arrive in order (forward propagation)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                self.out_host[self.done: f + 1].copy_(self.out_dev[self.done: f + 1], non_blocking=True)
+            self.done = f + 1
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.done = 0
 
 
 def cpu_oracle_rate(args, n_slices, threads=None):
@@ -554,15 +584,18 @@ def main_ours(args):
 
     out_host = torch.empty((T, S, S), dtype=torch.uint8).pin_memory()
 
+    sink = MaskSink(out_host)
+
     def step_e2e():
         l2_flush.zero_()
         if shard_encode:
             masks = run_sharded(vol_host.to("cuda", non_blocking=True))
+            if masks[0] is not None:
+                res = torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8)
+                out_host.copy_(res, non_blocking=True)
         else:
-            masks = run_volume(model, vol_host, boxes, S, args.prompt_every)   # H2D streamed inside the public API
-        if masks[0] is not None:
-            res = torch.stack([(m[0, 0] > 0) for m in masks]).to(torch.uint8)
-            out_host.copy_(res, non_blocking=True)
+            run_volume(model, vol_host, boxes, S, args.prompt_every, sink=sink)   # H2D streamed inside the public API,
+            sink.finish()                                                        # D2H of the binarised masks block by block
         torch.cuda.current_stream().synchronize()
 
     for _ in range(args.warmup):
