@@ -325,11 +325,20 @@ __global__ void __launch_bounds__(256) normalize_image_kernel(const void* __rest
   const int W4 = (W + 3) >> 2;
   const long n = (long)B * 3 * H * W4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    long t = i;
-    const int xq = t % W4; t /= W4;
-    const int yh = t % H; t /= H;
-    const int c = t % 3;
-    const int b = t / 3;
+    int xq, yh, c, b;
+    if (n < (1L << 31)) {                        // 32-bit index arithmetic (64-bit divisions cost ~100 clk each)
+      unsigned t = (unsigned)i;
+      xq = t % (unsigned)W4; t /= (unsigned)W4;
+      yh = t % (unsigned)H; t /= (unsigned)H;
+      c = t % 3u;
+      b = t / 3u;
+    } else {
+      long t = i;
+      xq = t % W4; t /= W4;
+      yh = t % H; t /= H;
+      c = t % 3;
+      b = t / 3;
+    }
     const long o0 = (((long)b * 3 + c) * H + yh) * W + 4 * xq;
     const int cnt = min(4, W - 4 * xq);
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -345,7 +354,20 @@ __global__ void __launch_bounds__(256) normalize_image_kernel(const void* __rest
       const uint8_t* p = (const uint8_t*)x + (((long)b * H + yh) * W + 4 * xq) * 3 + c;
       for (int e = 0; e < cnt; ++e) v[e] = (float)p[3 * e];
     }
-    for (int e = 0; e < cnt; ++e) out[o0 + e] = from_f<OUT>((v[e] / 255.0f - mean[c]) / stdv[c]);
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = (v[e] / 255.0f - mean[c]) / stdv[c];
+    OUT* po = out + o0;
+    if (cnt == 4 && ((uintptr_t)po & (4 * sizeof(OUT) - 1)) == 0) {          // one 16-byte (fp32) / 8-byte (bf16) store
+      if (sizeof(OUT) == 4) {
+        *(float4*)po = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
+        *(uint2*)po = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+      }
+    } else {
+      for (int e = 0; e < cnt; ++e) po[e] = from_f<OUT>(r[e]);
+    }
   }
 }
 
