@@ -293,17 +293,26 @@ def _sync_all(world):
         torch.cuda.synchronize()
 
 
+_LAST_STEPS = []
+
+
 def _timed(fn, steps, world):
     """CUDA events around `steps` calls, barrier + synchronize on both sides, max over ranks -> ms."""
     import torch.distributed as dist
     _sync_all(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [e0]
     e0.record()
-    for _ in range(steps):
+    for i in range(steps):
         fn()
+        if i + 1 < steps:                              # per-step markers (reported as `ms_steps`: outliers stay visible)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
     e1.record()
+    marks.append(e1)
     _sync_all(world)
     ms = e0.elapsed_time(e1)
+    _LAST_STEPS[:] = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -609,6 +618,7 @@ def main_ours(args):
         clocks.start()
     n0 = native.launch_count
     ms = timed(step_resident, args.steps)
+    ms_steps = [round(x, 2) for x in _LAST_STEPS]
     launches = native.launch_count - n0
     step_masks = {f: m.clone() for f, m in enumerate(last["masks"]) if m is not None} if rank == 0 else {}
     for _ in range(min(args.warmup, 2)):       # the host-upload path has its own first-use allocations (1.2 GB frame
@@ -710,7 +720,8 @@ def main_ours(args):
                "sample": cpu_sample_text(args, cores) + f", {secs:.1f} s"}
     total_slices = T * args.steps * (1 if shard_encode else world)
     line = {"metric": METRIC, "value": total_slices / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if shard_encode else "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_steps": ms_steps, "higher_is_better": True,
+            "scaling": "strong" if shard_encode else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_text(args),
                        "sharding": ("one volume: slice encoding sharded + NCCL all-gather of the pyramid; memory bank dealt to the ranks "
