@@ -13,7 +13,8 @@ import torch
 
 from . import ops
 from .modeling.sam2_base import NO_OBJ_SCORE, SAM2Base
-from .utils.misc import concat_points, fill_holes_in_mask_scores, load_video_frames, load_video_frames_from_data
+from .utils.misc import (concat_points, fill_holes_in_mask_scores, load_video_frames, load_video_frames_from_data,
+                         to_device_async)
 
 
 _ENCODE_STREAMS = {}
@@ -162,8 +163,8 @@ class SAM2VideoPredictor(SAM2Base):
             labels = labels.unsqueeze(0)
         if normalize_coords:
             points = points / torch.tensor([st["video_width"], st["video_height"]]).to(points.device)
-        points = (points * self.image_size).to(st["device"])
-        labels = labels.to(st["device"])
+        points = to_device_async(points * self.image_size, st["device"])
+        labels = to_device_async(labels, st["device"])
         old = None if clear_old_points else st["point_inputs_per_obj"][obj_idx].get(frame_idx, None)
         point_inputs = concat_points(old, points, labels)
         st["point_inputs_per_obj"][obj_idx][frame_idx] = point_inputs

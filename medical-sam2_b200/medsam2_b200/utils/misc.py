@@ -68,6 +68,49 @@ def _frame_dtype(device_frames=True):
     return compute_dtype() if device_frames else torch.float32
 
 
+class _PinnedRing:
+    """256 pinned 256-byte slots allocated ONCE (a pinned allocation per prompt would bring its own stalls): slot i is reused
+    only after the event recorded behind its previous copy has completed (normally long ago: 256 uploads earlier)."""
+    SLOTS, SLOT_BYTES = 256, 256
+
+    def __init__(self):
+        self.buf = torch.empty(self.SLOTS * self.SLOT_BYTES, dtype=torch.uint8, pin_memory=True)
+        self.events = [None] * self.SLOTS
+        self.next = 0
+
+    def stage(self, t, device):
+        nbytes = t.numel() * t.element_size()
+        if nbytes == 0 or nbytes > self.SLOT_BYTES:
+            return None
+        i, self.next = self.next, (self.next + 1) % self.SLOTS
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        view = self.buf[i * self.SLOT_BYTES: i * self.SLOT_BYTES + nbytes].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        out = view.to(device, non_blocking=True)
+        if self.events[i] is None:
+            self.events[i] = torch.cuda.Event()
+        self.events[i].record(torch.cuda.current_stream(out.device))
+        return out
+
+
+_RING = None
+
+
+def to_device_async(t, device):
+    """Small host tensor (prompt coordinates, labels) -> device WITHOUT draining the stream: `cudaMemcpyAsync` from
+    pageable memory synchronises the stream before the copy starts, which turns every prompt into a host<->GPU round
+    trip (the reference does exactly that: `points.to(device)`, sam2_video_predictor.py:222-224).  Staged through a pinned
+    slot the copy is a plain stream-ordered DMA; tensors beyond 256 bytes take the ordinary path."""
+    global _RING
+    if t.is_cuda or torch.device(device).type != "cuda":
+        return t.to(device)
+    if _RING is None:
+        _RING = _PinnedRing()
+    out = _RING.stage(t.contiguous(), device)
+    return out if out is not None else t.to(device)
+
+
 class StreamedFrames:
     """Frames of a HOST tensor uploaded and normalised chunk by chunk on a side stream (the counterpart of the
     reference's AsyncVideoFrameLoader, utils/misc.py:92-160, for frames that are already decoded): indexing a frame
