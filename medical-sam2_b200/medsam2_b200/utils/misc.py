@@ -103,8 +103,8 @@ def to_device_async(t, device):
     trip (the reference does exactly that: `points.to(device)`, sam2_video_predictor.py:222-224).  Staged through a pinned
     slot the copy is a plain stream-ordered DMA; tensors beyond 256 bytes take the ordinary path."""
     global _RING
-    if t.is_cuda or torch.device(device).type != "cuda":
-        return t.to(device)
+    if t.is_cuda or torch.device(device).type != "cuda" or os.environ.get("MS2_PINNED_PROMPTS", "1") == "0":
+        return t.to(device)              # (MS2_PINNED_PROMPTS=0: the reference's pageable copy, for A/B measurements)
     if _RING is None:
         _RING = _PinnedRing()
     out = _RING.stage(t.contiguous(), device)
