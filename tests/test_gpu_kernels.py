@@ -687,3 +687,22 @@ def test_patch_im2col_tiled(ops, B, H, W, dt):
     got = ops.patch_im2col(img)
     ref = ref_ops.patch_im2col(img.float())
     assert got.shape == ref.shape and torch.equal(got.float(), ref.float())
+
+
+def test_to_device_async_ring():
+    """prompt tensors staged through the pinned ring: values survive slot reuse (more uploads than slots, no host
+    synchronisation in between), oversize tensors take the ordinary path, device tensors pass through"""
+    from medsam2_b200.utils.misc import _PinnedRing, to_device_async
+    outs, refs = [], []
+    for i in range(3 * _PinnedRing.SLOTS + 5):
+        t = torch.full((1, 1 + i % 7, 2), float(i)) + torch.arange(2)
+        lab = torch.full((1, 1 + i % 7), i, dtype=torch.int32)
+        outs += [to_device_async(t, "cuda"), to_device_async(lab, "cuda")]
+        refs += [t, lab]
+    big = torch.arange(1000, dtype=torch.float32)
+    assert torch.equal(to_device_async(big, "cuda").cpu(), big)
+    d = torch.ones(3, device="cuda")
+    assert to_device_async(d, "cuda") is d
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert o.is_cuda and o.dtype == r.dtype and torch.equal(o.cpu(), r)
