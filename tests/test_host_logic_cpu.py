@@ -287,3 +287,21 @@ def test_jpeg_ingest_host_path(tmp_path):
         d2 = tmp_path / "empty"
         d2.mkdir()
         load_video_frames(str(d2), image_size=64)
+
+
+def test_dense_layout_predicate_and_prompt_staging_fallback():
+    """ops._dense decides whether a graph input / result can move as a raw byte copy (ms2_multi_copy); a host-to-host
+    `to_device_async` is the plain `.to` (the pinned staging ring only exists for CUDA destinations)."""
+    import torch
+    from medsam2_b200 import ops
+    from medsam2_b200.utils.misc import to_device_async
+    assert ops._dense(torch.zeros(4, 5, 6))
+    assert ops._dense(torch.zeros(2, 8, 16, 16).permute(0, 3, 1, 2))          # channels-last view: dense, not contiguous
+    assert ops._dense(torch.zeros(4, 1, 5).transpose(0, 2))
+    assert ops._dense(torch.zeros(0))
+    assert not ops._dense(torch.zeros(16, 16)[:, ::2])                       # gaps
+    assert not ops._dense(torch.zeros(3, 1).expand(3, 4))                    # overlapping (stride 0)
+    assert not ops._dense(torch.zeros(8, 8)[:4, :4])                         # window of a larger buffer
+    t = torch.arange(6, dtype=torch.float32).view(1, 3, 2)
+    out = to_device_async(t, "cpu")
+    assert out.device.type == "cpu" and torch.equal(out, t)
