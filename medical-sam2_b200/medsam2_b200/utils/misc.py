@@ -94,7 +94,7 @@ class _PinnedRing:
         return out
 
 
-_RING = None
+_RINGS = {}                      # one ring per destination device (its events belong to that device)
 
 
 def to_device_async(t, device):
@@ -102,12 +102,14 @@ def to_device_async(t, device):
     pageable memory synchronises the stream before the copy starts, which turns every prompt into a host<->GPU round
     trip (the reference does exactly that: `points.to(device)`, sam2_video_predictor.py:222-224).  Staged through a pinned
     slot the copy is a plain stream-ordered DMA; tensors beyond 256 bytes take the ordinary path."""
-    global _RING
-    if t.is_cuda or torch.device(device).type != "cuda" or os.environ.get("MS2_PINNED_PROMPTS", "1") == "0":
+    dev = torch.device(device)
+    if t.is_cuda or dev.type != "cuda" or os.environ.get("MS2_PINNED_PROMPTS", "1") == "0":
         return t.to(device)              # (MS2_PINNED_PROMPTS=0: the reference's pageable copy, for A/B measurements)
-    if _RING is None:
-        _RING = _PinnedRing()
-    out = _RING.stage(t.contiguous(), device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ring = _RINGS.get(key)
+    if ring is None:
+        ring = _RINGS[key] = _PinnedRing()
+    out = ring.stage(t.contiguous(), dev)
     return out if out is not None else t.to(device)
 
 
